@@ -1,0 +1,555 @@
+// C-ABI entry points (include/hrt_b200.h) and the launch logic behind them.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/hrt_b200.h"
+#include "hrt_fk.cuh"
+#include "hrt_retarget.cuh"
+
+using namespace hrt;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define HRT_CUDA(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail((int)e_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct Tree {
+    bool set = false;
+    bool has_dof = false;
+    TreeParams tp;
+    std::vector<float> t2z;       // host copy (J*4) or empty
+    float* d_t2z = nullptr;       // device copy
+    int* d_parents = nullptr;
+};
+
+constexpr int kHostStreams = 3;
+
+}  // namespace
+
+struct hrt_ctx {
+    int device = 0;
+    int sm_count = 0;
+    Tree trees[HRT_MAX_TREES];
+    bool bq_set = false;
+    BodyQuatParams bq;
+    // staging for the *_host call
+    cudaStream_t hs[kHostStreams] = {nullptr, nullptr, nullptr};
+    cudaEvent_t hs_done[kHostStreams] = {nullptr, nullptr, nullptr};
+    float* d_stage[kHostStreams] = {nullptr, nullptr, nullptr};
+    size_t d_stage_bytes = 0;
+    // streaming mailboxes (mapped pinned memory)
+    bool stream_open = false;
+    float* mb_in = nullptr;
+    float* mb_out = nullptr;
+    float *mb_in_d = nullptr, *mb_out_d = nullptr;
+    cudaStream_t ss = nullptr;
+    BodyQuatArgs stream_args;
+};
+
+namespace {
+
+int check_ctx(hrt_ctx* ctx) {
+    if (!ctx) return fail(HRT_E_INVALID_ARG, "null context");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail((int)e, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+    return 0;
+}
+
+int get_tree(hrt_ctx* ctx, int tree, Tree** out) {
+    if (tree < 0 || tree >= HRT_MAX_TREES) return fail(HRT_E_INVALID_ARG, "tree id %d out of range", tree);
+    if (!ctx->trees[tree].set) return fail(HRT_E_NOT_CONFIGURED, "tree %d not installed (hrt_set_tree)", tree);
+    *out = &ctx->trees[tree];
+    return 0;
+}
+
+template <typename K>
+int grid_for(hrt_ctx* ctx, K kernel, int threads, size_t smem, long long n_ctas_wanted, int* grid) {
+    int per_sm = 0;
+    HRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long cap = (long long)ctx->sm_count * per_sm;
+    *grid = (int)std::max(1LL, std::min(n_ctas_wanted, cap));
+    return 0;
+}
+
+template <bool FROM_ANGLES>
+int launch_fk(hrt_ctx* ctx, Tree* t, const FkArgs& a, unsigned flags, cudaStream_t st) {
+    const size_t smem = (size_t)FK_WARPS_PER_CTA * FK_WARP_WORDS * sizeof(float);
+    const long long groups = (a.B + 31) / 32;
+    const long long ctas = (groups + FK_WARPS_PER_CTA - 1) / FK_WARPS_PER_CTA;
+    int grid = 1;
+    if (flags & HRT_FK_EXACT) {
+        int rc = grid_for(ctx, fk_kernel<FROM_ANGLES, true>, FK_WARPS_PER_CTA * 32, smem, ctas, &grid);
+        if (rc) return rc;
+        fk_kernel<FROM_ANGLES, true><<<grid, FK_WARPS_PER_CTA * 32, smem, st>>>(t->tp, a);
+    } else {
+        int rc = grid_for(ctx, fk_kernel<FROM_ANGLES, false>, FK_WARPS_PER_CTA * 32, smem, ctas, &grid);
+        if (rc) return rc;
+        fk_kernel<FROM_ANGLES, false><<<grid, FK_WARPS_PER_CTA * 32, smem, st>>>(t->tp, a);
+    }
+    HRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_body_quat(hrt_ctx* ctx, const BodyQuatArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)BQ_WARPS_PER_CTA * BQ_TILE_WORDS * sizeof(float);
+    const long long groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
+    const long long ctas = (groups + BQ_WARPS_PER_CTA - 1) / BQ_WARPS_PER_CTA;
+    int grid = 1;
+    int rc = grid_for(ctx, body_quat_kernel, BQ_WARPS_PER_CTA * 32, smem, ctas, &grid);
+    if (rc) return rc;
+    body_quat_kernel<<<grid, BQ_WARPS_PER_CTA * 32, smem, st>>>(ctx->bq, a);
+    HRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fill_body_quat_args(hrt_ctx* ctx, int64_t B, const float* src, unsigned flags, int ik_iters, float damping,
+                        float rot_weight, float* lq, float* dof, float* lp, BodyQuatArgs* a) {
+    if (!ctx->bq_set) return fail(HRT_E_NOT_CONFIGURED, "hrt_configure_body_quat has not been called");
+    if (B < 0) return fail(HRT_E_INVALID_ARG, "negative frame count");
+    if ((flags & HRT_BQ_IK) && (ik_iters < 0 || ik_iters > 1000)) return fail(HRT_E_INVALID_ARG, "ik_iters out of range");
+    a->B = B;
+    a->src_gq = src;
+    a->pre_transformed = (flags & HRT_BQ_PRE_TRANSFORMED) ? 1 : 0;
+    a->flags = (flags & HRT_BQ_CLAMP ? BQ_CLAMP : 0u) | (flags & HRT_BQ_IK ? BQ_IK : 0u);
+    a->ik_iters = ik_iters;
+    a->damping = damping;
+    a->rot_weight = rot_weight;
+    a->out_local_q = lq;
+    a->out_dof = dof;
+    a->out_link_pos = lp;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hrt_abi_version(void) { return HRT_ABI_VERSION; }
+
+const char* hrt_last_error_string(void) { return g_err; }
+
+int hrt_ctx_create(int device, hrt_ctx** out) {
+    if (!out) return fail(HRT_E_INVALID_ARG, "out is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(HRT_E_NO_DEVICE, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(HRT_E_INVALID_ARG, "device %d out of range (0..%d)", device, n - 1);
+    HRT_CUDA(cudaSetDevice(device));
+    hrt_ctx* c = new (std::nothrow) hrt_ctx();
+    if (!c) return fail(HRT_E_INVALID_ARG, "out of host memory");
+    c->device = device;
+    HRT_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    // the Jacobian kernel needs more than the default 48 KB of dynamic shared memory
+    HRT_CUDA(cudaFuncSetAttribute(jacobian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    *out = c;
+    return 0;
+}
+
+int hrt_ctx_destroy(hrt_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    hrt_stream_close(ctx);
+    for (auto& t : ctx->trees) {
+        if (t.d_t2z) cudaFree(t.d_t2z);
+        if (t.d_parents) cudaFree(t.d_parents);
+    }
+    for (int i = 0; i < kHostStreams; ++i) {
+        if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+        if (ctx->hs_done[i]) cudaEventDestroy(ctx->hs_done[i]);
+        if (ctx->hs[i]) cudaStreamDestroy(ctx->hs[i]);
+    }
+    delete ctx;
+    return 0;
+}
+
+int hrt_ctx_sm_count(const hrt_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int hrt_set_tree(hrt_ctx* ctx, int tree, int J, const int32_t* parents, const float* offsets,
+                 const uint8_t* dof_axis, const float* lower, const float* upper, const float* t2z) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (tree < 0 || tree >= HRT_MAX_TREES) return fail(HRT_E_INVALID_ARG, "tree id %d out of range", tree);
+    if (J < 1 || J > HRT_MAX_JOINTS) return fail(HRT_E_UNSUPPORTED_TREE, "J=%d outside 1..%d", J, HRT_MAX_JOINTS);
+    if (!parents || !offsets) return fail(HRT_E_INVALID_ARG, "parents/offsets are required");
+    if (parents[0] != -1) return fail(HRT_E_UNSUPPORTED_TREE, "joint 0 must be the root (parent -1)");
+    for (int j = 1; j < J; ++j)
+        if (parents[j] < 0 || parents[j] >= j)
+            return fail(HRT_E_UNSUPPORTED_TREE, "parents[%d]=%d: parents must precede children, single root", j, parents[j]);
+    Tree& t = ctx->trees[tree];
+    TreeParams& tp = t.tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.J = J;
+    // liveness-based slot allocation for parents that are not the previous joint
+    std::vector<int> last_use(J, -1);
+    for (int j = 1; j < J; ++j)
+        if (parents[j] != j - 1) last_use[parents[j]] = j;
+    int owner[HRT_MAX_SLOTS];
+    for (int s = 0; s < HRT_MAX_SLOTS; ++s) owner[s] = -1;
+    std::vector<int> slot_of(J, -1);
+    int n_slots = 0;
+    for (int j = 0; j < J; ++j) {
+        tp.parent[j] = (int8_t)parents[j];
+        tp.src_slot[j] = -1;
+        tp.save_slot[j] = -1;
+        if (j > 0 && parents[j] != j - 1) tp.src_slot[j] = (int8_t)slot_of[parents[j]];
+        if (last_use[j] > j) {
+            int s = -1;
+            for (int k = 0; k < HRT_MAX_SLOTS; ++k)
+                if (owner[k] < 0 || last_use[owner[k]] <= j) { s = k; break; }
+            if (s < 0) return fail(HRT_E_UNSUPPORTED_TREE, "tree needs more than %d live branch points", HRT_MAX_SLOTS);
+            owner[s] = j;
+            slot_of[j] = s;
+            tp.save_slot[j] = (int8_t)s;
+            n_slots = std::max(n_slots, s + 1);
+        }
+        for (int k = 0; k < 3; ++k) tp.off[j * 3 + k] = offsets[j * 3 + k];
+    }
+    tp.n_slots = n_slots;
+    t.has_dof = dof_axis != nullptr;
+    for (int j = 1; j < J; ++j) {
+        if (dof_axis) {
+            if (dof_axis[j - 1] > 2) return fail(HRT_E_INVALID_ARG, "dof_axis[%d]=%d not in 0..2", j - 1, dof_axis[j - 1]);
+            tp.axis[j] = dof_axis[j - 1];
+        }
+        tp.lower[j] = lower ? lower[j - 1] : -INFINITY;
+        tp.upper[j] = upper ? upper[j - 1] : INFINITY;
+    }
+    if (t.d_t2z) { cudaFree(t.d_t2z); t.d_t2z = nullptr; }
+    if (t.d_parents) { cudaFree(t.d_parents); t.d_parents = nullptr; }
+    t.t2z.clear();
+    HRT_CUDA(cudaMalloc(&t.d_parents, J * sizeof(int)));
+    HRT_CUDA(cudaMemcpy(t.d_parents, parents, J * sizeof(int), cudaMemcpyHostToDevice));
+    if (t2z) {
+        t.t2z.assign(t2z, t2z + J * 4);
+        HRT_CUDA(cudaMalloc(&t.d_t2z, J * 4 * sizeof(float)));
+        HRT_CUDA(cudaMemcpy(t.d_t2z, t2z, J * 4 * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    t.set = true;
+    return 0;
+}
+
+int hrt_fk_local_quats(hrt_ctx* ctx, int tree, int64_t B, const float* d_local_q, const float* d_root_t,
+                       float* d_gq, float* d_gt, unsigned flags, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    Tree* t;
+    if ((rc = get_tree(ctx, tree, &t))) return rc;
+    if (B < 0 || !d_local_q) return fail(HRT_E_INVALID_ARG, "bad B / null input");
+    if (!aligned16(d_local_q) || !aligned16(d_gq)) return fail(HRT_E_ALIGNMENT, "quaternion buffers must be 16-byte aligned");
+    if (B == 0) return 0;
+    FkArgs a{};
+    a.B = B; a.local_q = d_local_q; a.root_t = d_root_t; a.out_gq = d_gq; a.out_gt = d_gt;
+    return launch_fk<false>(ctx, t, a, flags, (cudaStream_t)stream);
+}
+
+int hrt_fk_angles(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, const float* d_root_t,
+                  const float* d_root_q, int clip, float* d_gq, float* d_gt, unsigned flags, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    Tree* t;
+    if ((rc = get_tree(ctx, tree, &t))) return rc;
+    if (!t->has_dof) return fail(HRT_E_NOT_CONFIGURED, "tree %d has no dof_axis table", tree);
+    if (B < 0 || !d_angles) return fail(HRT_E_INVALID_ARG, "bad B / null input");
+    if (!aligned16(d_root_q) || !aligned16(d_gq)) return fail(HRT_E_ALIGNMENT, "quaternion buffers must be 16-byte aligned");
+    if (B == 0) return 0;
+    FkArgs a{};
+    a.B = B; a.angles = d_angles; a.root_t = d_root_t; a.root_q = d_root_q; a.out_gq = d_gq; a.out_gt = d_gt;
+    a.clip = clip;
+    return launch_fk<true>(ctx, t, a, flags, (cudaStream_t)stream);
+}
+
+int hrt_fk_jacobian(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, const float* d_root_t,
+                    const float* d_root_q, int clip, const int32_t* links, int K, float* d_jac, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    Tree* t;
+    if ((rc = get_tree(ctx, tree, &t))) return rc;
+    if (!t->has_dof) return fail(HRT_E_NOT_CONFIGURED, "tree %d has no dof_axis table", tree);
+    if (B < 0 || !d_angles || !d_jac || !links) return fail(HRT_E_INVALID_ARG, "bad B / null pointer");
+    if (K < 1 || K > HRT_MAX_LINKS) return fail(HRT_E_INVALID_ARG, "K=%d outside 1..%d", K, HRT_MAX_LINKS);
+    if (!aligned16(d_root_q)) return fail(HRT_E_ALIGNMENT, "root_q must be 16-byte aligned");
+    JacParams jp;
+    memset(&jp, 0, sizeof(jp));
+    jp.K = K;
+    for (int k = 0; k < K; ++k) {
+        int l = links[k];
+        if (l < 0 || l >= t->tp.J) return fail(HRT_E_INVALID_ARG, "links[%d]=%d out of range", k, l);
+        int tmp[HRT_MAX_JOINTS], n = 0;
+        for (int j = l; j > 0; j = t->tp.parent[j]) tmp[n++] = j;
+        if (n > HRT_MAX_CHAIN) return fail(HRT_E_UNSUPPORTED_TREE, "chain to link %d deeper than %d", l, HRT_MAX_CHAIN);
+        jp.link[k] = l;
+        jp.depth[k] = n;
+        for (int c = 0; c < n; ++c) jp.chain[k][c] = (int8_t)tmp[n - 1 - c];
+    }
+    if (B == 0) return 0;
+    FkArgs a{};
+    a.B = B; a.angles = d_angles; a.root_t = d_root_t; a.root_q = d_root_q; a.out_jac = d_jac; a.clip = clip;
+    const int D = t->tp.J - 1;
+    const size_t smem = (size_t)JAC_WARPS_PER_CTA * 32 * (6 * D + 1) * sizeof(float);
+    const long long groups = (B + 31) / 32;
+    const long long ctas = (groups + JAC_WARPS_PER_CTA - 1) / JAC_WARPS_PER_CTA;
+    int grid = 1;
+    if ((rc = grid_for(ctx, jacobian_kernel, JAC_WARPS_PER_CTA * 32, smem, ctas, &grid))) return rc;
+    jacobian_kernel<<<grid, JAC_WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(t->tp, jp, a);
+    HRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hrt_local_from_global(hrt_ctx* ctx, int tree, int64_t B, const float* d_gq, float* d_lq, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    Tree* t;
+    if ((rc = get_tree(ctx, tree, &t))) return rc;
+    if (B < 0 || !d_gq || !d_lq) return fail(HRT_E_INVALID_ARG, "bad B / null pointer");
+    if (!aligned16(d_gq) || !aligned16(d_lq)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
+    if (B == 0) return 0;
+    const long long n = (long long)B * t->tp.J;
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+    local_from_global_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(d_gq), t->d_parents, t->tp.J, n, reinterpret_cast<float4*>(d_lq));
+    HRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static void rot_quat(int variant, float out[4]) {
+    // quat_from_angle_axis(torch.tensor(pi/2), axis) as the reference evaluates it in fp32
+    // (rotation3d.py:123-143): sin(pi/4) = cos(pi/4) = 0x3f3504f3, norm 0x3f7fffff, quotient
+    // 0x3f3504f4 (= 0.70710683).  Pinned by tests/golden/zero_pose_transform.npz.
+    union { uint32_t u; float f; } h;
+    h.u = 0x3f3504f4u;
+    out[0] = out[1] = out[2] = 0.f;
+    out[variant == 1 ? 0 : 2] = h.f;
+    out[3] = h.f;
+}
+
+int hrt_zero_pose_transform(hrt_ctx* ctx, int tree, int64_t B, const float* d_gq, int variant, float* d_out,
+                            void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    Tree* t;
+    if ((rc = get_tree(ctx, tree, &t))) return rc;
+    if (!t->d_t2z) return fail(HRT_E_NOT_CONFIGURED, "tree %d has no T2Z table", tree);
+    if (B < 0 || !d_gq || !d_out) return fail(HRT_E_INVALID_ARG, "bad B / null pointer");
+    if (variant != 0 && variant != 1) return fail(HRT_E_INVALID_ARG, "variant must be 0 (z) or 1 (x, broadcast)");
+    if (!aligned16(d_gq) || !aligned16(d_out)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
+    if (B == 0) return 0;
+    float r[4];
+    rot_quat(variant, r);
+    const long long n = (long long)B * t->tp.J;
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+    zero_pose_transform_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(d_gq), reinterpret_cast<const float4*>(t->d_t2z),
+        make_float4(r[0], r[1], r[2], r[3]), t->tp.J, n, reinterpret_cast<float4*>(d_out));
+    HRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hrt_configure_body_quat(hrt_ctx* ctx, int src_tree, int rob_tree, const int32_t* src_joints,
+                            const int32_t* rob_first) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    Tree *s, *r;
+    if ((rc = get_tree(ctx, src_tree, &s))) return rc;
+    if ((rc = get_tree(ctx, rob_tree, &r))) return rc;
+    if (!src_joints || !rob_first) return fail(HRT_E_INVALID_ARG, "null joint tables");
+    if (s->t2z.empty()) return fail(HRT_E_NOT_CONFIGURED, "source tree has no T2Z table");
+    if (!r->has_dof) return fail(HRT_E_NOT_CONFIGURED, "robot tree has no dof tables");
+    const TreeParams& rt = r->tp;
+    BodyQuatParams& bp = ctx->bq;
+    memset(&bp, 0, sizeof(bp));
+    bp.J_src = s->tp.J;
+    bp.J_rob = rt.J;
+    if (bp.J_rob * 4 * BQ_FRAMES_PER_WARP > BQ_TILE_WORDS || bp.J_src * 4 * BQ_FRAMES_PER_WARP > BQ_TILE_WORDS)
+        return fail(HRT_E_UNSUPPORTED_TREE, "skeleton too large for the fused kernel tile (max 31 joints)");
+    rot_quat(0, bp.rot_z90);
+    // zero-pose positions of every robot joint: p_j = off_j + p_parent (identity rotations)
+    std::vector<float> pos(rt.J * 3, 0.f);
+    for (int j = 1; j < rt.J; ++j)
+        for (int k = 0; k < 3; ++k) pos[j * 3 + k] = rt.off[j * 3 + k] + pos[rt.parent[j] * 3 + k];
+    for (int i = 0; i < rt.J * 3; ++i) bp.rest_pos[i] = pos[i];
+    for (int j = 1; j < rt.J; ++j) {
+        bp.lower_all[j] = rt.lower[j];
+        bp.upper_all[j] = rt.upper[j];
+        bp.axis_all[j] = rt.axis[j];
+    }
+    static const int arm_axis[7] = {1, 0, 2, 1, 0, 1, 2};
+    for (int side = 0; side < 2; ++side) {
+        ArmParams& ap = bp.arm[side];
+        const int32_t* sj = src_joints + side * 5;
+        for (int n = 0; n < 5; ++n)
+            if (sj[n] < 0 || sj[n] >= s->tp.J) return fail(HRT_E_INVALID_ARG, "src_joints[%d][%d]=%d out of range", side, n, sj[n]);
+        ap.src_torso = sj[0]; ap.src_shoulder = sj[1]; ap.src_upper = sj[2]; ap.src_lower = sj[3]; ap.src_hand = sj[4];
+        const int f = rob_first[side];
+        if (f < 1 || f + 8 >= rt.J) return fail(HRT_E_INVALID_ARG, "rob_first[%d]=%d out of range", side, f);
+        ap.rob_first = f;
+        for (int c = 0; c < 7; ++c) {
+            if (rt.axis[f + c] != arm_axis[c])
+                return fail(HRT_E_UNSUPPORTED_TREE, "arm hinge %d has axis %d, the fused kernel is built for (y,x,z,y,x,y,z)", c, rt.axis[f + c]);
+            if (c > 0 && rt.parent[f + c] != f + c - 1) return fail(HRT_E_UNSUPPORTED_TREE, "arm joints must form a chain");
+            ap.lower[c] = rt.lower[f + c];
+            ap.upper[c] = rt.upper[f + c];
+        }
+        if (rt.parent[f + 7] != f + 6 || rt.parent[f + 8] != f + 6)
+            return fail(HRT_E_UNSUPPORTED_TREE, "expected two gripper links under the wrist-yaw link");
+        for (int c = 0; c < 9; ++c)
+            for (int k = 0; k < 3; ++k) ap.off[c][k] = rt.off[(f + c) * 3 + k];
+        for (int n = 0; n < 5; ++n)
+            for (int k = 0; k < 4; ++k) ap.t2z[n][k] = s->t2z[sj[n] * 4 + k];
+        for (int k = 0; k < 3; ++k) {
+            bp.shoulder_p[side][k] = pos[f * 3 + k];
+            ap.seg_elbow[k] = pos[(f + 3) * 3 + k] - pos[f * 3 + k];
+            ap.seg_wrist[k] = pos[(f + 6) * 3 + k] - pos[(f + 3) * 3 + k];
+        }
+        // the arm hangs off the torso link, which keeps identity rotation in this pipeline
+        const int torso = rt.parent[f];
+        for (int k = 0; k < 3; ++k) bp.torso_p[k] = pos[torso * 3 + k];
+    }
+    ctx->bq_set = true;
+    return 0;
+}
+
+int hrt_retarget_body_quat(hrt_ctx* ctx, int64_t B, const float* d_src_gq, unsigned flags, int ik_iters,
+                           float damping, float rot_weight, float* d_robot_local_q, float* d_dof,
+                           float* d_link_pos, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    BodyQuatArgs a;
+    if ((rc = fill_body_quat_args(ctx, B, d_src_gq, flags, ik_iters, damping, rot_weight, d_robot_local_q, d_dof,
+                                  d_link_pos, &a)))
+        return rc;
+    if (!d_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
+    if (!aligned16(d_src_gq) || !aligned16(d_robot_local_q) || !aligned16(d_dof) || !aligned16(d_link_pos))
+        return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
+    if (B == 0) return 0;
+    return launch_body_quat(ctx, a, (cudaStream_t)stream);
+}
+
+int hrt_retarget_body_quat_host(hrt_ctx* ctx, int64_t B, const float* h_src_gq, unsigned flags, int ik_iters,
+                                float damping, float rot_weight, float* h_robot_local_q, float* h_dof,
+                                float* h_link_pos) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    BodyQuatArgs proto;
+    if ((rc = fill_body_quat_args(ctx, B, nullptr, flags, ik_iters, damping, rot_weight, nullptr, nullptr, nullptr, &proto)))
+        return rc;
+    if (!h_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
+    if (B == 0) return 0;
+    const int JS = ctx->bq.J_src, JR = ctx->bq.J_rob;
+    const size_t in_b = (size_t)JS * 16, lq_b = (size_t)JR * 16, dof_b = (size_t)(JR - 1) * 4, lp_b = (size_t)JR * 12;
+    const long long chunk = 1 << 16;                 // frames per pipeline stage (multiple of 16)
+    const size_t per_frame = in_b + lq_b + dof_b + lp_b;
+    const size_t need = per_frame * chunk;
+    if (ctx->d_stage_bytes < need) {
+        for (int i = 0; i < kHostStreams; ++i) {
+            if (ctx->d_stage[i]) { cudaFree(ctx->d_stage[i]); ctx->d_stage[i] = nullptr; }
+            HRT_CUDA(cudaMalloc(&ctx->d_stage[i], need));
+            if (!ctx->hs[i]) HRT_CUDA(cudaStreamCreateWithFlags(&ctx->hs[i], cudaStreamNonBlocking));
+            if (!ctx->hs_done[i]) HRT_CUDA(cudaEventCreateWithFlags(&ctx->hs_done[i], cudaEventDisableTiming));
+        }
+        ctx->d_stage_bytes = need;
+    }
+    int slot = 0;
+    for (long long f0 = 0; f0 < B; f0 += chunk, slot = (slot + 1) % kHostStreams) {
+        const long long n = std::min(chunk, (long long)B - f0);
+        cudaStream_t st = ctx->hs[slot];
+        char* base = reinterpret_cast<char*>(ctx->d_stage[slot]);
+        float* d_in = reinterpret_cast<float*>(base);
+        float* d_lq = reinterpret_cast<float*>(base + in_b * chunk);
+        float* d_dof = reinterpret_cast<float*>(base + (in_b + lq_b) * chunk);
+        float* d_lp = reinterpret_cast<float*>(base + (in_b + lq_b + dof_b) * chunk);
+        // stream order on `st` already serialises reuse of this staging slot
+        HRT_CUDA(cudaMemcpyAsync(d_in, reinterpret_cast<const char*>(h_src_gq) + f0 * in_b, n * in_b, cudaMemcpyHostToDevice, st));
+        BodyQuatArgs a = proto;
+        a.B = n;
+        a.src_gq = d_in;
+        a.out_local_q = h_robot_local_q ? d_lq : nullptr;
+        a.out_dof = h_dof ? d_dof : nullptr;
+        a.out_link_pos = h_link_pos ? d_lp : nullptr;
+        if ((rc = launch_body_quat(ctx, a, st))) return rc;
+        if (h_robot_local_q)
+            HRT_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h_robot_local_q) + f0 * lq_b, d_lq, n * lq_b, cudaMemcpyDeviceToHost, st));
+        if (h_dof)
+            HRT_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h_dof) + f0 * dof_b, d_dof, n * dof_b, cudaMemcpyDeviceToHost, st));
+        if (h_link_pos)
+            HRT_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h_link_pos) + f0 * lp_b, d_lp, n * lp_b, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < kHostStreams; ++i) HRT_CUDA(cudaStreamSynchronize(ctx->hs[i]));
+    return 0;
+}
+
+int hrt_stream_open(hrt_ctx* ctx, unsigned flags, int ik_iters, float damping, float rot_weight) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (ctx->stream_open) hrt_stream_close(ctx);
+    BodyQuatArgs a;
+    if ((rc = fill_body_quat_args(ctx, 1, nullptr, flags, ik_iters, damping, rot_weight, nullptr, nullptr, nullptr, &a)))
+        return rc;
+    const int JS = ctx->bq.J_src, JR = ctx->bq.J_rob;
+    const size_t in_w = (size_t)JS * 4;
+    const size_t out_w = (size_t)JR * 4 + 32 + (size_t)JR * 3 + 3;   // local_q | dof (padded to 32) | link pos
+    HRT_CUDA(cudaHostAlloc(&ctx->mb_in, in_w * sizeof(float), cudaHostAllocMapped));
+    HRT_CUDA(cudaHostAlloc(&ctx->mb_out, out_w * sizeof(float), cudaHostAllocMapped));
+    HRT_CUDA(cudaHostGetDevicePointer(&ctx->mb_in_d, ctx->mb_in, 0));
+    HRT_CUDA(cudaHostGetDevicePointer(&ctx->mb_out_d, ctx->mb_out, 0));
+    HRT_CUDA(cudaStreamCreateWithFlags(&ctx->ss, cudaStreamNonBlocking));
+    a.src_gq = ctx->mb_in_d;
+    a.out_local_q = ctx->mb_out_d;
+    a.out_dof = ctx->mb_out_d + JR * 4;
+    a.out_link_pos = ctx->mb_out_d + JR * 4 + 32;
+    ctx->stream_args = a;
+    ctx->stream_open = true;
+    return 0;
+}
+
+int hrt_stream_frame(hrt_ctx* ctx, const float* h_src_gq, float* h_robot_local_q, float* h_dof,
+                     float* h_link_pos) {
+    if (!ctx || !ctx->stream_open) return fail(HRT_E_NOT_CONFIGURED, "hrt_stream_open has not been called");
+    if (!h_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
+    const int JS = ctx->bq.J_src, JR = ctx->bq.J_rob;
+    memcpy(ctx->mb_in, h_src_gq, (size_t)JS * 16);
+    const size_t smem = (size_t)BQ_WARPS_PER_CTA * BQ_TILE_WORDS * sizeof(float);
+    body_quat_kernel<<<1, BQ_WARPS_PER_CTA * 32, smem, ctx->ss>>>(ctx->bq, ctx->stream_args);
+    HRT_CUDA(cudaGetLastError());
+    HRT_CUDA(cudaStreamSynchronize(ctx->ss));
+    if (h_robot_local_q) memcpy(h_robot_local_q, ctx->mb_out, (size_t)JR * 16);
+    if (h_dof) memcpy(h_dof, ctx->mb_out + JR * 4, (size_t)(JR - 1) * 4);
+    if (h_link_pos) memcpy(h_link_pos, ctx->mb_out + JR * 4 + 32, (size_t)JR * 12);
+    return 0;
+}
+
+int hrt_stream_close(hrt_ctx* ctx) {
+    if (!ctx || !ctx->stream_open) return 0;
+    cudaSetDevice(ctx->device);
+    if (ctx->ss) { cudaStreamSynchronize(ctx->ss); cudaStreamDestroy(ctx->ss); ctx->ss = nullptr; }
+    if (ctx->mb_in) { cudaFreeHost(ctx->mb_in); ctx->mb_in = nullptr; }
+    if (ctx->mb_out) { cudaFreeHost(ctx->mb_out); ctx->mb_out = nullptr; }
+    ctx->stream_open = false;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+"""Thin Python handle on an hrt_ctx (include/hrt_b200.h).  PyTorch is plumbing only: it owns the
+device memory and the streams; every number is produced by the sm_100a kernels behind the C ABI."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import robot_config as cfg
+
+TREE_ROBOT, TREE_SOURCE, TREE_SOURCE_FULL = 0, 1, 2
+FK_EXACT = 1
+BQ_CLAMP, BQ_IK, BQ_PRE_TRANSFORMED = 1, 2, 4
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _np_ptr(a):
+    return C.c_void_p(0 if a is None else a.ctypes.data)
+
+
+def _f32c(t, device):
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(np.asarray(t))
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+class Engine:
+    """One hrt_ctx on one GPU.  Not thread-safe; make one per thread / stream of work."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.HrtError("no CUDA device visible: humanoid_real_time_retarget_b200 has no CPU path")
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        h = C.c_void_p()
+        _lib.check(self.lib.hrt_ctx_create(self.device.index, C.byref(h)))
+        self._h = h
+        self._trees = {}
+        self.sm_count = self.lib.hrt_ctx_sm_count(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.hrt_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ trees
+    def set_tree(self, tree, parents, offsets, dof_axis=None, lower=None, upper=None, t2z=None):
+        parents = np.ascontiguousarray(np.asarray(parents, dtype=np.int32))
+        offsets = np.ascontiguousarray(np.asarray(offsets, dtype=np.float32).reshape(-1, 3))
+        J = parents.shape[0]
+        assert offsets.shape[0] == J
+        ax = None if dof_axis is None else np.ascontiguousarray(np.asarray(dof_axis, dtype=np.uint8))
+        lo = None if lower is None else np.ascontiguousarray(np.asarray(lower, dtype=np.float32))
+        hi = None if upper is None else np.ascontiguousarray(np.asarray(upper, dtype=np.float32))
+        tz = None if t2z is None else np.ascontiguousarray(np.asarray(t2z, dtype=np.float32).reshape(J, 4))
+        for a in (ax, lo, hi):
+            assert a is None or a.shape[0] == J - 1
+        _lib.check(self.lib.hrt_set_tree(self._h, tree, J, _np_ptr(parents), _np_ptr(offsets), _np_ptr(ax),
+                                         _np_ptr(lo), _np_ptr(hi), _np_ptr(tz)))
+        self._trees[tree] = J
+
+    def set_standard_trees(self, robot="hu_v5"):
+        """Hu v5 (or Hu) robot + vtrdyn / vtrdyn_full sources from the bundled tables, and the fused
+        quaternion-path wiring of body_retargeter.py:40-73."""
+        sk = cfg.skeleton_tables()
+        if robot == "hu_v5":
+            self.set_tree(TREE_ROBOT, sk["hu_v5_zero_pose/parents"], sk["hu_v5_zero_pose/offsets"],
+                          cfg.Hu_v5_DOF_AXIS, cfg.Hu_v5_DOF_LOWER, cfg.Hu_v5_DOF_UPPER)
+        elif robot == "hu":
+            self.set_tree(TREE_ROBOT, sk["hu_zero_pose/parents"], sk["hu_zero_pose/offsets"],
+                          cfg.Hu_DOF_AXIS, cfg.Hu_DOF_LOWER, cfg.Hu_DOF_UPPER)
+        else:
+            raise ValueError(robot)
+        self.set_tree(TREE_SOURCE, sk["vtrdyn_zero_pose/parents"], sk["vtrdyn_zero_pose/offsets"], t2z=sk["t2z/vtrdyn"])
+        self.set_tree(TREE_SOURCE_FULL, sk["vtrdyn_full_zero_pose/parents"], sk["vtrdyn_full_zero_pose/offsets"],
+                      t2z=sk["t2z/vtrdyn_full"])
+        if robot == "hu_v5":
+            self.configure_body_quat(TREE_SOURCE, TREE_ROBOT, cfg.VTRDYN_ARM_JOINTS, cfg.HU_V5_ARM_FIRST)
+        return self
+
+    def configure_body_quat(self, src_tree, rob_tree, src_joints, rob_first):
+        sj = np.ascontiguousarray(np.asarray(src_joints, dtype=np.int32).reshape(2, 5))
+        rf = np.ascontiguousarray(np.asarray(rob_first, dtype=np.int32).reshape(2))
+        _lib.check(self.lib.hrt_configure_body_quat(self._h, src_tree, rob_tree, _np_ptr(sj), _np_ptr(rf)))
+        self._bq = (self._trees[src_tree], self._trees[rob_tree])
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ kernels on device tensors
+    def fk_local_quats(self, tree, local_q, root_t=None, exact=False, want_q=True, want_t=True):
+        J = self._trees[tree]
+        local_q = _f32c(local_q, self.device)
+        B = local_q.numel() // (J * 4)
+        assert local_q.numel() == B * J * 4
+        root_t = None if root_t is None else _f32c(root_t, self.device)
+        gq = torch.empty((B, J, 4), device=self.device, dtype=torch.float32) if want_q else None
+        gt = torch.empty((B, J, 3), device=self.device, dtype=torch.float32) if want_t else None
+        _lib.check(self.lib.hrt_fk_local_quats(self._h, tree, B, _ptr(local_q), _ptr(root_t), _ptr(gq), _ptr(gt),
+                                               FK_EXACT if exact else 0, self._stream()))
+        return gq, gt
+
+    def fk_angles(self, tree, angles, root_t=None, root_q=None, clip=True, exact=False, out=None):
+        J = self._trees[tree]
+        angles = _f32c(angles, self.device)
+        B = angles.numel() // (J - 1)
+        assert angles.numel() == B * (J - 1)
+        root_t = None if root_t is None else _f32c(root_t, self.device)
+        root_q = None if root_q is None else _f32c(root_q, self.device)
+        if out is None:
+            gq = torch.empty((B, J, 4), device=self.device, dtype=torch.float32)
+            gt = torch.empty((B, J, 3), device=self.device, dtype=torch.float32)
+        else:
+            gq, gt = out
+        _lib.check(self.lib.hrt_fk_angles(self._h, tree, B, _ptr(angles), _ptr(root_t), _ptr(root_q), int(bool(clip)),
+                                          _ptr(gq), _ptr(gt), FK_EXACT if exact else 0, self._stream()))
+        return gq, gt
+
+    def fk_jacobian(self, tree, angles, links, root_t=None, root_q=None, clip=True, out=None):
+        J = self._trees[tree]
+        angles = _f32c(angles, self.device)
+        B = angles.numel() // (J - 1)
+        links = np.ascontiguousarray(np.asarray(links, dtype=np.int32))
+        K = links.shape[0]
+        root_t = None if root_t is None else _f32c(root_t, self.device)
+        root_q = None if root_q is None else _f32c(root_q, self.device)
+        jac = out if out is not None else torch.empty((B, K, 6, J - 1), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.hrt_fk_jacobian(self._h, tree, B, _ptr(angles), _ptr(root_t), _ptr(root_q), int(bool(clip)),
+                                            _np_ptr(links), K, _ptr(jac), self._stream()))
+        return jac
+
+    def local_from_global(self, tree, global_q):
+        J = self._trees[tree]
+        global_q = _f32c(global_q, self.device)
+        B = global_q.numel() // (J * 4)
+        out = torch.empty_like(global_q)
+        _lib.check(self.lib.hrt_local_from_global(self._h, tree, B, _ptr(global_q), _ptr(out), self._stream()))
+        return out
+
+    def zero_pose_transform(self, tree, global_q, variant=0):
+        J = self._trees[tree]
+        global_q = _f32c(global_q, self.device)
+        B = global_q.numel() // (J * 4)
+        out = torch.empty_like(global_q)
+        _lib.check(self.lib.hrt_zero_pose_transform(self._h, tree, B, _ptr(global_q), variant, _ptr(out), self._stream()))
+        return out
+
+    def retarget_body_quat(self, src_gq, flags=0, ik_iters=10, damping=0.1, rot_weight=0.2,
+                           want_local_q=True, want_dof=True, want_link_pos=True, out=None):
+        """Fused quaternion path on device tensors.  Returns (robot_local_q, dof_pos, link_pos)."""
+        JS, JR = self._bq
+        src_gq = _f32c(src_gq, self.device)
+        B = src_gq.numel() // (JS * 4)
+        assert src_gq.numel() == B * JS * 4
+        if out is None:
+            lq = torch.empty((B, JR, 4), device=self.device, dtype=torch.float32) if want_local_q else None
+            dof = torch.empty((B, JR - 1), device=self.device, dtype=torch.float32) if want_dof else None
+            lp = torch.empty((B, JR, 3), device=self.device, dtype=torch.float32) if want_link_pos else None
+        else:
+            lq, dof, lp = out
+        _lib.check(self.lib.hrt_retarget_body_quat(self._h, B, _ptr(src_gq), flags, ik_iters, damping, rot_weight,
+                                                   _ptr(lq), _ptr(dof), _ptr(lp), self._stream()))
+        return lq, dof, lp
+
+    # ------------------------------------------------------------------ host-buffer (reference-facing) calls
+    def retarget_body_quat_host(self, src_gq, flags=0, ik_iters=10, damping=0.1, rot_weight=0.2,
+                                out_local_q=None, out_dof=None, out_link_pos=None):
+        """src_gq and the outputs are HOST tensors / arrays (pinned for full speed).  Copies are
+        inside the call (chunked, overlapped)."""
+        JS, JR = self._bq
+        assert src_gq.device.type == "cpu" and src_gq.dtype == torch.float32 and src_gq.is_contiguous()
+        B = src_gq.numel() // (JS * 4)
+        for t in (out_local_q, out_dof, out_link_pos):
+            assert t is None or (t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous())
+        _lib.check(self.lib.hrt_retarget_body_quat_host(self._h, B, _ptr(src_gq), flags, ik_iters, damping, rot_weight,
+                                                        _ptr(out_local_q), _ptr(out_dof), _ptr(out_link_pos)))
+        return out_local_q, out_dof, out_link_pos
+
+    def stream_open(self, flags=0, ik_iters=10, damping=0.1, rot_weight=0.2):
+        _lib.check(self.lib.hrt_stream_open(self._h, flags, ik_iters, damping, rot_weight))
+
+    def stream_frame(self, src_gq_np, out_local_q=None, out_dof=None, out_link_pos=None):
+        """numpy float32 in / out, one frame."""
+        _lib.check(self.lib.hrt_stream_frame(self._h, _np_ptr(src_gq_np), _np_ptr(out_local_q), _np_ptr(out_dof),
+                                             _np_ptr(out_link_pos)))
+
+    def stream_close(self):
+        _lib.check(self.lib.hrt_stream_close(self._h))
+
+
+_default = {}
+
+
+def default_engine(device=0, robot="hu_v5"):
+    key = (device, robot)
+    if key not in _default:
+        _default[key] = Engine(device).set_standard_trees(robot)
+    return _default[key]

@@ -1,0 +1,109 @@
+"""Drop-in for the quaternion-input retargeter and its helpers.
+
+  BaseHumanoidRetargeter            retarget/retarget_solver/base_retargeter.py:15-58
+  Mocap2HuBodyRetargeter            retarget/retarget_solver/body_retargeter.py:30-99
+  vtrdyn_zero_pose_transform & co.  retarget/utils/parse_mocap.py:81-89,106-114,126-134
+"""
+import numpy as np
+import torch
+
+from . import robot_config as cfg
+from .engine import (BQ_CLAMP, BQ_IK, BQ_PRE_TRANSFORMED, TREE_SOURCE, TREE_SOURCE_FULL, default_engine)
+from .kinematics import RobotZeroPose, cal_forward_kinematics
+
+
+def to_numpy(tensor):
+    """retarget/torch_ext.py:10-14."""
+    return tensor.cpu().numpy() if torch.is_tensor(tensor) else tensor
+
+
+def to_torch(tensor):
+    """retarget/torch_ext.py:17-21."""
+    return tensor if torch.is_tensor(tensor) else torch.from_numpy(tensor).to(torch.float32)
+
+
+def _zpt(global_rotation, tree, variant):
+    g = to_torch(global_rotation)
+    eng = default_engine(g.device.index or 0 if g.is_cuda else 0)
+    return eng.zero_pose_transform(tree, g, variant).reshape(g.shape).to(g.device)
+
+
+def vtrdyn_zero_pose_transform(global_rotation):
+    return _zpt(global_rotation, TREE_SOURCE, 0)
+
+
+def vtrdyn_full_zero_pose_transform(global_rotation):
+    return _zpt(global_rotation, TREE_SOURCE_FULL, 0)
+
+
+def vtrdyn_broadcast_zero_pose_transform(global_rotation):
+    return _zpt(global_rotation, TREE_SOURCE, 1)
+
+
+class BaseHumanoidRetargeter:
+    def __init__(self, source_zero_pose: RobotZeroPose, target_zero_pose: RobotZeroPose):
+        self.source_zero_pose = source_zero_pose
+        self.target_zero_pose = target_zero_pose
+        self._motion_local_rotation = []
+        self._motion_dof_pos = []
+
+    def _fk(self):
+        self._motion_global_rotation, self._motion_global_translation = cal_forward_kinematics(
+            motion_local_rotation=self.motion_local_rotation,
+            motion_root_translation=torch.zeros((self.motion_length, 3)),
+            parent_indices=self.target_zero_pose.parent_indices.tolist(),
+            zero_pose_local_translation=self.target_zero_pose.local_translation)
+
+    @property
+    def motion_global_rotation(self):
+        if not (hasattr(self, '_motion_global_rotation') and len(self._motion_global_rotation) == self.motion_length):
+            self._fk()
+        return self._motion_global_rotation.clone()
+
+    @property
+    def motion_global_translation(self):
+        if not (hasattr(self, '_motion_global_translation') and len(self._motion_global_translation) == self.motion_length):
+            self._fk()
+        return self._motion_global_translation.clone()
+
+    @property
+    def motion_local_rotation(self):
+        return torch.cat([x.reshape(-1, *x.shape[-2:]) for x in self._motion_local_rotation]).clone()
+
+    @property
+    def motion_dof_pos(self):
+        return torch.cat([x.reshape(-1, x.shape[-1]) for x in self._motion_dof_pos]).clone()
+
+    @property
+    def motion_length(self):
+        return sum(x.reshape(-1, *x.shape[-2:]).shape[0] for x in self._motion_local_rotation)
+
+
+class Mocap2HuBodyRetargeter(BaseHumanoidRetargeter):
+    """retarget_from_pose takes ONE frame (21,4) of zero-pose re-referenced global quats, like the
+    reference, or a batch (B,21,4).  Returns new tensors (robot_local_rotation, dof_pos)."""
+
+    def __init__(self, mocap_zero_pose: RobotZeroPose, target_zero_pose: RobotZeroPose, device=0):
+        super().__init__(mocap_zero_pose, target_zero_pose)
+        self._eng = default_engine(device)
+
+    def retarget_from_pose(self, source_global_rotation, record=True):
+        g = to_torch(source_global_rotation)
+        single = g.dim() == 2
+        lq, dof, _ = self._eng.retarget_body_quat(g.reshape(-1, 21, 4), flags=BQ_PRE_TRANSFORMED, want_link_pos=False)
+        lq, dof = lq.to(g.device), dof.to(g.device)
+        if single:
+            lq, dof = lq[0], dof[0]
+        if record:
+            self._motion_local_rotation.append(lq)
+            self._motion_dof_pos.append(dof)
+        return lq, dof
+
+    def retarget_clip(self, raw_global_rotation, clamp=True, ik_iters=10, damping=0.1, rot_weight=0.2):
+        """Whole pipeline on a (B,21,4) clip of RAW mocap quats: zero-pose transform, mapping, angle
+        decomposition, limits, IK refinement, FK.  Returns (robot_local_rotation, dof_pos, link_pos)."""
+        g = to_torch(raw_global_rotation)
+        flags = (BQ_CLAMP if clamp else 0) | (BQ_IK if ik_iters > 0 else 0)
+        out = self._eng.retarget_body_quat(g.reshape(-1, 21, 4), flags=flags, ik_iters=ik_iters, damping=damping,
+                                           rot_weight=rot_weight)
+        return tuple(o.to(g.device) for o in out)

@@ -1,0 +1,134 @@
+/* hrt_b200.h -- C ABI of the B200-native mocap -> humanoid retarget hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: its seam is the
+ * Python module boundary of retarget/spatial_transform/transform3d.py, retarget/torch_ext.py,
+ * robot_kinematics_model/ and retarget/retarget_solver/.  Every entry point below names the
+ * reference function whose numeric body it replaces (paths relative to the reference root).
+ * The Python host layer (humanoid_real_time_retarget_b200/) binds these with ctypes and keeps
+ * the reference's names and argument meanings; INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  `d_` = device pointer (the caller owns the
+ *     memory, e.g. a torch CUDA tensor's data_ptr), `h_` = host pointer.
+ *   - all tensors are contiguous fp32 in the reference's own layouts: quaternions xyzw (.., 4),
+ *     vectors (.., 3), frames on the leading axis.  Device pointers must be 16-byte aligned.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - every call returns 0 on success, a positive cudaError_t value on a CUDA failure, or a
+ *     negative HRT_E_* code on an argument error; hrt_last_error_string() describes the last
+ *     failure of the calling thread.  NaN in -> NaN out, like the reference.
+ *   - no global mutable state: skeleton tables live in the context and travel to the kernels as
+ *     __grid_constant__ parameter blocks.  A context may be used from one thread at a time;
+ *     different contexts are independent.  Nothing is allocated in the hot calls except by the
+ *     explicit *_host / stream entry points, which grow context-owned buffers on first use.
+ */
+#ifndef HRT_B200_H
+#define HRT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRT_ABI_VERSION 1
+
+#define HRT_E_INVALID_ARG (-1)
+#define HRT_E_NOT_CONFIGURED (-2)
+#define HRT_E_UNSUPPORTED_TREE (-3)
+#define HRT_E_ALIGNMENT (-4)
+#define HRT_E_NO_DEVICE (-5)
+
+#define HRT_MAX_TREES 4
+/* conventional tree slots used by the Python host layer */
+#define HRT_TREE_ROBOT 0      /* Hu / Hu v5 (robot_config/Hu.py, Hu_v5.py + zero-pose offsets) */
+#define HRT_TREE_SOURCE 1     /* vtrdyn, 21 joints (robot_config/VTRDYN.py:33-48) */
+#define HRT_TREE_SOURCE_FULL 2 /* vtrdyn_full, 59 joints (robot_config/VTRDYN_FULL.py:9-69) */
+
+/* flags of hrt_fk_* */
+#define HRT_FK_EXACT 1u       /* reference rounding order (bit-exact fp32 chain); default is FMA-fast */
+/* flags of hrt_retarget_body_quat */
+#define HRT_BQ_CLAMP 1u       /* clamp hinge angles to the joint limits */
+#define HRT_BQ_IK 2u          /* fused damped-least-squares refinement (implies clamp) */
+#define HRT_BQ_PRE_TRANSFORMED 4u /* input already zero-pose re-referenced: skip the a24 step */
+
+typedef struct hrt_ctx hrt_ctx;
+
+int hrt_abi_version(void);
+const char* hrt_last_error_string(void);
+
+/* Context: owns skeleton tables, streams and (for the *_host / stream calls) pinned + device staging. */
+int hrt_ctx_create(int device, hrt_ctx** out);
+int hrt_ctx_destroy(hrt_ctx* ctx);
+int hrt_ctx_sm_count(const hrt_ctx* ctx);
+
+/* Install a kinematic tree.  parents[J] (-1 for the root, parents before children), offsets[J*3] =
+ * zero-pose local translations (SkeletonTree.local_translation, skeleton3d.py:22-263; RobotZeroPose,
+ * robot_kinematics_model/base_robot.py:24-119).  dof_axis[J-1] / lower[J-1] / upper[J-1]: per-DOF hinge
+ * axis index and limits (robot_config/Hu.py:4-25, Hu_v5.py:12-33) or NULL for a mocap skeleton.
+ * t2z[J*4]: T-pose -> zero-pose global quats (parse_mocap.py:71-78,97-104) or NULL. */
+int hrt_set_tree(hrt_ctx* ctx, int tree, int J, const int32_t* parents, const float* offsets,
+                 const uint8_t* dof_axis, const float* lower, const float* upper, const float* t2z);
+
+/* cal_forward_kinematics (robot_kinematics_model/kinematics.py:13-39) and, through it,
+ * BaseForwardModel.forward_kinematics (base_forward_model.py:13-14):
+ * d_local_q (B,J,4), d_root_t (B,3) or NULL -> d_gq (B,J,4), d_gt (B,J,3) (either may be NULL). */
+int hrt_fk_local_quats(hrt_ctx* ctx, int tree, int64_t B, const float* d_local_q, const float* d_root_t,
+                       float* d_gq, float* d_gt, unsigned flags, void* stream);
+
+/* HuForwardModel.forward_kinematics (robot_kinematics_model/hu_forward_model.py:17-33):
+ * d_angles (B,J-1), d_root_t (B,3)|NULL, d_root_q (B,4)|NULL, clip -> joint limits with the forward
+ * value of the straight-through clamp (:27-33). */
+int hrt_fk_angles(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, const float* d_root_t,
+                  const float* d_root_q, int clip, float* d_gq, float* d_gt, unsigned flags, void* stream);
+
+/* Geometric Jacobian of K links (no reference counterpart):
+ * d_jac (B, K, 6, J-1): rows 0-2 linear a_i x (p_k - p_i), rows 3-5 angular a_i. */
+int hrt_fk_jacobian(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, const float* d_root_t,
+                    const float* d_root_q, int clip, const int32_t* links, int K, float* d_jac, void* stream);
+
+/* cal_local_rotation (robot_kinematics_model/kinematics.py:41-63); equals SkeletonState.local_rotation
+ * (skeleton3d.py:460-484) when tree.quat is identity. */
+int hrt_local_from_global(hrt_ctx* ctx, int tree, int64_t B, const float* d_gq, float* d_lq, void* stream);
+
+/* vtrdyn_zero_pose_transform / vtrdyn_full_zero_pose_transform (variant 0, about z) and
+ * vtrdyn_broadcast_zero_pose_transform (variant 1, about x): retarget/utils/parse_mocap.py:81-89,
+ * 106-114,126-134; retarget/retarget_solver/zero_pose_transform.py:33-41. */
+int hrt_zero_pose_transform(hrt_ctx* ctx, int tree, int64_t B, const float* d_gq, int variant, float* d_out,
+                            void* stream);
+
+/* Wire the fused quaternion-path pipeline: which source joints feed which arm.
+ * src_joints[2][5] = {torso, shoulder, upper arm, lower arm, hand} for the left then the right arm
+ * (vtrdyn: {10,17,18,19,20},{10,13,14,15,16}; body_retargeter.py:40-53), rob_first[2] = robot joint index
+ * of each shoulder-pitch link (Hu v5: 12, 21; body_retargeter.py:57-73). */
+int hrt_configure_body_quat(hrt_ctx* ctx, int src_tree, int rob_tree, const int32_t* src_joints,
+                            const int32_t* rob_first);
+
+/* Fused: zero-pose transform (a24) -> global-to-local (a21) -> Mocap2HuBodyRetargeter.retarget_from_pose
+ * (retarget/retarget_solver/body_retargeter.py:34-81: intrinsic 'YXZ'/'ZYX' Euler split in fp64 as SciPy
+ * does, transform3d.py:52-59) -> quat_to_dof_pos (transform3d.py:177-183) [-> limits -> ik_iters damped
+ * least-squares steps] -> FK of the result (kinematics.py:13-39).
+ * d_src_gq (B,Js,4) -> d_robot_local_q (B,Jr,4), d_dof (B,Jr-1), d_link_pos (B,Jr,3); any output may be NULL.
+ * With flags == 0 the first two outputs are the reference's (robot_local_rotation, dof_pos). */
+int hrt_retarget_body_quat(hrt_ctx* ctx, int64_t B, const float* d_src_gq, unsigned flags, int ik_iters,
+                           float damping, float rot_weight, float* d_robot_local_q, float* d_dof,
+                           float* d_link_pos, void* stream);
+
+/* The same call on HOST buffers (the reference-facing form: the reference works on CPU tensors).
+ * Chunks the clip, overlaps H2D / kernel / D2H on three streams with context-owned device staging.
+ * Pass page-locked memory for full PCIe speed; pageable memory works but is slower. Synchronous. */
+int hrt_retarget_body_quat_host(hrt_ctx* ctx, int64_t B, const float* h_src_gq, unsigned flags, int ik_iters,
+                                float damping, float rot_weight, float* h_robot_local_q, float* h_dof,
+                                float* h_link_pos);
+
+/* Streaming teleop: one frame at a time, host in -> host out (sim_full_body_teleop.py:83-129 call
+ * pattern).  open() allocates mapped pinned mailboxes and captures the launch; frame() is the hot call. */
+int hrt_stream_open(hrt_ctx* ctx, unsigned flags, int ik_iters, float damping, float rot_weight);
+int hrt_stream_frame(hrt_ctx* ctx, const float* h_src_gq, float* h_robot_local_q, float* h_dof,
+                     float* h_link_pos);
+int hrt_stream_close(hrt_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRT_B200_H */

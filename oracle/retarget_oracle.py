@@ -580,3 +580,161 @@ def retarget_full_body(body_q, body_t, lhand_t, rhand_t, src_offsets, num_robot_
     dof[:, 27] = torch.where(rc, zero, zero + 0.044)
     dof[:, 28] = torch.where(rc, zero, zero - 0.044)
     return rl, dof
+
+
+# ----------------------------------------------------------------------------------------------
+# Builder-specified parts: geometric Jacobian and damped-least-squares IK refinement.
+# NO reference implementation exists -> PARITY UNPINNED; this code is the spec
+# (DESIGN.md section 5).  The linear Jacobian rows are cross-checked against torch.autograd of the
+# reference-pinned FK above (tests/test_oracle_ik.py).
+# ----------------------------------------------------------------------------------------------
+def _axis_quat(theta, k):
+    """(.., ) angles about coordinate axis k -> (.., 4); plain (sin, cos) without renormalising."""
+    q = torch.zeros(theta.shape + (4,), dtype=theta.dtype)
+    q[..., k] = torch.sin(0.5 * theta)
+    q[..., 3] = torch.cos(0.5 * theta)
+    return q
+
+
+def geometric_jacobian(angles, root_t, root_q, parents, offsets, dof_axis, lower, upper, clip_angles, links):
+    """J (B, K, 6, D): for link k and hinge i (joint i = DOF i-1), a_i = R_parent(i) e_i,
+    J_v = a_i x (p_k - p_i), J_w = a_i if i is an ancestor-or-self of k, else 0.  Evaluated at the
+    clipped angles (straight-through clamp => no limit term)."""
+    B = angles.shape[0]
+    D = len(dof_axis)
+    gq, gt = hu_forward_kinematics(angles.reshape(B, D, 1), root_t, root_q.reshape(B, 1, 4), parents, offsets,
+                                   dof_axis, lower, upper, clip_angles)
+    eye = torch.eye(3)
+    J = torch.zeros(B, len(links), 6, D)
+    for n, k in enumerate(links):
+        j = k
+        while j > 0:
+            p = parents[j]
+            a = quat_rotate(gq[:, p], eye[dof_axis[j - 1]].expand(B, 3))
+            J[:, n, 0:3, j - 1] = torch.cross(a, gt[:, k] - gt[:, j], dim=-1)
+            J[:, n, 3:6, j - 1] = a
+            j = p
+    return J
+
+
+ARM_AXIS = [1, 0, 2, 1, 0, 1, 2]          # Hu_DOF_AXIS[11:18] == Hu_DOF_AXIS[20:27]
+
+
+def ik_refine_arm(theta0, p_sh, offs, lower, upper, pe_t, pw_t, qw_t, iters, damping, rot_weight):
+    """DESIGN.md section 5.  theta0 (B,7) warm start (already clamped); offs (9,3) offsets of the 7 arm
+    hinges + 2 gripper links; targets in the robot root frame.  Each step:
+      FK of the 7-hinge chain; e = [pe* - p_elbow; pw* - p_wrist; w_o * rotvec(qw* qw^-1)];
+      dtheta = (J^T J + lambda^2 I)^-1 J^T e;  theta <- clamp(theta + dtheta, lower, upper).
+    Exactly `iters` steps, no early exit."""
+    B = theta0.shape[0]
+    th = theta0.clone()
+    eye = torch.eye(3)
+    lo = torch.tensor(lower, dtype=torch.float32)
+    hi = torch.tensor(upper, dtype=torch.float32)
+    for _ in range(iters):
+        G = quat_identity((B,))
+        p = p_sh.expand(B, 3)
+        ax, pc = [], []
+        for c in range(7):
+            ax.append(quat_rotate(G, eye[ARM_AXIS[c]].expand(B, 3)))
+            pc.append(p)
+            G = quat_normalize(quat_mul(G, _axis_quat(th[:, c], ARM_AXIS[c])))
+            if c < 6:
+                p = p + quat_rotate(G, offs[c + 1].expand(B, 3))
+        qe = quat_normalize(quat_mul(qw_t, quat_conjugate(G)))
+        n = qe[:, :3].norm(dim=-1)
+        sc = torch.where(n > 1e-8, 2 * torch.atan2(n, qe[:, 3]) / n.clamp(min=1e-30), torch.full_like(n, 2.0))
+        e = torch.cat([pe_t - pc[3], pw_t - pc[6], rot_weight * sc.unsqueeze(-1) * qe[:, :3]], dim=-1)   # (B,9)
+        Jm = torch.zeros(B, 9, 7)
+        for c in range(7):
+            if c < 3:
+                Jm[:, 0:3, c] = torch.cross(ax[c], pc[3] - pc[c], dim=-1)
+            if c < 6:
+                Jm[:, 3:6, c] = torch.cross(ax[c], pc[6] - pc[c], dim=-1)
+            Jm[:, 6:9, c] = rot_weight * ax[c]
+        A = Jm.transpose(1, 2) @ Jm + (damping * damping) * torch.eye(7)
+        g = (Jm.transpose(1, 2) @ e.unsqueeze(-1))
+        L = torch.linalg.cholesky(A)
+        d = torch.cholesky_solve(g, L).squeeze(-1)
+        th = torch.minimum(torch.maximum(th + d, lo), hi)
+    return th
+
+
+def body_quat_pipeline(raw_gq, sk, clamp=True, ik_iters=10, damping=0.1, rot_weight=0.2, pre_transformed=False):
+    """The fused config-3q pipeline: a24 -> a21 -> a30 (+a16, a17) -> [limits -> IK] -> FK.
+    Returns robot_local_q (B,31,4), dof (B,30), link_pos (B,31,3).  With clamp=False, ik_iters=0 the
+    first two are exactly the reference's retarget_from_pose outputs."""
+    T = torch.from_numpy
+    src_par = sk["vtrdyn_zero_pose/parents"].tolist()
+    rob_par = sk["hu_v5_zero_pose/parents"].tolist()
+    rob_off = T(sk["hu_v5_zero_pose/offsets"])
+    zq = raw_gq if pre_transformed else zero_pose_transform(raw_gq, T(sk["t2z/vtrdyn"]))
+    rl, dof = retarget_body_quat(zq, src_par)
+    B = zq.shape[0]
+    do_ik = ik_iters > 0
+    if clamp or do_ik:
+        lo = torch.tensor(HU_V5_DOF_LOWER)
+        hi = torch.tensor(HU_V5_DOF_UPPER)
+        dof = dof.clone()
+        # zero-pose positions of the robot (identity rotations): p_j = off_j + p_parent
+        pos = torch.zeros(31, 3)
+        for j in range(1, 31):
+            pos[j] = rob_off[j] + pos[rob_par[j]]
+        for side, (first, sj) in enumerate([(12, [10, 17, 18, 19, 20]), (21, [10, 13, 14, 15, 16])]):
+            d0 = first - 1
+            th = torch.minimum(torch.maximum(dof[:, d0:d0 + 7], lo[d0:d0 + 7]), hi[d0:d0 + 7])
+            if do_ik:
+                Tc = quat_conjugate(zq[:, sj[0]])
+                Ru = quat_normalize(quat_mul(Tc, zq[:, sj[2]]))
+                Rf = quat_normalize(quat_mul(Tc, zq[:, sj[3]]))
+                Rh = quat_normalize(quat_mul(Tc, zq[:, sj[4]]))
+                p_sh = pos[first]
+                pe_t = p_sh + quat_rotate(Ru, (pos[first + 3] - pos[first]).expand(B, 3))
+                pw_t = pe_t + quat_rotate(Rf, (pos[first + 6] - pos[first + 3]).expand(B, 3))
+                th = ik_refine_arm(th, p_sh, rob_off[first:first + 9], HU_V5_DOF_LOWER[d0:d0 + 7],
+                                   HU_V5_DOF_UPPER[d0:d0 + 7], pe_t, pw_t, Rh, ik_iters, damping, rot_weight)
+            dof[:, d0:d0 + 7] = th
+            for c in range(7):
+                rl[:, first + c] = _axis_quat(th[:, c], ARM_AXIS[c])
+    _, link_pos = cal_forward_kinematics(rl, torch.zeros(B, 3), rob_par, rob_off)
+    return rl, dof, link_pos
+
+
+def ik_residual(dof, zq, sk, rot_weight=0.2):
+    """Residual norm of the IK objective at `dof` (for the 'refinement decreases the residual' test)."""
+    T = torch.from_numpy
+    rob_par = sk["hu_v5_zero_pose/parents"].tolist()
+    rob_off = T(sk["hu_v5_zero_pose/offsets"])
+    B = dof.shape[0]
+    pos = torch.zeros(31, 3)
+    for j in range(1, 31):
+        pos[j] = rob_off[j] + pos[rob_par[j]]
+    ax = torch.eye(3)[HU_V5_DOF_AXIS]
+    lq = quat_from_angle_axis(dof.reshape(-1), ax.repeat(B, 1, 1).reshape(-1, 3)).reshape(B, 30, 4)
+    lq = torch.cat([quat_identity((B, 1)), lq], dim=1)
+    gq, gt = cal_forward_kinematics(lq, torch.zeros(B, 3), rob_par, rob_off)
+    tot = torch.zeros(B)
+    for first, sj in [(12, [10, 17, 18, 19, 20]), (21, [10, 13, 14, 15, 16])]:
+        Tc = quat_conjugate(zq[:, sj[0]])
+        Ru = quat_normalize(quat_mul(Tc, zq[:, sj[2]]))
+        Rf = quat_normalize(quat_mul(Tc, zq[:, sj[3]]))
+        Rh = quat_normalize(quat_mul(Tc, zq[:, sj[4]]))
+        pe_t = pos[first] + quat_rotate(Ru, (pos[first + 3] - pos[first]).expand(B, 3))
+        pw_t = pe_t + quat_rotate(Rf, (pos[first + 6] - pos[first + 3]).expand(B, 3))
+        qe = quat_normalize(quat_mul(Rh, quat_conjugate(gq[:, first + 6])))
+        n = qe[:, :3].norm(dim=-1)
+        ang = 2 * torch.atan2(n, qe[:, 3])
+        tot = tot + ((pe_t - gt[:, first + 3]) ** 2).sum(-1) + ((pw_t - gt[:, first + 6]) ** 2).sum(-1) + (rot_weight * ang) ** 2
+    return tot.sqrt()
+
+
+def synth_clip_3q(L, seed=0, scale=0.5, sk=None):
+    """SURVEY.md 8(d) config 3q recipe (same as tools/make_golden.py clip_3q, through the oracle):
+    local exp-maps scale*N(0,1) on the vtrdyn T-pose tree -> FK -> raw global quats (L,21,4)."""
+    sk = load_skeletons() if sk is None else sk
+    g = torch.Generator().manual_seed(seed)
+    em = scale * torch.randn(L, 21, 3, generator=g)
+    lq = exp_map_to_quat(em)
+    gq, _ = cal_forward_kinematics(lq, torch.zeros(L, 3), sk["vtrdyn_t_pose/parents"].tolist(),
+                                   torch.from_numpy(sk["vtrdyn_t_pose/offsets"]))
+    return gq

@@ -1,0 +1,299 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against
+  (1) the golden fixtures produced by the UNMODIFIED reference (tests/golden, tools/make_golden.py),
+  (2) the CPU oracle on the same seeded inputs at sizes the oracle finishes in seconds,
+  (3) size-independent properties at BASELINE.json's full sizes (2^20 frames / 65,536 configs).
+
+Tolerances (BASELINE.json north_star): joint angles <= 1e-5 rad, FK link positions <= 1e-5 m,
+tables / pure fp32 arithmetic chains bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+T = torch.from_numpy
+ANGLE_TOL = 1e-5
+POS_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def hrt():
+    import __graft_entry__ as g
+    g.build()
+    import humanoid_real_time_retarget_b200 as h
+    return h
+
+
+@pytest.fixture(scope="module")
+def eng(hrt):
+    return hrt.default_engine(0)
+
+
+@pytest.fixture(scope="module")
+def eng_hu(hrt):
+    return hrt.default_engine(0, robot="hu")
+
+
+@pytest.fixture(scope="module")
+def oc():
+    from oracle import retarget_oracle
+    return retarget_oracle
+
+
+def maxdiff(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))) if a.size else 0.0
+
+
+# ------------------------------------------------------------------------------- FK (a20, a22)
+def test_fk_angles_vs_reference_golden(hrt, eng_hu, golden):
+    g = golden("fk_hu")
+    for clip, key in [(True, "clip"), (False, "noclip")]:
+        for exact in (False, True):
+            gq, gt = eng_hu.fk_angles(hrt.TREE_ROBOT, T(g["angles"]).reshape(256, 32), T(g["root_t"]),
+                                      T(g["root_q"]).reshape(256, 4), clip=clip, exact=exact)
+            assert maxdiff(gt, g[f"gt_{key}"]) <= POS_TOL
+            assert maxdiff(gq, g[f"gq_{key}"]) <= 3e-6
+    # zero angles -> zero-pose link positions (SURVEY 7.1 step 3 known answer)
+    gq, gt = eng_hu.fk_angles(hrt.TREE_ROBOT, torch.zeros(3, 32), None, None, clip=False)
+    from humanoid_real_time_retarget_b200 import robot_config as cfg
+    sk = cfg.skeleton_tables()
+    zero = np.zeros((33, 3), np.float32)
+    for j in range(1, 33):
+        zero[j] = sk["hu_zero_pose/offsets"][j] + zero[sk["hu_zero_pose/parents"][j]]
+    assert maxdiff(gt[0], zero) <= 1e-6
+
+
+@pytest.mark.parametrize("name,tree", [("hu_v5_zero_pose", 0), ("vtrdyn_t_pose", 1), ("vtrdyn_full_zero_pose", 2)])
+def test_fk_local_quats_and_local_rotation_vs_golden(hrt, eng, golden, name, tree):
+    g = golden(f"fk_{name}")
+    if name == "vtrdyn_t_pose":       # T-pose offsets differ from the zero-pose tree installed in slot 1
+        from humanoid_real_time_retarget_b200 import robot_config as cfg
+        sk = cfg.skeleton_tables()
+        e = hrt.Engine(0)
+        e.set_tree(3, sk["vtrdyn_t_pose/parents"], sk["vtrdyn_t_pose/offsets"])
+        tree, engine = 3, e
+    else:
+        engine = eng
+    gq, gt = engine.fk_local_quats(tree, T(g["local_q"]), T(g["root_t"]), exact=True)
+    assert np.array_equal(gq.cpu().numpy(), g["gq"]), "exact-mode FK rotations must be bit-exact"
+    assert np.array_equal(gt.cpu().numpy(), g["gt"]), "exact-mode FK positions must be bit-exact"
+    gq, gt = engine.fk_local_quats(tree, T(g["local_q"]), T(g["root_t"]), exact=False)
+    assert maxdiff(gq, g["gq"]) <= 3e-6 and maxdiff(gt, g["gt"]) <= POS_TOL
+    lq = engine.local_from_global(tree, T(g["gq"]))
+    assert np.array_equal(lq.cpu().numpy(), g["local_back"]), "cal_local_rotation must be bit-exact"
+    # poselib SkeletonState FK agrees (tree.quat == identity)
+    assert maxdiff(gq, g["sk_global_rotation"]) <= 3e-6 and maxdiff(gt, g["sk_global_translation"]) <= POS_TOL
+
+
+def test_drop_in_functional_api(hrt, golden, skeletons):
+    g = golden("fk_hu_v5_zero_pose")
+    parents = skeletons["hu_v5_zero_pose/parents"].tolist()
+    off = T(skeletons["hu_v5_zero_pose/offsets"])
+    # CPU tensors in -> CPU tensors out, like the reference
+    gq, gt = hrt.cal_forward_kinematics(T(g["local_q"]), T(g["root_t"]), parents, off)
+    assert gq.device.type == "cpu" and maxdiff(gt, g["gt"]) <= POS_TOL
+    lq = hrt.cal_local_rotation(T(g["gq"]), parents)
+    assert np.array_equal(lq.numpy(), g["local_back"])
+    # HuForwardModel on the 33-joint Hu tree
+    gh = golden("fk_hu")
+
+    class Tree:
+        local_translation = T(skeletons["hu_zero_pose/offsets"])
+        parent_indices = T(skeletons["hu_zero_pose/parents"]).long()
+        num_joints = 33
+    model = hrt.HuForwardModel(Tree())
+    gq, gt = model.forward_kinematics(T(gh["angles"]), T(gh["root_t"]), T(gh["root_q"]), True)
+    assert maxdiff(gt, gh["gt_clip"]) <= POS_TOL and gq.shape == (256, 33, 4)
+
+
+# ------------------------------------------------------------------------------- a24
+def test_zero_pose_transform_bit_exact(hrt, eng, golden):
+    g = golden("zero_pose_transform")
+    assert np.array_equal(eng.zero_pose_transform(hrt.TREE_SOURCE, T(g["q21"])).cpu().numpy(), g["vtrdyn"])
+    assert np.array_equal(eng.zero_pose_transform(hrt.TREE_SOURCE_FULL, T(g["q59"])).cpu().numpy(), g["vtrdyn_full"])
+    assert np.array_equal(eng.zero_pose_transform(hrt.TREE_SOURCE, T(g["q21"]), 1).cpu().numpy(), g["vtrdyn_broadcast"])
+    out = hrt.vtrdyn_zero_pose_transform(T(g["q21"]))
+    assert out.device.type == "cpu" and np.array_equal(out.numpy(), g["vtrdyn"])
+
+
+# ------------------------------------------------------------------------------- fused quaternion path
+def test_body_quat_vs_reference_golden(hrt, eng, golden):
+    g = golden("body_quat")
+    lq, dof, lp = eng.retarget_body_quat(T(g["raw_global_q"]), flags=0)
+    assert maxdiff(lq, g["robot_local_q"]) <= 1.2e-7
+    assert maxdiff(dof, g["dof_pos"]) <= ANGLE_TOL
+    assert maxdiff(lp, g["fk_gt"]) <= POS_TOL
+    # pre-transformed input + the reference-named class, one frame at a time like the reference
+    lq2, dof2, _ = eng.retarget_body_quat(T(g["zero_pose_q"]), flags=hrt.BQ_PRE_TRANSFORMED)
+    assert torch.equal(lq2, lq) and torch.equal(dof2, dof)
+    src = hrt.RobotZeroPose.from_asset("vtrdyn_zero_pose")
+    tgt = hrt.RobotZeroPose.from_asset("hu_v5_zero_pose")
+    solver = hrt.Mocap2HuBodyRetargeter(src, tgt)
+    for i in range(8):
+        rl_i, dof_i = solver.retarget_from_pose(T(g["zero_pose_q"][i]))
+        assert rl_i.shape == (31, 4) and dof_i.shape == (30,) and rl_i.device.type == "cpu"
+        assert maxdiff(dof_i, g["dof_pos"][i]) <= ANGLE_TOL
+    assert solver.motion_dof_pos.shape == (8, 30)
+    assert maxdiff(solver.motion_global_translation, g["fk_gt"][:8]) <= POS_TOL
+
+
+def test_body_quat_vs_oracle_all_frames(hrt, eng, oc, skeletons):
+    B = 50_000
+    raw = oc.synth_clip_3q(B, seed=21, sk=skeletons)
+    lq, dof, lp = eng.retarget_body_quat(raw, flags=0)
+    rl_o, dof_o, lp_o = oc.body_quat_pipeline(raw, skeletons, clamp=False, ik_iters=0)
+    err = (dof.cpu() - dof_o).abs().max(dim=-1).values
+    assert float(err.max()) <= ANGLE_TOL, f"{int((err > ANGLE_TOL).sum())} of {B} frames exceed {ANGLE_TOL}"
+    assert maxdiff(lp, lp_o) <= POS_TOL
+    assert maxdiff(lq, rl_o) <= 1.2e-7
+
+
+def test_body_quat_with_clamp_and_ik_vs_oracle(hrt, eng, oc, skeletons):
+    B = 8192
+    raw = oc.synth_clip_3q(B, seed=22, sk=skeletons)
+    lq, dof, lp = eng.retarget_body_quat(raw, flags=hrt.BQ_CLAMP)
+    rl_o, dof_o, lp_o = oc.body_quat_pipeline(raw, skeletons, clamp=True, ik_iters=0)
+    assert maxdiff(dof, dof_o) <= ANGLE_TOL and maxdiff(lp, lp_o) <= POS_TOL
+    lq, dof, lp = eng.retarget_body_quat(raw, flags=hrt.BQ_CLAMP | hrt.BQ_IK, ik_iters=10, damping=0.1, rot_weight=0.2)
+    rl_o, dof_o, lp_o = oc.body_quat_pipeline(raw, skeletons, clamp=True, ik_iters=10, damping=0.1, rot_weight=0.2)
+    err = (dof.cpu() - dof_o).abs().max(dim=-1).values
+    # builder-specified stage (parity unpinned by the reference): kernel vs own oracle
+    assert float(np.quantile(err.numpy(), 0.999)) <= ANGLE_TOL, float(np.quantile(err.numpy(), 0.999))
+    assert float(err.max()) <= 1e-4
+    assert maxdiff(lp, lp_o) <= 1e-4
+    zq = oc.zero_pose_transform(raw, T(skeletons["t2z/vtrdyn"]))
+    _, dof0, _ = eng.retarget_body_quat(raw, flags=hrt.BQ_CLAMP)
+    r0 = oc.ik_residual(dof0.cpu(), zq, skeletons)
+    r1 = oc.ik_residual(dof.cpu(), zq, skeletons)
+    assert float(r1.mean()) < 0.7 * float(r0.mean())
+
+
+def test_body_quat_edge_cases(hrt, eng, oc, skeletons):
+    # empty, single, ragged (not a multiple of the 16-frame warp group)
+    for B in (0, 1, 15, 17, 33):
+        raw = oc.synth_clip_3q(max(B, 1), seed=B, sk=skeletons)[:B]
+        lq, dof, lp = eng.retarget_body_quat(raw, flags=0)
+        assert lq.shape == (B, 31, 4) and dof.shape == (B, 30) and lp.shape == (B, 31, 3)
+        if B:
+            _, dof_o, lp_o = oc.body_quat_pipeline(raw, skeletons, clamp=False, ik_iters=0)
+            assert maxdiff(dof, dof_o) <= ANGLE_TOL and maxdiff(lp, lp_o) <= POS_TOL
+    # T-pose sensors (all identity) and the pre-transformed zero pose -> all-zero angles (inv. 1)
+    ident = oc.quat_identity((4, 21))
+    _, dof, lp = eng.retarget_body_quat(ident, flags=hrt.BQ_PRE_TRANSFORMED | hrt.BQ_CLAMP | hrt.BQ_IK)
+    assert float(dof.abs().max()) <= 1e-6
+    assert maxdiff(lp[0], skeletons["hu_v5_zero_pose/global_translation"]) <= 1e-6
+    # NaN in -> NaN out for the affected arm only, never a crash
+    raw = oc.synth_clip_3q(32, seed=3, sk=skeletons)
+    raw[5, 18] = float("nan")
+    _, dof, _ = eng.retarget_body_quat(raw, flags=0)
+    assert torch.isfinite(dof[:5]).all() and torch.isfinite(dof[6:]).all()
+    # quaternion double cover: -q gives the same answer
+    raw = oc.synth_clip_3q(64, seed=4, sk=skeletons)
+    _, d1, _ = eng.retarget_body_quat(raw, flags=0)
+    _, d2, _ = eng.retarget_body_quat(-raw, flags=0)
+    assert maxdiff(d1, d2) <= 1e-6
+
+
+def test_error_behaviour(hrt, eng):
+    import ctypes as C
+    e = hrt.Engine(0)
+    buf = torch.zeros(64, device="cuda")
+    p = C.c_void_p(buf.data_ptr())
+    assert e.lib.hrt_fk_local_quats(e._h, 0, 1, p, None, p, None, 0, None) == -2      # tree not installed
+    assert b"not installed" in e.lib.hrt_last_error_string()
+    assert e.lib.hrt_retarget_body_quat(e._h, 1, p, 0, 0, 0.1, 0.2, None, None, None, None) == -2
+    with pytest.raises(hrt.HrtError):
+        e.set_tree(0, [0, -1], np.zeros((2, 3)))          # root must come first
+    with pytest.raises(hrt.HrtError):
+        e.set_tree(0, [-1] + [0] * 70, np.zeros((71, 3)))  # too many joints
+    # misaligned device pointer is refused, not silently mis-read
+    buf = torch.zeros(21 * 4 * 4 + 1, device="cuda")
+    import ctypes as C
+    rc = eng.lib.hrt_retarget_body_quat(eng._h, 4, C.c_void_p(buf.data_ptr() + 4), 0, 0, 0.1, 0.2, None, None, None, None)
+    assert rc == -4
+
+
+# ------------------------------------------------------------------------------- Jacobian
+def test_jacobian_vs_oracle(hrt, eng_hu, oc, skeletons):
+    g = torch.Generator().manual_seed(9)
+    B = 200
+    lo, hi = torch.tensor(oc.HU_DOF_LOWER), torch.tensor(oc.HU_DOF_UPPER)
+    ang = lo + (hi - lo) * (torch.rand(B, 32, generator=g) * 1.2 - 0.1)
+    root_t = torch.randn(B, 3, generator=g)
+    root_q = oc.quat_normalize(torch.randn(B, 4, generator=g))
+    links = [20, 29, 5, 32]
+    J = eng_hu.fk_jacobian(hrt.TREE_ROBOT, ang, links, root_t, root_q, clip=True)
+    Jo = oc.geometric_jacobian(ang, root_t, root_q, skeletons["hu_zero_pose/parents"].tolist(),
+                               T(skeletons["hu_zero_pose/offsets"]), oc.HU_DOF_AXIS, oc.HU_DOF_LOWER, oc.HU_DOF_UPPER,
+                               True, links)
+    assert J.shape == (B, 4, 6, 32)
+    assert maxdiff(J, Jo) <= 5e-6
+
+
+# ------------------------------------------------------------------------------- host / streaming calls
+def test_host_call_and_streaming_match_device_call(hrt, eng, oc, skeletons):
+    B = 70_000                                   # > one 65,536-frame pipeline chunk, ragged tail
+    raw = oc.synth_clip_3q(B, seed=31, sk=skeletons)
+    flags = hrt.BQ_CLAMP | hrt.BQ_IK
+    lq, dof, lp = eng.retarget_body_quat(raw, flags=flags)
+    h_in = raw.pin_memory()
+    h_lq = torch.empty(B, 31, 4).pin_memory()
+    h_dof = torch.empty(B, 30).pin_memory()
+    h_lp = torch.empty(B, 31, 3).pin_memory()
+    eng.retarget_body_quat_host(h_in, flags=flags, out_local_q=h_lq, out_dof=h_dof, out_link_pos=h_lp)
+    assert torch.equal(h_dof, dof.cpu()) and torch.equal(h_lp, lp.cpu()) and torch.equal(h_lq, lq.cpu())
+    # pageable host memory also works
+    h_dof2 = torch.empty(B, 30)
+    eng.retarget_body_quat_host(raw, flags=flags, out_dof=h_dof2)
+    assert torch.equal(h_dof2, dof.cpu())
+    # streaming: one frame at a time through the mapped mailboxes
+    eng.stream_open(flags=flags)
+    o_dof = np.empty(30, np.float32)
+    o_lp = np.empty((31, 3), np.float32)
+    raw_np = raw.numpy()
+    for i in range(64):
+        eng.stream_frame(raw_np[i], None, o_dof, o_lp)
+        assert np.array_equal(o_dof, dof[i].cpu().numpy()) and np.array_equal(o_lp, lp[i].cpu().numpy())
+    eng.stream_close()
+
+
+# ------------------------------------------------------------------------------- full-size properties
+def test_full_size_properties(hrt, eng, eng_hu, oc, skeletons):
+    # config 2 size: 65,536 Hu configs.  FK -> global-to-local -> FK is the identity on rotations.
+    g = torch.Generator().manual_seed(0)
+    L = 65_536
+    lo, hi = torch.tensor(oc.HU_DOF_LOWER), torch.tensor(oc.HU_DOF_UPPER)
+    ang = (lo + (hi - lo) * (torch.rand(L, 32, generator=g) * 1.2 - 0.1)).cuda()
+    gq, gt = eng_hu.fk_angles(hrt.TREE_ROBOT, ang, clip=True)
+    assert float((gq.norm(dim=-1) - 1).abs().max()) <= 2e-6 and bool((gq[..., 3] >= 0).all())
+    lq = eng_hu.local_from_global(hrt.TREE_ROBOT, gq)
+    gq2, gt2 = eng_hu.fk_local_quats(hrt.TREE_ROBOT, lq)
+    assert maxdiff(gq2, gq) <= 5e-6 and maxdiff(gt2, gt) <= POS_TOL
+    # clipped angles: clamping twice changes nothing (idempotence), and matches FK of pre-clamped input
+    gq3, gt3 = eng_hu.fk_angles(hrt.TREE_ROBOT, torch.minimum(torch.maximum(ang, lo.cuda()), hi.cuda()), clip=False)
+    assert maxdiff(gt3, gt) <= 2e-6
+    # bone lengths are preserved by FK
+    par = skeletons["hu_zero_pose/parents"]
+    off = T(skeletons["hu_zero_pose/offsets"]).cuda()
+    seg = (gt[:, 1:] - gt[:, par[1:]]).norm(dim=-1)
+    assert float((seg - off[1:].norm(dim=-1)).abs().max()) <= 2e-6
+    # config 3 size: 2^20 frames through the fused pipeline with IK; angles inside limits, finite,
+    # link positions consistent with an independent FK of the returned angles
+    B = 1 << 20
+    raw = oc.synth_clip_3q(B, seed=0, sk=skeletons).cuda()
+    lq, dof, lp = eng.retarget_body_quat(raw, flags=hrt.BQ_CLAMP | hrt.BQ_IK)
+    assert torch.isfinite(dof).all() and torch.isfinite(lp).all()
+    arm = list(range(11, 18)) + list(range(20, 27))
+    lo5, hi5 = torch.tensor(oc.HU_V5_DOF_LOWER).cuda(), torch.tensor(oc.HU_V5_DOF_UPPER).cuda()
+    assert bool(((dof[:, arm] >= lo5[arm]) & (dof[:, arm] <= hi5[arm])).all())
+    rest = [i for i in range(30) if i not in arm]
+    assert float(dof[:, rest].abs().max()) == 0.0
+    _, gt5 = eng.fk_angles(hrt.TREE_ROBOT, dof, clip=False)
+    assert maxdiff(gt5, lp) <= POS_TOL
+    # a checksum of a strided sample against the oracle
+    idx = torch.arange(0, B, 257)
+    _, dof_o, lp_o = oc.body_quat_pipeline(raw[idx].cpu(), skeletons, clamp=True, ik_iters=10)
+    err = (dof[idx].cpu() - dof_o).abs().max(dim=-1).values
+    assert float(np.quantile(err.numpy(), 0.999)) <= ANGLE_TOL and float(err.max()) <= 1e-4
