@@ -97,7 +97,7 @@ int grid_for(hrt_ctx* ctx, K kernel, int threads, size_t smem, long long n_ctas_
 
 template <bool FROM_ANGLES>
 int launch_fk(hrt_ctx* ctx, Tree* t, const FkArgs& a, unsigned flags, cudaStream_t st) {
-    const size_t smem = (size_t)FK_WARPS_PER_CTA * FK_WARP_WORDS * sizeof(float);
+    const size_t smem = (size_t)FK_WARPS_PER_CTA * fk_warp_words(t->tp.n_slots) * sizeof(float);
     const long long groups = (a.B + 31) / 32;
     const long long ctas = (groups + FK_WARPS_PER_CTA - 1) / FK_WARPS_PER_CTA;
     int grid = 1;
@@ -212,11 +212,13 @@ int hrt_set_tree(hrt_ctx* ctx, int tree, int J, const int32_t* parents, const fl
     for (int s = 0; s < HRT_MAX_SLOTS; ++s) owner[s] = -1;
     std::vector<int> slot_of(J, -1);
     int n_slots = 0;
+    if (dof_axis)
+        for (int j = 1; j < J; ++j)
+            if (dof_axis[j - 1] > 2) return fail(HRT_E_INVALID_ARG, "dof_axis[%d]=%d not in 0..2", j - 1, dof_axis[j - 1]);
     for (int j = 0; j < J; ++j) {
         tp.parent[j] = (int8_t)parents[j];
-        tp.src_slot[j] = -1;
-        tp.save_slot[j] = -1;
-        if (j > 0 && parents[j] != j - 1) tp.src_slot[j] = (int8_t)slot_of[parents[j]];
+        int src = -1, save = -1;
+        if (j > 0 && parents[j] != j - 1) src = slot_of[parents[j]];
         if (last_use[j] > j) {
             int s = -1;
             for (int k = 0; k < HRT_MAX_SLOTS; ++k)
@@ -224,21 +226,17 @@ int hrt_set_tree(hrt_ctx* ctx, int tree, int J, const int32_t* parents, const fl
             if (s < 0) return fail(HRT_E_UNSUPPORTED_TREE, "tree needs more than %d live branch points", HRT_MAX_SLOTS);
             owner[s] = j;
             slot_of[j] = s;
-            tp.save_slot[j] = (int8_t)s;
+            save = s;
             n_slots = std::max(n_slots, s + 1);
         }
-        for (int k = 0; k < 3; ++k) tp.off[j * 3 + k] = offsets[j * 3 + k];
+        for (int k = 0; k < 3; ++k) tp.jr[j].off[k] = offsets[j * 3 + k];
+        const uint32_t axis = (dof_axis && j > 0) ? dof_axis[j - 1] : 0u;
+        tp.jr[j].meta = axis | ((uint32_t)(src + 1) << 4) | ((uint32_t)(save + 1) << 8);
+        tp.lim[j][0] = (lower && j > 0) ? lower[j - 1] : -INFINITY;
+        tp.lim[j][1] = (upper && j > 0) ? upper[j - 1] : INFINITY;
     }
     tp.n_slots = n_slots;
     t.has_dof = dof_axis != nullptr;
-    for (int j = 1; j < J; ++j) {
-        if (dof_axis) {
-            if (dof_axis[j - 1] > 2) return fail(HRT_E_INVALID_ARG, "dof_axis[%d]=%d not in 0..2", j - 1, dof_axis[j - 1]);
-            tp.axis[j] = dof_axis[j - 1];
-        }
-        tp.lower[j] = lower ? lower[j - 1] : -INFINITY;
-        tp.upper[j] = upper ? upper[j - 1] : INFINITY;
-    }
     if (t.d_t2z) { cudaFree(t.d_t2z); t.d_t2z = nullptr; }
     if (t.d_parents) { cudaFree(t.d_parents); t.d_parents = nullptr; }
     t.t2z.clear();
@@ -259,9 +257,9 @@ int hrt_fk_local_quats(hrt_ctx* ctx, int tree, int64_t B, const float* d_local_q
     if (rc) return rc;
     Tree* t;
     if ((rc = get_tree(ctx, tree, &t))) return rc;
+    if (B == 0) return 0;
     if (B < 0 || !d_local_q) return fail(HRT_E_INVALID_ARG, "bad B / null input");
     if (!aligned16(d_local_q) || !aligned16(d_gq)) return fail(HRT_E_ALIGNMENT, "quaternion buffers must be 16-byte aligned");
-    if (B == 0) return 0;
     FkArgs a{};
     a.B = B; a.local_q = d_local_q; a.root_t = d_root_t; a.out_gq = d_gq; a.out_gt = d_gt;
     return launch_fk<false>(ctx, t, a, flags, (cudaStream_t)stream);
@@ -274,9 +272,10 @@ int hrt_fk_angles(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, cons
     Tree* t;
     if ((rc = get_tree(ctx, tree, &t))) return rc;
     if (!t->has_dof) return fail(HRT_E_NOT_CONFIGURED, "tree %d has no dof_axis table", tree);
-    if (B < 0 || !d_angles) return fail(HRT_E_INVALID_ARG, "bad B / null input");
-    if (!aligned16(d_root_q) || !aligned16(d_gq)) return fail(HRT_E_ALIGNMENT, "quaternion buffers must be 16-byte aligned");
     if (B == 0) return 0;
+    if (B < 0 || !d_angles) return fail(HRT_E_INVALID_ARG, "bad B / null input");
+    if (!aligned16(d_root_q) || !aligned16(d_gq) || !aligned16(d_angles))
+        return fail(HRT_E_ALIGNMENT, "angle / quaternion buffers must be 16-byte aligned");
     FkArgs a{};
     a.B = B; a.angles = d_angles; a.root_t = d_root_t; a.root_q = d_root_q; a.out_gq = d_gq; a.out_gt = d_gt;
     a.clip = clip;
@@ -325,9 +324,9 @@ int hrt_local_from_global(hrt_ctx* ctx, int tree, int64_t B, const float* d_gq, 
     if (rc) return rc;
     Tree* t;
     if ((rc = get_tree(ctx, tree, &t))) return rc;
+    if (B == 0) return 0;
     if (B < 0 || !d_gq || !d_lq) return fail(HRT_E_INVALID_ARG, "bad B / null pointer");
     if (!aligned16(d_gq) || !aligned16(d_lq)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
-    if (B == 0) return 0;
     const long long n = (long long)B * t->tp.J;
     const int grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
     local_from_global_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
@@ -354,10 +353,10 @@ int hrt_zero_pose_transform(hrt_ctx* ctx, int tree, int64_t B, const float* d_gq
     Tree* t;
     if ((rc = get_tree(ctx, tree, &t))) return rc;
     if (!t->d_t2z) return fail(HRT_E_NOT_CONFIGURED, "tree %d has no T2Z table", tree);
-    if (B < 0 || !d_gq || !d_out) return fail(HRT_E_INVALID_ARG, "bad B / null pointer");
     if (variant != 0 && variant != 1) return fail(HRT_E_INVALID_ARG, "variant must be 0 (z) or 1 (x, broadcast)");
-    if (!aligned16(d_gq) || !aligned16(d_out)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
     if (B == 0) return 0;
+    if (B < 0 || !d_gq || !d_out) return fail(HRT_E_INVALID_ARG, "bad B / null pointer");
+    if (!aligned16(d_gq) || !aligned16(d_out)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
     float r[4];
     rot_quat(variant, r);
     const long long n = (long long)B * t->tp.J;
@@ -390,12 +389,12 @@ int hrt_configure_body_quat(hrt_ctx* ctx, int src_tree, int rob_tree, const int3
     // zero-pose positions of every robot joint: p_j = off_j + p_parent (identity rotations)
     std::vector<float> pos(rt.J * 3, 0.f);
     for (int j = 1; j < rt.J; ++j)
-        for (int k = 0; k < 3; ++k) pos[j * 3 + k] = rt.off[j * 3 + k] + pos[rt.parent[j] * 3 + k];
+        for (int k = 0; k < 3; ++k) pos[j * 3 + k] = rt.jr[j].off[k] + pos[rt.parent[j] * 3 + k];
     for (int i = 0; i < rt.J * 3; ++i) bp.rest_pos[i] = pos[i];
     for (int j = 1; j < rt.J; ++j) {
-        bp.lower_all[j] = rt.lower[j];
-        bp.upper_all[j] = rt.upper[j];
-        bp.axis_all[j] = rt.axis[j];
+        bp.lower_all[j] = rt.lim[j][0];
+        bp.upper_all[j] = rt.lim[j][1];
+        bp.axis_all[j] = (uint8_t)jr_axis(rt.jr[j].meta);
     }
     static const int arm_axis[7] = {1, 0, 2, 1, 0, 1, 2};
     for (int side = 0; side < 2; ++side) {
@@ -408,16 +407,17 @@ int hrt_configure_body_quat(hrt_ctx* ctx, int src_tree, int rob_tree, const int3
         if (f < 1 || f + 8 >= rt.J) return fail(HRT_E_INVALID_ARG, "rob_first[%d]=%d out of range", side, f);
         ap.rob_first = f;
         for (int c = 0; c < 7; ++c) {
-            if (rt.axis[f + c] != arm_axis[c])
-                return fail(HRT_E_UNSUPPORTED_TREE, "arm hinge %d has axis %d, the fused kernel is built for (y,x,z,y,x,y,z)", c, rt.axis[f + c]);
+            if (jr_axis(rt.jr[f + c].meta) != arm_axis[c])
+                return fail(HRT_E_UNSUPPORTED_TREE, "arm hinge %d has axis %d, the fused kernel is built for (y,x,z,y,x,y,z)", c,
+                            jr_axis(rt.jr[f + c].meta));
             if (c > 0 && rt.parent[f + c] != f + c - 1) return fail(HRT_E_UNSUPPORTED_TREE, "arm joints must form a chain");
-            ap.lower[c] = rt.lower[f + c];
-            ap.upper[c] = rt.upper[f + c];
+            ap.lower[c] = rt.lim[f + c][0];
+            ap.upper[c] = rt.lim[f + c][1];
         }
         if (rt.parent[f + 7] != f + 6 || rt.parent[f + 8] != f + 6)
             return fail(HRT_E_UNSUPPORTED_TREE, "expected two gripper links under the wrist-yaw link");
         for (int c = 0; c < 9; ++c)
-            for (int k = 0; k < 3; ++k) ap.off[c][k] = rt.off[(f + c) * 3 + k];
+            for (int k = 0; k < 3; ++k) ap.off[c][k] = rt.jr[f + c].off[k];
         for (int n = 0; n < 5; ++n)
             for (int k = 0; k < 4; ++k) ap.t2z[n][k] = s->t2z[sj[n] * 4 + k];
         for (int k = 0; k < 3; ++k) {
@@ -442,10 +442,10 @@ int hrt_retarget_body_quat(hrt_ctx* ctx, int64_t B, const float* d_src_gq, unsig
     if ((rc = fill_body_quat_args(ctx, B, d_src_gq, flags, ik_iters, damping, rot_weight, d_robot_local_q, d_dof,
                                   d_link_pos, &a)))
         return rc;
+    if (B == 0) return 0;
     if (!d_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
     if (!aligned16(d_src_gq) || !aligned16(d_robot_local_q) || !aligned16(d_dof) || !aligned16(d_link_pos))
         return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
-    if (B == 0) return 0;
     return launch_body_quat(ctx, a, (cudaStream_t)stream);
 }
 
@@ -457,8 +457,8 @@ int hrt_retarget_body_quat_host(hrt_ctx* ctx, int64_t B, const float* h_src_gq, 
     BodyQuatArgs proto;
     if ((rc = fill_body_quat_args(ctx, B, nullptr, flags, ik_iters, damping, rot_weight, nullptr, nullptr, nullptr, &proto)))
         return rc;
-    if (!h_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
     if (B == 0) return 0;
+    if (!h_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
     const int JS = ctx->bq.J_src, JR = ctx->bq.J_rob;
     const size_t in_b = (size_t)JS * 16, lq_b = (size_t)JR * 16, dof_b = (size_t)(JR - 1) * 4, lp_b = (size_t)JR * 12;
     const long long chunk = 1 << 16;                 // frames per pipeline stage (multiple of 16)

@@ -9,23 +9,46 @@
 #define HRT_MAX_CHAIN 16
 #define HRT_MAX_LINKS 4
 
+#ifdef __CUDACC__
+#define HRT_HD __host__ __device__
+#else
+#define HRT_HD
+#endif
+
 namespace hrt {
 
 // A kinematic tree (robot_kinematics_model/kinematics.py: parent_indices + zero-pose offsets),
 // plus, for the robot, the per-DOF hinge axis and limits (retarget/robot_config/Hu*.py).
+// Per-joint data is packed so that one LDC.128 + one LDC.64 fetch everything joint j needs.
+struct JointRec {
+    float off[3];     // zero-pose offset of joint j in its parent's frame
+    // bits 0-1: hinge axis of joint j (DOF j-1); bits 4-7: 1 + slot holding the parent's
+    // transform (0 = registers: parent == j-1); bits 8-11: 1 + slot to park joint j in (0 = none)
+    uint32_t meta;
+};
 struct TreeParams {
     int J;
     int n_slots;
     int8_t parent[HRT_MAX_JOINTS];
-    // where joint j finds its parent's global transform: -1 = registers (parent == j-1),
-    // s >= 0 = warp-private shared-memory slot s
-    int8_t src_slot[HRT_MAX_JOINTS];
-    // after computing joint j, park it in slot s for a later non-adjacent child (-1 = no)
-    int8_t save_slot[HRT_MAX_JOINTS];
-    uint8_t axis[HRT_MAX_JOINTS];        // hinge axis of joint j (DOF j-1); axis[0] unused
-    float off[HRT_MAX_JOINTS * 3];
-    float lower[HRT_MAX_JOINTS];         // limits of joint j (DOF j-1)
-    float upper[HRT_MAX_JOINTS];
+    JointRec jr[HRT_MAX_JOINTS];
+    float lim[HRT_MAX_JOINTS][2];        // lower / upper limit of joint j (DOF j-1)
+};
+
+HRT_HD inline int jr_axis(uint32_t m) { return (int)(m & 3u); }
+HRT_HD inline int jr_src(uint32_t m) { return (int)((m >> 4) & 15u) - 1; }
+HRT_HD inline int jr_save(uint32_t m) { return (int)((m >> 8) & 15u) - 1; }
+
+// Limb-parallel FK schedule (built on the host by hrt_set_tree): FK_LANES lanes cooperate on one
+// configuration; at step t lane p computes joint sched[t][p] (or idles).  24 bytes per entry so a
+// lane fetches it with one LDS.128 + one LDS.64.
+#define HRT_FK_LANES 4
+#define HRT_MAX_STEPS 64
+struct StepRec {
+    float off[3];      // zero-pose offset of the joint
+    // bits 0-7 joint index (0xFF = idle), 8-15 parent joint, 16-17 hinge axis,
+    // bit 18: the parent is the joint this lane computed in the previous step (carried in registers)
+    uint32_t meta;
+    float lo, hi;      // joint limits
 };
 
 // Links whose Jacobian is requested: chain[k][c] = joints from the first non-root ancestor down
