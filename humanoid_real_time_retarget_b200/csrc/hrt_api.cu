@@ -40,6 +40,8 @@ struct Tree {
     bool set = false;
     bool has_dof = false;
     TreeParams tp;
+    int T = 0;                    // steps of the limb-parallel FK schedule
+    float4* d_sched = nullptr;    // T * 4 entries of 32 bytes
     std::vector<float> t2z;       // host copy (J*4) or empty
     float* d_t2z = nullptr;       // device copy
     int* d_parents = nullptr;
@@ -95,23 +97,28 @@ int grid_for(hrt_ctx* ctx, K kernel, int threads, size_t smem, long long n_ctas_
     return 0;
 }
 
-template <bool FROM_ANGLES>
-int launch_fk(hrt_ctx* ctx, Tree* t, const FkArgs& a, unsigned flags, cudaStream_t st) {
-    const size_t smem = (size_t)FK_WARPS_PER_CTA * fk_warp_words(t->tp.n_slots) * sizeof(float);
-    const long long groups = (a.B + 31) / 32;
-    const long long ctas = (groups + FK_WARPS_PER_CTA - 1) / FK_WARPS_PER_CTA;
+template <bool FROM_ANGLES, bool EXACT>
+int launch_fk_variant(hrt_ctx* ctx, Tree* t, FkArgs a, cudaStream_t st) {
+    const int J = t->tp.J;
+    a.sched = t->d_sched;
+    a.T = t->T;
+    const size_t smem = fkl_smem_bytes(J, t->T, FROM_ANGLES);
+    auto kern = fk_limb_kernel<FROM_ANGLES, EXACT>;
+    if (smem > 48 * 1024) HRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long tasks = (a.B + FKL_CFG - 1) / FKL_CFG;
+    const long long ctas = (tasks + FKL_WARPS_PER_CTA - 1) / FKL_WARPS_PER_CTA;
     int grid = 1;
-    if (flags & HRT_FK_EXACT) {
-        int rc = grid_for(ctx, fk_kernel<FROM_ANGLES, true>, FK_WARPS_PER_CTA * 32, smem, ctas, &grid);
-        if (rc) return rc;
-        fk_kernel<FROM_ANGLES, true><<<grid, FK_WARPS_PER_CTA * 32, smem, st>>>(t->tp, a);
-    } else {
-        int rc = grid_for(ctx, fk_kernel<FROM_ANGLES, false>, FK_WARPS_PER_CTA * 32, smem, ctas, &grid);
-        if (rc) return rc;
-        fk_kernel<FROM_ANGLES, false><<<grid, FK_WARPS_PER_CTA * 32, smem, st>>>(t->tp, a);
-    }
+    int rc = grid_for(ctx, kern, FKL_WARPS_PER_CTA * 32, smem, ctas, &grid);
+    if (rc) return rc;
+    kern<<<grid, FKL_WARPS_PER_CTA * 32, smem, st>>>(J, a);
     HRT_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <bool FROM_ANGLES>
+int launch_fk(hrt_ctx* ctx, Tree* t, const FkArgs& a, unsigned flags, cudaStream_t st) {
+    return (flags & HRT_FK_EXACT) ? launch_fk_variant<FROM_ANGLES, true>(ctx, t, a, st)
+                                  : launch_fk_variant<FROM_ANGLES, false>(ctx, t, a, st);
 }
 
 int launch_body_quat(hrt_ctx* ctx, const BodyQuatArgs& a, cudaStream_t st) {
@@ -123,6 +130,61 @@ int launch_body_quat(hrt_ctx* ctx, const BodyQuatArgs& a, cudaStream_t st) {
     if (rc) return rc;
     body_quat_kernel<<<grid, BQ_WARPS_PER_CTA * 32, smem, st>>>(ctx->bq, a);
     HRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// List-schedule the tree's joints onto HRT_FK_LANES lanes: at every step each lane takes one ready
+// joint (all ancestors computed in EARLIER steps), longest remaining chain first, preferring the child
+// of the joint it has just computed.  Entry layout: see StepRec (32 bytes with padding).
+int build_schedule(const TreeParams& tp, std::vector<float>* out, int* T_out) {
+    const int J = tp.J;
+    std::vector<int> height(J, 1), done(J, -1);
+    for (int j = J - 1; j >= 1; --j) height[tp.parent[j]] = std::max(height[tp.parent[j]], height[j] + 1);
+    done[0] = -1;                                   // the root is available before step 0
+    std::vector<char> scheduled(J, 0);
+    scheduled[0] = 1;
+    int remaining = J - 1, T = 0;
+    int last[HRT_FK_LANES];
+    for (int p = 0; p < HRT_FK_LANES; ++p) last[p] = -1;
+    out->clear();
+    while (remaining > 0) {
+        if (T >= HRT_MAX_STEPS) return -1;
+        int pick[HRT_FK_LANES];
+        for (int p = 0; p < HRT_FK_LANES; ++p) pick[p] = -1;
+        std::vector<char> taken(J, 0);
+        // first pass: continue a chain (child of the joint this lane computed in the previous step)
+        for (int pass = 0; pass < 2; ++pass)
+            for (int p = 0; p < HRT_FK_LANES; ++p) {
+                if (pick[p] >= 0) continue;
+                int best = -1;
+                for (int j = 1; j < J; ++j) {
+                    if (scheduled[j] || taken[j]) continue;
+                    const int par = tp.parent[j];
+                    if (!scheduled[par] || done[par] >= T) continue;          // parent not finished before this step
+                    if (pass == 0 && par != last[p]) continue;
+                    if (best < 0 || height[j] > height[best]) best = j;
+                }
+                if (best >= 0) { pick[p] = best; taken[best] = 1; }
+            }
+        for (int p = 0; p < HRT_FK_LANES; ++p) {
+            const int j = pick[p];
+            float rec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            uint32_t meta = 0xFFu;
+            if (j >= 0) {
+                meta = (uint32_t)j | ((uint32_t)tp.parent[j] << 8) | ((uint32_t)jr_axis(tp.jr[j].meta) << 16);
+                rec[0] = tp.jr[j].off[0]; rec[1] = tp.jr[j].off[1]; rec[2] = tp.jr[j].off[2];
+                rec[4] = tp.lim[j][0]; rec[5] = tp.lim[j][1];
+                scheduled[j] = 1;
+                done[j] = T;
+                --remaining;
+            }
+            memcpy(&rec[3], &meta, 4);
+            out->insert(out->end(), rec, rec + 8);
+            last[p] = j;
+        }
+        ++T;
+    }
+    *T_out = T;
     return 0;
 }
 
@@ -177,6 +239,7 @@ int hrt_ctx_destroy(hrt_ctx* ctx) {
     for (auto& t : ctx->trees) {
         if (t.d_t2z) cudaFree(t.d_t2z);
         if (t.d_parents) cudaFree(t.d_parents);
+        if (t.d_sched) cudaFree(t.d_sched);
     }
     for (int i = 0; i < kHostStreams; ++i) {
         if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
@@ -239,6 +302,15 @@ int hrt_set_tree(hrt_ctx* ctx, int tree, int J, const int32_t* parents, const fl
     t.has_dof = dof_axis != nullptr;
     if (t.d_t2z) { cudaFree(t.d_t2z); t.d_t2z = nullptr; }
     if (t.d_parents) { cudaFree(t.d_parents); t.d_parents = nullptr; }
+    if (t.d_sched) { cudaFree(t.d_sched); t.d_sched = nullptr; }
+    {
+        std::vector<float> sched;
+        if (build_schedule(tp, &sched, &t.T)) return fail(HRT_E_UNSUPPORTED_TREE, "FK schedule longer than %d steps", HRT_MAX_STEPS);
+        if (!sched.empty()) {
+            HRT_CUDA(cudaMalloc(&t.d_sched, sched.size() * sizeof(float)));
+            HRT_CUDA(cudaMemcpy(t.d_sched, sched.data(), sched.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+    }
     t.t2z.clear();
     HRT_CUDA(cudaMalloc(&t.d_parents, J * sizeof(int)));
     HRT_CUDA(cudaMemcpy(t.d_parents, parents, J * sizeof(int), cudaMemcpyHostToDevice));
@@ -259,7 +331,8 @@ int hrt_fk_local_quats(hrt_ctx* ctx, int tree, int64_t B, const float* d_local_q
     if ((rc = get_tree(ctx, tree, &t))) return rc;
     if (B == 0) return 0;
     if (B < 0 || !d_local_q) return fail(HRT_E_INVALID_ARG, "bad B / null input");
-    if (!aligned16(d_local_q) || !aligned16(d_gq)) return fail(HRT_E_ALIGNMENT, "quaternion buffers must be 16-byte aligned");
+    if (!aligned16(d_local_q) || !aligned16(d_gq) || !aligned16(d_gt) || !aligned16(d_root_t))
+        return fail(HRT_E_ALIGNMENT, "device buffers must be 16-byte aligned");
     FkArgs a{};
     a.B = B; a.local_q = d_local_q; a.root_t = d_root_t; a.out_gq = d_gq; a.out_gt = d_gt;
     return launch_fk<false>(ctx, t, a, flags, (cudaStream_t)stream);
@@ -274,8 +347,8 @@ int hrt_fk_angles(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, cons
     if (!t->has_dof) return fail(HRT_E_NOT_CONFIGURED, "tree %d has no dof_axis table", tree);
     if (B == 0) return 0;
     if (B < 0 || !d_angles) return fail(HRT_E_INVALID_ARG, "bad B / null input");
-    if (!aligned16(d_root_q) || !aligned16(d_gq) || !aligned16(d_angles))
-        return fail(HRT_E_ALIGNMENT, "angle / quaternion buffers must be 16-byte aligned");
+    if (!aligned16(d_root_q) || !aligned16(d_gq) || !aligned16(d_angles) || !aligned16(d_gt) || !aligned16(d_root_t))
+        return fail(HRT_E_ALIGNMENT, "device buffers must be 16-byte aligned");
     FkArgs a{};
     a.B = B; a.angles = d_angles; a.root_t = d_root_t; a.root_q = d_root_q; a.out_gq = d_gq; a.out_gt = d_gt;
     a.clip = clip;

@@ -1,0 +1,240 @@
+// Limb-parallel batched tree forward kinematics for sm_100a.
+//
+// Replaces the numeric bodies of
+//   cal_forward_kinematics              robot_kinematics_model/kinematics.py:13-39
+//   HuForwardModel.forward_kinematics   robot_kinematics_model/hu_forward_model.py:17-33
+//
+// Why this shape.  FK moves 156 B in / 924 B out per Hu configuration at ~2.4 flop/B: HBM should
+// be the bound.  A thread-per-configuration walk of the 32-joint tree is one long dependent chain
+// per warp and its AoS outputs (rows 528 B / 396 B apart) need per-row address arithmetic; ncu
+// showed that version issue- and latency-bound at 29 % of the HBM roofline (profiles/r01_fk.md).
+// Here FOUR lanes cooperate on one configuration, each walking one limb (the host list-schedules
+// the tree's chains onto the four lanes: sched[step][lane], 10 steps for Hu instead of 32), so
+//   * the dependent chain per warp is 3x shorter,
+//   * a warp owns 8 WHOLE configurations, whose outputs are ONE contiguous span of HBM each
+//     (8*J*16 B of quats, 8*J*12 B of positions): they are staged in a warp-private shared-memory
+//     image of that span and leave with two TMA bulk stores (cp.async.bulk.global.shared::cta,
+//     SASS UBLKCP) -- no per-row address math, no partially written sectors,
+//   * a child finds its parent's global transform in that same staged image (one LDS.128 + three
+//     LDS), so no transform is kept in registers across steps and there is no branch on topology,
+//   * inputs (8*D angles, 8 root quats, 8 root translations: contiguous too) arrive by cp.async
+//     (LDGSTS) into a double buffer one task ahead of their use.
+// All control flow is warp-uniform; idle lane-steps (18 % for Hu) are predicated off.
+#pragma once
+#include "hrt_math.cuh"
+#include "hrt_params.h"
+
+namespace hrt {
+
+constexpr int FKL_CFG = 32 / HRT_FK_LANES;        // 8 configurations per warp task
+constexpr int FKL_WARPS_PER_CTA = 4;
+
+struct FkArgs {
+    long long B;
+    const float* __restrict__ angles;    // (B, J-1)      [FROM_ANGLES]
+    const float* __restrict__ local_q;   // (B, J, 4)     [!FROM_ANGLES]
+    const float* __restrict__ root_t;    // (B, 3) or nullptr (= 0)
+    const float* __restrict__ root_q;    // (B, 4) [FROM_ANGLES] or nullptr (= identity)
+    float* __restrict__ out_gq;          // (B, J, 4) or nullptr
+    float* __restrict__ out_gt;          // (B, J, 3) or nullptr
+    float* __restrict__ out_jac;         // (B, K, 6, J-1) or nullptr  (jacobian kernel)
+    const float4* __restrict__ sched;    // device copy of the schedule: T * 4 entries of 32 bytes
+    int T;
+    int clip;
+};
+
+// shared-memory carve-up, in words.  Every region is a multiple of 4 words (16 bytes).
+HRT_HD inline int fkl_in_words(int J, bool from_angles) {
+    return from_angles ? (FKL_CFG * (J - 1) + 3) / 4 * 4 + 32 + 32 : 32;   // angles | root_q | root_t(24, padded)
+}
+HRT_HD inline int fkl_warp_words(int J, bool from_angles) {
+    return FKL_CFG * J * 4 + FKL_CFG * J * 3 + 2 * fkl_in_words(J, from_angles);
+}
+HRT_HD inline size_t fkl_smem_bytes(int J, int T, bool from_angles) {
+    return (size_t)T * HRT_FK_LANES * 32 + (size_t)FKL_WARPS_PER_CTA * fkl_warp_words(J, from_angles) * 4;
+}
+
+HRT_DEV void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+HRT_DEV void cp_async4(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+HRT_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+HRT_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// contiguous span global -> shared by the whole warp: 16-byte pieces + a 4-byte tail
+HRT_DEV void warp_span_g2s(float* dst, const float* src, int n_words, int lane) {
+    const int n4 = n_words >> 2;
+    for (int i = lane; i < n4; i += 32) cp_async16(dst + i * 4, src + i * 4);
+    for (int i = (n4 << 2) + lane; i < n_words; i += 32) cp_async4(dst + i, src + i);
+}
+
+HRT_DEV void bulk_store_s2g(float* gmem_dst, const float* smem_src, unsigned bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_src);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(s), "r"(bytes) : "memory");
+}
+HRT_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+HRT_DEV void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+HRT_DEV void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+template <bool FROM_ANGLES, bool EXACT>
+__global__ void __launch_bounds__(FKL_WARPS_PER_CTA * 32)
+fk_limb_kernel(const int J, const FkArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int cfg = lane >> 2;                  // configuration within the warp task
+    const int p = lane & 3;                     // limb lane
+    const int D = J - 1;
+    const int T = a.T;
+
+    // ---- the schedule goes to shared memory once per CTA -------------------------------------
+    float4* sched_s = reinterpret_cast<float4*>(smem);
+    for (int i = threadIdx.x; i < T * HRT_FK_LANES * 2; i += blockDim.x) sched_s[i] = __ldg(a.sched + i);
+    __syncthreads();
+
+    const int in_words = fkl_in_words(J, FROM_ANGLES);
+    float* qtile = smem + T * HRT_FK_LANES * 8 + warp * fkl_warp_words(J, FROM_ANGLES);
+    float* ptile = qtile + FKL_CFG * J * 4;
+    float* inbuf = ptile + FKL_CFG * J * 3;
+    const int ang_words = (FKL_CFG * D + 3) / 4 * 4;
+
+    const long long n_tasks = (a.B + FKL_CFG - 1) / FKL_CFG;
+    const long long stride = (long long)gridDim.x * FKL_WARPS_PER_CTA;
+    long long task = (long long)blockIdx.x * FKL_WARPS_PER_CTA + warp;
+
+    // issue the asynchronous input copies of `tk` into buffer `b`
+    auto stage_inputs = [&](long long tk, int b) {
+        if (FROM_ANGLES && tk < n_tasks) {
+            const long long f0 = tk * FKL_CFG;
+            const int rows = (int)min((long long)FKL_CFG, a.B - f0);
+            float* in = inbuf + b * in_words;
+            warp_span_g2s(in, a.angles + f0 * D, rows * D, lane);
+            if (a.root_q && lane < rows) cp_async16(in + ang_words + lane * 4, a.root_q + (f0 + lane) * 4);
+            if (a.root_t) warp_span_g2s(in + ang_words + 32, a.root_t + f0 * 3, rows * 3, lane);
+        }
+        cp_async_commit();
+    };
+
+    int buf = 0;
+    stage_inputs(task, 0);
+    bool pending_store = false;
+
+    for (; task < n_tasks; task += stride, buf ^= 1) {
+        const long long f0 = task * FKL_CFG;
+        const int rows = (int)min((long long)FKL_CFG, a.B - f0);
+        const bool cfg_ok = cfg < rows;
+        const int c = cfg_ok ? cfg : rows - 1;            // tail lanes shadow the last valid configuration
+        float* qrow = qtile + c * J * 4;
+        float* prow = ptile + c * J * 3;
+
+        // the previous task's bulk stores must have finished READING the tiles before we overwrite them
+        if (pending_store) {
+            if (lane == 0) bulk_wait_read_all();
+            __syncwarp();
+            pending_store = false;
+        }
+        if (FROM_ANGLES) {
+            stage_inputs(task + stride, buf ^ 1);         // next task's inputs, one task ahead
+            cp_async_wait<1>();                           // ... and this task's have landed
+        } else {
+            // local quats are staged IN PLACE in the quat tile (a joint's slot is rewritten with its
+            // global quat by the only lane that read it)
+            warp_span_g2s(qtile, a.local_q + f0 * J * 4, rows * J * 4, lane);
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const float* in = inbuf + buf * in_words;
+
+        // ---- root (joint 0): G_r[0] = l[0] as given (NOT normalised), G_t[0] = root translation
+        if (p == 0 && cfg_ok) {
+            if (FROM_ANGLES) {
+                const float4 rq = a.root_q ? *reinterpret_cast<const float4*>(in + ang_words + c * 4) : make_float4(0.f, 0.f, 0.f, 1.f);
+                *reinterpret_cast<float4*>(qrow) = rq;
+            }
+            if (a.root_t) {
+                const float* rt = FROM_ANGLES ? in + ang_words + 32 + c * 3 : nullptr;
+                if (FROM_ANGLES) { prow[0] = rt[0]; prow[1] = rt[1]; prow[2] = rt[2]; }
+                else { const float* g = a.root_t + (f0 + c) * 3; prow[0] = __ldg(g); prow[1] = __ldg(g + 1); prow[2] = __ldg(g + 2); }
+            } else {
+                prow[0] = 0.f; prow[1] = 0.f; prow[2] = 0.f;
+            }
+        }
+        __syncwarp();
+
+        // ---- the scheduled walk: step t, lane p -> joint sched[t][p] ---------------------------
+        for (int t = 0; t < T; ++t) {
+            const float4 r0 = sched_s[(t * HRT_FK_LANES + p) * 2];
+            const float2 lim = *reinterpret_cast<const float2*>(&sched_s[(t * HRT_FK_LANES + p) * 2 + 1]);
+            const uint32_t meta = __float_as_uint(r0.w);
+            const int jraw = (int)(meta & 0xFFu);
+            const bool active = (jraw != 0xFF) && cfg_ok;
+            const int j = (jraw != 0xFF) ? jraw : 1;
+            const int par = (jraw != 0xFF) ? (int)((meta >> 8) & 0xFFu) : 0;
+            const int k = (int)((meta >> 16) & 3u);
+            const float4 pq = *reinterpret_cast<const float4*>(qrow + par * 4);
+            const vec3 pp = make_vec3(prow[par * 3], prow[par * 3 + 1], prow[par * 3 + 2]);
+            const vec3 off = make_vec3(r0.x, r0.y, r0.z);
+            float4 gq;
+            if (FROM_ANGLES) {
+                float th = in[c * D + (j - 1)];
+                if (a.clip) {
+                    // forward value of the straight-through clamp: (clamp(x) - x) + x
+                    const float cl = fminf(fmaxf(th, lim.x), lim.y);
+                    th = add_rn(sub_rn(cl, th), th);
+                }
+                if (EXACT) {
+                    gq = quat_mul_norm_x(pq, quat_from_angle_axis_k_x(th, k));
+                } else {
+                    float s, cs;
+                    sincos_half_f(0.5f * th, &s, &cs);
+                    if (cs < 0.f) { s = -s; cs = -cs; }                  // quat_normalize's sign flip
+                    const float4 lq = make_float4(k == 0 ? s : 0.f, k == 1 ? s : 0.f, k == 2 ? s : 0.f, cs);
+                    gq = quat_normalize_f(quat_mul_f(pq, lq));
+                }
+            } else {
+                const float4 lq = *reinterpret_cast<const float4*>(qrow + j * 4);
+                gq = EXACT ? quat_mul_norm_x(pq, lq) : quat_mul_norm_f(pq, lq);
+            }
+            vec3 gp;
+            if (EXACT) {
+                const vec3 r = quat_rotate_x(pq, off);
+                gp = make_vec3(add_rn(r.x, pp.x), add_rn(r.y, pp.y), add_rn(r.z, pp.z));
+            } else {
+                gp = add3(quat_rotate_f(pq, off), pp);
+            }
+            if (active) {
+                *reinterpret_cast<float4*>(qrow + j * 4) = gq;
+                prow[j * 3] = gp.x; prow[j * 3 + 1] = gp.y; prow[j * 3 + 2] = gp.z;
+            }
+            __syncwarp();
+        }
+
+        // ---- results leave as whole contiguous spans ---------------------------------------------
+        if (rows == FKL_CFG) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (a.out_gq) bulk_store_s2g(a.out_gq + f0 * J * 4, qtile, (unsigned)(FKL_CFG * J * 16));
+                if (a.out_gt) bulk_store_s2g(a.out_gt + f0 * J * 3, ptile, (unsigned)(FKL_CFG * J * 12));
+                bulk_commit();
+            }
+            pending_store = true;
+        } else {
+            // ragged tail: plain stores
+            if (a.out_gq) for (int i = lane; i < rows * J; i += 32)
+                *reinterpret_cast<float4*>(a.out_gq + (f0 * J + i) * 4) = *reinterpret_cast<const float4*>(qtile + i * 4);
+            if (a.out_gt) for (int i = lane; i < rows * J * 3; i += 32) a.out_gt[f0 * J * 3 + i] = ptile[i];
+            __syncwarp();
+        }
+    }
+    cp_async_wait<0>();
+    if (pending_store && lane == 0) bulk_wait_read_all();
+}
+
+}  // namespace hrt
