@@ -121,14 +121,18 @@ int launch_fk(hrt_ctx* ctx, Tree* t, const FkArgs& a, unsigned flags, cudaStream
                                   : launch_fk_variant<FROM_ANGLES, false>(ctx, t, a, st);
 }
 
-int launch_body_quat(hrt_ctx* ctx, const BodyQuatArgs& a, cudaStream_t st) {
-    const size_t smem = (size_t)BQ_WARPS_PER_CTA * BQ_TILE_WORDS * sizeof(float);
+int body_quat_warps(const BodyQuatArgs& a) { return a.out_local_q ? BQ_WARPS_NARROW : BQ_WARPS_WIDE; }
+
+size_t body_quat_smem(const hrt_ctx* ctx, const BodyQuatArgs& a);
+
+int launch_body_quat(hrt_ctx* ctx, const BodyQuatArgs& a, cudaStream_t st, int force_grid = 0) {
+    const size_t smem = body_quat_smem(ctx, a);
+    const int warps = body_quat_warps(a);
     const long long groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
-    const long long ctas = (groups + BQ_WARPS_PER_CTA - 1) / BQ_WARPS_PER_CTA;
-    int grid = 1;
-    int rc = grid_for(ctx, body_quat_kernel, BQ_WARPS_PER_CTA * 32, smem, ctas, &grid);
-    if (rc) return rc;
-    body_quat_kernel<<<grid, BQ_WARPS_PER_CTA * 32, smem, st>>>(ctx->bq, a);
+    const long long ctas = (groups + warps - 1) / warps;
+    const int grid = force_grid ? force_grid : (int)std::max(1LL, std::min(ctas, (long long)ctx->sm_count));
+    if (warps == BQ_WARPS_WIDE) body_quat_kernel<BQ_WARPS_WIDE><<<grid, BQ_WARPS_WIDE * 32, smem, st>>>(ctx->bq, a);
+    else body_quat_kernel<BQ_WARPS_NARROW><<<grid, BQ_WARPS_NARROW * 32, smem, st>>>(ctx->bq, a);
     HRT_CUDA(cudaGetLastError());
     return 0;
 }
@@ -208,6 +212,13 @@ int fill_body_quat_args(hrt_ctx* ctx, int64_t B, const float* src, unsigned flag
 
 }  // namespace
 
+namespace {
+size_t body_quat_smem(const hrt_ctx* ctx, const BodyQuatArgs& a) {
+    return ((size_t)BQ_CONST_WORDS +
+            (size_t)body_quat_warps(a) * bq_tile_words(ctx->bq.J_src, ctx->bq.J_rob, a.out_local_q != nullptr)) * sizeof(float);
+}
+}  // namespace
+
 extern "C" {
 
 int hrt_abi_version(void) { return HRT_ABI_VERSION; }
@@ -226,8 +237,10 @@ int hrt_ctx_create(int device, hrt_ctx** out) {
     if (!c) return fail(HRT_E_INVALID_ARG, "out of host memory");
     c->device = device;
     HRT_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-    // the Jacobian kernel needs more than the default 48 KB of dynamic shared memory
+    // these kernels need more than the default 48 KB of dynamic shared memory
     HRT_CUDA(cudaFuncSetAttribute(jacobian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     *out = c;
     return 0;
 }
@@ -456,7 +469,7 @@ int hrt_configure_body_quat(hrt_ctx* ctx, int src_tree, int rob_tree, const int3
     memset(&bp, 0, sizeof(bp));
     bp.J_src = s->tp.J;
     bp.J_rob = rt.J;
-    if (bp.J_rob * 4 * BQ_FRAMES_PER_WARP > BQ_TILE_WORDS || bp.J_src * 4 * BQ_FRAMES_PER_WARP > BQ_TILE_WORDS)
+    if (bp.J_rob > 31 || bp.J_src > 31)
         return fail(HRT_E_UNSUPPORTED_TREE, "skeleton too large for the fused kernel tile (max 31 joints)");
     rot_quat(0, bp.rot_z90);
     // zero-pose positions of every robot joint: p_j = off_j + p_parent (identity rotations)
@@ -605,9 +618,10 @@ int hrt_stream_frame(hrt_ctx* ctx, const float* h_src_gq, float* h_robot_local_q
     if (!h_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
     const int JS = ctx->bq.J_src, JR = ctx->bq.J_rob;
     memcpy(ctx->mb_in, h_src_gq, (size_t)JS * 16);
-    const size_t smem = (size_t)BQ_WARPS_PER_CTA * BQ_TILE_WORDS * sizeof(float);
-    body_quat_kernel<<<1, BQ_WARPS_PER_CTA * 32, smem, ctx->ss>>>(ctx->bq, ctx->stream_args);
-    HRT_CUDA(cudaGetLastError());
+    {
+        int rc = launch_body_quat(ctx, ctx->stream_args, ctx->ss, 1);
+        if (rc) return rc;
+    }
     HRT_CUDA(cudaStreamSynchronize(ctx->ss));
     if (h_robot_local_q) memcpy(h_robot_local_q, ctx->mb_out, (size_t)JR * 16);
     if (h_dof) memcpy(h_dof, ctx->mb_out + JR * 4, (size_t)(JR - 1) * 4);

@@ -65,6 +65,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--fk-log2", default="16,20,22")
     ap.add_argument("--fk-fast-only", action="store_true")
+    ap.add_argument("--bq-only", default="", help="substring filter on body_quat case names")
     args = ap.parse_args()
     cases = args.cases.split(",")
     eng = hrt.default_engine(0)
@@ -102,6 +103,8 @@ def main():
             ("bq_ik1_dof+linkpos", hrt.BQ_CLAMP | hrt.BQ_IK, 1, (None, dof, lp), 828),
             ("bq_ik10_dof+linkpos", hrt.BQ_CLAMP | hrt.BQ_IK, 10, (None, dof, lp), 828),
         ]:
+            if args.bq_only and args.bq_only not in name:
+                continue
             med, mn = timeit(lambda: eng.retarget_body_quat(raw, flags=flags, ik_iters=iters_ik, out=outs), args.iters, flush=True)
             report(name, B, nbytes, med, mn)
 
