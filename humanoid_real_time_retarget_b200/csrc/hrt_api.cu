@@ -12,6 +12,7 @@
 #include "../../include/hrt_b200.h"
 #include "hrt_fk.cuh"
 #include "hrt_retarget.cuh"
+#include "hrt_pos.cuh"
 
 using namespace hrt;
 
@@ -57,6 +58,8 @@ struct hrt_ctx {
     Tree trees[HRT_MAX_TREES];
     bool bq_set = false;
     BodyQuatParams bq;
+    bool pos_set[3] = {false, false, false};
+    PosParams pos[3];
     // staging for the *_host call
     cudaStream_t hs[kHostStreams] = {nullptr, nullptr, nullptr};
     cudaEvent_t hs_done[kHostStreams] = {nullptr, nullptr, nullptr};
@@ -586,6 +589,141 @@ int hrt_retarget_body_quat_host(hrt_ctx* ctx, int64_t B, const float* h_src_gq, 
     }
     for (int i = 0; i < kHostStreams; ++i) HRT_CUDA(cudaStreamSynchronize(ctx->hs[i]));
     return 0;
+}
+
+int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const float* src_global_t, int precise_gripper) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (mode < 0 || mode > 2) return fail(HRT_E_INVALID_ARG, "mode must be 0 (full_body_pos), 1 (upper_body) or 2 (full_body)");
+    Tree *s, *r;
+    if ((rc = get_tree(ctx, src_tree, &s))) return rc;
+    if ((rc = get_tree(ctx, rob_tree, &r))) return rc;
+    const TreeParams& st = s->tp;
+    PosParams& pp = ctx->pos[mode];
+    memset(&pp, 0, sizeof(pp));
+    pp.mode = mode;
+    pp.J_rob = r->tp.J;
+    if (pp.J_rob != 31) return fail(HRT_E_UNSUPPORTED_TREE, "the position-path solvers write Hu v5 joints 12-29 (31-joint robot)");
+    pp.n_body = 21;
+    pp.n_hand = 20;
+    pp.precise_gripper = precise_gripper ? 1 : 0;
+    auto off = [&](int j, float* dst) { for (int k = 0; k < 3; ++k) dst[k] = st.jr[j].off[k]; };
+    // body indices are the vtrdyn 21-joint order in every mode (retarget_solver.py:49-86,
+    // full_body_pos_retargeter.py:68-110, full_body_retargeter.py:59-99)
+    const int tp3[3] = {17, 13, 11};
+    for (int n = 0; n < 3; ++n) pp.torso_pts[n] = tp3[n];
+    pp.torso_org = 10;
+    pp.bq_torso = 10;
+    const int hk[5] = {2, 6, 10, 14, 17};
+    for (int n = 0; n < 5; ++n) pp.hand_kabsch[n] = hk[n];
+    pp.hand_org = 0;
+    pp.flip[0] = pp.flip[1] = pp.flip[2] = 1.f;
+    const int body_arm[2][3] = {{18, 19, 20}, {14, 15, 16}};
+    const int rob_first[2] = {12, 21};
+    for (int side = 0; side < 2; ++side) {
+        PosArm& ar = pp.arm[side];
+        ar.b_sh = body_arm[side][0]; ar.b_el = body_arm[side][1]; ar.b_wr = body_arm[side][2];
+        ar.rob_first = rob_first[side];
+        ar.q_parent = side == 0 ? 17 : 13;
+        ar.q_wrist = side == 0 ? 20 : 16;
+        ar.bq_wrist = side == 0 ? 14 : 39;
+    }
+    if (mode == POS_UPPER_BODY) {
+        if (st.J != 21) return fail(HRT_E_UNSUPPORTED_TREE, "upper-body solver needs the 21-joint vtrdyn zero pose");
+        const int zt[3] = {17, 13, 11};                                   // retarget_solver.py:50
+        for (int n = 0; n < 3; ++n) off(zt[n], pp.ztorso[n]);
+        off(19, pp.arm[0].v0_upper); off(20, pp.arm[0].v0_lower);         // :56,76
+        off(15, pp.arm[1].v0_upper); off(16, pp.arm[1].v0_lower);         // :62,84
+        pp.flip[0] = -1.f; pp.flip[1] = -1.f;                             // :41
+    } else {
+        if (st.J != 59) return fail(HRT_E_UNSUPPORTED_TREE, "full-body solvers need the 59-joint vtrdyn_full zero pose");
+        const int zt[3] = {11, 36, 34};                                   // full_body_pos_retargeter.py:69
+        for (int n = 0; n < 3; ++n) off(zt[n], pp.ztorso[n]);
+        off(13, pp.arm[0].v0_upper); off(14, pp.arm[0].v0_lower);         // :78,86
+        off(38, pp.arm[1].v0_upper); off(39, pp.arm[1].v0_lower);         // :99,107
+        const int zl[5] = {16, 20, 24, 28, 32}, zr[5] = {41, 45, 49, 53, 56};   // :139,162
+        for (int n = 0; n < 5; ++n) { off(zl[n], pp.arm[0].zwrist[n]); off(zr[n], pp.arm[1].zwrist[n]); }
+        const int tips_pos[5] = {4, 8, 12, 16, 19}, tips_full[5] = {3, 7, 11, 15, 19};
+        const int ext[5] = {18, 22, 26, 30, 33};
+        float sum = 0.f;
+        if (mode == POS_FULL_BODY_POS) {
+            if (!src_global_t) return fail(HRT_E_INVALID_ARG, "full_body_pos needs the source zero pose's global translations");
+            pp.J_bq = 59;
+            for (int n = 0; n < 5; ++n) {
+                pp.hand_tips[n] = tips_pos[n];
+                const float d = src_global_t[ext[n] * 3] - src_global_t[14 * 3];        // :184
+                sum = n == 0 ? d : sum + d;
+            }
+        } else {
+            for (int n = 0; n < 5; ++n) {
+                pp.hand_tips[n] = tips_full[n];
+                const float d = st.jr[ext[n]].off[0] - st.jr[24].off[0];                // full_body_retargeter.py:152
+                sum = n == 0 ? d : sum + d;
+            }
+        }
+        pp.orig_x = sum / 5.f;
+    }
+    ctx->pos_set[mode] = true;
+    return 0;
+}
+
+static int launch_pos(hrt_ctx* ctx, int mode, const PosArgs& a, cudaStream_t st) {
+    if (!ctx->pos_set[mode]) return fail(HRT_E_NOT_CONFIGURED, "hrt_configure_pos(mode %d) has not been called", mode);
+    if (a.B < 0) return fail(HRT_E_INVALID_ARG, "negative frame count");
+    if (a.B == 0) return 0;
+    const void* ptrs[] = {a.body_t, a.lhand_t, a.rhand_t, a.body_q, a.out_local_q, a.out_dof, a.out_body_gq};
+    for (const void* p : ptrs)
+        if (!aligned16(p)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
+    const PosParams& pp = ctx->pos[mode];
+    const bool with_bq = mode == POS_FULL_BODY_POS && a.out_body_gq;
+    const int const_words = (2 * (int)sizeof(PosArm) / 4 + 8 + 3) / 4 * 4;
+    const size_t smem = ((size_t)const_words + (size_t)POS_WARPS * pos_tile_words(pp, a.out_local_q != nullptr, with_bq)) * sizeof(float);
+    const long long groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
+    const long long ctas = (groups + POS_WARPS - 1) / POS_WARPS;
+    const int grid = (int)std::max(1LL, std::min(ctas, (long long)ctx->sm_count));
+    if (mode == POS_FULL_BODY_POS) {
+        HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_FULL_BODY_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        pos_retarget_kernel<POS_FULL_BODY_POS><<<grid, POS_WARPS * 32, smem, st>>>(pp, a);
+    } else if (mode == POS_UPPER_BODY) {
+        HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_UPPER_BODY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        pos_retarget_kernel<POS_UPPER_BODY><<<grid, POS_WARPS * 32, smem, st>>>(pp, a);
+    } else {
+        HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_FULL_BODY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        pos_retarget_kernel<POS_FULL_BODY><<<grid, POS_WARPS * 32, smem, st>>>(pp, a);
+    }
+    HRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hrt_retarget_full_body_pos(hrt_ctx* ctx, int64_t B, const float* d_body_t, const float* d_lhand_t, const float* d_rhand_t,
+                               float* d_robot_local_q, float* d_dof, float* d_body_gq, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (B > 0 && (!d_body_t || !d_lhand_t || !d_rhand_t)) return fail(HRT_E_INVALID_ARG, "null input");
+    PosArgs a{};
+    a.B = B; a.body_t = d_body_t; a.lhand_t = d_lhand_t; a.rhand_t = d_rhand_t;
+    a.out_local_q = d_robot_local_q; a.out_dof = d_dof; a.out_body_gq = d_body_gq;
+    return launch_pos(ctx, POS_FULL_BODY_POS, a, (cudaStream_t)stream);
+}
+
+int hrt_retarget_upper_body(hrt_ctx* ctx, int64_t B, const float* d_body_t, float* d_robot_local_q, float* d_dof, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (B > 0 && !d_body_t) return fail(HRT_E_INVALID_ARG, "null input");
+    PosArgs a{};
+    a.B = B; a.body_t = d_body_t; a.out_local_q = d_robot_local_q; a.out_dof = d_dof;
+    return launch_pos(ctx, POS_UPPER_BODY, a, (cudaStream_t)stream);
+}
+
+int hrt_retarget_full_body(hrt_ctx* ctx, int64_t B, const float* d_body_q, const float* d_body_t, const float* d_lhand_t,
+                           const float* d_rhand_t, float* d_robot_local_q, float* d_dof, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (B > 0 && (!d_body_q || !d_body_t || !d_lhand_t || !d_rhand_t)) return fail(HRT_E_INVALID_ARG, "null input");
+    PosArgs a{};
+    a.B = B; a.body_q = d_body_q; a.body_t = d_body_t; a.lhand_t = d_lhand_t; a.rhand_t = d_rhand_t;
+    a.out_local_q = d_robot_local_q; a.out_dof = d_dof;
+    return launch_pos(ctx, POS_FULL_BODY, a, (cudaStream_t)stream);
 }
 
 int hrt_stream_open(hrt_ctx* ctx, unsigned flags, int ik_iters, float damping, float rot_weight) {

@@ -1,0 +1,446 @@
+// Position-input retarget paths for sm_100a (what the live teleop loop runs).
+//
+// Replaces the numeric bodies of
+//   cal_joint_quat (Kabsch)                      retarget/spatial_transform/transform3d.py:32-50
+//   proj_in_plane / radians_between_vecs         transform3d.py:62-75, 78-100
+//   cal_shoulderPR / cal_elbowP_and_shoulderY    retarget/retarget_solver/full_body_pos_retargeter.py:221-278
+//                                                (= retarget_solver.py:103-158 = full_body_retargeter.py:184-241)
+//   VtrdynFullBodyPosRetargeter.retarget         full_body_pos_retargeter.py:25-217            (mode POS)
+//   HuUpperBodyFromMocapRetarget.retarget_from_global_translation   retarget_solver.py:40-99   (mode UPPER)
+//   VtrdynFullBodyRetargeter.retarget            full_body_retargeter.py:19-177                (mode FULL)
+//   quat_in_xyz_axis 'XYZ' (SciPy, fp64), quat_to_dof_pos
+//
+// One thread per (frame, arm), as in the quaternion path.  The fp32 steps restate the reference's
+// formulas in its own evaluation order (acos(clamp(dot)) * sign(..), not atan2), because the
+// reference is ill-conditioned there and only the same rounding sequence tracks it.
+// The 3x3 SVD of the Kabsch step runs in fp64 as a Jacobi eigen-decomposition of A^T A: only
+// the two leading singular pairs are used, the third axis is their cross product, which is exactly
+// what the reference's det < 0 fix-up selects and stays well defined for the rank-2 torso frame.
+#pragma once
+#include "hrt_fk_limb.cuh"
+#include "hrt_math.cuh"
+#include "hrt_params.h"
+#include "hrt_retarget.cuh"
+
+namespace hrt {
+
+enum PosMode { POS_FULL_BODY_POS = 0, POS_UPPER_BODY = 1, POS_FULL_BODY = 2 };
+
+struct PosArm {
+    int b_sh, b_el, b_wr;          // body joints: shoulder-end, elbow, wrist (vtrdyn: 18,19,20 / 14,15,16)
+    int q_parent, q_wrist;         // mode FULL: measured quats used as arm parent / wrist (17,20 / 13,16)
+    int rob_first;                 // robot shoulder-pitch joint (12 / 21)
+    int bq_wrist;                  // mode POS: slot of the wrist quat in body_global_rotation (14 / 39)
+    float v0_upper[3], v0_lower[3];
+    float zwrist[5][3];            // zero-pose offsets paired with the 5 finger points
+};
+
+struct PosParams {
+    int mode;
+    int J_rob;                     // 31
+    int J_bq;                      // 59 (mode POS output), else 0
+    int n_body, n_hand;            // 21, 20
+    int torso_pts[3], torso_org;   // 17,13,11 ; 10
+    int bq_torso;                  // 10
+    int hand_kabsch[5], hand_org;  // 2,6,10,14,17 ; 0
+    int hand_tips[5];              // POS: 4,8,12,16,19   FULL: 3,7,11,15,19
+    float ztorso[3][3];            // zero-pose offsets paired with torso_pts
+    float flip[3];                 // coord_transform dir (UPPER: -1,-1,1), else 1,1,1
+    float orig_x;                  // mean zero-pose finger-tip x extent
+    int precise_gripper;
+    PosArm arm[2];
+};
+
+struct PosArgs {
+    long long B;
+    const float* __restrict__ body_t;    // (B, 21, 3)
+    const float* __restrict__ lhand_t;   // (B, 20, 3) or nullptr (UPPER)
+    const float* __restrict__ rhand_t;   // (B, 20, 3) or nullptr
+    const float* __restrict__ body_q;    // (B, 21, 4), mode FULL only
+    float* __restrict__ out_local_q;     // (B, 31, 4) or nullptr
+    float* __restrict__ out_dof;         // (B, 30) or nullptr
+    float* __restrict__ out_body_gq;     // (B, 59, 4) or nullptr (mode POS)
+};
+
+// ---------------------------------------------------------------------------------------------
+// reference-order fp32 helpers
+// ---------------------------------------------------------------------------------------------
+HRT_DEV vec3 scale3_x(const vec3 v, float s) { return make_vec3(mul_rn(v.x, s), mul_rn(v.y, s), mul_rn(v.z, s)); }
+HRT_DEV vec3 sub3_x(const vec3 a, const vec3 b) { return make_vec3(sub_rn(a.x, b.x), sub_rn(a.y, b.y), sub_rn(a.z, b.z)); }
+HRT_DEV vec3 div3_x(const vec3 v, float s) { return make_vec3(div_rn(v.x, s), div_rn(v.y, s), div_rn(v.z, s)); }
+HRT_DEV float sign_f(float x) { return (float)((x > 0.f) - (x < 0.f)); }
+
+// transform3d.py:62-75   v - (dot(v,n) / ||n||^2) * n
+HRT_DEV vec3 proj_in_plane_x(const vec3 v, const vec3 n) {
+    const float nn = norm3_x(n);
+    const float d = div_rn(dot3_x(v, n), mul_rn(nn, nn));
+    return sub3_x(v, scale3_x(n, d));
+}
+
+// transform3d.py:78-100   acos(clamp(v1.v2)) * sign(n.(v1 x v2)) after normalising all three
+HRT_DEV float radians_between_x(vec3 v1, vec3 v2, vec3 n) {
+    v1 = div3_x(v1, norm3_x(v1));
+    v2 = div3_x(v2, norm3_x(v2));
+    n = div3_x(n, norm3_x(n));
+    const float c = fminf(fmaxf(dot3_x(v1, v2), -1.f), 1.f);
+    const float ang = acosf(c);
+    const float dir = dot3_x(n, cross3_x(v1, v2));
+    return mul_rn(ang, sign_f(dir));
+}
+
+// theta / phi of a bone for the shoulder pitch-roll solve (plane normal y) or the
+// shoulder-yaw / elbow-pitch solve (plane normal z); v already in the parent frame
+template <int PLANE>   // 1: xz-plane (normal y), 2: xy-plane (normal z)
+HRT_DEV void bone_angles_x(const vec3 v, float* theta, float* phi) {
+    const vec3 ex = make_vec3(1.f, 0.f, 0.f);
+    const vec3 nrm = (PLANE == 1) ? make_vec3(0.f, 1.f, 0.f) : make_vec3(0.f, 0.f, 1.f);
+    const vec3 vp = proj_in_plane_x(v, nrm);
+    *theta = radians_between_x(ex, vp, nrm);
+    // shoulderPR: n = cross(v_proj, y);  elbow: n = cross(z, v_proj)
+    const vec3 n2 = (PLANE == 1) ? cross3_x(vp, nrm) : cross3_x(nrm, vp);
+    *phi = radians_between_x(vp, v, n2);
+}
+
+// rotation3d.py:147-193 in the reference's order, including the four sequential masked fix-ups
+HRT_DEV float4 quat_from_rotation_matrix_x(const float m[3][3]) {
+    const float d0 = m[0][0], d1 = m[1][1], d2 = m[2][2];
+    float w = sqrt_rn(fmaxf(div_rn(add_rn(add_rn(add_rn(d0, d1), d2), 1.f), 4.f), 0.f));
+    float x = sqrt_rn(fmaxf(div_rn(add_rn(sub_rn(sub_rn(d0, d1), d2), 1.f), 4.f), 0.f));
+    float y = sqrt_rn(fmaxf(div_rn(add_rn(sub_rn(add_rn(-d0, d1), d2), 1.f), 4.f), 0.f));
+    float z = sqrt_rn(fmaxf(div_rn(add_rn(add_rn(sub_rn(-d0, d1), d2), 1.f), 4.f), 0.f));
+    if ((w >= x) && (w >= y) && (w >= z)) {
+        x = mul_rn(x, sign_f(sub_rn(m[2][1], m[1][2])));
+        y = mul_rn(y, sign_f(sub_rn(m[0][2], m[2][0])));
+        z = mul_rn(z, sign_f(sub_rn(m[1][0], m[0][1])));
+    }
+    if ((x >= w) && (x >= y) && (x >= z)) {
+        w = mul_rn(w, sign_f(sub_rn(m[2][1], m[1][2])));
+        y = mul_rn(y, sign_f(add_rn(m[1][0], m[0][1])));
+        z = mul_rn(z, sign_f(add_rn(m[0][2], m[2][0])));
+    }
+    if ((y >= w) && (y >= x) && (y >= z)) {
+        w = mul_rn(w, sign_f(sub_rn(m[0][2], m[2][0])));
+        x = mul_rn(x, sign_f(add_rn(m[1][0], m[0][1])));
+        z = mul_rn(z, sign_f(add_rn(m[2][1], m[1][2])));
+    }
+    if ((z >= w) && (z >= x) && (z >= y)) {
+        w = mul_rn(w, sign_f(sub_rn(m[1][0], m[0][1])));
+        x = mul_rn(x, sign_f(add_rn(m[2][0], m[0][2])));
+        y = mul_rn(y, sign_f(add_rn(m[2][1], m[1][2])));
+    }
+    return quat_normalize_x(make_float4(x, y, z, w));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kabsch (transform3d.py:32-50): A = M^T Z (3x3), R = U diag(1,1,det) V^T.  fp64.
+// ---------------------------------------------------------------------------------------------
+HRT_DEV void jacobi_rot(double& app, double& aqq, double& apq, double& arp, double& arq,
+                        double& v0p, double& v0q, double& v1p, double& v1q, double& v2p, double& v2q) {
+    if (fabs(apq) > 1e-300) {
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = rsqrt(t * t + 1.0);
+        const double s = t * c;
+        const double app_n = app - t * apq, aqq_n = aqq + t * apq;
+        app = app_n; aqq = aqq_n; apq = 0.0;
+        const double rp = c * arp - s * arq, rq = s * arp + c * arq;
+        arp = rp; arq = rq;
+        double a, b;
+        a = c * v0p - s * v0q; b = s * v0p + c * v0q; v0p = a; v0q = b;
+        a = c * v1p - s * v1q; b = s * v1p + c * v1q; v1p = a; v1q = b;
+        a = c * v2p - s * v2q; b = s * v2p + c * v2q; v2p = a; v2q = b;
+    }
+}
+
+// M: measured offsets (n x 3), Z: zero-pose offsets (n x 3), both fp32.  Returns the quaternion.
+template <int N>
+HRT_DEV float4 kabsch_quat(const vec3* M, const vec3* Z) {
+    double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        const double m[3] = {(double)M[n].x, (double)M[n].y, (double)M[n].z};
+        const double z[3] = {(double)Z[n].x, (double)Z[n].y, (double)Z[n].z};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) A[i][k] += m[i] * z[k];
+    }
+    // S = A^T A (symmetric), eigenvectors -> right singular vectors
+    double s00 = 0, s01 = 0, s02 = 0, s11 = 0, s12 = 0, s22 = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        s00 += A[i][0] * A[i][0]; s01 += A[i][0] * A[i][1]; s02 += A[i][0] * A[i][2];
+        s11 += A[i][1] * A[i][1]; s12 += A[i][1] * A[i][2]; s22 += A[i][2] * A[i][2];
+    }
+    double v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
+    for (int sweep = 0; sweep < 8; ++sweep) {
+        jacobi_rot(s00, s11, s01, s02, s12, v00, v01, v10, v11, v20, v21);   // (p,q) = (0,1), r = 2
+        jacobi_rot(s00, s22, s02, s01, s12, v00, v02, v10, v12, v20, v22);   // (0,2), r = 1
+        jacobi_rot(s11, s22, s12, s01, s02, v01, v02, v11, v12, v21, v22);   // (1,2), r = 0
+    }
+    // order the eigenvalues: (a) largest, (b) second
+    double e[3] = {s00, s11, s22};
+    double V[3][3] = {{v00, v10, v20}, {v01, v11, v21}, {v02, v12, v22}};   // V[k] = k-th eigenvector
+    int ia = 0, ib = 1, ic = 2;
+    if (e[ib] > e[ia]) { int t = ia; ia = ib; ib = t; }
+    if (e[ic] > e[ia]) { int t = ia; ia = ic; ic = t; }
+    if (e[ic] > e[ib]) { int t = ib; ib = ic; ic = t; }
+    double va[3], vb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        va[k] = (ia == 0) ? V[0][k] : (ia == 1) ? V[1][k] : V[2][k];
+        vb[k] = (ib == 0) ? V[0][k] : (ib == 1) ? V[1][k] : V[2][k];
+    }
+    double ua[3], ub[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        ua[i] = A[i][0] * va[0] + A[i][1] * va[1] + A[i][2] * va[2];
+        ub[i] = A[i][0] * vb[0] + A[i][1] * vb[1] + A[i][2] * vb[2];
+    }
+    double na = rsqrt(ua[0] * ua[0] + ua[1] * ua[1] + ua[2] * ua[2]);
+    ua[0] *= na; ua[1] *= na; ua[2] *= na;
+    const double d = ua[0] * ub[0] + ua[1] * ub[1] + ua[2] * ub[2];
+    ub[0] -= d * ua[0]; ub[1] -= d * ua[1]; ub[2] -= d * ua[2];
+    double nb = rsqrt(ub[0] * ub[0] + ub[1] * ub[1] + ub[2] * ub[2]);
+    ub[0] *= nb; ub[1] *= nb; ub[2] *= nb;
+    const double uc[3] = {ua[1] * ub[2] - ua[2] * ub[1], ua[2] * ub[0] - ua[0] * ub[2], ua[0] * ub[1] - ua[1] * ub[0]};
+    const double vc[3] = {va[1] * vb[2] - va[2] * vb[1], va[2] * vb[0] - va[0] * vb[2], va[0] * vb[1] - va[1] * vb[0]};
+    float R[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) R[i][k] = (float)(ua[i] * va[k] + ub[i] * vb[k] + uc[i] * vc[k]);
+    return quat_from_rotation_matrix_x(R);
+}
+
+HRT_DEV vec3 ld3(const float* p) { return make_vec3(p[0], p[1], p[2]); }
+
+// staging sizes (words per warp of 16 frames)
+HRT_HD inline int pos_in_words(int n_body, int n_hand, bool hands, bool quats) {
+    return BQ_FRAMES_PER_WARP * (n_body * 3 + (hands ? 2 * n_hand * 3 : 0) + (quats ? n_body * 4 : 0));
+}
+HRT_HD inline int pos_tile_words(const PosParams& pp, bool with_lq, bool with_bq) {
+    const bool hands = pp.mode != POS_UPPER_BODY;
+    int in = pos_in_words(pp.n_body, pp.n_hand, hands, pp.mode == POS_FULL_BODY);
+    int bq = with_bq ? BQ_FRAMES_PER_WARP * pp.J_bq * 4 : 0;
+    int io = in > bq ? in : bq;                         // body_global_rotation image reuses the input rows
+    return (io + 3) / 4 * 4 + bq_dof_words(pp.J_rob) + (with_lq ? BQ_FRAMES_PER_WARP * pp.J_rob * 4 : 0);
+}
+constexpr int POS_WARPS = 8;
+
+template <int MODE>
+__global__ void __launch_bounds__(POS_WARPS * 32, 1)
+pos_retarget_kernel(const __grid_constant__ PosParams pp, const PosArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int fl = lane >> 1;
+    const int side = lane & 1;
+    constexpr bool HANDS = MODE != POS_UPPER_BODY;
+    constexpr bool QUATS = MODE == POS_FULL_BODY;
+    // ---- CTA-shared constants: both PosArm tables + zero-pose bone angles -----------------------
+    PosArm* arms_s = reinterpret_cast<PosArm*>(smem);
+    float* zero_ang = smem + 2 * sizeof(PosArm) / 4;      // [side][4] = theta0_sh, phi0_sh, theta0_el, phi0_el
+    {
+        const float* src = reinterpret_cast<const float*>(&pp.arm[0]);
+        for (int i = threadIdx.x; i < 2 * (int)sizeof(PosArm) / 4; i += blockDim.x) smem[i] = src[i];
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            const PosArm& ar = arms_s[threadIdx.x];
+            float t, p;
+            bone_angles_x<1>(make_vec3(ar.v0_upper[0], ar.v0_upper[1], ar.v0_upper[2]), &t, &p);
+            zero_ang[threadIdx.x * 4 + 0] = t; zero_ang[threadIdx.x * 4 + 1] = p;
+            bone_angles_x<2>(make_vec3(ar.v0_lower[0], ar.v0_lower[1], ar.v0_lower[2]), &t, &p);
+            zero_ang[threadIdx.x * 4 + 2] = t; zero_ang[threadIdx.x * 4 + 3] = p;
+        }
+        __syncthreads();
+    }
+    const PosArm& ap = arms_s[side];
+    const int const_words = (2 * (int)sizeof(PosArm) / 4 + 8 + 3) / 4 * 4;
+    const bool with_lq = a.out_local_q != nullptr;
+    const bool with_bq = (MODE == POS_FULL_BODY_POS) && a.out_body_gq != nullptr;
+    float* tile = smem + const_words + warp * pos_tile_words(pp, with_lq, with_bq);
+    const int NB = pp.n_body, NH = pp.n_hand, JR = pp.J_rob, D = JR - 1;
+    const int in_words = pos_in_words(NB, NH, HANDS, QUATS);
+    const int bq_words = with_bq ? BQ_FRAMES_PER_WARP * pp.J_bq * 4 : 0;
+    float* dof_t = tile + ((in_words > bq_words ? in_words : bq_words) + 3) / 4 * 4;
+    float* lq_t = dof_t + bq_dof_words(JR);
+    // input sub-regions (each a contiguous image of 16 rows)
+    float* body_s = tile;
+    float* lh_s = body_s + BQ_FRAMES_PER_WARP * NB * 3;
+    float* rh_s = lh_s + BQ_FRAMES_PER_WARP * NH * 3;
+    float* bodyq_s = HANDS ? rh_s + BQ_FRAMES_PER_WARP * NH * 3 : lh_s;
+    bool pending_store = false;
+
+    const long long n_groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
+    const long long total_warps = (long long)gridDim.x * POS_WARPS;
+    const long long rounds = (n_groups + total_warps - 1) / total_warps;
+    for (long long rnd = 0; rnd < rounds; ++rnd) {
+        const long long grp_raw = rnd * total_warps + (long long)blockIdx.x * POS_WARPS + warp;
+        const bool live = grp_raw < n_groups;
+        const long long grp = live ? grp_raw : n_groups - 1;
+        const long long f0 = grp * BQ_FRAMES_PER_WARP;
+        const int nld = (int)min((long long)BQ_FRAMES_PER_WARP, a.B - f0);
+        const int nfr = live ? nld : 0;
+        const int fr = min(fl, nld - 1);
+
+        if (pending_store) {
+            if (lane == 0) bulk_wait_read_all();
+            __syncwarp();
+            pending_store = false;
+        }
+        // ---- 1. stage inputs (contiguous spans) -------------------------------------------------
+        warp_span_g2s(body_s, a.body_t + f0 * NB * 3, nld * NB * 3, lane);
+        if (HANDS) {
+            warp_span_g2s(lh_s, a.lhand_t + f0 * NH * 3, nld * NH * 3, lane);
+            warp_span_g2s(rh_s, a.rhand_t + f0 * NH * 3, nld * NH * 3, lane);
+        }
+        if (QUATS) warp_span_g2s(bodyq_s, a.body_q + f0 * NB * 4, nld * NB * 4, lane);
+        cp_async_commit();
+        if (a.out_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
+        if (with_lq)
+            for (int i = lane; i < nfr * JR; i += 32) *reinterpret_cast<float4*>(lq_t + i * 4) = make_float4(0.f, 0.f, 0.f, 1.f);
+        cp_async_wait<0>();
+        __syncwarp();
+
+        const float* body = body_s + fr * NB * 3;
+        const vec3 flip = make_vec3(pp.flip[0], pp.flip[1], pp.flip[2]);
+        auto bpt = [&](int j) {      // coord_transform (transform3d.py:24-29): p * dir
+            const vec3 p = ld3(body + j * 3);
+            return (MODE == POS_UPPER_BODY) ? make_vec3(mul_rn(p.x, flip.x), mul_rn(p.y, flip.y), mul_rn(p.z, flip.z)) : p;
+        };
+        // ---- 2. arm parent frame ------------------------------------------------------------------
+        float4 torso = make_float4(0.f, 0.f, 0.f, 1.f);
+        float4 parent;
+        if (MODE == POS_FULL_BODY) {
+            parent = *reinterpret_cast<const float4*>(bodyq_s + (fr * NB + ap.q_parent) * 4);
+        } else {
+            smsp_align<POS_WARPS>(warp);
+            vec3 M[3], Z[3];
+            const vec3 org = bpt(pp.torso_org);
+#pragma unroll
+            for (int n = 0; n < 3; ++n) {
+                M[n] = sub3_x(bpt(pp.torso_pts[n]), org);
+                Z[n] = make_vec3(pp.ztorso[n][0], pp.ztorso[n][1], pp.ztorso[n][2]);
+            }
+            torso = kabsch_quat<3>(M, Z);
+            parent = torso;
+        }
+        // ---- 3. shoulder pitch / roll, shoulder yaw / elbow pitch ----------------------------------
+        smsp_align<POS_WARPS>(warp);
+        float4 rl[7];
+        {
+            const vec3 v_up = sub3_x(bpt(ap.b_el), bpt(ap.b_sh));
+            float th1, ph1;
+            bone_angles_x<1>(quat_rotate_x(quat_conj(parent), v_up), &th1, &ph1);
+            rl[0] = quat_from_angle_axis_k_x(sub_rn(th1, zero_ang[side * 4 + 0]), 1);
+            rl[1] = quat_from_angle_axis_k_x(sub_rn(ph1, zero_ang[side * 4 + 1]), 0);
+            const float4 elbow_parent = quat_mul_x(quat_mul_x(parent, rl[0]), rl[1]);
+            const vec3 v_lo = sub3_x(bpt(ap.b_wr), bpt(ap.b_el));
+            bone_angles_x<2>(quat_rotate_x(quat_conj(elbow_parent), v_lo), &th1, &ph1);
+            rl[2] = quat_from_angle_axis_k_x(sub_rn(th1, zero_ang[side * 4 + 2]), 2);
+            rl[3] = quat_from_angle_axis_k_x(sub_rn(ph1, zero_ang[side * 4 + 3]), 1);
+        }
+        rl[4] = rl[5] = rl[6] = make_float4(0.f, 0.f, 0.f, 1.f);
+        // ---- 4. wrist -------------------------------------------------------------------------------
+        float4 wrist_g = make_float4(0.f, 0.f, 0.f, 1.f);
+        const float* hand = HANDS ? (side == 0 ? lh_s : rh_s) + fr * NH * 3 : nullptr;
+        if (HANDS) {
+            smsp_align<POS_WARPS>(warp);
+            const float4 chain = quat_mul_x(quat_mul_x(quat_mul_x(rl[0], rl[1]), rl[2]), rl[3]);
+            const float4 base = (MODE == POS_FULL_BODY) ? parent : torso;
+            const float4 wparent = quat_mul_norm_x(base, chain);
+            if (MODE == POS_FULL_BODY) {
+                wrist_g = *reinterpret_cast<const float4*>(bodyq_s + (fr * NB + ap.q_wrist) * 4);
+            } else {
+                vec3 M[5], Z[5];
+                const vec3 org = ld3(hand + pp.hand_org * 3);
+#pragma unroll
+                for (int n = 0; n < 5; ++n) {
+                    M[n] = sub3_x(ld3(hand + pp.hand_kabsch[n] * 3), org);
+                    Z[n] = make_vec3(ap.zwrist[n][0], ap.zwrist[n][1], ap.zwrist[n][2]);
+                }
+                wrist_g = kabsch_quat<5>(M, Z);
+            }
+            const float4 wlocal = quat_mul_norm_x(quat_conj(wparent), wrist_g);
+            smsp_align<POS_WARPS>(warp);
+            double e[3];
+            euler_intrinsic_f64<0, 1, 2>(wlocal, e);          // 'XYZ'
+            rl[4] = axis_quat_from_f64(e[0], 0);
+            rl[5] = axis_quat_from_f64(e[1], 1);
+            rl[6] = axis_quat_from_f64(e[2], 2);
+        }
+        // ---- 5. hinge angles + gripper -----------------------------------------------------------------
+        smsp_align<POS_WARPS>(warp);
+        float th[9];
+        th[0] = quat_to_dof_x(rl[0], 1); th[1] = quat_to_dof_x(rl[1], 0); th[2] = quat_to_dof_x(rl[2], 2);
+        th[3] = quat_to_dof_x(rl[3], 1);
+        th[4] = HANDS ? quat_to_dof_x(rl[4], 0) : 0.f;
+        th[5] = HANDS ? quat_to_dof_x(rl[5], 1) : 0.f;
+        th[6] = HANDS ? quat_to_dof_x(rl[6], 2) : 0.f;
+        th[7] = 0.f; th[8] = 0.f;
+        if (HANDS) {
+            // finger tips in the wrist frame (POS: rotate by the inverse; FULL: by the quat itself)
+            const float4 q = (MODE == POS_FULL_BODY_POS) ? quat_conj(wrist_g) : wrist_g;
+            const float x0 = quat_rotate_x(q, ld3(hand)).x;
+            float sum = 0.f;
+#pragma unroll
+            for (int n = 0; n < 5; ++n) {
+                const float xn = quat_rotate_x(q, ld3(hand + pp.hand_tips[n] * 3)).x;
+                const float dxn = sub_rn(xn, x0);
+                sum = (n == 0) ? dxn : add_rn(sum, dxn);
+            }
+            const float ratio = div_rn(div_rn(sum, 5.f), pp.orig_x);
+            if (MODE == POS_FULL_BODY_POS && pp.precise_gripper) {
+                const float s = div_rn(fminf(fmaxf(sub_rn(ratio, 0.5f), 0.f), 0.5f), 0.5f);
+                th[7] = mul_rn(s, 0.044f);
+                th[8] = mul_rn(s, -0.044f);
+            } else {
+                const bool closed = ratio < 0.7f;
+                th[7] = closed ? 0.f : 0.044f;
+                th[8] = closed ? 0.f : -0.044f;
+            }
+        }
+        __syncwarp();                                  // every lane is done with the input rows
+
+        // ---- 6. outputs --------------------------------------------------------------------------------
+        if (a.out_dof && fl < nfr) {
+            float* r = dof_t + fl * D + (ap.rob_first - 1);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) r[c] = th[c];
+        }
+        if (with_lq && fl < nfr) {
+            float* r = lq_t + (fl * JR + ap.rob_first) * 4;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) *reinterpret_cast<float4*>(r + c * 4) = rl[c];
+        }
+        if (with_bq) {
+            for (int i = lane; i < nfr * pp.J_bq; i += 32) *reinterpret_cast<float4*>(tile + i * 4) = make_float4(0.f, 0.f, 0.f, 1.f);
+            __syncwarp();
+            if (fl < nfr) {
+                if (side == 0) *reinterpret_cast<float4*>(tile + (fl * pp.J_bq + pp.bq_torso) * 4) = torso;
+                *reinterpret_cast<float4*>(tile + (fl * pp.J_bq + ap.bq_wrist) * 4) = wrist_g;
+            }
+        }
+        if (nfr == BQ_FRAMES_PER_WARP) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (a.out_dof) bulk_store_s2g(a.out_dof + f0 * D, dof_t, (unsigned)(BQ_FRAMES_PER_WARP * D * 4));
+                if (with_lq) bulk_store_s2g(a.out_local_q + f0 * JR * 4, lq_t, (unsigned)(BQ_FRAMES_PER_WARP * JR * 16));
+                if (with_bq) bulk_store_s2g(a.out_body_gq + f0 * pp.J_bq * 4, tile, (unsigned)(BQ_FRAMES_PER_WARP * pp.J_bq * 16));
+                bulk_commit();
+            }
+            pending_store = true;
+        } else if (nfr > 0) {
+            __syncwarp();
+            if (a.out_dof) warp_store_span(a.out_dof + f0 * D, dof_t, nfr * D, lane);
+            if (with_lq) warp_store_span(a.out_local_q + f0 * JR * 4, lq_t, nfr * JR * 4, lane);
+            if (with_bq) warp_store_span(a.out_body_gq + f0 * pp.J_bq * 4, tile, nfr * pp.J_bq * 4, lane);
+            __syncwarp();
+        }
+    }
+    if (pending_store && lane == 0) bulk_wait_read_all();
+}
+
+}  // namespace hrt

@@ -11,6 +11,7 @@ from . import robot_config as cfg
 TREE_ROBOT, TREE_SOURCE, TREE_SOURCE_FULL = 0, 1, 2
 FK_EXACT = 1
 BQ_CLAMP, BQ_IK, BQ_PRE_TRANSFORMED = 1, 2, 4
+POS_FULL_BODY_POS, POS_UPPER_BODY, POS_FULL_BODY = 0, 1, 2
 
 
 def _ptr(t):
@@ -85,6 +86,9 @@ class Engine:
                       t2z=sk["t2z/vtrdyn_full"])
         if robot == "hu_v5":
             self.configure_body_quat(TREE_SOURCE, TREE_ROBOT, cfg.VTRDYN_ARM_JOINTS, cfg.HU_V5_ARM_FIRST)
+            self.configure_pos(POS_FULL_BODY_POS, TREE_SOURCE_FULL, TREE_ROBOT, sk["vtrdyn_full_zero_pose/global_translation"], True)
+            self.configure_pos(POS_UPPER_BODY, TREE_SOURCE, TREE_ROBOT)
+            self.configure_pos(POS_FULL_BODY, TREE_SOURCE_FULL, TREE_ROBOT)
         return self
 
     def configure_body_quat(self, src_tree, rob_tree, src_joints, rob_first):
@@ -92,6 +96,10 @@ class Engine:
         rf = np.ascontiguousarray(np.asarray(rob_first, dtype=np.int32).reshape(2))
         _lib.check(self.lib.hrt_configure_body_quat(self._h, src_tree, rob_tree, _np_ptr(sj), _np_ptr(rf)))
         self._bq = (self._trees[src_tree], self._trees[rob_tree])
+
+    def configure_pos(self, mode, src_tree, rob_tree, src_global_t=None, precise_gripper=False):
+        gt = None if src_global_t is None else np.ascontiguousarray(np.asarray(src_global_t, dtype=np.float32))
+        _lib.check(self.lib.hrt_configure_pos(self._h, mode, src_tree, rob_tree, _np_ptr(gt), int(bool(precise_gripper))))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -170,6 +178,39 @@ class Engine:
         _lib.check(self.lib.hrt_retarget_body_quat(self._h, B, _ptr(src_gq), flags, ik_iters, damping, rot_weight,
                                                    _ptr(lq), _ptr(dof), _ptr(lp), self._stream()))
         return lq, dof, lp
+
+    def _pos_outputs(self, B, want_local_q, want_dof, want_body_gq=False):
+        lq = torch.empty((B, 31, 4), device=self.device, dtype=torch.float32) if want_local_q else None
+        dof = torch.empty((B, 30), device=self.device, dtype=torch.float32) if want_dof else None
+        bq = torch.empty((B, 59, 4), device=self.device, dtype=torch.float32) if want_body_gq else None
+        return lq, dof, bq
+
+    def retarget_full_body_pos(self, body_t, lhand_t, rhand_t, want_local_q=True, want_dof=True, want_body_gq=True, out=None):
+        """VtrdynFullBodyPosRetargeter.retarget on (B,21,3), (B,20,3), (B,20,3) device tensors."""
+        body_t, lhand_t, rhand_t = (_f32c(x, self.device) for x in (body_t, lhand_t, rhand_t))
+        B = body_t.numel() // 63
+        assert lhand_t.numel() == B * 60 and rhand_t.numel() == B * 60
+        lq, dof, bq = out if out is not None else self._pos_outputs(B, want_local_q, want_dof, want_body_gq)
+        _lib.check(self.lib.hrt_retarget_full_body_pos(self._h, B, _ptr(body_t), _ptr(lhand_t), _ptr(rhand_t),
+                                                       _ptr(lq), _ptr(dof), _ptr(bq), self._stream()))
+        return lq, dof, bq
+
+    def retarget_upper_body(self, body_t, want_local_q=True, want_dof=True):
+        """HuUpperBodyFromMocapRetarget.retarget_from_global_translation on (B,21,3)."""
+        body_t = _f32c(body_t, self.device)
+        B = body_t.numel() // 63
+        lq, dof, _ = self._pos_outputs(B, want_local_q, want_dof)
+        _lib.check(self.lib.hrt_retarget_upper_body(self._h, B, _ptr(body_t), _ptr(lq), _ptr(dof), self._stream()))
+        return lq, dof
+
+    def retarget_full_body(self, body_q, body_t, lhand_t, rhand_t, want_local_q=True, want_dof=True):
+        """VtrdynFullBodyRetargeter.retarget on (B,21,4), (B,21,3), (B,20,3), (B,20,3)."""
+        body_q, body_t, lhand_t, rhand_t = (_f32c(x, self.device) for x in (body_q, body_t, lhand_t, rhand_t))
+        B = body_t.numel() // 63
+        lq, dof, _ = self._pos_outputs(B, want_local_q, want_dof)
+        _lib.check(self.lib.hrt_retarget_full_body(self._h, B, _ptr(body_q), _ptr(body_t), _ptr(lhand_t), _ptr(rhand_t),
+                                                   _ptr(lq), _ptr(dof), self._stream()))
+        return lq, dof
 
     # ------------------------------------------------------------------ host-buffer (reference-facing) calls
     def retarget_body_quat_host(self, src_gq, flags=0, ik_iters=10, damping=0.1, rot_weight=0.2,

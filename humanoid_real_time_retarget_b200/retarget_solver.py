@@ -8,7 +8,8 @@ import numpy as np
 import torch
 
 from . import robot_config as cfg
-from .engine import (BQ_CLAMP, BQ_IK, BQ_PRE_TRANSFORMED, TREE_SOURCE, TREE_SOURCE_FULL, default_engine)
+from .engine import (BQ_CLAMP, BQ_IK, BQ_PRE_TRANSFORMED, POS_FULL_BODY_POS, TREE_ROBOT, TREE_SOURCE, TREE_SOURCE_FULL,
+                     default_engine)
 from .kinematics import RobotZeroPose, cal_forward_kinematics
 
 
@@ -107,3 +108,65 @@ class Mocap2HuBodyRetargeter(BaseHumanoidRetargeter):
         out = self._eng.retarget_body_quat(g.reshape(-1, 21, 4), flags=flags, ik_iters=ik_iters, damping=damping,
                                            rot_weight=rot_weight)
         return tuple(o.to(g.device) for o in out)
+
+
+class _PosRetargeterBase(BaseHumanoidRetargeter):
+    def __init__(self, mocap_zero_pose, target_zero_pose, device=0):
+        super().__init__(mocap_zero_pose, target_zero_pose)
+        self._eng = default_engine(device)
+
+    def _finish(self, ref, lq, dof, single, record, extra=None):
+        lq, dof = lq.to(ref.device), dof.to(ref.device)
+        if single:
+            lq, dof = lq[0], dof[0]
+        if record:
+            self._motion_local_rotation.append(lq)
+            self._motion_dof_pos.append(dof)
+        if extra is None:
+            return lq, dof
+        extra = extra.to(ref.device)
+        return lq, dof, (extra[0] if single else extra)
+
+
+class VtrdynFullBodyPosRetargeter(_PosRetargeterBase):
+    """retarget/retarget_solver/full_body_pos_retargeter.py:17-217.  One frame ((21,3), (20,3), (20,3)) like
+    the reference, or a batch with a leading frame axis.  Returns (robot_local_rotation, dof_pos,
+    body_global_rotation)."""
+
+    def __init__(self, mocap_zero_pose, target_zero_pose, precise_gripper=False, device=0):
+        super().__init__(mocap_zero_pose, target_zero_pose, device)
+        self.precise_gripper = precise_gripper
+        from . import robot_config as _cfg
+        self._eng.configure_pos(POS_FULL_BODY_POS, TREE_SOURCE_FULL, TREE_ROBOT,
+                                _cfg.skeleton_tables()["vtrdyn_full_zero_pose/global_translation"], precise_gripper)
+
+    def retarget(self, body_global_translation, left_hand_global_translation, right_hand_global_translation, record=True):
+        b = to_torch(body_global_translation)
+        single = b.dim() == 2
+        lq, dof, bq = self._eng.retarget_full_body_pos(b.reshape(-1, 21, 3), to_torch(left_hand_global_translation).reshape(-1, 20, 3),
+                                                       to_torch(right_hand_global_translation).reshape(-1, 20, 3))
+        return self._finish(b, lq, dof, single, record, bq)
+
+
+class HuUpperBodyFromMocapRetarget(_PosRetargeterBase):
+    """retarget/retarget_solver/retarget_solver.py:27-99."""
+
+    def retarget_from_global_translation(self, source_global_translation, record=True):
+        b = to_torch(source_global_translation)
+        single = b.dim() == 2
+        lq, dof = self._eng.retarget_upper_body(b.reshape(-1, 21, 3))
+        return self._finish(b, lq, dof, single, record)
+
+
+class VtrdynFullBodyRetargeter(_PosRetargeterBase):
+    """retarget/retarget_solver/full_body_retargeter.py:15-177 (the two hand-rotation arguments are unused
+    there and here)."""
+
+    def retarget(self, body_global_rotation, body_global_translation, left_hand_global_rotation,
+                 left_hand_global_translation, right_hand_global_rotation, right_hand_global_translation, record=True):
+        b = to_torch(body_global_translation)
+        single = b.dim() == 2
+        lq, dof = self._eng.retarget_full_body(to_torch(body_global_rotation).reshape(-1, 21, 4), b.reshape(-1, 21, 3),
+                                               to_torch(left_hand_global_translation).reshape(-1, 20, 3),
+                                               to_torch(right_hand_global_translation).reshape(-1, 20, 3))
+        return self._finish(b, lq, dof, single, record)

@@ -121,6 +121,36 @@ int hrt_retarget_body_quat_host(hrt_ctx* ctx, int64_t B, const float* h_src_gq, 
                                 float damping, float rot_weight, float* h_robot_local_q, float* h_dof,
                                 float* h_link_pos);
 
+/* Position-input solvers.  mode 0: VtrdynFullBodyPosRetargeter (retarget/retarget_solver/
+ * full_body_pos_retargeter.py:25-217), mode 1: HuUpperBodyFromMocapRetarget (retarget_solver.py:40-99),
+ * mode 2: VtrdynFullBodyRetargeter (full_body_retargeter.py:19-177).  The joint indices those classes
+ * hard-code are hard-coded here too; the zero-pose offsets come from the installed source tree (59-joint
+ * vtrdyn_full for modes 0 and 2, 21-joint vtrdyn for mode 1).  src_global_t[J*3]: zero-pose global
+ * translations (mode 0 gripper reference, :184); precise_gripper as in the class constructor (:21,199). */
+#define HRT_POS_FULL_BODY_POS 0
+#define HRT_POS_UPPER_BODY 1
+#define HRT_POS_FULL_BODY 2
+int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const float* src_global_t,
+                      int precise_gripper);
+
+/* VtrdynFullBodyPosRetargeter.retarget: d_body_t (B,21,3), d_lhand_t / d_rhand_t (B,20,3) ->
+ * d_robot_local_q (B,31,4), d_dof (B,30), d_body_gq (B,59,4) (any output may be NULL).  Built from
+ * cal_joint_quat (Kabsch, transform3d.py:32-50), cal_shoulderPR / cal_elbowP_and_shoulderY
+ * (full_body_pos_retargeter.py:221-278), quat_in_xyz_axis 'XYZ' (transform3d.py:52-59), quat_to_dof_pos. */
+int hrt_retarget_full_body_pos(hrt_ctx* ctx, int64_t B, const float* d_body_t, const float* d_lhand_t,
+                               const float* d_rhand_t, float* d_robot_local_q, float* d_dof, float* d_body_gq,
+                               void* stream);
+
+/* HuUpperBodyFromMocapRetarget.retarget_from_global_translation: d_body_t (B,21,3), flipped by
+ * coord_transform(dir=[-1,-1,1]) inside (retarget_solver.py:41) -> d_robot_local_q (B,31,4), d_dof (B,30). */
+int hrt_retarget_upper_body(hrt_ctx* ctx, int64_t B, const float* d_body_t, float* d_robot_local_q, float* d_dof,
+                            void* stream);
+
+/* VtrdynFullBodyRetargeter.retarget: measured quats d_body_q (B,21,4) give the arm parents and wrists. */
+int hrt_retarget_full_body(hrt_ctx* ctx, int64_t B, const float* d_body_q, const float* d_body_t,
+                           const float* d_lhand_t, const float* d_rhand_t, float* d_robot_local_q, float* d_dof,
+                           void* stream);
+
 /* Streaming teleop: one frame at a time, host in -> host out (sim_full_body_teleop.py:83-129 call
  * pattern).  open() allocates mapped pinned mailboxes and captures the launch; frame() is the hot call. */
 int hrt_stream_open(hrt_ctx* ctx, unsigned flags, int ik_iters, float damping, float rot_weight);
