@@ -10,7 +10,27 @@ from .retarget_solver import (BaseHumanoidRetargeter, HuUpperBodyFromMocapRetarg
                               vtrdyn_broadcast_zero_pose_transform, vtrdyn_full_zero_pose_transform,
                               vtrdyn_zero_pose_transform)
 
+from . import rotation3d, transform3d, skeleton3d
+from .skeleton3d import MotionDICT, SkeletonMotion, SkeletonState, SkeletonTree
+from .retarget_main import Retarget, RetargetHuV5fromMocap
+
+import os as _os
+COMPAT_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "compat")
+
+
+def enable_compat():
+    """Put the import shims on sys.path: `poselib.poselib.core.rotation3d`, `poselib.poselib.skeleton.skeleton3d`,
+    `retarget.spatial_transform.transform3d`, `retarget.torch_ext`, `retarget.retarget_solver`, `retarget.utils.parse_mocap`,
+    `retarget.main`, `robot_kinematics_model` then resolve to this package, so the reference's callers
+    (sim_full_body_teleop.py:15-23 ...) and its asset pickles work unchanged."""
+    import sys
+    if COMPAT_PATH not in sys.path:
+        sys.path.insert(0, COMPAT_PATH)
+
+
 __all__ = [
+    "rotation3d", "transform3d", "skeleton3d", "SkeletonTree", "SkeletonState", "SkeletonMotion", "MotionDICT",
+    "Retarget", "RetargetHuV5fromMocap", "enable_compat", "COMPAT_PATH",
     "Engine", "default_engine", "HrtError", "robot_config",
     "cal_forward_kinematics", "cal_local_rotation", "RobotZeroPose", "BaseForwardModel", "HuForwardModel",
     "BaseHumanoidRetargeter", "Mocap2HuBodyRetargeter", "HuUpperBodyFromMocapRetarget", "VtrdynFullBodyRetargeter",

@@ -33,6 +33,19 @@ _SIGNATURES = {
     "hrt_stream_open": (C.c_int, [_P, C.c_uint, C.c_int, C.c_float, C.c_float]),
     "hrt_stream_frame": (C.c_int, [_P, _P, _P, _P, _P]),
     "hrt_stream_close": (C.c_int, [_P]),
+    "hrt_retarget_full_body_pos_wire": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "hrt_stream_pos_open": (C.c_int, [_P, C.c_int]),
+    "hrt_stream_pos_frame": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "hrt_stream_pos_close": (C.c_int, [_P]),
+    "hrt_retarget_main_arms": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
+    "hrt_rescale_motion": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, _P]),
+    "hrt_rebuild_global_rotation": (C.c_int, [_P, C.c_int, C.c_int64, _P, C.c_int, _P, _P, _P, _P]),
+    "hrt_motion_velocity": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_float, C.c_int, _P, _P, _P]),
+    "hrt_motion_angular_velocity": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_float, C.c_int, _P, _P, _P]),
+    "hrt_rot_op_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "hrt_rot_op": (C.c_int, [_P, C.c_int, C.c_int64, C.POINTER(_P), C.POINTER(C.c_int64), C.c_int, C.c_float, C.POINTER(_P), _P]),
+    "hrt_max_norm3": (C.c_int, [_P, C.c_int64, _P, C.POINTER(C.c_float), _P]),
+    "hrt_cal_joint_quat": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int64, _P, _P, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

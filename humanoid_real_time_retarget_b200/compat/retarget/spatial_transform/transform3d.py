@@ -1,0 +1,3 @@
+"""Import shim: the reference module path, served by humanoid_real_time_retarget_b200 (see enable_compat)."""
+from humanoid_real_time_retarget_b200.transform3d import *  # noqa: F401,F403
+from humanoid_real_time_retarget_b200.transform3d import np, torch, copy, Dict  # noqa: F401

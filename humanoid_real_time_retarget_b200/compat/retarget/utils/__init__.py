@@ -1,0 +1,1 @@
+"""Import shim: the reference module path, served by humanoid_real_time_retarget_b200 (see enable_compat)."""

@@ -1,0 +1,2 @@
+"""Import shim: the reference module path, served by humanoid_real_time_retarget_b200 (see enable_compat)."""
+from humanoid_real_time_retarget_b200.kinematics import cal_forward_kinematics, cal_local_rotation  # noqa: F401

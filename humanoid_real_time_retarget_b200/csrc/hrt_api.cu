@@ -13,6 +13,8 @@
 #include "hrt_fk.cuh"
 #include "hrt_retarget.cuh"
 #include "hrt_pos.cuh"
+#include "hrt_ops.cuh"
+#include "hrt_motion.cuh"
 
 using namespace hrt;
 
@@ -58,8 +60,9 @@ struct hrt_ctx {
     Tree trees[HRT_MAX_TREES];
     bool bq_set = false;
     BodyQuatParams bq;
-    bool pos_set[3] = {false, false, false};
-    PosParams pos[3];
+    bool pos_set[5] = {false, false, false, false, false};
+    PosParams pos[5];                 // modes 0-3 + [4] = mode 0 reading the mocap wire layout
+    unsigned* d_scalars = nullptr;    // HRT_MAX_JOINTS + 2 words of device scratch for batch-wide maxima
     // staging for the *_host call
     cudaStream_t hs[kHostStreams] = {nullptr, nullptr, nullptr};
     cudaEvent_t hs_done[kHostStreams] = {nullptr, nullptr, nullptr};
@@ -72,6 +75,12 @@ struct hrt_ctx {
     float *mb_in_d = nullptr, *mb_out_d = nullptr;
     cudaStream_t ss = nullptr;
     BodyQuatArgs stream_args;
+    // position-path streaming
+    bool pstream_open = false;
+    int pstream_mode = 0;
+    float *pmb_in = nullptr, *pmb_out = nullptr, *pmb_in_d = nullptr, *pmb_out_d = nullptr;
+    cudaStream_t pss = nullptr;
+    PosArgs pstream_args;
 };
 
 namespace {
@@ -244,6 +253,13 @@ int hrt_ctx_create(int device, hrt_ctx** out) {
     HRT_CUDA(cudaFuncSetAttribute(jacobian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_FULL_BODY_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_UPPER_BODY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_FULL_BODY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(rescale_motion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(rebuild_rotation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    HRT_CUDA(cudaMalloc(&c->d_scalars, (HRT_MAX_JOINTS + 2) * sizeof(unsigned)));
     *out = c;
     return 0;
 }
@@ -252,6 +268,8 @@ int hrt_ctx_destroy(hrt_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     hrt_stream_close(ctx);
+    hrt_stream_pos_close(ctx);
+    if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     for (auto& t : ctx->trees) {
         if (t.d_t2z) cudaFree(t.d_t2z);
         if (t.d_parents) cudaFree(t.d_parents);
@@ -594,7 +612,7 @@ int hrt_retarget_body_quat_host(hrt_ctx* ctx, int64_t B, const float* h_src_gq, 
 int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const float* src_global_t, int precise_gripper) {
     int rc = check_ctx(ctx);
     if (rc) return rc;
-    if (mode < 0 || mode > 2) return fail(HRT_E_INVALID_ARG, "mode must be 0 (full_body_pos), 1 (upper_body) or 2 (full_body)");
+    if (mode < 0 || mode > 3) return fail(HRT_E_INVALID_ARG, "mode must be 0 (full_body_pos), 1 (upper_body), 2 (full_body) or 3 (main)");
     Tree *s, *r;
     if ((rc = get_tree(ctx, src_tree, &s))) return rc;
     if ((rc = get_tree(ctx, rob_tree, &r))) return rc;
@@ -605,6 +623,7 @@ int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const 
     pp.J_rob = r->tp.J;
     if (pp.J_rob != 31) return fail(HRT_E_UNSUPPORTED_TREE, "the position-path solvers write Hu v5 joints 12-29 (31-joint robot)");
     pp.n_body = 21;
+    pp.n_bodyq = 21;
     pp.n_hand = 20;
     pp.precise_gripper = precise_gripper ? 1 : 0;
     auto off = [&](int j, float* dst) { for (int k = 0; k < 3; ++k) dst[k] = st.jr[j].off[k]; };
@@ -628,13 +647,14 @@ int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const 
         ar.q_wrist = side == 0 ? 20 : 16;
         ar.bq_wrist = side == 0 ? 14 : 39;
     }
-    if (mode == POS_UPPER_BODY) {
-        if (st.J != 21) return fail(HRT_E_UNSUPPORTED_TREE, "upper-body solver needs the 21-joint vtrdyn zero pose");
+    if (mode == POS_UPPER_BODY || mode == POS_MAIN) {
+        if (st.J != 21) return fail(HRT_E_UNSUPPORTED_TREE, "upper-body / main solvers need the 21-joint vtrdyn zero pose");
         const int zt[3] = {17, 13, 11};                                   // retarget_solver.py:50
         for (int n = 0; n < 3; ++n) off(zt[n], pp.ztorso[n]);
         off(19, pp.arm[0].v0_upper); off(20, pp.arm[0].v0_lower);         // :56,76
         off(15, pp.arm[1].v0_upper); off(16, pp.arm[1].v0_lower);         // :62,84
-        pp.flip[0] = -1.f; pp.flip[1] = -1.f;                             // :41
+        if (mode == POS_UPPER_BODY) { pp.flip[0] = -1.f; pp.flip[1] = -1.f; }   // :41 (main.py:170 flips before the rescale)
+        if (mode == POS_MAIN) pp.arm[0].q_parent = pp.arm[1].q_parent = 10;     // main.py:206,212
     } else {
         if (st.J != 59) return fail(HRT_E_UNSUPPORTED_TREE, "full-body solvers need the 59-joint vtrdyn_full zero pose");
         const int zt[3] = {11, 36, 34};                                   // full_body_pos_retargeter.py:69
@@ -664,31 +684,50 @@ int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const 
         pp.orig_x = sum / 5.f;
     }
     ctx->pos_set[mode] = true;
+    if (mode == POS_FULL_BODY_POS) {
+        // the same solver reading the mocap wire layout (sim_full_body_teleop.py:109-112): body rows
+        // 23 -> 21 and the HandNodes -> solver finger order are index remaps, applied to the tables once
+        static const int body_map[21] = {0, 1, 2, 3, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22};
+        static const int hand_map[20] = {0, 4, 5, 6, 7, 8, 9, 10, 11, 16, 17, 18, 19, 12, 13, 14, 15, 1, 2, 3};
+        PosParams& w = ctx->pos[4];
+        w = pp;
+        w.n_body = 23;
+        for (int n = 0; n < 3; ++n) w.torso_pts[n] = body_map[pp.torso_pts[n]];
+        w.torso_org = body_map[pp.torso_org];
+        for (int n = 0; n < 5; ++n) { w.hand_kabsch[n] = hand_map[pp.hand_kabsch[n]]; w.hand_tips[n] = hand_map[pp.hand_tips[n]]; }
+        w.hand_org = hand_map[pp.hand_org];
+        for (int side = 0; side < 2; ++side) {
+            w.arm[side].b_sh = body_map[pp.arm[side].b_sh];
+            w.arm[side].b_el = body_map[pp.arm[side].b_el];
+            w.arm[side].b_wr = body_map[pp.arm[side].b_wr];
+        }
+        ctx->pos_set[4] = true;
+    }
     return 0;
 }
 
-static int launch_pos(hrt_ctx* ctx, int mode, const PosArgs& a, cudaStream_t st) {
-    if (!ctx->pos_set[mode]) return fail(HRT_E_NOT_CONFIGURED, "hrt_configure_pos(mode %d) has not been called", mode);
+static int launch_pos(hrt_ctx* ctx, int slot, const PosArgs& a, cudaStream_t st, int force_grid = 0) {
+    if (!ctx->pos_set[slot]) return fail(HRT_E_NOT_CONFIGURED, "hrt_configure_pos(mode %d) has not been called", slot == 4 ? 0 : slot);
+    const int mode = ctx->pos[slot].mode;
     if (a.B < 0) return fail(HRT_E_INVALID_ARG, "negative frame count");
     if (a.B == 0) return 0;
     const void* ptrs[] = {a.body_t, a.lhand_t, a.rhand_t, a.body_q, a.out_local_q, a.out_dof, a.out_body_gq};
     for (const void* p : ptrs)
         if (!aligned16(p)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
-    const PosParams& pp = ctx->pos[mode];
+    const PosParams& pp = ctx->pos[slot];
     const bool with_bq = mode == POS_FULL_BODY_POS && a.out_body_gq;
     const int const_words = (2 * (int)sizeof(PosArm) / 4 + 8 + 3) / 4 * 4;
     const size_t smem = ((size_t)const_words + (size_t)POS_WARPS * pos_tile_words(pp, a.out_local_q != nullptr, with_bq)) * sizeof(float);
     const long long groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
     const long long ctas = (groups + POS_WARPS - 1) / POS_WARPS;
-    const int grid = (int)std::max(1LL, std::min(ctas, (long long)ctx->sm_count));
-    if (mode == POS_FULL_BODY_POS) {
-        HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_FULL_BODY_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const int grid = force_grid ? force_grid : (int)std::max(1LL, std::min(ctas, (long long)ctx->sm_count));
+    if (mode == POS_MAIN) {
+        pos_retarget_kernel<POS_MAIN><<<grid, POS_WARPS * 32, smem, st>>>(pp, a);
+    } else if (mode == POS_FULL_BODY_POS) {
         pos_retarget_kernel<POS_FULL_BODY_POS><<<grid, POS_WARPS * 32, smem, st>>>(pp, a);
     } else if (mode == POS_UPPER_BODY) {
-        HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_UPPER_BODY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         pos_retarget_kernel<POS_UPPER_BODY><<<grid, POS_WARPS * 32, smem, st>>>(pp, a);
     } else {
-        HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_FULL_BODY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         pos_retarget_kernel<POS_FULL_BODY><<<grid, POS_WARPS * 32, smem, st>>>(pp, a);
     }
     HRT_CUDA(cudaGetLastError());
@@ -776,5 +815,307 @@ int hrt_stream_close(hrt_ctx* ctx) {
     ctx->stream_open = false;
     return 0;
 }
+
+int hrt_retarget_full_body_pos_wire(hrt_ctx* ctx, int64_t B, const float* d_body23_t, const float* d_lhand_t, const float* d_rhand_t,
+                                    float* d_robot_local_q, float* d_dof, float* d_body_gq, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (B > 0 && (!d_body23_t || !d_lhand_t || !d_rhand_t)) return fail(HRT_E_INVALID_ARG, "null input");
+    PosArgs a{};
+    a.B = B; a.body_t = d_body23_t; a.lhand_t = d_lhand_t; a.rhand_t = d_rhand_t;
+    a.out_local_q = d_robot_local_q; a.out_dof = d_dof; a.out_body_gq = d_body_gq;
+    return launch_pos(ctx, 4, a, (cudaStream_t)stream);
+}
+
+int hrt_retarget_main_arms(hrt_ctx* ctx, int64_t B, const float* d_body_q, const float* d_body_t,
+                           float* d_robot_local_q, float* d_dof, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (B > 0 && (!d_body_q || !d_body_t)) return fail(HRT_E_INVALID_ARG, "null input");
+    PosArgs a{};
+    a.B = B; a.body_q = d_body_q; a.body_t = d_body_t; a.out_local_q = d_robot_local_q; a.out_dof = d_dof;
+    return launch_pos(ctx, POS_MAIN, a, (cudaStream_t)stream);
+}
+
+int hrt_stream_pos_open(hrt_ctx* ctx, int wire_layout) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    const int slot = wire_layout ? 4 : 0;
+    if (!ctx->pos_set[slot]) return fail(HRT_E_NOT_CONFIGURED, "hrt_configure_pos(mode 0) has not been called");
+    if (ctx->pstream_open) hrt_stream_pos_close(ctx);
+    const PosParams& pp = ctx->pos[slot];
+    const size_t in_w = (size_t)(pp.n_body * 3 + 3) / 4 * 4 + 2 * (size_t)pp.n_hand * 3;   // body | lhand | rhand (16-byte aligned parts)
+    const size_t out_w = (size_t)pp.J_rob * 4 + 32;                                       // local_q | dof (padded)
+    HRT_CUDA(cudaHostAlloc(&ctx->pmb_in, in_w * sizeof(float), cudaHostAllocMapped));
+    HRT_CUDA(cudaHostAlloc(&ctx->pmb_out, out_w * sizeof(float), cudaHostAllocMapped));
+    HRT_CUDA(cudaHostGetDevicePointer(&ctx->pmb_in_d, ctx->pmb_in, 0));
+    HRT_CUDA(cudaHostGetDevicePointer(&ctx->pmb_out_d, ctx->pmb_out, 0));
+    HRT_CUDA(cudaStreamCreateWithFlags(&ctx->pss, cudaStreamNonBlocking));
+    PosArgs a{};
+    a.B = 1;
+    a.body_t = ctx->pmb_in_d;
+    a.lhand_t = ctx->pmb_in_d + (pp.n_body * 3 + 3) / 4 * 4;
+    a.rhand_t = a.lhand_t + pp.n_hand * 3;
+    a.out_local_q = ctx->pmb_out_d;
+    a.out_dof = ctx->pmb_out_d + pp.J_rob * 4;
+    ctx->pstream_args = a;
+    ctx->pstream_mode = slot;
+    ctx->pstream_open = true;
+    return 0;
+}
+
+int hrt_stream_pos_frame(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
+                         float* h_robot_local_q, float* h_dof) {
+    if (!ctx || !ctx->pstream_open) return fail(HRT_E_NOT_CONFIGURED, "hrt_stream_pos_open has not been called");
+    if (!h_body_t || !h_lhand_t || !h_rhand_t) return fail(HRT_E_INVALID_ARG, "null input");
+    const PosParams& pp = ctx->pos[ctx->pstream_mode];
+    const size_t body_w = (size_t)pp.n_body * 3, hand_w = (size_t)pp.n_hand * 3;
+    memcpy(ctx->pmb_in, h_body_t, body_w * 4);
+    memcpy(ctx->pmb_in + (body_w + 3) / 4 * 4, h_lhand_t, hand_w * 4);
+    memcpy(ctx->pmb_in + (body_w + 3) / 4 * 4 + hand_w, h_rhand_t, hand_w * 4);
+    int rc = launch_pos(ctx, ctx->pstream_mode, ctx->pstream_args, ctx->pss, 1);
+    if (rc) return rc;
+    HRT_CUDA(cudaStreamSynchronize(ctx->pss));
+    if (h_robot_local_q) memcpy(h_robot_local_q, ctx->pmb_out, (size_t)pp.J_rob * 16);
+    if (h_dof) memcpy(h_dof, ctx->pmb_out + pp.J_rob * 4, (size_t)(pp.J_rob - 1) * 4);
+    return 0;
+}
+
+int hrt_stream_pos_close(hrt_ctx* ctx) {
+    if (!ctx || !ctx->pstream_open) return 0;
+    cudaSetDevice(ctx->device);
+    if (ctx->pss) { cudaStreamSynchronize(ctx->pss); cudaStreamDestroy(ctx->pss); ctx->pss = nullptr; }
+    if (ctx->pmb_in) { cudaFreeHost(ctx->pmb_in); ctx->pmb_in = nullptr; }
+    if (ctx->pmb_out) { cudaFreeHost(ctx->pmb_out); ctx->pmb_out = nullptr; }
+    ctx->pstream_open = false;
+    return 0;
+}
+
+int hrt_rescale_motion(hrt_ctx* ctx, int tree, int64_t B, const float* d_gt, const float* dir3, float* d_out, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    Tree* t;
+    if ((rc = get_tree(ctx, tree, &t))) return rc;
+    if (B == 0) return 0;
+    if (B < 0 || !d_gt || !d_out) return fail(HRT_E_INVALID_ARG, "bad B / null pointer");
+    RescaleParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.J = t->tp.J;
+    for (int j = 0; j < rp.J; ++j) {
+        rp.parent[j] = t->tp.parent[j];
+        for (int k = 0; k < 3; ++k) rp.off[j][k] = t->tp.jr[j].off[k];
+    }
+    for (int k = 0; k < 3; ++k) rp.dir[k] = dir3 ? dir3[k] : 1.f;
+    const size_t smem = (size_t)MOT_WARPS * 2 * 32 * rp.J * 3 * sizeof(float);
+    const long long tiles = (B + 31) / 32;
+    const int grid = (int)std::max(1LL, std::min((tiles + MOT_WARPS - 1) / MOT_WARPS, (long long)ctx->sm_count * 2));
+    rescale_motion_kernel<<<grid, MOT_WARPS * 32, smem, (cudaStream_t)stream>>>(rp, d_gt, B, d_out);
+    HRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hrt_rebuild_global_rotation(hrt_ctx* ctx, int tree, int64_t B, const float* d_gt, int n_kabsch,
+                                const int32_t* kabsch_joint, const int32_t* kabsch_pts, float* d_out_gq, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    Tree* t;
+    if ((rc = get_tree(ctx, tree, &t))) return rc;
+    if (n_kabsch < 0 || n_kabsch > 2 || (n_kabsch && (!kabsch_joint || !kabsch_pts)))
+        return fail(HRT_E_INVALID_ARG, "n_kabsch must be 0..2 with its tables");
+    if (B == 0) return 0;
+    if (B < 0 || !d_gt || !d_out_gq) return fail(HRT_E_INVALID_ARG, "bad B / null pointer");
+    if (!aligned16(d_out_gq)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
+    RebuildParams rp;
+    memset(&rp, 0, sizeof(rp));
+    const int J = rp.J = t->tp.J;
+    for (int j = 0; j < J; ++j) {
+        rp.parent[j] = t->tp.parent[j];
+        for (int k = 0; k < 3; ++k) rp.off[j][k] = t->tp.jr[j].off[k];
+    }
+    rp.n_kabsch = n_kabsch;
+    for (int k = 0; k < n_kabsch; ++k) {
+        if (kabsch_joint[k] < 0 || kabsch_joint[k] >= J) return fail(HRT_E_INVALID_ARG, "kabsch_joint[%d] out of range", k);
+        rp.kabsch_joint[k] = kabsch_joint[k];
+        for (int n = 0; n < 3; ++n) {
+            const int pj = kabsch_pts[k * 3 + n];
+            if (pj < 0 || pj >= J) return fail(HRT_E_INVALID_ARG, "kabsch_pts[%d][%d] out of range", k, n);
+            rp.kabsch_pts[k][n] = pj;
+        }
+    }
+    // main.py:146: skip the root and every child of a Kabsch-fitted joint
+    for (int j = 0; j < J; ++j) {
+        bool skip = j == 0 || rp.parent[j] < 0;
+        for (int k = 0; k < n_kabsch; ++k) skip |= rp.parent[j] == rp.kabsch_joint[k];
+        rp.skip[j] = skip ? 1 : 0;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    HRT_CUDA(cudaMemsetAsync(ctx->d_scalars, 0, HRT_MAX_JOINTS * sizeof(unsigned), st));
+    {
+        dim3 grid((unsigned)std::max(1LL, std::min(((long long)B + 255) / 256, (long long)ctx->sm_count)), (unsigned)J);
+        bone_max_norm_kernel<<<grid, 256, 0, st>>>(rp, d_gt, B, ctx->d_scalars);
+        HRT_CUDA(cudaGetLastError());
+    }
+    const size_t smem = (size_t)MOT_WARPS * 32 * J * 7 * sizeof(float);
+    const long long tiles = (B + 31) / 32;
+    const int grid = (int)std::max(1LL, std::min((tiles + MOT_WARPS - 1) / MOT_WARPS, (long long)ctx->sm_count * 2));
+    rebuild_rotation_kernel<<<grid, MOT_WARPS * 32, smem, st>>>(rp, d_gt, B, ctx->d_scalars, d_out_gq);
+    HRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static void gauss_params(GaussParams* gp) {
+    // scipy.ndimage._filters._gaussian_kernel1d(sigma=2, order=0, radius=int(4*2+0.5)=8)
+    const double sigma = 2.0;
+    gp->radius = 8;
+    double sum = 0.0;
+    for (int k = 0; k <= 16; ++k) {
+        const double x = (double)(k - 8);
+        gp->w[k] = std::exp(-0.5 / (sigma * sigma) * x * x);
+        sum += gp->w[k];
+    }
+    for (int k = 0; k <= 16; ++k) gp->w[k] /= sum;
+}
+
+static int ew_grid(hrt_ctx* ctx, long long n) { return (int)std::max(1LL, std::min((n + 255) / 256, (long long)ctx->sm_count * 16)); }
+
+int hrt_motion_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gt, float dt, int gaussian,
+                        float* d_scratch, float* d_out, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (T < 2) return fail(HRT_E_INVALID_ARG, "np.gradient needs at least 2 frames");
+    if (J < 1 || !d_gt || !d_out || (gaussian && !d_scratch)) return fail(HRT_E_INVALID_ARG, "bad J / null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long C = J * 3, n = T * C;
+    frame_gradient_kernel<<<ew_grid(ctx, n), 256, 0, st>>>(d_gt, T, C, dt, gaussian ? d_scratch : d_out);
+    HRT_CUDA(cudaGetLastError());
+    if (gaussian) {
+        GaussParams gp;
+        gauss_params(&gp);
+        gauss_filter_frames_kernel<<<ew_grid(ctx, n), 256, 0, st>>>(gp, d_scratch, T, C, d_out);
+        HRT_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int hrt_motion_angular_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gq, float dt, int gaussian,
+                                float* d_scratch, float* d_out, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (T < 1 || J < 1 || !d_gq || !d_out || (gaussian && !d_scratch)) return fail(HRT_E_INVALID_ARG, "bad T / J / null pointer");
+    if (!aligned16(d_gq)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = T * J;
+    angular_velocity_raw_kernel<<<ew_grid(ctx, n), 256, 0, st>>>(reinterpret_cast<const float4*>(d_gq), T, J, dt, gaussian ? d_scratch : d_out);
+    HRT_CUDA(cudaGetLastError());
+    if (gaussian) {
+        GaussParams gp;
+        gauss_params(&gp);
+        gauss_filter_frames_kernel<<<ew_grid(ctx, n * 3), 256, 0, st>>>(gp, d_scratch, T, J * 3, d_out);
+        HRT_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C++" {
+namespace {
+template <int OP>
+int launch_rot_op(hrt_ctx* ctx, const RotOpArgs& a, cudaStream_t st) {
+    const long long tiles = (a.n + 31) / 32;
+    const int grid = (int)std::max(1LL, std::min((tiles + ROT_WARPS - 1) / ROT_WARPS, (long long)ctx->sm_count * 8));
+    rot_op_kernel<OP><<<grid, ROT_WARPS * 32, 0, st>>>(a);
+    return 0;
+}
+template <int OP>
+void rot_op_info(int* ni, int* wi, int* no, int* wo) {
+    using Tr = RotOpTraits<OP>;
+    *ni = Tr::NI; *no = Tr::NO;
+    for (int k = 0; k < 4; ++k) wi[k] = Tr::WI[k];
+    for (int k = 0; k < 3; ++k) wo[k] = Tr::WO[k];
+}
+#define HRT_FOR_EACH_OP(X)                                                                                          \
+    X(OP_QUAT_MUL) X(OP_QUAT_MUL_NORM) X(OP_QUAT_MUL_THREE) X(OP_QUAT_MUL_FOUR) X(OP_QUAT_POS) X(OP_QUAT_ABS)       \
+    X(OP_QUAT_UNIT) X(OP_QUAT_NORMALIZE) X(OP_QUAT_CONJUGATE) X(OP_QUAT_ROTATE) X(OP_QUAT_FROM_ANGLE_AXIS)          \
+    X(OP_QUAT_FROM_ROTATION_MATRIX) X(OP_QUAT_ANGLE_AXIS) X(OP_QUAT_YAW_ROTATION) X(OP_TRANSFORM_INVERSE)           \
+    X(OP_TRANSFORM_MUL) X(OP_TRANSFORM_APPLY) X(OP_ROT_MATRIX_DET) X(OP_ROT_MATRIX_FROM_QUATERNION)                 \
+    X(OP_PROJECT_QUAT_TO_AXIS) X(OP_EXTRACT_ROTATION_ALONG_AXIS) X(OP_NORMALIZE_ANGLE) X(OP_QUAT_TO_ANGLE_AXIS)     \
+    X(OP_QUAT_TO_EXP_MAP) X(OP_EXP_MAP_TO_ANGLE_AXIS) X(OP_EXP_MAP_TO_QUAT) X(OP_ANGLE_AXIS_TO_EXP_MAP)             \
+    X(OP_QUAT_BETWEEN_TWO_VECS) X(OP_PROJ_IN_PLANE) X(OP_RADIANS_BETWEEN_VECS) X(OP_QUAT_SLERP)                     \
+    X(OP_QUAT_TO_DOF_POS) X(OP_EULER_SPLIT) X(OP_EULER_ANGLES_F64) X(OP_COORD_TRANSFORM)
+}  // namespace
+}  // extern "C++"
+
+int hrt_rot_op_info(int op, int* n_in, int* in_width4, int* n_out, int* out_width3) {
+    if (!n_in || !in_width4 || !n_out || !out_width3) return fail(HRT_E_INVALID_ARG, "null pointer");
+    switch (op) {
+#define X(OP) case OP: rot_op_info<OP>(n_in, in_width4, n_out, out_width3); return 0;
+        HRT_FOR_EACH_OP(X)
+#undef X
+    }
+    return fail(HRT_E_INVALID_ARG, "unknown op %d", op);
+}
+
+int hrt_rot_op(hrt_ctx* ctx, int op, int64_t n, const float* const* d_in4, const int64_t* period4, int iparam,
+               float fparam, float* const* d_out3, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    int ni, wi[4], no, wo[3];
+    if ((rc = hrt_rot_op_info(op, &ni, wi, &no, wo))) return rc;
+    if (n < 0 || !d_in4 || !period4 || !d_out3) return fail(HRT_E_INVALID_ARG, "bad n / null pointer");
+    if (n == 0) return 0;
+    RotOpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.iparam = iparam; a.fparam = fparam;
+    for (int k = 0; k < ni; ++k) {
+        if (!d_in4[k]) return fail(HRT_E_INVALID_ARG, "operand %d is null", k);
+        if (period4[k] < 0) return fail(HRT_E_INVALID_ARG, "period[%d] < 0", k);
+        a.in[k] = d_in4[k];
+        a.period[k] = period4[k];
+    }
+    for (int k = 0; k < no; ++k) {
+        if (!d_out3[k]) return fail(HRT_E_INVALID_ARG, "result %d is null", k);
+        a.out[k] = d_out3[k];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (op) {
+#define X(OP) case OP: launch_rot_op<OP>(ctx, a, st); break;
+        HRT_FOR_EACH_OP(X)
+#undef X
+    }
+    HRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hrt_max_norm3(hrt_ctx* ctx, int64_t n, const float* d_v, float* h_out, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (n < 0 || !h_out || (n > 0 && !d_v)) return fail(HRT_E_INVALID_ARG, "bad n / null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned* slot = ctx->d_scalars + HRT_MAX_JOINTS;
+    HRT_CUDA(cudaMemsetAsync(slot, 0, sizeof(unsigned), st));
+    if (n > 0) {
+        max_norm3_kernel<<<ew_grid(ctx, n), 256, 0, st>>>(d_v, n, slot);
+        HRT_CUDA(cudaGetLastError());
+    }
+    unsigned bits = 0;
+    HRT_CUDA(cudaMemcpyAsync(&bits, slot, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    HRT_CUDA(cudaStreamSynchronize(st));
+    memcpy(h_out, &bits, 4);
+    return 0;
+}
+
+int hrt_cal_joint_quat(hrt_ctx* ctx, int64_t n, int n_points, const float* d_zero, int64_t zero_period,
+                       const float* d_motion, float* d_out_q, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (n < 0 || n_points < 1 || zero_period < 0) return fail(HRT_E_INVALID_ARG, "bad n / n_points / zero_period");
+    if (n == 0) return 0;
+    if (!d_zero || !d_motion || !d_out_q) return fail(HRT_E_INVALID_ARG, "null pointer");
+    if (!aligned16(d_out_q)) return fail(HRT_E_ALIGNMENT, "d_out_q must be 16-byte aligned");
+    const int grid = (int)std::max(1LL, std::min(((long long)n + 127) / 128, (long long)ctx->sm_count * 8));
+    kabsch_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d_zero, zero_period, d_motion, n, n_points, d_out_q);
+    HRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
 
 }  // extern "C"

@@ -1,0 +1,197 @@
+// Clip-level stages around the per-frame solvers (sm_100a):
+//   Retarget.rescale_motion_to_standard_size          retarget/main.py:36-47
+//   RetargetHuV5fromMocap._rebuild_with_vtrdyn_zero_pose (global-rotation rebuild)   retarget/main.py:116-152
+//   SkeletonMotion._compute_velocity / _compute_angular_velocity                      poselib/poselib/skeleton/skeleton3d.py:1126-1146
+//     (np.gradient + scipy.ndimage.gaussian_filter1d(sigma=2, mode="nearest"))
+// Frames lead; a warp owns 32 consecutive frames of a clip, staged as one contiguous span.
+#pragma once
+#include "hrt_fk_limb.cuh"
+#include "hrt_math.cuh"
+#include "hrt_ops.cuh"
+#include "hrt_pos.cuh"
+
+namespace hrt {
+
+constexpr int MOT_WARPS = 4;
+
+struct RescaleParams {
+    int J;
+    int8_t parent[HRT_MAX_JOINTS];
+    float off[HRT_MAX_JOINTS][3];      // zero-pose local translations
+    float dir[3];                      // coord_transform(dir=...) applied first (main.py:170), 1,1,1 = none
+};
+
+// p'[j] = p'[parent] + (p[j] - p[parent]) / (||p[j] - p[parent]|| / ||off[j]||), joints in index order
+__global__ void __launch_bounds__(MOT_WARPS * 32)
+rescale_motion_kernel(const __grid_constant__ RescaleParams rp, const float* __restrict__ gt, long long B,
+                      float* __restrict__ out) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = rp.J * 3;
+    float* src = smem + (size_t)warp * 2 * 32 * W;
+    float* dst = src + 32 * W;
+    const long long n_tiles = (B + 31) / 32;
+    for (long long t = (long long)blockIdx.x * MOT_WARPS + warp; t < n_tiles; t += (long long)gridDim.x * MOT_WARPS) {
+        const long long f0 = t * 32;
+        const int cnt = (int)min(32LL, B - f0);
+        for (int w = lane; w < cnt * W; w += 32) src[w] = __ldcs(gt + f0 * W + w);
+        __syncwarp();
+        if (lane < cnt) {
+            float* s = src + lane * W;
+            float* d = dst + lane * W;
+            for (int w = 0; w < W; ++w) s[w] = mul_rn(s[w], rp.dir[w % 3]);
+            for (int j = 0; j < rp.J; ++j) {
+                const int p = rp.parent[j];
+                if (p < 0) { d[j * 3] = s[j * 3]; d[j * 3 + 1] = s[j * 3 + 1]; d[j * 3 + 2] = s[j * 3 + 2]; continue; }
+                const vec3 v = sub3_x(ld3(s + j * 3), ld3(s + p * 3));
+                const float scale = div_rn(norm3_x(v), norm3_x(make_vec3(rp.off[j][0], rp.off[j][1], rp.off[j][2])));
+                d[j * 3] = add_rn(d[p * 3], div_rn(v.x, scale));
+                d[j * 3 + 1] = add_rn(d[p * 3 + 1], div_rn(v.y, scale));
+                d[j * 3 + 2] = add_rn(d[p * 3 + 2], div_rn(v.z, scale));
+            }
+        }
+        __syncwarp();
+        for (int w = lane; w < cnt * W; w += 32) __stcs(out + f0 * W + w, dst[w]);
+        __syncwarp();
+    }
+}
+
+struct RebuildParams {
+    int J;
+    int8_t parent[HRT_MAX_JOINTS];
+    float off[HRT_MAX_JOINTS][3];
+    int n_kabsch;                      // joints whose rotation comes from a 3-point Kabsch fit
+    int kabsch_joint[2];               // main.py:126-136: joints 0 and 10
+    int kabsch_pts[2][3];              // [4,1,7] and [17,13,11]
+    uint8_t skip[HRT_MAX_JOINTS];      // main.py:146: joint 0, children of joint 0 / joint 10
+};
+
+// per-bone max over the clip of ||p[j] - p[parent]|| (quat_between_two_vecs' whole-batch early-out)
+__global__ void __launch_bounds__(256)
+bone_max_norm_kernel(const __grid_constant__ RebuildParams rp, const float* __restrict__ gt, long long B,
+                     unsigned* __restrict__ out_bits) {
+    const int j = blockIdx.y;
+    const int p = rp.parent[j];
+    if (p < 0) return;
+    float m = 0.f;
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < B; f += (long long)gridDim.x * blockDim.x) {
+        const float* r = gt + f * rp.J * 3;
+        m = fmaxf(m, norm3_x(sub3_x(ld3(r + j * 3), ld3(r + p * 3))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits + j, __float_as_uint(m));
+}
+
+// global rotations of the mocap skeleton rebuilt from joint positions (main.py:116-152)
+__global__ void __launch_bounds__(MOT_WARPS * 32)
+rebuild_rotation_kernel(const __grid_constant__ RebuildParams rp, const float* __restrict__ gt, long long B,
+                        const unsigned* __restrict__ bone_max_bits, float* __restrict__ out_gq) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = rp.J * 3, Q = rp.J * 4;
+    float* src = smem + (size_t)warp * 32 * (W + Q);
+    float* dst = src + 32 * W;
+    const long long n_tiles = (B + 31) / 32;
+    for (long long t = (long long)blockIdx.x * MOT_WARPS + warp; t < n_tiles; t += (long long)gridDim.x * MOT_WARPS) {
+        const long long f0 = t * 32;
+        const int cnt = (int)min(32LL, B - f0);
+        for (int w = lane; w < cnt * W; w += 32) src[w] = __ldcs(gt + f0 * W + w);
+        for (int w = lane; w < cnt * rp.J; w += 32) *reinterpret_cast<float4*>(dst + w * 4) = make_float4(0.f, 0.f, 0.f, 1.f);
+        __syncwarp();
+        if (lane < cnt) {
+            const float* s = src + lane * W;
+            float* d = dst + lane * Q;
+            for (int k = 0; k < rp.n_kabsch; ++k) {
+                vec3 M[3], Z[3];
+                const int jk = rp.kabsch_joint[k];
+#pragma unroll
+                for (int n = 0; n < 3; ++n) {
+                    const int pj = rp.kabsch_pts[k][n];
+                    M[n] = sub3_x(ld3(s + pj * 3), ld3(s + jk * 3));
+                    Z[n] = make_vec3(rp.off[pj][0], rp.off[pj][1], rp.off[pj][2]);
+                }
+                *reinterpret_cast<float4*>(d + jk * 4) = kabsch_quat<3>(M, Z);
+            }
+            for (int j = 0; j < rp.J; ++j) {
+                if (rp.skip[j]) continue;
+                const int p = rp.parent[j];
+                vec3 a = make_vec3(rp.off[j][0], rp.off[j][1], rp.off[j][2]);
+                vec3 b = sub3_x(ld3(s + j * 3), ld3(s + p * 3));
+                float4 q = make_float4(0.f, 0.f, 0.f, 1.f);
+                const bool early = !(norm3_x(a) > 1e-6f) || !(__uint_as_float(bone_max_bits[j]) > 1e-6f);
+                if (!early) {
+                    a = div3_x(a, norm3_x(a));
+                    b = div3_x(b, norm3_x(b));
+                    const vec3 c = cross3_x(a, b);
+                    q = quat_normalize_x(make_float4(c.x, c.y, c.z, add_rn(1.f, dot3_x(a, b))));
+                }
+                *reinterpret_cast<float4*>(d + p * 4) = q;       // written at the PARENT index (main.py:149)
+            }
+        }
+        __syncwarp();
+        for (int w = lane; w < cnt * Q; w += 32) __stcs(out_gq + f0 * Q + w, dst[w]);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// velocities along the frame axis
+// ---------------------------------------------------------------------------------------------
+// np.gradient(p, axis=frames) / dt in fp32: central differences inside, one-sided at both ends
+__global__ void __launch_bounds__(256)
+frame_gradient_kernel(const float* __restrict__ p, long long T, long long C, float dt, float* __restrict__ out) {
+    const long long n = T * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long t = i / C;
+        float g;
+        if (t == 0) g = div_rn(sub_rn(p[i + C], p[i]), 1.f);
+        else if (t == T - 1) g = div_rn(sub_rn(p[i], p[i - C]), 1.f);
+        else g = div_rn(sub_rn(p[i + C], p[i - C]), 2.f);
+        out[i] = div_rn(g, dt);
+    }
+}
+
+// diff[t] = norm(r[t+1] * inv(r[t])) (identity at the last frame); (angle, axis) = quat_angle_axis;
+// w = axis * angle / dt        skeleton3d.py:1137-1143
+__global__ void __launch_bounds__(256)
+angular_velocity_raw_kernel(const float4* __restrict__ r, long long T, long long J, float dt, float* __restrict__ out) {
+    const long long n = T * J;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long t = i / J;
+        float4 q = make_float4(0.f, 0.f, 0.f, 1.f);
+        if (t < T - 1) q = quat_mul_norm_x(__ldg(r + i + J), quat_conj(__ldg(r + i)));
+        const float s = sub_rn(mul_rn(2.f, mul_rn(q.w, q.w)), 1.f);
+        const float angle = acosf(fminf(fmaxf(s, -1.f), 1.f));
+        const vec3 v = make_vec3(q.x, q.y, q.z);
+        const vec3 ax = div3_x(v, fmaxf(norm3_x(v), 1e-9f));
+        out[i * 3] = div_rn(mul_rn(ax.x, angle), dt);
+        out[i * 3 + 1] = div_rn(mul_rn(ax.y, angle), dt);
+        out[i * 3 + 2] = div_rn(mul_rn(ax.z, angle), dt);
+    }
+}
+
+struct GaussParams {
+    int radius;                 // int(4 * sigma + 0.5) = 8 for sigma = 2
+    double w[33];               // w[k] = weight of offset k - radius (normalised, fp64, as scipy builds it)
+};
+
+// scipy.ndimage.gaussian_filter1d along frames, mode="nearest": fp64 accumulation in correlate1d's
+// symmetric order (centre, then the +-j pairs from the outside in), result rounded to fp32
+__global__ void __launch_bounds__(256)
+gauss_filter_frames_kernel(const __grid_constant__ GaussParams gp, const float* __restrict__ x, long long T, long long C,
+                           float* __restrict__ out) {
+    const long long n = T * C;
+    const int R = gp.radius;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long t = i / C, c = i - t * C;
+        double acc = (double)x[i] * gp.w[R];
+        for (int j = -R; j < 0; ++j) {
+            const long long ta = min(max(t + j, 0LL), T - 1), tb = min(max(t - j, 0LL), T - 1);
+            acc += ((double)__ldg(x + ta * C + c) + (double)__ldg(x + tb * C + c)) * gp.w[j + R];
+        }
+        out[i] = (float)acc;
+    }
+}
+
+}  // namespace hrt

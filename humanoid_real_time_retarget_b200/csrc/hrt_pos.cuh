@@ -24,7 +24,8 @@
 
 namespace hrt {
 
-enum PosMode { POS_FULL_BODY_POS = 0, POS_UPPER_BODY = 1, POS_FULL_BODY = 2 };
+// POS_MAIN: RetargetHuV5fromMocap (retarget/main.py:201-240): positions + ONE measured parent quat for both arms
+enum PosMode { POS_FULL_BODY_POS = 0, POS_UPPER_BODY = 1, POS_FULL_BODY = 2, POS_MAIN = 3 };
 
 struct PosArm {
     int b_sh, b_el, b_wr;          // body joints: shoulder-end, elbow, wrist (vtrdyn: 18,19,20 / 14,15,16)
@@ -39,7 +40,8 @@ struct PosParams {
     int mode;
     int J_rob;                     // 31
     int J_bq;                      // 59 (mode POS output), else 0
-    int n_body, n_hand;            // 21, 20
+    int n_body, n_hand;            // rows per frame of body_t / hand_t: 21 (23 in the wire layout), 20
+    int n_bodyq;                   // rows per frame of body_q (21)
     int torso_pts[3], torso_org;   // 17,13,11 ; 10
     int bq_torso;                  // 10
     int hand_kabsch[5], hand_org;  // 2,6,10,14,17 ; 0
@@ -152,19 +154,8 @@ HRT_DEV void jacobi_rot(double& app, double& aqq, double& apq, double& arp, doub
     }
 }
 
-// M: measured offsets (n x 3), Z: zero-pose offsets (n x 3), both fp32.  Returns the quaternion.
-template <int N>
-HRT_DEV float4 kabsch_quat(const vec3* M, const vec3* Z) {
-    double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-        const double m[3] = {(double)M[n].x, (double)M[n].y, (double)M[n].z};
-        const double z[3] = {(double)Z[n].x, (double)Z[n].y, (double)Z[n].z};
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) A[i][k] += m[i] * z[k];
-    }
+// A = M^T Z in fp64 (exact products of fp32 inputs) -> the rotation quaternion.
+HRT_DEV float4 kabsch_quat_from_A(const double A[3][3]) {
     // S = A^T A (symmetric), eigenvectors -> right singular vectors
     double s00 = 0, s01 = 0, s02 = 0, s11 = 0, s12 = 0, s22 = 0;
 #pragma unroll
@@ -213,15 +204,31 @@ HRT_DEV float4 kabsch_quat(const vec3* M, const vec3* Z) {
     return quat_from_rotation_matrix_x(R);
 }
 
+// M: measured offsets (n x 3), Z: zero-pose offsets (n x 3), both fp32.  Returns the quaternion.
+template <int N>
+HRT_DEV float4 kabsch_quat(const vec3* M, const vec3* Z) {
+    double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        const double m[3] = {(double)M[n].x, (double)M[n].y, (double)M[n].z};
+        const double z[3] = {(double)Z[n].x, (double)Z[n].y, (double)Z[n].z};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) A[i][k] += m[i] * z[k];
+    }
+    return kabsch_quat_from_A(A);
+}
+
 HRT_DEV vec3 ld3(const float* p) { return make_vec3(p[0], p[1], p[2]); }
 
 // staging sizes (words per warp of 16 frames)
 HRT_HD inline int pos_in_words(int n_body, int n_hand, bool hands, bool quats) {
-    return BQ_FRAMES_PER_WARP * (n_body * 3 + (hands ? 2 * n_hand * 3 : 0) + (quats ? n_body * 4 : 0));
+    return BQ_FRAMES_PER_WARP * (n_body * 3 + (hands ? 2 * n_hand * 3 : 0) + (quats ? 21 * 4 : 0));
 }
 HRT_HD inline int pos_tile_words(const PosParams& pp, bool with_lq, bool with_bq) {
-    const bool hands = pp.mode != POS_UPPER_BODY;
-    int in = pos_in_words(pp.n_body, pp.n_hand, hands, pp.mode == POS_FULL_BODY);
+    const bool hands = pp.mode == POS_FULL_BODY_POS || pp.mode == POS_FULL_BODY;
+    int in = pos_in_words(pp.n_body, pp.n_hand, hands, pp.mode == POS_FULL_BODY || pp.mode == POS_MAIN);
     int bq = with_bq ? BQ_FRAMES_PER_WARP * pp.J_bq * 4 : 0;
     int io = in > bq ? in : bq;                         // body_global_rotation image reuses the input rows
     return (io + 3) / 4 * 4 + bq_dof_words(pp.J_rob) + (with_lq ? BQ_FRAMES_PER_WARP * pp.J_rob * 4 : 0);
@@ -236,8 +243,8 @@ pos_retarget_kernel(const __grid_constant__ PosParams pp, const PosArgs a) {
     const int warp = threadIdx.x >> 5;
     const int fl = lane >> 1;
     const int side = lane & 1;
-    constexpr bool HANDS = MODE != POS_UPPER_BODY;
-    constexpr bool QUATS = MODE == POS_FULL_BODY;
+    constexpr bool HANDS = MODE == POS_FULL_BODY_POS || MODE == POS_FULL_BODY;
+    constexpr bool QUATS = MODE == POS_FULL_BODY || MODE == POS_MAIN;
     // ---- CTA-shared constants: both PosArm tables + zero-pose bone angles -----------------------
     PosArm* arms_s = reinterpret_cast<PosArm*>(smem);
     float* zero_ang = smem + 2 * sizeof(PosArm) / 4;      // [side][4] = theta0_sh, phi0_sh, theta0_el, phi0_el
@@ -295,7 +302,7 @@ pos_retarget_kernel(const __grid_constant__ PosParams pp, const PosArgs a) {
             warp_span_g2s(lh_s, a.lhand_t + f0 * NH * 3, nld * NH * 3, lane);
             warp_span_g2s(rh_s, a.rhand_t + f0 * NH * 3, nld * NH * 3, lane);
         }
-        if (QUATS) warp_span_g2s(bodyq_s, a.body_q + f0 * NB * 4, nld * NB * 4, lane);
+        if (QUATS) warp_span_g2s(bodyq_s, a.body_q + f0 * pp.n_bodyq * 4, nld * pp.n_bodyq * 4, lane);
         cp_async_commit();
         if (a.out_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
         if (with_lq)
@@ -312,8 +319,8 @@ pos_retarget_kernel(const __grid_constant__ PosParams pp, const PosArgs a) {
         // ---- 2. arm parent frame ------------------------------------------------------------------
         float4 torso = make_float4(0.f, 0.f, 0.f, 1.f);
         float4 parent;
-        if (MODE == POS_FULL_BODY) {
-            parent = *reinterpret_cast<const float4*>(bodyq_s + (fr * NB + ap.q_parent) * 4);
+        if (QUATS) {
+            parent = *reinterpret_cast<const float4*>(bodyq_s + (fr * pp.n_bodyq + ap.q_parent) * 4);
         } else {
             smsp_align<POS_WARPS>(warp);
             vec3 M[3], Z[3];
@@ -351,7 +358,7 @@ pos_retarget_kernel(const __grid_constant__ PosParams pp, const PosArgs a) {
             const float4 base = (MODE == POS_FULL_BODY) ? parent : torso;
             const float4 wparent = quat_mul_norm_x(base, chain);
             if (MODE == POS_FULL_BODY) {
-                wrist_g = *reinterpret_cast<const float4*>(bodyq_s + (fr * NB + ap.q_wrist) * 4);
+                wrist_g = *reinterpret_cast<const float4*>(bodyq_s + (fr * pp.n_bodyq + ap.q_wrist) * 4);
             } else {
                 vec3 M[5], Z[5];
                 const vec3 org = ld3(hand + pp.hand_org * 3);

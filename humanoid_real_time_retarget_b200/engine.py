@@ -11,7 +11,7 @@ from . import robot_config as cfg
 TREE_ROBOT, TREE_SOURCE, TREE_SOURCE_FULL = 0, 1, 2
 FK_EXACT = 1
 BQ_CLAMP, BQ_IK, BQ_PRE_TRANSFORMED = 1, 2, 4
-POS_FULL_BODY_POS, POS_UPPER_BODY, POS_FULL_BODY = 0, 1, 2
+POS_FULL_BODY_POS, POS_UPPER_BODY, POS_FULL_BODY, POS_MAIN = 0, 1, 2, 3
 
 
 def _ptr(t):
@@ -89,6 +89,7 @@ class Engine:
             self.configure_pos(POS_FULL_BODY_POS, TREE_SOURCE_FULL, TREE_ROBOT, sk["vtrdyn_full_zero_pose/global_translation"], True)
             self.configure_pos(POS_UPPER_BODY, TREE_SOURCE, TREE_ROBOT)
             self.configure_pos(POS_FULL_BODY, TREE_SOURCE_FULL, TREE_ROBOT)
+            self.configure_pos(POS_MAIN, TREE_SOURCE, TREE_ROBOT)
         return self
 
     def configure_body_quat(self, src_tree, rob_tree, src_joints, rob_first):
@@ -211,6 +212,110 @@ class Engine:
         _lib.check(self.lib.hrt_retarget_full_body(self._h, B, _ptr(body_q), _ptr(body_t), _ptr(lhand_t), _ptr(rhand_t),
                                                    _ptr(lq), _ptr(dof), self._stream()))
         return lq, dof
+
+    def retarget_full_body_pos_wire(self, body23_t, lhand_t, rhand_t, want_local_q=True, want_dof=True, want_body_gq=False):
+        """The same solver on the mocap WIRE layout (sim_full_body_teleop.py:109-112): body (B,23,3), hands in
+        HandNodes order (B,20,3); the 23->21 / finger reorder happens inside the kernel's index tables."""
+        body23_t, lhand_t, rhand_t = (_f32c(x, self.device) for x in (body23_t, lhand_t, rhand_t))
+        B = body23_t.numel() // 69
+        assert body23_t.numel() == B * 69 and lhand_t.numel() == B * 60 and rhand_t.numel() == B * 60
+        lq, dof, bq = self._pos_outputs(B, want_local_q, want_dof, want_body_gq)
+        _lib.check(self.lib.hrt_retarget_full_body_pos_wire(self._h, B, _ptr(body23_t), _ptr(lhand_t), _ptr(rhand_t),
+                                                            _ptr(lq), _ptr(dof), _ptr(bq), self._stream()))
+        return lq, dof, bq
+
+    def retarget_main_arms(self, body_q, body_t, want_local_q=True, want_dof=True):
+        """The per-frame arm solves of RetargetHuV5fromMocap (retarget/main.py:201-240), batched."""
+        body_q, body_t = _f32c(body_q, self.device), _f32c(body_t, self.device)
+        B = body_t.numel() // 63
+        assert body_q.numel() == B * 84
+        lq, dof, _ = self._pos_outputs(B, want_local_q, want_dof)
+        _lib.check(self.lib.hrt_retarget_main_arms(self._h, B, _ptr(body_q), _ptr(body_t), _ptr(lq), _ptr(dof), self._stream()))
+        return lq, dof
+
+    # ------------------------------------------------------------------ clip-level stages
+    def rescale_motion(self, tree, global_t, dir=None):
+        """Retarget.rescale_motion_to_standard_size (retarget/main.py:36-47) [+ coord_transform(dir)]."""
+        J = self._trees[tree]
+        global_t = _f32c(global_t, self.device)
+        B = global_t.numel() // (J * 3)
+        out = torch.empty_like(global_t)
+        d = None if dir is None else np.ascontiguousarray(np.asarray(dir, dtype=np.float32).reshape(3))
+        _lib.check(self.lib.hrt_rescale_motion(self._h, tree, B, _ptr(global_t), _np_ptr(d), _ptr(out), self._stream()))
+        return out
+
+    def rebuild_global_rotation(self, tree, global_t, kabsch_joints=(0, 10), kabsch_pts=((4, 1, 7), (17, 13, 11))):
+        """Global rotations rebuilt from joint positions (retarget/main.py:116-152)."""
+        J = self._trees[tree]
+        global_t = _f32c(global_t, self.device)
+        B = global_t.numel() // (J * 3)
+        kj = np.ascontiguousarray(np.asarray(kabsch_joints, dtype=np.int32))
+        kp = np.ascontiguousarray(np.asarray(kabsch_pts, dtype=np.int32).reshape(-1))
+        out = torch.empty((B, J, 4), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.hrt_rebuild_global_rotation(self._h, tree, B, _ptr(global_t), kj.shape[0], _np_ptr(kj), _np_ptr(kp),
+                                                        _ptr(out), self._stream()))
+        return out
+
+    def motion_velocity(self, global_t, dt, gaussian=True):
+        """SkeletonMotion._compute_velocity (skeleton3d.py:1126-1135) on (T,J,3)."""
+        global_t = _f32c(global_t, self.device)
+        T, J = global_t.shape[0], global_t.shape[1]
+        out = torch.empty_like(global_t)
+        scratch = torch.empty_like(global_t) if gaussian else None
+        _lib.check(self.lib.hrt_motion_velocity(self._h, T, J, _ptr(global_t), float(np.float32(dt)), int(bool(gaussian)),
+                                                _ptr(scratch), _ptr(out), self._stream()))
+        return out
+
+    def motion_angular_velocity(self, global_q, dt, gaussian=True):
+        """SkeletonMotion._compute_angular_velocity (skeleton3d.py:1137-1146) on (T,J,4)."""
+        global_q = _f32c(global_q, self.device)
+        T, J = global_q.shape[0], global_q.shape[1]
+        out = torch.empty((T, J, 3), device=self.device, dtype=torch.float32)
+        scratch = torch.empty_like(out) if gaussian else None
+        _lib.check(self.lib.hrt_motion_angular_velocity(self._h, T, J, _ptr(global_q), float(np.float32(dt)), int(bool(gaussian)),
+                                                        _ptr(scratch), _ptr(out), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ element-wise rotation algebra
+    def rot_op_info(self, op):
+        ni, no = C.c_int(), C.c_int()
+        wi, wo = (C.c_int * 4)(), (C.c_int * 3)()
+        _lib.check(self.lib.hrt_rot_op_info(op, C.byref(ni), wi, C.byref(no), wo))
+        return list(wi)[:ni.value], list(wo)[:no.value]
+
+    def rot_op(self, op, n, ins, periods, outs, iparam=0, fparam=0.0):
+        """ins / outs: contiguous fp32 device tensors; periods[k] = 0 (n rows) or the row count that repeats."""
+        pin = (C.c_void_p * 4)(*([t.data_ptr() for t in ins] + [0] * (4 - len(ins))))
+        per = (C.c_int64 * 4)(*(list(periods) + [0] * (4 - len(periods))))
+        pout = (C.c_void_p * 3)(*([t.data_ptr() for t in outs] + [0] * (3 - len(outs))))
+        _lib.check(self.lib.hrt_rot_op(self._h, op, n, pin, per, iparam, fparam, pout, self._stream()))
+
+    def max_norm3(self, v):
+        v = _f32c(v, self.device)
+        out = C.c_float()
+        _lib.check(self.lib.hrt_max_norm3(self._h, v.numel() // 3, _ptr(v), C.byref(out), self._stream()))
+        return out.value
+
+    def cal_joint_quat(self, zero_t, motion_t):
+        """cal_joint_quat (transform3d.py:32-50): zero_t (b|1,n,3), motion_t (b,n,3) -> (b,4)."""
+        zero_t, motion_t = _f32c(zero_t, self.device), _f32c(motion_t, self.device)
+        b, n = motion_t.shape[0], motion_t.shape[1]
+        zb = zero_t.numel() // (n * 3)
+        out = torch.empty((b, 4), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.hrt_cal_joint_quat(self._h, b, n, _ptr(zero_t), 0 if zb == b else zb, _ptr(motion_t), _ptr(out),
+                                               self._stream()))
+        return out
+
+    def stream_pos_open(self, wire_layout=False):
+        _lib.check(self.lib.hrt_stream_pos_open(self._h, int(bool(wire_layout))))
+
+    def stream_pos_frame(self, body_np, lhand_np, rhand_np, out_local_q=None, out_dof=None):
+        """numpy float32 in / out, one frame of the position path."""
+        _lib.check(self.lib.hrt_stream_pos_frame(self._h, _np_ptr(body_np), _np_ptr(lhand_np), _np_ptr(rhand_np),
+                                                 _np_ptr(out_local_q), _np_ptr(out_dof)))
+
+    def stream_pos_close(self):
+        _lib.check(self.lib.hrt_stream_pos_close(self._h))
 
     # ------------------------------------------------------------------ host-buffer (reference-facing) calls
     def retarget_body_quat_host(self, src_gq, flags=0, ik_iters=10, damping=0.1, rot_weight=0.2,

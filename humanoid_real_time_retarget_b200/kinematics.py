@@ -92,9 +92,38 @@ class RobotZeroPose:
     @classmethod
     def from_asset(cls, name):
         """Bundled tables (tools/extract_assets.py), e.g. 'hu_v5_zero_pose', 'vtrdyn_zero_pose'."""
+        from .skeleton3d import SkeletonTree
         sk = cfg.skeleton_tables()
+        names = [str(s) for s in sk[f"{name}/node_names"]]
+        tree = SkeletonTree(names, torch.from_numpy(sk[f"{name}/parents"].astype(np.int64)),
+                            torch.from_numpy(sk[f"{name}/offsets"].copy()), torch.from_numpy(sk[f"{name}/tree_quat"].copy()))
         return cls(sk[f"{name}/offsets"], sk[f"{name}/global_translation"], sk[f"{name}/parents"],
-                   sk[f"{name}/parents"].shape[0], [str(s) for s in sk[f"{name}/node_names"]])
+                   sk[f"{name}/parents"].shape[0], names, tree)
+
+    @classmethod
+    def from_urdf(cls, urdf_path):
+        """base_robot.py:68-78 parses a URDF with urdfpy; file readers are out of scope.
+        The Hu v5 zero pose that the reference's callers build this way is bundled: from_asset('hu_v5_zero_pose')."""
+        if "hu_v5" in str(urdf_path):
+            return cls.from_asset("hu_v5_zero_pose")
+        raise NotImplementedError("URDF parsing is outside the retarget hot path; use from_asset / from_skeleton_state")
+
+    @classmethod
+    def from_dict(cls, robot_dict, is_local=False):
+        """base_robot.py:90-96"""
+        if is_local:
+            robot_dict['global_translation'] = cls.cal_global_translation(robot_dict['local_translation'], robot_dict['parent_indices'])
+        else:
+            robot_dict['local_translation'] = cls.cal_local_translation(robot_dict['global_translation'], robot_dict['parent_indices'])
+        return cls(**robot_dict)
+
+    @staticmethod
+    def cal_global_translation(local_translation, parent_indices):
+        raise NotImplementedError          # as in the reference (base_robot.py:103-104)
+
+    def get_sk_zero_pose(self):
+        from .skeleton3d import SkeletonState
+        return SkeletonState.zero_pose(self.skeleton_tree)
 
     @staticmethod
     def cal_local_translation(global_translation, parent_indices):

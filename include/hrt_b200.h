@@ -158,6 +158,105 @@ int hrt_stream_frame(hrt_ctx* ctx, const float* h_src_gq, float* h_robot_local_q
                      float* h_link_pos);
 int hrt_stream_close(hrt_ctx* ctx);
 
+/* Streaming teleop on the POSITION path (what sim_full_body_teleop.py:83-129 runs every frame):
+ * VtrdynFullBodyPosRetargeter.retarget on one frame, host in -> host out through mapped pinned
+ * mailboxes.  h_body_t (21*3), h_lhand_t / h_rhand_t (20*3) -> h_robot_local_q (31*4)|NULL, h_dof (30)|NULL.
+ * wire_layout != 0: the inputs are in the mocap wire layout instead -- h_body_t (23*3) and hands in
+ * HandNodes order -- and the 23->21 / hand reorder of sim_full_body_teleop.py:109-112 runs in the
+ * kernel prologue. */
+int hrt_retarget_full_body_pos_wire(hrt_ctx* ctx, int64_t B, const float* d_body23_t, const float* d_lhand_t,
+                                    const float* d_rhand_t, float* d_robot_local_q, float* d_dof, float* d_body_gq,
+                                    void* stream);       /* batched form of the same wire-layout call */
+int hrt_stream_pos_open(hrt_ctx* ctx, int wire_layout);
+int hrt_stream_pos_frame(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
+                         float* h_robot_local_q, float* h_dof);
+int hrt_stream_pos_close(hrt_ctx* ctx);
+
+/* RetargetHuV5fromMocap (retarget/main.py:51-279), mode 3 of the position solvers: arms from joint
+ * positions with BOTH arm parents = the measured/rebuilt global quat of joint 10 (main.py:203-240).
+ * d_body_q (B,21,4), d_body_t (B,21,3) -> d_robot_local_q (B,31,4), d_dof (B,30). */
+#define HRT_POS_MAIN 3
+int hrt_retarget_main_arms(hrt_ctx* ctx, int64_t B, const float* d_body_q, const float* d_body_t,
+                           float* d_robot_local_q, float* d_dof, void* stream);
+
+/* Retarget.rescale_motion_to_standard_size (retarget/main.py:36-47) on the installed tree's offsets, with
+ * coord_transform(dir) (main.py:170, transform3d.py:24-29) folded in (dir = NULL: none).
+ * d_gt (B,J,3) -> d_out (B,J,3). */
+int hrt_rescale_motion(hrt_ctx* ctx, int tree, int64_t B, const float* d_gt, const float* dir3, float* d_out,
+                       void* stream);
+
+/* RetargetHuV5fromMocap._rebuild_with_vtrdyn_zero_pose, rotations only (main.py:116-152): Kabsch fits
+ * (cal_joint_quat) for n_kabsch <= 2 joints from 3 points each, quat_between_two_vecs per remaining bone
+ * written at the parent's index, identity elsewhere.  kabsch_joint[n_kabsch], kabsch_pts[n_kabsch*3].
+ * d_gt (B,J,3) -> d_out_gq (B,J,4). */
+int hrt_rebuild_global_rotation(hrt_ctx* ctx, int tree, int64_t B, const float* d_gt, int n_kabsch,
+                                const int32_t* kabsch_joint, const int32_t* kabsch_pts, float* d_out_gq,
+                                void* stream);
+
+/* SkeletonMotion._compute_velocity / _compute_angular_velocity (poselib/poselib/skeleton/skeleton3d.py:
+ * 1126-1146): np.gradient along frames / dt, resp. axis*angle of r[t+1]*inv(r[t]) / dt, then
+ * scipy.ndimage.gaussian_filter1d(sigma=2, mode="nearest") when gaussian != 0.  T frames, J joints.
+ * d_scratch: T*J*3 floats.  d_gt (T,J,3) | d_gq (T,J,4) -> d_out (T,J,3). */
+int hrt_motion_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gt, float dt, int gaussian,
+                        float* d_scratch, float* d_out, void* stream);
+int hrt_motion_angular_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gq, float dt, int gaussian,
+                                float* d_scratch, float* d_out, void* stream);
+
+/* Element-wise rotation algebra: the free functions of poselib/poselib/core/rotation3d.py:15-661 and
+ * retarget/spatial_transform/transform3d.py:9-183, one op code each (HRT_OP_*; rows AoS fp32 like the
+ * reference's tensors).  Operand k has n rows when period[k] == 0, else period[k] rows that repeat
+ * (broadcast of a single row or of a (J,W) table against (B,J,W)).  hrt_rot_op_info reports the row
+ * widths of an op's operands and results. */
+enum {
+    HRT_OP_QUAT_MUL = 0,             /* rotation3d.py:15-27      (4),(4) -> (4) */
+    HRT_OP_QUAT_MUL_NORM,            /* :197-202 */
+    HRT_OP_QUAT_MUL_THREE,           /* :571-577 */
+    HRT_OP_QUAT_MUL_FOUR,            /* :560-567 */
+    HRT_OP_QUAT_POS,                 /* :31-38 */
+    HRT_OP_QUAT_ABS,                 /* :42-47                   (4) -> (1) */
+    HRT_OP_QUAT_UNIT,                /* :51-56 */
+    HRT_OP_QUAT_NORMALIZE,           /* :93-98 */
+    HRT_OP_QUAT_CONJUGATE,           /* :60-64, quat_inverse :215-219 */
+    HRT_OP_QUAT_ROTATE,              /* :206-211                 (4),(3) -> (3) */
+    HRT_OP_QUAT_FROM_ANGLE_AXIS,     /* :123-143                 (1),(3) -> (4); iparam: degree */
+    HRT_OP_QUAT_FROM_ROTATION_MATRIX,/* :147-193                 (9) -> (4) */
+    HRT_OP_QUAT_ANGLE_AXIS,          /* :231-240                 (4) -> (1),(3) */
+    HRT_OP_QUAT_YAW_ROTATION,        /* :244-261                 iparam: z_up */
+    HRT_OP_TRANSFORM_INVERSE,        /* :301-306                 (7) -> (7) */
+    HRT_OP_TRANSFORM_MUL,            /* :318-326 */
+    HRT_OP_TRANSFORM_APPLY,          /* :330-335                 (7),(3) -> (3) */
+    HRT_OP_ROT_MATRIX_DET,           /* :339-350                 (9) -> (1) */
+    HRT_OP_ROT_MATRIX_FROM_QUATERNION,/* :399-427                (4) -> (9) */
+    HRT_OP_PROJECT_QUAT_TO_AXIS,     /* :480-530                 iparam: 0 x, 1 y, 2 z, 3 xy, 4 xz */
+    HRT_OP_EXTRACT_ROTATION_ALONG_AXIS,/* :535-556               (4) -> (1); iparam: axis */
+    HRT_OP_NORMALIZE_ANGLE,          /* :583-584 */
+    HRT_OP_QUAT_TO_ANGLE_AXIS,       /* :588-608 */
+    HRT_OP_QUAT_TO_EXP_MAP,          /* :621-627 */
+    HRT_OP_EXP_MAP_TO_ANGLE_AXIS,    /* :630-646 */
+    HRT_OP_EXP_MAP_TO_QUAT,          /* :649-652, transform3d.py:146-150 */
+    HRT_OP_ANGLE_AXIS_TO_EXP_MAP,    /* :612-617 */
+    HRT_OP_QUAT_BETWEEN_TWO_VECS,    /* transform3d.py:9-21      iparam: whole-batch early-out taken */
+    HRT_OP_PROJ_IN_PLANE,            /* transform3d.py:62-75 */
+    HRT_OP_RADIANS_BETWEEN_VECS,     /* transform3d.py:78-100    (3),(3),(3) -> (1) */
+    HRT_OP_QUAT_SLERP,               /* transform3d.py:153-174   (4),(4),(1) -> (4) */
+    HRT_OP_QUAT_TO_DOF_POS,          /* transform3d.py:177-183   (4),(1: hinge axis as float) -> (1) */
+    HRT_OP_EULER_SPLIT,              /* transform3d.py:52-59     (4) -> (4),(4),(4); iparam: sequence code */
+    HRT_OP_EULER_ANGLES_F64,         /* rotation3d.py:659-661    (4) -> 3 doubles; iparam: code | 0x80 degrees */
+    HRT_OP_COORD_TRANSFORM,          /* transform3d.py:24-29     (3),(3: dir) -> (3); iparam: axis order code */
+    HRT_OP_COUNT
+};
+int hrt_rot_op_info(int op, int* n_in, int* in_width4, int* n_out, int* out_width3);
+int hrt_rot_op(hrt_ctx* ctx, int op, int64_t n, const float* const* d_in4, const int64_t* period4, int iparam,
+               float fparam, float* const* d_out3, void* stream);
+
+/* torch.norm(v, dim=-1).max() of (n,3) rows (transform3d.py:11), returned on the host (synchronises). */
+int hrt_max_norm3(hrt_ctx* ctx, int64_t n, const float* d_v, float* h_out, void* stream);
+
+/* cal_joint_quat (transform3d.py:32-50): Kabsch fit of n_points point pairs per row.
+ * d_zero (n or zero_period rows, n_points, 3), d_motion (n, n_points, 3) -> d_out_q (n, 4). */
+int hrt_cal_joint_quat(hrt_ctx* ctx, int64_t n, int n_points, const float* d_zero, int64_t zero_period,
+                       const float* d_motion, float* d_out_q, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

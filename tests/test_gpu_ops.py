@@ -1,0 +1,266 @@
+"""GPU parity of the drop-in modules rotation3d / transform3d / skeleton3d / retarget_main against golden
+vectors produced by the UNMODIFIED reference (tools/make_golden_ops.py).
+
+Tolerances: pure fp32 multiply/add/divide/sqrt chains must be BIT-EXACT; results that pass through a
+transcendental (sin/cos/acos/atan2: CUDA libm vs glibc/SLEEF, <= 2 ulp apart) to 2e-6 absolute; the fp64
+SciPy Euler split to 1.2e-7 (one fp32 rounding)."""
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+TRANS_TOL = 2e-6
+
+
+@pytest.fixture(scope="module")
+def hrt():
+    import __graft_entry__ as g
+    g.build()
+    import humanoid_real_time_retarget_b200 as h
+    return h
+
+
+def md(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))) if a.size else 0.0
+
+
+def exact(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    return a.shape == np.asarray(b).shape and np.array_equal(a, b)
+
+
+def test_rotation3d_exact_chains(hrt, golden):
+    r, g1, g2 = hrt.rotation3d, golden("rotation_ops"), golden("rotation_ops2")
+    qa, qb, v, raw = T(g1["qa"]), T(g1["qb"]), T(g1["v"]), T(g1["raw"])
+    assert exact(r.quat_mul(qa, qb), g1["quat_mul"])
+    assert exact(r.quat_mul_norm(qa, qb), g1["quat_mul_norm"])
+    assert exact(r.quat_normalize(raw), g1["quat_normalize"])
+    assert exact(r.quat_rotate(qa, v), g1["quat_rotate"])
+    assert exact(r.quat_mul_three(qa, qb, qa), g1["quat_mul_three"])
+    assert exact(r.quat_mul_four(qa, qb, qb, qa), g1["quat_mul_four"])
+    # torch's element-wise sqrt / **0.5 on CPU is MKL VML (HA mode), not IEEE: 0.6 % of results are 1 ulp off the
+    # correctly rounded value the kernel produces -> one ulp of a unit quaternion component
+    assert md(r.quat_from_rotation_matrix(T(g1["R"])), g1["quat_from_rotation_matrix"]) <= 6e-8
+    raw2, qa2 = T(g2["raw"]), T(g2["qa"])
+    assert exact(r.quat_pos(raw2), g2["quat_pos"])
+    assert exact(r.quat_abs(raw2), g2["quat_abs"])
+    assert exact(r.quat_unit(raw2), g2["quat_unit"])
+    assert exact(r.quat_conjugate(raw2), g2["quat_conjugate"]) and exact(r.quat_inverse(raw2), g2["quat_conjugate"])
+    assert exact(r.quat_yaw_rotation(qa2, True), g2["quat_yaw_z"]) and exact(r.quat_yaw_rotation(qa2, z_up=False), g2["quat_yaw_y"])
+    tra, trb, v2 = T(g2["tr_a"]), T(g2["tr_b"]), T(g2["v"])
+    assert exact(r.transform_inverse(tra), g2["transform_inverse"])
+    assert exact(r.transform_mul(tra, trb), g2["transform_mul"])
+    assert exact(r.transform_apply(tra, v2), g2["transform_apply"])
+    assert exact(r.rot_matrix_det(T(g2["R"])), g2["rot_matrix_det"])
+    assert md(r.rot_matrix_from_quaternion(qa2), g2["rot_matrix_from_quaternion"]) <= 2.4e-7     # torch's 4-term sum order
+    assert md(r.rot_matrix_from_quaternion(raw2), g2["rot_matrix_from_quaternion_raw"]) <= 2.4e-7
+    # views / constructors
+    assert torch.equal(r.quat_real(qa2), qa2[..., 3]) and torch.equal(r.quat_imaginary(qa2), qa2[..., :3])
+    assert torch.equal(r.quat_identity([2, 3]), torch.tensor([0., 0., 0., 1.]).expand(2, 3, 4))
+    assert r.quat_identity_like(qa2).shape == qa2.shape
+    assert torch.equal(r.transform_identity([5])[..., :4], r.quat_identity([5]))
+    assert torch.equal(r.transform_rotation(tra), tra[..., :4]) and torch.equal(r.transform_translation(tra), tra[..., 4:])
+    r.quat_norm_check(r.quat_normalize(raw2))
+    with pytest.raises(AssertionError):
+        r.quat_norm_check(raw2)
+    r.rot_matrix_integrity_check(T(g2["R"]))
+
+
+def test_rotation3d_transcendental(hrt, golden):
+    r, g1, g2 = hrt.rotation3d, golden("rotation_ops"), golden("rotation_ops2")
+    assert md(r.quat_from_angle_axis(T(g1["ang"]), T(g1["ax"])), g1["quat_from_angle_axis"]) <= TRANS_TOL
+    assert md(r.quat_from_angle_axis(T(g2["ang"]), T(g2["v"]), degree=True), g2["quat_from_angle_axis_deg"]) <= TRANS_TOL
+    assert md(r.quat_to_exp_map(r.quat_normalize(T(g1["qa"]))), g1["quat_to_exp_map"]) <= 4e-6
+    assert md(r.quat_to_exp_map(T(g1["qsmall"])), g1["quat_to_exp_map_small"]) <= 4e-6
+    assert md(r.exp_map_to_quat(T(g1["em"])), g1["exp_map_to_quat"]) <= TRANS_TOL
+    qa = T(g2["qa"])
+    x = qa.clone()
+    ang, ax = r.quat_angle_axis(x)
+    assert md(ang, g2["quat_angle_axis_angle"]) <= 4e-6 and exact(ax, g2["quat_angle_axis_axis"])
+    assert torch.equal(x[..., :3], ax)                        # the reference normalises its argument's xyz in place
+    for name in ["x", "y", "z", "xy", "xz"]:
+        assert md(getattr(r, f"project_quat_to_axis_{name}")(qa), g2[f"project_{name}"]) <= TRANS_TOL
+    for k in range(3):
+        assert md(r.extract_rotation_along_axis(qa, k), g2[f"extract_{k}"]) <= TRANS_TOL
+    with pytest.raises(ValueError):
+        r.extract_rotation_along_axis(qa, 3)
+    assert md(r.normalize_angle(T(g2["ang_rad"])), g2["normalize_angle"]) <= TRANS_TOL
+    a, axv = r.quat_to_angle_axis(r.quat_normalize(qa))
+    assert md(a, g2["quat_to_angle_axis_angle"]) <= 4e-6 and md(axv, g2["quat_to_angle_axis_axis"]) <= 1e-6
+    a, axv = r.exp_map_to_angle_axis(T(g2["v"]))
+    assert md(a, g2["exp_map_to_angle_axis_angle"]) <= TRANS_TOL and md(axv, g2["exp_map_to_angle_axis_axis"]) <= 1e-6
+    assert exact(r.angle_axis_to_exp_map(T(g2["ang_rad"]), T(g2["v"])), g2["angle_axis_to_exp_map"])
+    e = r.quat_to_eular(g2["qa"])
+    assert e.dtype == np.float64 and md(e, g2["quat_to_eular"]) <= 1e-4          # degrees, fp32 input quantisation
+    # broadcasting: a single quaternion against a batch, a (J,4) table against (B,J,4), and device tensors
+    q1 = qa[3]
+    assert exact(r.quat_mul(q1, T(g2["qb"])), r.quat_mul(q1.expand(384, 4).contiguous(), T(g2["qb"])).numpy())
+    tab, big = qa[:21], T(g2["qb"])[:336].reshape(16, 21, 4)
+    ref = torch.stack([r.quat_mul_norm(tab, big[i]) for i in range(16)])
+    assert torch.equal(r.quat_mul_norm(tab, big), ref)
+    out = r.quat_mul(qa.cuda(), T(g2["qb"]).cuda())
+    assert out.is_cuda and exact(out, r.quat_mul(qa, T(g2["qb"])).numpy())
+    assert r.quat_mul(qa[:0], T(g2["qb"])[:0]).shape == (0, 4)
+
+
+def test_transform3d(hrt, golden):
+    t, g = hrt.transform3d, golden("rotation_ops2")
+    v, w, nn, qa, qb = T(g["v"]), T(g["w"]), T(g["nn"]), T(g["qa"]), T(g["qb"])
+    assert exact(t.quat_between_two_vecs(v, w), g["quat_between_two_vecs"])
+    assert exact(t.quat_between_two_vecs(v * 1e-8, w), g["quat_between_two_vecs_early"])
+    assert exact(t.proj_in_plane(v, nn), g["proj_in_plane"])
+    assert exact(t.proj_in_plane(v[0], nn[0]), g["proj_in_plane"][0])                 # the reference's 1-D call shape
+    with pytest.raises(AssertionError):
+        t.proj_in_plane(v[0], torch.zeros(3))
+    assert md(t.radians_between_vecs(v, w, nn), g["radians_between_vecs"]) <= 4e-6
+    qpos = hrt.rotation3d.quat_normalize(qa)
+    qbn = hrt.rotation3d.quat_normalize(qb)
+    assert md(t.quat_slerp(qpos, qbn, T(g["tt"])), g["quat_slerp"]) <= TRANS_TOL
+    assert md(t.quat_slerp(qpos, hrt.rotation3d.quat_normalize(qpos + 1e-5 * T(g["raw"])), T(g["tt"])), g["quat_slerp_near"]) <= TRANS_TOL
+    assert md(t.quat_to_dof_pos(T(g["q30"]), g["dof_axis30"].tolist()), g["quat_to_dof_pos"]) <= 4e-6
+    assert exact(t.coord_transform(v, order=[2, 0, 1], dir=torch.Tensor([-1, 1, -1])), g["coord_transform"])
+    assert t.coord_transform(v) is v
+    for seq in ["xyz", "zyx", "XYZ", "YXZ", "ZYX", "ZXZ", "yzy", "XZY"]:
+        q1, q2, q3 = t.quat_in_xyz_axis(qa, seq)
+        for m, q in enumerate((q1, q2, q3)):
+            assert md(q, g[f"euler_{seq}_{m + 1}"]) <= 1.2e-7, (seq, m)
+    q1, _, _ = t.quat_in_xyz_axis(qa[5], "XYZ")                                       # the reference's per-frame call shape
+    assert q1.shape == (4,) and md(q1, g["euler_XYZ_1"][5]) <= 1.2e-7
+    with pytest.raises(ValueError):
+        t.quat_in_xyz_axis(qa, "xxz")
+    # Kabsch with 4 points per row (well conditioned random clouds): rotation geodesic error
+    zero = torch.randn(384, 4, 3, generator=torch.Generator().manual_seed(5))
+    mot = torch.randn(384, 4, 3, generator=torch.Generator().manual_seed(6))
+    q = t.cal_joint_quat(zero, mot)
+    dots = (q * T(g["cal_joint_quat_n4"])).sum(-1).abs().clamp(max=1.0)
+    assert float(np.quantile((2 * torch.acos(dots)).numpy(), 0.99)) <= 1e-3 and q.shape == (384, 4)
+    gp = golden("primitives")
+    assert md(t.cal_joint_quat(T(gp["Z3"]), T(gp["M3"])), gp["kabsch3"]) <= 1e-3
+    assert float(np.median(np.abs(t.cal_joint_quat(T(gp["Z5"]), T(gp["M5"])).numpy() - gp["kabsch5"]))) <= 2e-7
+    # names the reference module re-exports for `from transform3d import *` users
+    assert t.torch is torch and t.np is np and callable(t.quat_mul) and callable(t.exp_map_to_quat)
+
+
+def _tree(hrt, g):
+    names = [str(i) for i in range(g["parents"].shape[0])]
+    return hrt.SkeletonTree(names, T(g["parents"]), T(g["offsets"]), T(g["tree_quat"]))
+
+
+def test_skeleton_state_and_motion(hrt, golden):
+    g = golden("skeleton_state")
+    tree = _tree(hrt, g)
+    st = hrt.SkeletonState.from_rotation_and_root_translation(tree, T(g["local_q"]), T(g["root_t"]), is_local=True)
+    assert exact(st.tensor, g["state_tensor"])
+    assert exact(st.global_rotation, g["global_rotation"]), "FK with tree.quat must be bit-exact (exact-order kernels)"
+    assert exact(st.global_translation, g["global_translation"])
+    assert exact(st.global_repr().tensor, g["global_repr_tensor"])
+    st_g = hrt.SkeletonState.from_rotation_and_root_translation(tree, T(g["global_rotation"]), T(g["root_t"]), is_local=False)
+    assert exact(st_g.local_rotation, g["local_back"])
+    assert exact(hrt.SkeletonState.zero_pose(tree).tensor, g["zero_pose_tensor"])
+    assert exact(hrt.SkeletonState.zero_pose(tree).global_translation, g["zero_pose_global_translation"])
+    # velocities (np.gradient + gaussian_filter1d sigma=2 'nearest' in the reference)
+    mot = hrt.SkeletonMotion.from_skeleton_state(st, fps=30)
+    assert mot.tensor.shape == (40, 21 * 10 + 3)
+    v_nf = hrt.SkeletonMotion._compute_velocity(st.global_translation, 1 / 30, guassian_filter=False)
+    assert md(v_nf, g["velocity_nofilter"]) <= 1e-5 * max(1.0, float(np.abs(g["velocity_nofilter"]).max()))
+    assert md(mot.global_velocity, g["global_velocity"]) <= 2e-6 * max(1.0, float(np.abs(g["global_velocity"]).max()))
+    w_nf = hrt.SkeletonMotion._compute_angular_velocity(st.global_rotation, 1 / 30, guassian_filter=False)
+    scale = max(1.0, float(np.abs(g["angular_velocity_nofilter"]).max()))
+    assert md(w_nf, g["angular_velocity_nofilter"]) <= 2e-4 * scale          # acos(2w^2-1) near w=1 amplifies 1 ulp
+    assert md(mot.global_angular_velocity, g["global_angular_velocity"]) <= 1e-4 * scale
+    assert mot.fps == 30 and abs(mot.time_delta - 1 / 30) < 1e-12
+    assert mot.crop(4, 20).tensor.shape[0] == 16 and mot.clone().tensor.data_ptr() != mot.tensor.data_ptr()
+    # dict round trip and tree utilities
+    st2 = hrt.SkeletonState.from_dict(st.to_dict())
+    assert torch.equal(st2.tensor, st.tensor) and st2.skeleton_tree.node_names == tree.node_names
+    assert tree.parent_of("5") == "4" and tree.index("7") == 7 and len(tree) == 21 and tree[3] == "3"
+
+
+def test_retarget_to_and_asset_pickles(hrt, golden, skeletons):
+    g = golden("skeleton_state")
+    src_zero = hrt.RobotZeroPose.from_asset("vtrdyn_t_pose")
+    hu = hrt.RobotZeroPose.from_asset("hu_zero_pose")
+    mapping = dict(zip([str(k) for k in g["rt_mapping_keys"]], [str(v) for v in g["rt_mapping_vals"]]))
+    src_tree = src_zero.skeleton_tree
+    src = hrt.SkeletonState.from_rotation_and_root_translation(src_tree, T(g["rt_src_local_q"]), T(g["rt_src_root_t"]), is_local=True)
+    res = src.retarget_to(mapping, T(skeletons["vtrdyn_t_pose/local_rotation"]), T(skeletons["vtrdyn_t_pose/root_translation"]),
+                          hu.skeleton_tree, T(skeletons["hu_zero_pose/local_rotation"]), T(skeletons["hu_zero_pose/root_translation"]),
+                          rotation_to_target_skeleton=T(g["rt_rot"]), scale_to_target_skeleton=0.9)
+    assert res.is_local == bool(g["rt_out_is_local"])
+    assert md(res.tensor, g["rt_out_tensor"]) <= 2e-6
+    # the reference's asset pickles load into these classes through the import shims
+    hrt.enable_compat()
+    import poselib.poselib.skeleton.skeleton3d as shim
+    assert shim.SkeletonState is hrt.SkeletonState
+    blob = pickle.dumps(res, protocol=2)                       # protocol 2 stores the class path as plain text
+    assert b"humanoid_real_time_retarget_b200.skeleton3d" in blob
+    back = pickle.loads(blob.replace(b"humanoid_real_time_retarget_b200.skeleton3d", b"poselib.poselib.skeleton.skeleton3d"))
+    assert type(back) is hrt.SkeletonState and back.skeleton_tree.node_names == res.skeleton_tree.node_names
+    assert torch.equal(back.tensor, res.tensor)
+    from retarget.spatial_transform.transform3d import quat_mul, torch as t2   # noqa: F401
+    from retarget.retarget_solver import VtrdynFullBodyPosRetargeter          # noqa: F401
+    from robot_kinematics_model import RobotZeroPose                          # noqa: F401
+    assert RobotZeroPose is hrt.RobotZeroPose
+
+
+def test_main_path(hrt, golden):
+    g = golden("main_path")
+    eng = hrt.default_engine(0)
+    gt = T(g["global_t"])
+    rescaled = eng.rescale_motion(hrt.TREE_SOURCE, gt, dir=[-1.0, -1.0, 1.0])
+    assert exact(rescaled, g["rescaled"]), "limb-length rescale must be bit-exact"
+    src = hrt.RobotZeroPose.from_asset("vtrdyn_zero_pose")
+    assert exact(hrt.Retarget.rescale_motion_to_standard_size(gt * torch.tensor([-1.0, -1.0, 1.0]), src), g["rescaled"])
+    gq = eng.rebuild_global_rotation(hrt.TREE_SOURCE, T(g["rescaled"]))
+    # joints 0 and 10 come from Kabsch (SVD in the reference): rotation error, the rest is a pure fp32 chain
+    kab = [0, 10]
+    rest = [j for j in range(21) if j not in kab]
+    # SkeletonState normalises the rebuilt rotations; compare after that
+    gqn = hrt.rotation3d.quat_normalize(gq).cpu()
+    assert exact(gqn[:, rest], g["rebuilt_global_rotation"][:, rest])
+    assert md(gqn[:, kab], g["rebuilt_global_rotation"][:, kab]) <= 2e-4
+    r = hrt.RetargetHuV5fromMocap(src, hrt.RobotZeroPose.from_asset("hu_v5_zero_pose"))
+    mocap_motion, retargeted = r.retarget_from_global_translation(gt)
+    assert md(mocap_motion.global_translation, g["rebuilt_global_translation"]) <= 2e-5
+    assert r.rebuild_error <= 1e-4
+    assert md(mocap_motion.global_velocity, g["rebuilt_velocity"]) <= 1e-3
+    err = (retargeted.local_rotation - T(g["robot_local_rotation"])).abs().amax(dim=(1, 2))
+    print(f"main path robot_local_rotation: median {float(err.median()):.2e} p90 {float(np.quantile(err.numpy(), 0.9)):.2e} max {float(err.max()):.2e}")
+    assert float(np.quantile(err.numpy(), 0.9)) <= 2e-4 and float(err.max()) <= 5e-3
+    assert md(retargeted.global_translation, g["robot_global_translation"]) <= 2e-3
+    assert retargeted.tensor.shape == g["robot_tensor"].shape
+
+
+def test_wire_layout_and_position_streaming(hrt, golden):
+    g = golden("full_body_pos")
+    eng = hrt.default_engine(0)
+    body, lh, rh = T(g["body_t"]), T(g["lhand_t"]), T(g["rhand_t"])
+    lq, dof, _ = eng.retarget_full_body_pos(body, lh, rh)
+    from humanoid_real_time_retarget_b200 import robot_config as cfg
+    # build the wire layout (23 body rows, HandNodes finger order) whose remap gives back the solver layout
+    body23 = torch.zeros(body.shape[0], 23, 3)
+    body23[:, cfg.BODY_23_TO_21] = body
+    body23[:, [4, 8]] = 123.0                                   # the two rows the solver never reads
+    lh_w, rh_w = torch.zeros_like(lh), torch.zeros_like(rh)
+    lh_w[:, cfg.HAND_20_REORDER] = lh
+    rh_w[:, cfg.HAND_20_REORDER] = rh
+    lq_w, dof_w, _ = eng.retarget_full_body_pos_wire(body23, lh_w, rh_w)
+    assert torch.equal(dof_w, dof) and torch.equal(lq_w, lq)
+    # streaming, both layouts, one frame at a time through the mapped mailboxes
+    o_dof, o_lq = np.empty(30, np.float32), np.empty((31, 4), np.float32)
+    eng.stream_pos_open(wire_layout=False)
+    for i in range(32):
+        eng.stream_pos_frame(body[i].numpy(), lh[i].numpy(), rh[i].numpy(), o_lq, o_dof)
+        assert np.array_equal(o_dof, dof[i].cpu().numpy()) and np.array_equal(o_lq, lq[i].cpu().numpy())
+    eng.stream_pos_close()
+    eng.stream_pos_open(wire_layout=True)
+    for i in range(32):
+        eng.stream_pos_frame(body23[i].numpy(), lh_w[i].numpy(), rh_w[i].numpy(), None, o_dof)
+        assert np.array_equal(o_dof, dof[i].cpu().numpy())
+    eng.stream_pos_close()
