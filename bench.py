@@ -41,6 +41,16 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel, from the committed
+    `ncu --set full` summary of this same command (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return float(json.load(open(p))["body_quat_kernel"]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -63,7 +73,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def wait_samples(self, n, spin, timeout_s=6.0):
+        """keep the GPU busy with `spin()` until nvidia-smi has delivered n samples"""
+        t0 = time.perf_counter()
+        while self.proc and len(self.rows) < n and time.perf_counter() - t0 < timeout_s:
+            spin()
+
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self, first=0):
+        self.rows = self.rows[first:] if first < len(self.rows) else self.rows
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -126,6 +146,73 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def side_measurements(eng, hrt, oc, sk, dev):
+    """BASELINE.json configs[1] (65,536-configuration FK) and configs[3] (single-frame streaming latency of the
+    teleop position path, sim_full_body_teleop.py:83-129): reported beside the headline, not part of it."""
+    import numpy as np
+    import torch
+    out = {}
+    # configs[3]: one frame at a time, pinned mapped mailboxes, host-visible in -> host-visible dof_pos
+    g = torch.Generator().manual_seed(0)
+    n = 20000
+    em = 0.4 * torch.randn(2048, 59, 3, generator=g)
+    root = torch.zeros(2048, 3)
+    root[:, 2] = 1.0
+    _, gt = oc.cal_forward_kinematics(oc.exp_map_to_quat(em), root, sk["vtrdyn_full_zero_pose/parents"].tolist(),
+                                      torch.from_numpy(sk["vtrdyn_full_zero_pose/offsets"]))
+    full2body = [0, 4, 5, 6, 1, 2, 3, 7, 8, 9, 10, 34, 35, 36, 37, 38, 39, 11, 12, 13, 14]
+    body, lh, rh = gt[:, full2body].contiguous().numpy(), gt[:, 14:34].contiguous().numpy(), gt[:, 39:59].contiguous().numpy()
+    o_dof = np.empty(30, np.float32)
+    eng.stream_pos_open(wire_layout=False)
+    for i in range(1000):
+        eng.stream_pos_frame(body[i % 2048], lh[i % 2048], rh[i % 2048], None, o_dof)
+    ts = np.empty(n)
+    for i in range(n):
+        k = i % 2048
+        t0 = time.perf_counter_ns()
+        eng.stream_pos_frame(body[k], lh[k], rh[k], None, o_dof)
+        ts[i] = time.perf_counter_ns() - t0
+    paced = np.empty(240)
+    period = 1.0 / 120.0
+    nxt = time.perf_counter() + period
+    for i in range(240):                                   # 2 s at the teleop loop's 120 Hz pacing (GPU idles in between)
+        while time.perf_counter() < nxt:
+            pass
+        nxt += period
+        t0 = time.perf_counter_ns()
+        eng.stream_pos_frame(body[i], lh[i], rh[i], None, o_dof)
+        paced[i] = time.perf_counter_ns() - t0
+    eng.stream_pos_close()
+    out["latency_us"] = {"path": "VtrdynFullBodyPosRetargeter single frame, host in -> host dof_pos (hrt_stream_pos_frame via ctypes)",
+                         "back_to_back": {"frames": n, "p50": float(np.percentile(ts, 50)) / 1e3, "p99": float(np.percentile(ts, 99)) / 1e3,
+                                          "p999": float(np.percentile(ts, 99.9)) / 1e3},
+                         "paced_120hz": {"frames": 240, "p50": float(np.percentile(paced, 50)) / 1e3, "p99": float(np.percentile(paced, 99)) / 1e3}}
+    # configs[1]: 65,536 Hu (33-joint) configurations, FK with joint limits; L2 flushed between launches
+    eng_hu = hrt.default_engine(dev.index or 0, robot="hu")
+    lo, hi = torch.tensor(oc.HU_DOF_LOWER), torch.tensor(oc.HU_DOF_UPPER)
+    ang = (lo + (hi - lo) * (torch.rand(65536, 32, generator=g) * 1.2 - 0.1)).to(dev)
+    gq = torch.empty((65536, 33, 4), device=dev)
+    gtt = torch.empty((65536, 33, 3), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    times = []
+    for i in range(13):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng_hu.fk_angles(hrt.TREE_ROBOT, ang, clip=True, out=(gq, gtt))
+        b.record()
+        torch.cuda.synchronize(dev)
+        if i >= 3:
+            times.append(a.elapsed_time(b))
+    ms = float(np.median(times))
+    peak, _ = hbm_peak()
+    out["fk_65536"] = {"workload": "configs[1]: Hu (33 joints) FK with limits, 65,536 configurations, L2 flushed between launches",
+                       "ms": ms, "configs_per_s": 65536 / (ms * 1e-3), "algorithmic_bytes_per_config": 1080,
+                       "hbm_frac": 65536 * 1080 / (ms * 1e-3) / 1e9 / peak,
+                       "note": "70.8 MB = 11 us at peak: launch-bound at this size; see profiles/ for 2^20-2^22 configurations"}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -173,12 +260,15 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident timing (value, roofline) -------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step_dev()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    if rank == 0:                       # nvidia-smi needs ~0.3 s to deliver its first row: stay under load meanwhile
+        sampler.wait_samples(2, lambda: (step_dev(), torch.cuda.synchronize(dev)))
+    first_sample = sampler.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -200,7 +290,10 @@ def run_ours(args):
         step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
+    # keep the same load up until a few rows have been sampled inside the measurement window
+    if rank == 0:
+        sampler.wait_samples(first_sample + 4, lambda: (step_dev(), torch.cuda.synchronize(dev)))
+    clocks = sampler.stop(first_sample) if rank == 0 else None
 
     t = torch.tensor([total_ms, kern_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -222,6 +315,9 @@ def run_ours(args):
         dist.all_reduce(gt, op=dist.ReduceOp.MAX)
         gather_ms = gt.item()
 
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = side_measurements(eng, hrt, oc, sk, dev)
     if rank == 0:
         peak, peak_src = hbm_peak()
         value = world * B * args.steps / (total_ms * 1e-3)
@@ -244,13 +340,14 @@ def run_ours(args):
                     "h2d_bytes_per_step": B * 21 * 16, "d2h_bytes_per_step": B * (30 * 4 + 31 * 12)},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "body_quat_kernel",
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "body_quat_kernel",
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_frame": ALG_BYTES_PER_FRAME,
                          "note": "with 10 IK iterations the kernel is issue-bound by construction (~0.4 Mflop/frame); "
                                  "see profiles/ for issue-slot utilisation"},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
+        line.update(extras)
         if gather_ms is not None:
             line["allgather_dof_ms"] = gather_ms
         print(json.dumps(line), flush=True)
@@ -268,6 +365,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=1 << 16, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-frames", type=int, default=1 << 15, help="frames per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[1] / configs[3] side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
