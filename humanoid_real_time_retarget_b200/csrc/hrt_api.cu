@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -137,7 +138,23 @@ int body_quat_warps(const BodyQuatArgs& a) { return a.out_local_q ? BQ_WARPS_NAR
 
 size_t body_quat_smem(const hrt_ctx* ctx, const BodyQuatArgs& a);
 
+// HRT_BQ_PACKED_IK selects the two-arms-per-thread FFMA2 variant of the refinement.  Measured on B200 it
+// is ~4 % SLOWER end to end than the one-arm-per-thread kernel (profiles/r01_notes.md, "packed fp32x2"): the
+// packed iteration is 17 % faster, but 168-246 registers per thread leave 8-12 warps per SM and the
+// latency-bound closed-form phase loses more than the refinement gains.  Kept selectable, off by default.
+bool use_packed_ik(const BodyQuatArgs& a) { return (a.flags & BQ_IK) && (a.flags & BQ_PACKED_IK) && !a.out_local_q; }
+
 int launch_body_quat(hrt_ctx* ctx, const BodyQuatArgs& a, cudaStream_t st, int force_grid = 0) {
+    if (use_packed_ik(a)) {
+        const size_t smem2 = ((size_t)BQ_CONST_WORDS + (size_t)BQ2_WARPS * bq2_warp_words(ctx->bq.J_src, ctx->bq.J_rob)) * sizeof(float);
+        const long long groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
+        const long long pairs = (groups + 1) / 2;
+        const long long ctas = (pairs + BQ2_WARPS - 1) / BQ2_WARPS;
+        const int grid = force_grid ? force_grid : (int)std::max(1LL, std::min(ctas, (long long)ctx->sm_count));
+        body_quat_ik2_kernel<BQ2_WARPS><<<grid, BQ2_WARPS * 32, smem2, st>>>(ctx->bq, a);
+        HRT_CUDA(cudaGetLastError());
+        return 0;
+    }
     const size_t smem = body_quat_smem(ctx, a);
     const int warps = body_quat_warps(a);
     const long long groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
@@ -212,7 +229,7 @@ int fill_body_quat_args(hrt_ctx* ctx, int64_t B, const float* src, unsigned flag
     a->B = B;
     a->src_gq = src;
     a->pre_transformed = (flags & HRT_BQ_PRE_TRANSFORMED) ? 1 : 0;
-    a->flags = (flags & HRT_BQ_CLAMP ? BQ_CLAMP : 0u) | (flags & HRT_BQ_IK ? BQ_IK : 0u);
+    a->flags = (flags & HRT_BQ_CLAMP ? BQ_CLAMP : 0u) | (flags & HRT_BQ_IK ? BQ_IK : 0u) | (flags & HRT_BQ_PACKED_IK ? BQ_PACKED_IK : 0u);
     a->ik_iters = ik_iters;
     a->damping = damping;
     a->rot_weight = rot_weight;
@@ -253,6 +270,7 @@ int hrt_ctx_create(int device, hrt_ctx** out) {
     HRT_CUDA(cudaFuncSetAttribute(jacobian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(body_quat_ik2_kernel<BQ2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_FULL_BODY_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_UPPER_BODY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_FULL_BODY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -11,6 +11,7 @@
 #pragma once
 #include "hrt_fk_limb.cuh"
 #include "hrt_math.cuh"
+#include "hrt_pack2.cuh"
 #include "hrt_params.h"
 
 namespace hrt {
@@ -56,11 +57,15 @@ local_from_global_kernel(const float4* __restrict__ gq, const int* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 constexpr unsigned BQ_CLAMP = 1u;     // clamp hinge angles to the robot limits
 constexpr unsigned BQ_IK = 2u;        // run the damped-least-squares refinement (implies clamp)
+constexpr unsigned BQ_PACKED_IK = 8u; // refinement on packed fp32x2 registers, two arms per thread (experimental)
 
 constexpr int BQ_FRAMES_PER_WARP = 16;
 // One CTA per SM.  16 warps when only dof / link positions are published (the headline path),
 // 8 when the 496-byte local-rotation rows are staged as well (shared-memory budget).
-constexpr int BQ_WARPS_WIDE = 16;
+#ifndef HRT_BQ_WARPS_WIDE
+#define HRT_BQ_WARPS_WIDE 16
+#endif
+constexpr int BQ_WARPS_WIDE = HRT_BQ_WARPS_WIDE;
 constexpr int BQ_WARPS_NARROW = 8;
 // warp-private staging, in words: [input rows, later the link-position image] [dof image]
 // [local-rotation image, only when that output is requested]
@@ -381,6 +386,283 @@ body_quat_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a
             if (a.out_link_pos) warp_store_span(a.out_link_pos + f0 * W, lp_t, nfr * W, lane);
             __syncwarp();
         }
+    }
+    if (pending_store && lane == 0) bulk_wait_read_all();
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same pipeline with the IK refinement on packed fp32x2 registers (FFMA2): the headline path
+// (dof + link positions published, flag BQ_IK).  A warp owns 32 consecutive frames as two halves of
+// 16; the closed form (exact-order fp32 + fp64 Euler) runs per half with one lane per (frame, arm) as
+// above and parks its result in shared memory; the refinement and the final FK then run ONCE with
+// lane l holding the arm (frame l/2, side l&1) of BOTH halves in the .x / .y of every register pair.
+// The per-arm tables are the same for both (same side) and enter FFMA2 as broadcast scalars.
+// ---------------------------------------------------------------------------------------------
+#ifndef HRT_BQ2_WARPS
+#define HRT_BQ2_WARPS 12
+#endif
+constexpr int BQ2_WARPS = HRT_BQ2_WARPS;
+#ifndef HRT_BQ2_UNROLL_HALVES
+#define HRT_BQ2_UNROLL_HALVES 1
+#endif
+constexpr int kBq2UnrollHalves = HRT_BQ2_UNROLL_HALVES;
+constexpr int BQ2_PARK = 17;      // th[7], pe_t[3], pw_t[3], Rh[4] per arm
+// the parked values (17 x 64 words) alias the first half's input rows, which are dead by then
+HRT_HD inline int bq2_warp_words(int JS, int JR) { return 2 * bq_tile_words(JS, JR, false); }
+
+template <int WARPS>
+HRT_DEV void bq_closed_form(const BodyQuatParams& bp, const ArmParams& ap, const float* row, bool pre_transformed,
+                            bool do_clamp, int warp, float th[7], float4& zT, float4& zU, float4& zL, float4& zH) {
+    zT = *reinterpret_cast<const float4*>(row + ap.src_torso * 4);
+    float4 zS = *reinterpret_cast<const float4*>(row + ap.src_shoulder * 4);
+    zU = *reinterpret_cast<const float4*>(row + ap.src_upper * 4);
+    zL = *reinterpret_cast<const float4*>(row + ap.src_lower * 4);
+    zH = *reinterpret_cast<const float4*>(row + ap.src_hand * 4);
+    smsp_align<WARPS>(warp);
+    if (!pre_transformed) {
+        const float4 rot = make_float4(bp.rot_z90[0], bp.rot_z90[1], bp.rot_z90[2], bp.rot_z90[3]);
+#define HRT_ZPT(q, n) q = quat_mul_norm_x(quat_mul_norm_x(q, rot), \
+        make_float4(-ap.t2z[n][0], -ap.t2z[n][1], -ap.t2z[n][2], ap.t2z[n][3]))
+        HRT_ZPT(zT, 0); HRT_ZPT(zS, 1); HRT_ZPT(zU, 2); HRT_ZPT(zL, 3); HRT_ZPT(zH, 4);
+#undef HRT_ZPT
+    }
+    const float4 lU = quat_mul_norm_x(quat_conj(zS), zU);
+    const float4 lL = quat_mul_norm_x(quat_conj(zU), zL);
+    double eS[3], eE[3];
+    smsp_align<WARPS>(warp);
+    euler_intrinsic_f64<1, 0, 2>(lU, eS);
+    smsp_align<WARPS>(warp);
+    euler_intrinsic_f64<2, 1, 0>(lL, eE);
+    smsp_align<WARPS>(warp);
+    th[0] = quat_to_dof_x(axis_quat_from_f64(eS[0], 1), 1);
+    th[1] = quat_to_dof_x(axis_quat_from_f64(eS[1], 0), 0);
+    th[2] = quat_to_dof_x(quat_mul_norm_x(axis_quat_from_f64(eE[0], 2), axis_quat_from_f64(eS[2], 2)), 2);
+    th[3] = quat_to_dof_x(axis_quat_from_f64(eE[1], 1), 1);
+    th[4] = quat_to_dof_x(axis_quat_from_f64(eE[2], 0), 0);
+    th[5] = 0.f;
+    th[6] = 0.f;
+    if (do_clamp) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) th[c] = fminf(fmaxf(th[c], ap.lower[c]), ap.upper[c]);
+    }
+}
+
+template <int C>
+HRT_DEV void ik2_joint(q4p& G, v3p& p, v3p* ax, v3p* pc, const f2 th, const ArmParams& ap) {
+    constexpr int K = HRT_ARM_AXIS(C);
+    ax[C] = quat_axis_p<K>(G);
+    pc[C] = p;
+    f2 s, cs;
+    sincos_half_p(mul2(dup2(0.5f), th), &s, &cs);
+    G = quat_mul_axis_p<K>(G, s, cs);
+    if (C < 6) p = quat_rotate_add_p(G, ap.off[C + 1], p);
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+body_quat_ik2_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int fl = lane >> 1;
+    const int side = lane & 1;
+    {
+        const float* src = reinterpret_cast<const float*>(&bp.arm[0]);
+        for (int i = threadIdx.x; i < 2 * (int)sizeof(ArmParams) / 4; i += blockDim.x) smem[i] = src[i];
+        float* rp = smem + 2 * sizeof(ArmParams) / 4;
+        for (int i = threadIdx.x; i < bp.J_rob * 3; i += blockDim.x) rp[i] = bp.rest_pos[i];
+    }
+    __syncthreads();
+    const ArmParams& ap = reinterpret_cast<const ArmParams*>(smem)[side];
+    const float* rest_s = smem + 2 * sizeof(ArmParams) / 4;
+    const int JS = bp.J_src, JR = bp.J_rob;
+    const int D = JR - 1, W = JR * 3;
+    const int tile_words = bq_tile_words(JS, JR, false);
+    float* wbase = smem + BQ_CONST_WORDS + warp * bq2_warp_words(JS, JR);
+    float* park = wbase;                                   // [value][lane] as float2 {half 0, half 1}; aliases half 0's input rows
+    bool pending_store = false;
+    const long long n_groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
+    const long long n_pairs = (n_groups + 1) / 2;
+    const long long total_warps = (long long)gridDim.x * WARPS;
+    const long long rounds = (n_pairs + total_warps - 1) / total_warps;
+    const float p_sh[3] = {bp.shoulder_p[side][0], bp.shoulder_p[side][1], bp.shoulder_p[side][2]};
+    const f2 lam2 = dup2(a.damping * a.damping);
+    const f2 wo = dup2(a.rot_weight), wo2 = dup2(a.rot_weight * a.rot_weight);
+
+    for (long long rnd = 0; rnd < rounds; ++rnd) {
+        const long long pair_raw = rnd * total_warps + (long long)blockIdx.x * WARPS + warp;
+        const bool pair_live = pair_raw < n_pairs;
+        const long long pair = pair_live ? pair_raw : n_pairs - 1;
+        if (pending_store) {
+            if (lane == 0) bulk_wait_read_all();
+            __syncwarp();
+            pending_store = false;
+        }
+        // ---- inputs of both halves (two contiguous spans; the second may be ragged or absent) ------
+        int nfr_h[2];
+        long long f0_h[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long grp = min(pair * 2 + h, n_groups - 1);
+            f0_h[h] = grp * BQ_FRAMES_PER_WARP;
+            const int nld = (int)min((long long)BQ_FRAMES_PER_WARP, a.B - f0_h[h]);
+            nfr_h[h] = (pair_live && pair * 2 + h < n_groups) ? nld : 0;
+            warp_span_g2s(wbase + h * tile_words, a.src_gq + f0_h[h] * JS * 4, nld * JS * 4, lane);
+        }
+        cp_async_commit();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float* dof_t = wbase + h * tile_words + bq_io_words(JS, JR);
+            if (a.out_dof) for (int i = lane; i < nfr_h[h] * D; i += 32) dof_t[i] = 0.f;
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+
+        // ---- closed form per half, parked as {half 0, half 1} pairs ---------------------------------
+#pragma unroll kBq2UnrollHalves
+        for (int h = 0; h < 2; ++h) {
+            const long long grp = min(pair * 2 + h, n_groups - 1);
+            const int nld = (int)min((long long)BQ_FRAMES_PER_WARP, a.B - grp * BQ_FRAMES_PER_WARP);
+            const float* row = wbase + h * tile_words + min(fl, nld - 1) * JS * 4;
+            float th[7];
+            float4 zT, zU, zL, zH;
+            bq_closed_form<WARPS>(bp, ap, row, a.pre_transformed != 0, true, warp, th, zT, zU, zL, zH);
+            const float4 Tc = quat_conj(zT);
+            const float4 Ru = quat_mul_norm_f(Tc, zU);
+            const float4 Rf = quat_mul_norm_f(Tc, zL);
+            const float4 Rh = quat_mul_norm_f(Tc, zH);
+            const vec3 pe_t = add3(make_vec3(p_sh[0], p_sh[1], p_sh[2]),
+                                   quat_rotate_f(Ru, make_vec3(ap.seg_elbow[0], ap.seg_elbow[1], ap.seg_elbow[2])));
+            const vec3 pw_t = add3(pe_t, quat_rotate_f(Rf, make_vec3(ap.seg_wrist[0], ap.seg_wrist[1], ap.seg_wrist[2])));
+            __syncwarp();                                  // every lane has read its input row of this half
+            float* pk = park + lane * 2 + h;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) pk[c * 64] = th[c];
+            pk[7 * 64] = pe_t.x; pk[8 * 64] = pe_t.y; pk[9 * 64] = pe_t.z;
+            pk[10 * 64] = pw_t.x; pk[11 * 64] = pw_t.y; pk[12 * 64] = pw_t.z;
+            pk[13 * 64] = Rh.x; pk[14 * 64] = Rh.y; pk[15 * 64] = Rh.z; pk[16 * 64] = Rh.w;
+        }
+        __syncwarp();
+
+        // ---- packed refinement: .x = half 0, .y = half 1 ---------------------------------------------
+        const f2* pk2 = reinterpret_cast<const f2*>(park) + lane;
+        f2 th[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) th[c] = pk2[c * 32];
+        const v3p pe_t = make_v3p(pk2[7 * 32], pk2[8 * 32], pk2[9 * 32]);
+        const v3p pw_t = make_v3p(pk2[10 * 32], pk2[11 * 32], pk2[12 * 32]);
+        q4p Rh;
+        Rh.x = pk2[13 * 32]; Rh.y = pk2[14 * 32]; Rh.z = pk2[15 * 32]; Rh.w = pk2[16 * 32];
+        const v3p p0 = make_v3p(dup2(p_sh[0]), dup2(p_sh[1]), dup2(p_sh[2]));
+        __syncwarp();
+        // link-position images start as the robot's rest pose (input rows and parked values are dead now)
+        if (a.out_link_pos)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                for (int r = 0; r < nfr_h[h]; ++r)
+                    for (int i = lane; i < W; i += 32) wbase[h * tile_words + r * W + i] = rest_s[i];
+        __syncwarp();
+        for (int it = 0; it < a.ik_iters; ++it) {
+            smsp_align<WARPS>(warp);
+            v3p ax[7], pc[7];
+            q4p G;
+            G.x = dup2(0.f); G.y = dup2(0.f); G.z = dup2(0.f); G.w = dup2(1.f);
+            v3p p = p0;
+            ik2_joint<0>(G, p, ax, pc, th[0], ap); ik2_joint<1>(G, p, ax, pc, th[1], ap); ik2_joint<2>(G, p, ax, pc, th[2], ap);
+            ik2_joint<3>(G, p, ax, pc, th[3], ap); ik2_joint<4>(G, p, ax, pc, th[4], ap); ik2_joint<5>(G, p, ax, pc, th[5], ap);
+            ik2_joint<6>(G, p, ax, pc, th[6], ap);
+            // residual
+            const v3p ee = sub3p(pe_t, pc[3]), ew = sub3p(pw_t, pc[6]);
+            v3p eo;
+            {
+                const q4p qe = quat_normalize_p(quat_mul_p(Rh, quat_conj_p(G)));
+                const f2 n2 = fma2(qe.z, qe.z, fma2(qe.y, qe.y, mul2(qe.x, qe.x)));
+                const f2 n = make_float2(sqrtf(n2.x), sqrtf(n2.y));
+                const f2 sc = mul2(wo, make_float2(rotvec_scale_f(n.x, qe.w.x), rotvec_scale_f(n.y, qe.w.y)));
+                eo = make_v3p(mul2(qe.x, sc), mul2(qe.y, sc), mul2(qe.z, sc));
+            }
+            v3p je[3], jw[6];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) je[c] = cross3p(ax[c], sub3p(pc[3], pc[c]));
+#pragma unroll
+            for (int c = 0; c < 6; ++c) jw[c] = cross3p(ax[c], sub3p(pc[6], pc[c]));
+            f2 A[28], g[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                f2 gi = mul2(wo, dot3p(ax[i], eo));
+                if (i < 6) gi = fma2(jw[i].z, ew.z, fma2(jw[i].y, ew.y, fma2(jw[i].x, ew.x, gi)));
+                if (i < 3) gi = fma2(je[i].z, ee.z, fma2(je[i].y, ee.y, fma2(je[i].x, ee.x, gi)));
+                g[i] = gi;
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    f2 s = (i == j) ? add2(wo2, lam2) : mul2(wo2, dot3p(ax[i], ax[j]));
+                    if (i < 6) s = fma2(jw[i].z, jw[j].z, fma2(jw[i].y, jw[j].y, fma2(jw[i].x, jw[j].x, s)));
+                    if (i < 3) s = fma2(je[i].z, je[j].z, fma2(je[i].y, je[j].y, fma2(je[i].x, je[j].x, s)));
+                    A[i * (i + 1) / 2 + j] = s;
+                }
+            }
+            chol_solve7_p(A, g);
+#pragma unroll
+            for (int c = 0; c < 7; ++c) th[c] = min2(max2(add2(th[c], g[c]), dup2(ap.lower[c])), dup2(ap.upper[c]));
+        }
+
+        // ---- final FK of the refined angles (packed) and the output images ---------------------------
+        smsp_align<WARPS>(warp);
+        {
+            v3p ax[7], pc[9];
+            q4p G;
+            G.x = dup2(0.f); G.y = dup2(0.f); G.z = dup2(0.f); G.w = dup2(1.f);
+            v3p p = p0;
+            if (a.out_link_pos) {
+                ik2_joint<0>(G, p, ax, pc, th[0], ap); ik2_joint<1>(G, p, ax, pc, th[1], ap); ik2_joint<2>(G, p, ax, pc, th[2], ap);
+                ik2_joint<3>(G, p, ax, pc, th[3], ap); ik2_joint<4>(G, p, ax, pc, th[4], ap); ik2_joint<5>(G, p, ax, pc, th[5], ap);
+                ik2_joint<6>(G, p, ax, pc, th[6], ap);
+                G = quat_normalize_p(G);
+                pc[7] = quat_rotate_add_p(G, ap.off[7], pc[6]);      // the two gripper links: identity local rotation
+                pc[8] = quat_rotate_add_p(G, ap.off[8], pc[6]);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (fl < nfr_h[h]) {
+                    float* lp_t = wbase + h * tile_words;
+                    float* dof_t = lp_t + bq_io_words(JS, JR);
+                    if (a.out_dof) {
+                        float* r = dof_t + fl * D + (ap.rob_first - 1);
+#pragma unroll
+                        for (int c = 0; c < 7; ++c) r[c] = h ? th[c].y : th[c].x;
+                    }
+                    if (a.out_link_pos) {
+                        float* r = lp_t + fl * W + ap.rob_first * 3;
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) {
+                            r[c * 3] = h ? pc[c].x.y : pc[c].x.x;
+                            r[c * 3 + 1] = h ? pc[c].y.y : pc[c].y.x;
+                            r[c * 3 + 2] = h ? pc[c].z.y : pc[c].z.x;
+                        }
+                    }
+                }
+            }
+        }
+        // ---- the images leave as whole contiguous spans ----------------------------------------------
+        fence_proxy_async_smem();
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float* lp_t = wbase + h * tile_words;
+            float* dof_t = lp_t + bq_io_words(JS, JR);
+            if (nfr_h[h] == BQ_FRAMES_PER_WARP) {
+                if (lane == 0) {
+                    if (a.out_dof) bulk_store_s2g(a.out_dof + f0_h[h] * D, dof_t, (unsigned)(BQ_FRAMES_PER_WARP * D * 4));
+                    if (a.out_link_pos) bulk_store_s2g(a.out_link_pos + f0_h[h] * W, lp_t, (unsigned)(BQ_FRAMES_PER_WARP * W * 4));
+                    bulk_commit();
+                }
+                pending_store = true;
+            } else if (nfr_h[h] > 0) {
+                if (a.out_dof) warp_store_span(a.out_dof + f0_h[h] * D, dof_t, nfr_h[h] * D, lane);
+                if (a.out_link_pos) warp_store_span(a.out_link_pos + f0_h[h] * W, lp_t, nfr_h[h] * W, lane);
+            }
+        }
+        __syncwarp();
     }
     if (pending_store && lane == 0) bulk_wait_read_all();
 }

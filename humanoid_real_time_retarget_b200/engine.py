@@ -10,7 +10,7 @@ from . import robot_config as cfg
 
 TREE_ROBOT, TREE_SOURCE, TREE_SOURCE_FULL = 0, 1, 2
 FK_EXACT = 1
-BQ_CLAMP, BQ_IK, BQ_PRE_TRANSFORMED = 1, 2, 4
+BQ_CLAMP, BQ_IK, BQ_PRE_TRANSFORMED, BQ_PACKED_IK = 1, 2, 4, 8
 POS_FULL_BODY_POS, POS_UPPER_BODY, POS_FULL_BODY, POS_MAIN = 0, 1, 2, 3
 
 

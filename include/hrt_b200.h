@@ -51,6 +51,7 @@ extern "C" {
 #define HRT_BQ_CLAMP 1u       /* clamp hinge angles to the joint limits */
 #define HRT_BQ_IK 2u          /* fused damped-least-squares refinement (implies clamp) */
 #define HRT_BQ_PRE_TRANSFORMED 4u /* input already zero-pose re-referenced: skip the a24 step */
+#define HRT_BQ_PACKED_IK 8u   /* experimental: refinement on packed fp32x2 (FFMA2), two arms per thread; dof / link-position outputs only */
 
 typedef struct hrt_ctx hrt_ctx;
 

@@ -183,6 +183,21 @@ def test_body_quat_with_clamp_and_ik_vs_oracle(hrt, eng, oc, skeletons):
     assert float(r1.mean()) < 0.7 * float(r0.mean())
 
 
+def test_packed_ik_variant_matches_scalar(hrt, eng, oc, skeletons):
+    """The FFMA2 (two arms per thread) refinement is the same algorithm with a different rounding sequence:
+    it must agree with the default kernel like the default kernel agrees with the oracle, on ragged sizes too."""
+    for B in (1, 16, 17, 33, 4097):
+        raw = oc.synth_clip_3q(B, seed=40 + B, sk=skeletons)
+        flags = hrt.BQ_CLAMP | hrt.BQ_IK
+        _, d0, p0 = eng.retarget_body_quat(raw, flags=flags, want_local_q=False)
+        _, d1, p1 = eng.retarget_body_quat(raw, flags=flags | hrt.BQ_PACKED_IK, want_local_q=False)
+        err = (d1 - d0).abs().max(dim=-1).values.cpu().numpy()
+        assert float(np.quantile(err, 0.97)) <= ANGLE_TOL and float(err.max()) <= 1e-3
+        assert float(np.quantile((p1 - p0).abs().amax(dim=(1, 2)).cpu().numpy(), 0.97)) <= POS_TOL
+        rest = [i for i in range(30) if i not in list(range(11, 18)) + list(range(20, 27))]
+        assert float(d1[:, rest].abs().max()) == 0.0
+
+
 def test_body_quat_edge_cases(hrt, eng, oc, skeletons):
     # empty, single, ragged (not a multiple of the 16-frame warp group)
     for B in (0, 1, 15, 17, 33):
@@ -261,6 +276,10 @@ def test_host_call_and_streaming_match_device_call(hrt, eng, oc, skeletons):
     h_dof2 = torch.empty(B, 30)
     eng.retarget_body_quat_host(raw, flags=flags, out_dof=h_dof2)
     assert torch.equal(h_dof2, dof.cpu())
+    h_dof3 = torch.empty(B, 30)
+    eng.retarget_body_quat_host(raw, flags=flags | hrt.BQ_PACKED_IK, out_dof=h_dof3)
+    _, dof3, _ = eng.retarget_body_quat(raw, flags=flags | hrt.BQ_PACKED_IK, want_local_q=False, want_link_pos=False)
+    assert torch.equal(h_dof3, dof3.cpu())
     # streaming: one frame at a time through the mapped mailboxes
     eng.stream_open(flags=flags)
     o_dof = np.empty(30, np.float32)
