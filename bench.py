@@ -163,30 +163,32 @@ def side_measurements(eng, hrt, oc, sk, dev):
     full2body = [0, 4, 5, 6, 1, 2, 3, 7, 8, 9, 10, 34, 35, 36, 37, 38, 39, 11, 12, 13, 14]
     body, lh, rh = gt[:, full2body].contiguous().numpy(), gt[:, 14:34].contiguous().numpy(), gt[:, 39:59].contiguous().numpy()
     o_dof = np.empty(30, np.float32)
-    eng.stream_pos_open(wire_layout=False)
-    for i in range(1000):
-        eng.stream_pos_frame(body[i % 2048], lh[i % 2048], rh[i % 2048], None, o_dof)
-    ts = np.empty(n)
-    for i in range(n):
-        k = i % 2048
-        t0 = time.perf_counter_ns()
-        eng.stream_pos_frame(body[k], lh[k], rh[k], None, o_dof)
-        ts[i] = time.perf_counter_ns() - t0
-    paced = np.empty(240)
-    period = 1.0 / 120.0
-    nxt = time.perf_counter() + period
-    for i in range(240):                                   # 2 s at the teleop loop's 120 Hz pacing (GPU idles in between)
-        while time.perf_counter() < nxt:
-            pass
-        nxt += period
-        t0 = time.perf_counter_ns()
-        eng.stream_pos_frame(body[i], lh[i], rh[i], None, o_dof)
-        paced[i] = time.perf_counter_ns() - t0
-    eng.stream_pos_close()
-    out["latency_us"] = {"path": "VtrdynFullBodyPosRetargeter single frame, host in -> host dof_pos (hrt_stream_pos_frame via ctypes)",
-                         "back_to_back": {"frames": n, "p50": float(np.percentile(ts, 50)) / 1e3, "p99": float(np.percentile(ts, 99)) / 1e3,
-                                          "p999": float(np.percentile(ts, 99.9)) / 1e3},
-                         "paced_120hz": {"frames": 240, "p50": float(np.percentile(paced, 50)) / 1e3, "p99": float(np.percentile(paced, 99)) / 1e3}}
+    lat = {"path": "VtrdynFullBodyPosRetargeter single frame, host in -> host dof_pos (hrt_stream_pos_frame via ctypes)"}
+    for mode, persistent in (("launch_per_frame", False), ("resident_server", True)):
+        eng.stream_pos_open(wire_layout=False, persistent=persistent)
+        for i in range(1000):
+            eng.stream_pos_frame(body[i % 2048], lh[i % 2048], rh[i % 2048], None, o_dof)
+        ts = np.empty(n)
+        for i in range(n):
+            k = i % 2048
+            t0 = time.perf_counter_ns()
+            eng.stream_pos_frame(body[k], lh[k], rh[k], None, o_dof)
+            ts[i] = time.perf_counter_ns() - t0
+        paced = np.empty(240)
+        period = 1.0 / 120.0
+        nxt = time.perf_counter() + period
+        for i in range(240):                               # 2 s at the teleop loop's 120 Hz pacing
+            while time.perf_counter() < nxt:
+                pass
+            nxt += period
+            t0 = time.perf_counter_ns()
+            eng.stream_pos_frame(body[i], lh[i], rh[i], None, o_dof)
+            paced[i] = time.perf_counter_ns() - t0
+        eng.stream_pos_close()
+        lat[mode] = {"back_to_back": {"frames": n, "p50": float(np.percentile(ts, 50)) / 1e3, "p99": float(np.percentile(ts, 99)) / 1e3,
+                                      "p999": float(np.percentile(ts, 99.9)) / 1e3},
+                     "paced_120hz": {"frames": 240, "p50": float(np.percentile(paced, 50)) / 1e3, "p99": float(np.percentile(paced, 99)) / 1e3}}
+    out["latency_us"] = lat
     # configs[1]: 65,536 Hu (33-joint) configurations, FK with joint limits; L2 flushed between launches
     eng_hu = hrt.default_engine(dev.index or 0, robot="hu")
     lo, hi = torch.tensor(oc.HU_DOF_LOWER), torch.tensor(oc.HU_DOF_UPPER)

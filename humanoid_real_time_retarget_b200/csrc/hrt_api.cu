@@ -2,6 +2,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -79,6 +81,11 @@ struct hrt_ctx {
     // position-path streaming
     bool pstream_open = false;
     int pstream_mode = 0;
+    bool pstream_persistent = false;   // resident server kernel instead of one launch per frame
+    bool pserver_launched = false;
+    unsigned pseq = 0;                 // last sequence number posted
+    volatile unsigned* pctrl = nullptr; // mapped pinned control words (host view)
+    unsigned* pctrl_d = nullptr;
     float *pmb_in = nullptr, *pmb_out = nullptr, *pmb_in_d = nullptr, *pmb_out_d = nullptr;
     cudaStream_t pss = nullptr;
     PosArgs pstream_args;
@@ -855,10 +862,31 @@ int hrt_retarget_main_arms(hrt_ctx* ctx, int64_t B, const float* d_body_q, const
     return launch_pos(ctx, POS_MAIN, a, (cudaStream_t)stream);
 }
 
-int hrt_stream_pos_open(hrt_ctx* ctx, int wire_layout) {
+namespace {
+constexpr unsigned long long kServerIdleNs = 20ull * 1000 * 1000;     // the resident kernel leaves after 20 ms without a frame
+
+size_t pos_smem_bytes(const PosParams& pp, const PosArgs& a) {
+    const bool with_bq = pp.mode == POS_FULL_BODY_POS && a.out_body_gq;
+    const int const_words = (2 * (int)sizeof(PosArm) / 4 + 8 + 3) / 4 * 4;
+    return ((size_t)const_words + (size_t)POS_WARPS * pos_tile_words(pp, a.out_local_q != nullptr, with_bq)) * sizeof(float);
+}
+
+int launch_pos_server(hrt_ctx* ctx) {
+    const PosParams& pp = ctx->pos[ctx->pstream_mode];
+    ctx->pctrl[17] = 0u;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    pos_stream_server_kernel<POS_FULL_BODY_POS><<<1, 32, pos_smem_bytes(pp, ctx->pstream_args), ctx->pss>>>(
+        pp, ctx->pstream_args, ctx->pctrl_d, ctx->pseq, kServerIdleNs);
+    HRT_CUDA(cudaGetLastError());
+    ctx->pserver_launched = true;
+    return 0;
+}
+}  // namespace
+
+int hrt_stream_pos_open(hrt_ctx* ctx, int flags) {
     int rc = check_ctx(ctx);
     if (rc) return rc;
-    const int slot = wire_layout ? 4 : 0;
+    const int slot = (flags & HRT_STREAM_WIRE_LAYOUT) ? 4 : 0;
     if (!ctx->pos_set[slot]) return fail(HRT_E_NOT_CONFIGURED, "hrt_configure_pos(mode 0) has not been called");
     if (ctx->pstream_open) hrt_stream_pos_close(ctx);
     const PosParams& pp = ctx->pos[slot];
@@ -878,6 +906,17 @@ int hrt_stream_pos_open(hrt_ctx* ctx, int wire_layout) {
     a.out_dof = ctx->pmb_out_d + pp.J_rob * 4;
     ctx->pstream_args = a;
     ctx->pstream_mode = slot;
+    ctx->pstream_persistent = (flags & HRT_STREAM_PERSISTENT) != 0;
+    ctx->pserver_launched = false;
+    ctx->pseq = 0;
+    if (ctx->pstream_persistent) {
+        unsigned* c = nullptr;
+        HRT_CUDA(cudaHostAlloc(&c, 32 * sizeof(unsigned), cudaHostAllocMapped));
+        memset(c, 0, 32 * sizeof(unsigned));
+        ctx->pctrl = c;
+        HRT_CUDA(cudaHostGetDevicePointer(&ctx->pctrl_d, c, 0));
+        HRT_CUDA(cudaFuncSetAttribute(pos_stream_server_kernel<POS_FULL_BODY_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
     ctx->pstream_open = true;
     return 0;
 }
@@ -891,9 +930,40 @@ int hrt_stream_pos_frame(hrt_ctx* ctx, const float* h_body_t, const float* h_lha
     memcpy(ctx->pmb_in, h_body_t, body_w * 4);
     memcpy(ctx->pmb_in + (body_w + 3) / 4 * 4, h_lhand_t, hand_w * 4);
     memcpy(ctx->pmb_in + (body_w + 3) / 4 * 4 + hand_w, h_rhand_t, hand_w * 4);
-    int rc = launch_pos(ctx, ctx->pstream_mode, ctx->pstream_args, ctx->pss, 1);
-    if (rc) return rc;
-    HRT_CUDA(cudaStreamSynchronize(ctx->pss));
+    if (!ctx->pstream_persistent) {
+        int rc = launch_pos(ctx, ctx->pstream_mode, ctx->pstream_args, ctx->pss, 1);
+        if (rc) return rc;
+        HRT_CUDA(cudaStreamSynchronize(ctx->pss));
+    } else {
+        // post the frame: inputs first, then the sequence number (x86 keeps store order; the fence stops the compiler)
+        if (!ctx->pserver_launched || ctx->pctrl[17] != 0u) {
+            int rc = launch_pos_server(ctx);
+            if (rc) return rc;
+        }
+        unsigned seq = ctx->pseq + 1u;
+        if (seq == 0u) seq = 1u;
+        std::atomic_thread_fence(std::memory_order_seq_cst);
+        ctx->pctrl[0] = seq;
+        ctx->pseq = seq;
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned spins = 0;
+        while (ctx->pctrl[16] != seq) {
+            if (ctx->pctrl[17] != 0u) {               // the server timed out just before this frame was posted
+                ctx->pseq = seq - 1u;                 // it will see `seq` as new
+                int rc = launch_pos_server(ctx);
+                ctx->pseq = seq;
+                if (rc) return rc;
+            }
+            if ((++spins & 0xfffu) == 0u) {
+                cudaError_t e = cudaStreamQuery(ctx->pss);
+                if (e != cudaSuccess && e != cudaErrorNotReady)
+                    return fail((int)e, "stream server failed: %s", cudaGetErrorString(e));
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2))
+                    return fail(HRT_E_INVALID_ARG, "stream server did not answer within 2 s");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_seq_cst);
+    }
     if (h_robot_local_q) memcpy(h_robot_local_q, ctx->pmb_out, (size_t)pp.J_rob * 16);
     if (h_dof) memcpy(h_dof, ctx->pmb_out + pp.J_rob * 4, (size_t)(pp.J_rob - 1) * 4);
     return 0;
@@ -902,10 +972,13 @@ int hrt_stream_pos_frame(hrt_ctx* ctx, const float* h_body_t, const float* h_lha
 int hrt_stream_pos_close(hrt_ctx* ctx) {
     if (!ctx || !ctx->pstream_open) return 0;
     cudaSetDevice(ctx->device);
+    if (ctx->pctrl) ctx->pctrl[1] = 1u;               // tell a resident server to leave
     if (ctx->pss) { cudaStreamSynchronize(ctx->pss); cudaStreamDestroy(ctx->pss); ctx->pss = nullptr; }
     if (ctx->pmb_in) { cudaFreeHost(ctx->pmb_in); ctx->pmb_in = nullptr; }
     if (ctx->pmb_out) { cudaFreeHost(ctx->pmb_out); ctx->pmb_out = nullptr; }
+    if (ctx->pctrl) { cudaFreeHost(const_cast<unsigned*>(ctx->pctrl)); ctx->pctrl = nullptr; ctx->pctrl_d = nullptr; }
     ctx->pstream_open = false;
+    ctx->pserver_launched = false;
     return 0;
 }
 

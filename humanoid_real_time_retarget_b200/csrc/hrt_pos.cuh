@@ -136,78 +136,111 @@ HRT_DEV float4 quat_from_rotation_matrix_x(const float m[3][3]) {
 // ---------------------------------------------------------------------------------------------
 // Kabsch (transform3d.py:32-50): A = M^T Z (3x3), R = U diag(1,1,det) V^T.  fp64.
 // ---------------------------------------------------------------------------------------------
+// One Jacobi rotation annihilating a_pq, branch-free so that independent problems interleave:
+// tau = (a_qq - a_pp)/2, r = sqrt(tau^2 + a_pq^2), t = a_pq / (tau + copysign(r, tau)), c = rsqrt(1 + t^2), s = t c
 HRT_DEV void jacobi_rot(double& app, double& aqq, double& apq, double& arp, double& arq,
                         double& v0p, double& v0q, double& v1p, double& v1q, double& v2p, double& v2q) {
-    if (fabs(apq) > 1e-300) {
-        const double theta = (aqq - app) / (2.0 * apq);
-        const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = rsqrt(t * t + 1.0);
-        const double s = t * c;
-        const double app_n = app - t * apq, aqq_n = aqq + t * apq;
-        app = app_n; aqq = aqq_n; apq = 0.0;
-        const double rp = c * arp - s * arq, rq = s * arp + c * arq;
-        arp = rp; arq = rq;
-        double a, b;
-        a = c * v0p - s * v0q; b = s * v0p + c * v0q; v0p = a; v0q = b;
-        a = c * v1p - s * v1q; b = s * v1p + c * v1q; v1p = a; v1q = b;
-        a = c * v2p - s * v2q; b = s * v2p + c * v2q; v2p = a; v2q = b;
+    const double tau = 0.5 * (aqq - app);
+    const double r = sqrt(fma(tau, tau, apq * apq));
+    const double den = tau + copysign(r, tau);
+    const double t = (fabs(apq) > 1e-300) ? apq / den : 0.0;
+    const double c = rsqrt(fma(t, t, 1.0));
+    const double s = t * c;
+    const double app_n = fma(-t, apq, app), aqq_n = fma(t, apq, aqq);
+    app = app_n; aqq = aqq_n; apq = 0.0;
+    const double rp = c * arp - s * arq, rq = s * arp + c * arq;
+    arp = rp; arq = rq;
+    double a, b;
+    a = c * v0p - s * v0q; b = s * v0p + c * v0q; v0p = a; v0q = b;
+    a = c * v1p - s * v1q; b = s * v1p + c * v1q; v1p = a; v1q = b;
+    a = c * v2p - s * v2q; b = s * v2p + c * v2q; v2p = a; v2q = b;
+}
+
+// NK independent Kabsch problems solved together (their fp64 dependency chains interleave: the torso
+// and the wrist fit of one arm cost little more than one).  A = M^T Z in fp64 (exact products of fp32
+// inputs) -> rotation quaternions.  Cyclic Jacobi on A^T A converges quadratically: sweeps stop when the
+// off-diagonal mass is below 1e-18 of the trace for every problem (2-3 sweeps; 8 at most).
+template <int NK>
+HRT_DEV void kabsch_multi(const double (*A)[3][3], float4* out) {
+    double s00[NK], s01[NK], s02[NK], s11[NK], s12[NK], s22[NK];
+    double v00[NK], v01[NK], v02[NK], v10[NK], v11[NK], v12[NK], v20[NK], v21[NK], v22[NK];
+#pragma unroll
+    for (int n = 0; n < NK; ++n) {
+        s00[n] = s01[n] = s02[n] = s11[n] = s12[n] = s22[n] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            s00[n] = fma(A[n][i][0], A[n][i][0], s00[n]); s01[n] = fma(A[n][i][0], A[n][i][1], s01[n]);
+            s02[n] = fma(A[n][i][0], A[n][i][2], s02[n]); s11[n] = fma(A[n][i][1], A[n][i][1], s11[n]);
+            s12[n] = fma(A[n][i][1], A[n][i][2], s12[n]); s22[n] = fma(A[n][i][2], A[n][i][2], s22[n]);
+        }
+        v00[n] = 1; v01[n] = 0; v02[n] = 0; v10[n] = 0; v11[n] = 1; v12[n] = 0; v20[n] = 0; v21[n] = 0; v22[n] = 1;
+    }
+    for (int sweep = 0; sweep < 8; ++sweep) {
+        bool done = true;
+#pragma unroll
+        for (int n = 0; n < NK; ++n) {
+            const double off = fma(s01[n], s01[n], fma(s02[n], s02[n], s12[n] * s12[n]));
+            const double tr = s00[n] + s11[n] + s22[n];
+            done = done && !(off > 1e-36 * tr * tr);
+        }
+        if (done) break;
+#pragma unroll
+        for (int n = 0; n < NK; ++n) jacobi_rot(s00[n], s11[n], s01[n], s02[n], s12[n], v00[n], v01[n], v10[n], v11[n], v20[n], v21[n]);
+#pragma unroll
+        for (int n = 0; n < NK; ++n) jacobi_rot(s00[n], s22[n], s02[n], s01[n], s12[n], v00[n], v02[n], v10[n], v12[n], v20[n], v22[n]);
+#pragma unroll
+        for (int n = 0; n < NK; ++n) jacobi_rot(s11[n], s22[n], s12[n], s01[n], s02[n], v01[n], v02[n], v11[n], v12[n], v21[n], v22[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < NK; ++n) {
+        // order the eigenvalues: (a) largest, (b) second; only these two singular pairs are used
+        const double e[3] = {s00[n], s11[n], s22[n]};
+        const double V[3][3] = {{v00[n], v10[n], v20[n]}, {v01[n], v11[n], v21[n]}, {v02[n], v12[n], v22[n]}};
+        int ia = 0, ib = 1, ic = 2;
+        if (e[ib] > e[ia]) { int t = ia; ia = ib; ib = t; }
+        if (e[ic] > e[ia]) { int t = ia; ia = ic; ic = t; }
+        if (e[ic] > e[ib]) { int t = ib; ib = ic; ic = t; }
+        double va[3], vb[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            va[k] = (ia == 0) ? V[0][k] : (ia == 1) ? V[1][k] : V[2][k];
+            vb[k] = (ib == 0) ? V[0][k] : (ib == 1) ? V[1][k] : V[2][k];
+        }
+        double ua[3], ub[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            ua[i] = A[n][i][0] * va[0] + A[n][i][1] * va[1] + A[n][i][2] * va[2];
+            ub[i] = A[n][i][0] * vb[0] + A[n][i][1] * vb[1] + A[n][i][2] * vb[2];
+        }
+        const double na = rsqrt(ua[0] * ua[0] + ua[1] * ua[1] + ua[2] * ua[2]);
+        ua[0] *= na; ua[1] *= na; ua[2] *= na;
+        const double d = ua[0] * ub[0] + ua[1] * ub[1] + ua[2] * ub[2];
+        ub[0] -= d * ua[0]; ub[1] -= d * ua[1]; ub[2] -= d * ua[2];
+        const double nb = rsqrt(ub[0] * ub[0] + ub[1] * ub[1] + ub[2] * ub[2]);
+        ub[0] *= nb; ub[1] *= nb; ub[2] *= nb;
+        const double uc[3] = {ua[1] * ub[2] - ua[2] * ub[1], ua[2] * ub[0] - ua[0] * ub[2], ua[0] * ub[1] - ua[1] * ub[0]};
+        const double vc[3] = {va[1] * vb[2] - va[2] * vb[1], va[2] * vb[0] - va[0] * vb[2], va[0] * vb[1] - va[1] * vb[0]};
+        float R[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) R[i][k] = (float)(ua[i] * va[k] + ub[i] * vb[k] + uc[i] * vc[k]);
+        out[n] = quat_from_rotation_matrix_x(R);
     }
 }
 
-// A = M^T Z in fp64 (exact products of fp32 inputs) -> the rotation quaternion.
 HRT_DEV float4 kabsch_quat_from_A(const double A[3][3]) {
-    // S = A^T A (symmetric), eigenvectors -> right singular vectors
-    double s00 = 0, s01 = 0, s02 = 0, s11 = 0, s12 = 0, s22 = 0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        s00 += A[i][0] * A[i][0]; s01 += A[i][0] * A[i][1]; s02 += A[i][0] * A[i][2];
-        s11 += A[i][1] * A[i][1]; s12 += A[i][1] * A[i][2]; s22 += A[i][2] * A[i][2];
-    }
-    double v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
-    for (int sweep = 0; sweep < 8; ++sweep) {
-        jacobi_rot(s00, s11, s01, s02, s12, v00, v01, v10, v11, v20, v21);   // (p,q) = (0,1), r = 2
-        jacobi_rot(s00, s22, s02, s01, s12, v00, v02, v10, v12, v20, v22);   // (0,2), r = 1
-        jacobi_rot(s11, s22, s12, s01, s02, v01, v02, v11, v12, v21, v22);   // (1,2), r = 0
-    }
-    // order the eigenvalues: (a) largest, (b) second
-    double e[3] = {s00, s11, s22};
-    double V[3][3] = {{v00, v10, v20}, {v01, v11, v21}, {v02, v12, v22}};   // V[k] = k-th eigenvector
-    int ia = 0, ib = 1, ic = 2;
-    if (e[ib] > e[ia]) { int t = ia; ia = ib; ib = t; }
-    if (e[ic] > e[ia]) { int t = ia; ia = ic; ic = t; }
-    if (e[ic] > e[ib]) { int t = ib; ib = ic; ic = t; }
-    double va[3], vb[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        va[k] = (ia == 0) ? V[0][k] : (ia == 1) ? V[1][k] : V[2][k];
-        vb[k] = (ib == 0) ? V[0][k] : (ib == 1) ? V[1][k] : V[2][k];
-    }
-    double ua[3], ub[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        ua[i] = A[i][0] * va[0] + A[i][1] * va[1] + A[i][2] * va[2];
-        ub[i] = A[i][0] * vb[0] + A[i][1] * vb[1] + A[i][2] * vb[2];
-    }
-    double na = rsqrt(ua[0] * ua[0] + ua[1] * ua[1] + ua[2] * ua[2]);
-    ua[0] *= na; ua[1] *= na; ua[2] *= na;
-    const double d = ua[0] * ub[0] + ua[1] * ub[1] + ua[2] * ub[2];
-    ub[0] -= d * ua[0]; ub[1] -= d * ua[1]; ub[2] -= d * ua[2];
-    double nb = rsqrt(ub[0] * ub[0] + ub[1] * ub[1] + ub[2] * ub[2]);
-    ub[0] *= nb; ub[1] *= nb; ub[2] *= nb;
-    const double uc[3] = {ua[1] * ub[2] - ua[2] * ub[1], ua[2] * ub[0] - ua[0] * ub[2], ua[0] * ub[1] - ua[1] * ub[0]};
-    const double vc[3] = {va[1] * vb[2] - va[2] * vb[1], va[2] * vb[0] - va[0] * vb[2], va[0] * vb[1] - va[1] * vb[0]};
-    float R[3][3];
+    float4 q;
+    kabsch_multi<1>(reinterpret_cast<const double (*)[3][3]>(A), &q);
+    return q;
+}
+
+template <int N>
+HRT_DEV void kabsch_accumulate(const vec3* M, const vec3* Z, double A[3][3]) {
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) R[i][k] = (float)(ua[i] * va[k] + ub[i] * vb[k] + uc[i] * vc[k]);
-    return quat_from_rotation_matrix_x(R);
-}
-
-// M: measured offsets (n x 3), Z: zero-pose offsets (n x 3), both fp32.  Returns the quaternion.
-template <int N>
-HRT_DEV float4 kabsch_quat(const vec3* M, const vec3* Z) {
-    double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int k = 0; k < 3; ++k) A[i][k] = 0.0;
 #pragma unroll
     for (int n = 0; n < N; ++n) {
         const double m[3] = {(double)M[n].x, (double)M[n].y, (double)M[n].z};
@@ -215,8 +248,15 @@ HRT_DEV float4 kabsch_quat(const vec3* M, const vec3* Z) {
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) A[i][k] += m[i] * z[k];
+            for (int k = 0; k < 3; ++k) A[i][k] = fma(m[i], z[k], A[i][k]);
     }
+}
+
+// M: measured offsets (n x 3), Z: zero-pose offsets (n x 3), both fp32.  Returns the quaternion.
+template <int N>
+HRT_DEV float4 kabsch_quat(const vec3* M, const vec3* Z) {
+    double A[3][3];
+    kabsch_accumulate<N>(M, Z, A);
     return kabsch_quat_from_A(A);
 }
 
@@ -235,33 +275,59 @@ HRT_HD inline int pos_tile_words(const PosParams& pp, bool with_lq, bool with_bq
 }
 constexpr int POS_WARPS = 8;
 
-template <int MODE>
-__global__ void __launch_bounds__(POS_WARPS * 32, 1)
-pos_retarget_kernel(const __grid_constant__ PosParams pp, const PosArgs a) {
-    extern __shared__ __align__(16) float smem[];
+// host-visible (mapped, pinned) inputs must bypass the caches when a resident kernel re-reads them per frame
+template <bool SYSMEM>
+HRT_DEV void pos_stage_span(float* dst, const float* src, int n_words, int lane) {
+    if (SYSMEM) {
+        // every PCIe read is ~2 us: issue all of a lane's loads before the first use (one frame is <= 96 words)
+        if (n_words <= 96) {
+            float v[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) v[k] = (lane + 32 * k < n_words) ? __ldcv(src + lane + 32 * k) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) if (lane + 32 * k < n_words) dst[lane + 32 * k] = v[k];
+        } else {
+            for (int i = lane; i < n_words; i += 32) dst[i] = __ldcv(src + i);
+        }
+    } else {
+        warp_span_g2s(dst, src, n_words, lane);
+    }
+}
+// the resident server runs ONE warp: no cross-warp instruction-fetch alignment there
+template <bool SYSMEM>
+HRT_DEV void pos_align(int warp) {
+    if (!SYSMEM) smsp_align<POS_WARPS>(warp);
+}
+
+// CTA-shared constants: both PosArm tables + the zero-pose bone angles (once per CTA)
+HRT_DEV void pos_setup(const PosParams& pp, float* smem) {
+    PosArm* arms_s = reinterpret_cast<PosArm*>(smem);
+    float* zero_ang = smem + 2 * sizeof(PosArm) / 4;      // [side][4] = theta0_sh, phi0_sh, theta0_el, phi0_el
+    const float* src = reinterpret_cast<const float*>(&pp.arm[0]);
+    for (int i = threadIdx.x; i < 2 * (int)sizeof(PosArm) / 4; i += blockDim.x) smem[i] = src[i];
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const PosArm& ar = arms_s[threadIdx.x];
+        float t, p;
+        bone_angles_x<1>(make_vec3(ar.v0_upper[0], ar.v0_upper[1], ar.v0_upper[2]), &t, &p);
+        zero_ang[threadIdx.x * 4 + 0] = t; zero_ang[threadIdx.x * 4 + 1] = p;
+        bone_angles_x<2>(make_vec3(ar.v0_lower[0], ar.v0_lower[1], ar.v0_lower[2]), &t, &p);
+        zero_ang[threadIdx.x * 4 + 2] = t; zero_ang[threadIdx.x * 4 + 3] = p;
+    }
+    __syncthreads();
+}
+
+// all frame groups of `a` that fall to CTA `cta` of `n_ctas`
+template <int MODE, bool SYSMEM>
+HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int n_ctas, int cta) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int fl = lane >> 1;
     const int side = lane & 1;
     constexpr bool HANDS = MODE == POS_FULL_BODY_POS || MODE == POS_FULL_BODY;
     constexpr bool QUATS = MODE == POS_FULL_BODY || MODE == POS_MAIN;
-    // ---- CTA-shared constants: both PosArm tables + zero-pose bone angles -----------------------
-    PosArm* arms_s = reinterpret_cast<PosArm*>(smem);
-    float* zero_ang = smem + 2 * sizeof(PosArm) / 4;      // [side][4] = theta0_sh, phi0_sh, theta0_el, phi0_el
-    {
-        const float* src = reinterpret_cast<const float*>(&pp.arm[0]);
-        for (int i = threadIdx.x; i < 2 * (int)sizeof(PosArm) / 4; i += blockDim.x) smem[i] = src[i];
-        __syncthreads();
-        if (threadIdx.x < 2) {
-            const PosArm& ar = arms_s[threadIdx.x];
-            float t, p;
-            bone_angles_x<1>(make_vec3(ar.v0_upper[0], ar.v0_upper[1], ar.v0_upper[2]), &t, &p);
-            zero_ang[threadIdx.x * 4 + 0] = t; zero_ang[threadIdx.x * 4 + 1] = p;
-            bone_angles_x<2>(make_vec3(ar.v0_lower[0], ar.v0_lower[1], ar.v0_lower[2]), &t, &p);
-            zero_ang[threadIdx.x * 4 + 2] = t; zero_ang[threadIdx.x * 4 + 3] = p;
-        }
-        __syncthreads();
-    }
+    const PosArm* arms_s = reinterpret_cast<const PosArm*>(smem);
+    const float* zero_ang = smem + 2 * sizeof(PosArm) / 4;
     const PosArm& ap = arms_s[side];
     const int const_words = (2 * (int)sizeof(PosArm) / 4 + 8 + 3) / 4 * 4;
     const bool with_lq = a.out_local_q != nullptr;
@@ -280,10 +346,10 @@ pos_retarget_kernel(const __grid_constant__ PosParams pp, const PosArgs a) {
     bool pending_store = false;
 
     const long long n_groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
-    const long long total_warps = (long long)gridDim.x * POS_WARPS;
+    const long long total_warps = (long long)n_ctas * POS_WARPS;
     const long long rounds = (n_groups + total_warps - 1) / total_warps;
     for (long long rnd = 0; rnd < rounds; ++rnd) {
-        const long long grp_raw = rnd * total_warps + (long long)blockIdx.x * POS_WARPS + warp;
+        const long long grp_raw = rnd * total_warps + (long long)cta * POS_WARPS + warp;
         const bool live = grp_raw < n_groups;
         const long long grp = live ? grp_raw : n_groups - 1;
         const long long f0 = grp * BQ_FRAMES_PER_WARP;
@@ -297,12 +363,28 @@ pos_retarget_kernel(const __grid_constant__ PosParams pp, const PosArgs a) {
             pending_store = false;
         }
         // ---- 1. stage inputs (contiguous spans) -------------------------------------------------
-        warp_span_g2s(body_s, a.body_t + f0 * NB * 3, nld * NB * 3, lane);
-        if (HANDS) {
-            warp_span_g2s(lh_s, a.lhand_t + f0 * NH * 3, nld * NH * 3, lane);
-            warp_span_g2s(rh_s, a.rhand_t + f0 * NH * 3, nld * NH * 3, lane);
+        if (SYSMEM && HANDS && nld == 1 && NB * 3 <= 96 && NH * 3 <= 96) {
+            // resident server, one frame in host memory: all PCIe reads of the frame in flight together
+            const float* src[3] = {a.body_t, a.lhand_t, a.rhand_t};
+            float* dst[3] = {body_s, lh_s, rh_s};
+            const int cnt[3] = {NB * 3, NH * 3, NH * 3};
+            float v[3][3];
+#pragma unroll
+            for (int sp = 0; sp < 3; ++sp)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) v[sp][k] = (lane + 32 * k < cnt[sp]) ? __ldcv(src[sp] + lane + 32 * k) : 0.f;
+#pragma unroll
+            for (int sp = 0; sp < 3; ++sp)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) if (lane + 32 * k < cnt[sp]) dst[sp][lane + 32 * k] = v[sp][k];
+        } else {
+            pos_stage_span<SYSMEM>(body_s, a.body_t + f0 * NB * 3, nld * NB * 3, lane);
+            if (HANDS) {
+                pos_stage_span<SYSMEM>(lh_s, a.lhand_t + f0 * NH * 3, nld * NH * 3, lane);
+                pos_stage_span<SYSMEM>(rh_s, a.rhand_t + f0 * NH * 3, nld * NH * 3, lane);
+            }
         }
-        if (QUATS) warp_span_g2s(bodyq_s, a.body_q + f0 * pp.n_bodyq * 4, nld * pp.n_bodyq * 4, lane);
+        if (QUATS) pos_stage_span<SYSMEM>(bodyq_s, a.body_q + f0 * pp.n_bodyq * 4, nld * pp.n_bodyq * 4, lane);
         cp_async_commit();
         if (a.out_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
         if (with_lq)
@@ -319,22 +401,44 @@ pos_retarget_kernel(const __grid_constant__ PosParams pp, const PosArgs a) {
         // ---- 2. arm parent frame ------------------------------------------------------------------
         float4 torso = make_float4(0.f, 0.f, 0.f, 1.f);
         float4 parent;
+        float4 wrist_g = make_float4(0.f, 0.f, 0.f, 1.f);
+        const float* hand = HANDS ? (side == 0 ? lh_s : rh_s) + fr * NH * 3 : nullptr;
         if (QUATS) {
             parent = *reinterpret_cast<const float4*>(bodyq_s + (fr * pp.n_bodyq + ap.q_parent) * 4);
         } else {
-            smsp_align<POS_WARPS>(warp);
-            vec3 M[3], Z[3];
-            const vec3 org = bpt(pp.torso_org);
+            pos_align<SYSMEM>(warp);
+            // the torso fit and (full_body_pos) this arm's wrist fit are independent: solved together
+            double A[2][3][3];
+            {
+                vec3 M[3], Z[3];
+                const vec3 org = bpt(pp.torso_org);
 #pragma unroll
-            for (int n = 0; n < 3; ++n) {
-                M[n] = sub3_x(bpt(pp.torso_pts[n]), org);
-                Z[n] = make_vec3(pp.ztorso[n][0], pp.ztorso[n][1], pp.ztorso[n][2]);
+                for (int n = 0; n < 3; ++n) {
+                    M[n] = sub3_x(bpt(pp.torso_pts[n]), org);
+                    Z[n] = make_vec3(pp.ztorso[n][0], pp.ztorso[n][1], pp.ztorso[n][2]);
+                }
+                kabsch_accumulate<3>(M, Z, A[0]);
             }
-            torso = kabsch_quat<3>(M, Z);
+            if (MODE == POS_FULL_BODY_POS) {
+                vec3 M[5], Z[5];
+                const vec3 org = ld3(hand + pp.hand_org * 3);
+#pragma unroll
+                for (int n = 0; n < 5; ++n) {
+                    M[n] = sub3_x(ld3(hand + pp.hand_kabsch[n] * 3), org);
+                    Z[n] = make_vec3(ap.zwrist[n][0], ap.zwrist[n][1], ap.zwrist[n][2]);
+                }
+                kabsch_accumulate<5>(M, Z, A[1]);
+                float4 q[2];
+                kabsch_multi<2>(A, q);
+                torso = q[0];
+                wrist_g = q[1];
+            } else {
+                kabsch_multi<1>(A, &torso);
+            }
             parent = torso;
         }
         // ---- 3. shoulder pitch / roll, shoulder yaw / elbow pitch ----------------------------------
-        smsp_align<POS_WARPS>(warp);
+        pos_align<SYSMEM>(warp);
         float4 rl[7];
         {
             const vec3 v_up = sub3_x(bpt(ap.b_el), bpt(ap.b_sh));
@@ -350,27 +454,14 @@ pos_retarget_kernel(const __grid_constant__ PosParams pp, const PosArgs a) {
         }
         rl[4] = rl[5] = rl[6] = make_float4(0.f, 0.f, 0.f, 1.f);
         // ---- 4. wrist -------------------------------------------------------------------------------
-        float4 wrist_g = make_float4(0.f, 0.f, 0.f, 1.f);
-        const float* hand = HANDS ? (side == 0 ? lh_s : rh_s) + fr * NH * 3 : nullptr;
         if (HANDS) {
-            smsp_align<POS_WARPS>(warp);
+            pos_align<SYSMEM>(warp);
             const float4 chain = quat_mul_x(quat_mul_x(quat_mul_x(rl[0], rl[1]), rl[2]), rl[3]);
             const float4 base = (MODE == POS_FULL_BODY) ? parent : torso;
             const float4 wparent = quat_mul_norm_x(base, chain);
-            if (MODE == POS_FULL_BODY) {
-                wrist_g = *reinterpret_cast<const float4*>(bodyq_s + (fr * pp.n_bodyq + ap.q_wrist) * 4);
-            } else {
-                vec3 M[5], Z[5];
-                const vec3 org = ld3(hand + pp.hand_org * 3);
-#pragma unroll
-                for (int n = 0; n < 5; ++n) {
-                    M[n] = sub3_x(ld3(hand + pp.hand_kabsch[n] * 3), org);
-                    Z[n] = make_vec3(ap.zwrist[n][0], ap.zwrist[n][1], ap.zwrist[n][2]);
-                }
-                wrist_g = kabsch_quat<5>(M, Z);
-            }
+            if (MODE == POS_FULL_BODY) wrist_g = *reinterpret_cast<const float4*>(bodyq_s + (fr * pp.n_bodyq + ap.q_wrist) * 4);
             const float4 wlocal = quat_mul_norm_x(quat_conj(wparent), wrist_g);
-            smsp_align<POS_WARPS>(warp);
+            pos_align<SYSMEM>(warp);
             double e[3];
             euler_intrinsic_f64<0, 1, 2>(wlocal, e);          // 'XYZ'
             rl[4] = axis_quat_from_f64(e[0], 0);
@@ -378,7 +469,7 @@ pos_retarget_kernel(const __grid_constant__ PosParams pp, const PosArgs a) {
             rl[6] = axis_quat_from_f64(e[2], 2);
         }
         // ---- 5. hinge angles + gripper -----------------------------------------------------------------
-        smsp_align<POS_WARPS>(warp);
+        pos_align<SYSMEM>(warp);
         float th[9];
         th[0] = quat_to_dof_x(rl[0], 1); th[1] = quat_to_dof_x(rl[1], 0); th[2] = quat_to_dof_x(rl[2], 2);
         th[3] = quat_to_dof_x(rl[3], 1);
@@ -448,6 +539,69 @@ pos_retarget_kernel(const __grid_constant__ PosParams pp, const PosArgs a) {
         }
     }
     if (pending_store && lane == 0) bulk_wait_read_all();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(POS_WARPS * 32, 1)
+pos_retarget_kernel(const __grid_constant__ PosParams pp, const PosArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    pos_setup(pp, smem);
+    pos_process<MODE, false>(pp, a, smem, (int)gridDim.x, (int)blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Resident single-frame server for the 120 Hz teleop loop (sim_full_body_teleop.py:83-129).
+// One CTA stays on one SM and polls a sequence number in mapped pinned host memory; the host posts a
+// frame by writing the inputs and then the next sequence number, and spins on the answer's sequence
+// number: no kernel launch, no stream synchronisation, no driver call on the per-frame path.
+// ctrl words (host memory): [0] seq_in (host), [1] stop (host), [16] seq_out (device), [17] exited (device).
+// The kernel leaves when told to stop or after `idle_ns` without a frame, so an abandoned context
+// never holds the GPU (the host relaunches it on the next frame).
+// ---------------------------------------------------------------------------------------------
+HRT_DEV unsigned ld_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+HRT_DEV void st_sys(unsigned* p, unsigned v) { asm volatile("st.volatile.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
+HRT_DEV unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+    return t;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32, 1)
+pos_stream_server_kernel(const __grid_constant__ PosParams pp, const PosArgs a, unsigned* ctrl, unsigned served,
+                         unsigned long long idle_ns) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ unsigned s_cmd;
+    pos_setup(pp, smem);
+    for (;;) {
+        if (threadIdx.x == 0) {
+            const unsigned long long t0 = global_timer_ns();
+            unsigned cmd = 0;
+            for (;;) {
+                const unsigned s = ld_sys(ctrl);
+                if (s != served) { cmd = s; break; }
+                if (ld_sys(ctrl + 1) != 0u || global_timer_ns() - t0 > idle_ns) break;
+            }
+            s_cmd = cmd;
+        }
+        __syncthreads();
+        const unsigned cmd = s_cmd;
+        __syncthreads();
+        if (cmd == 0u) break;
+        pos_process<MODE, true>(pp, a, smem, 1, 0);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) st_sys(ctrl + 16, cmd);
+        served = cmd;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        st_sys(ctrl + 17, 1u);
+    }
 }
 
 }  // namespace hrt

@@ -306,8 +306,9 @@ class Engine:
                                                self._stream()))
         return out
 
-    def stream_pos_open(self, wire_layout=False):
-        _lib.check(self.lib.hrt_stream_pos_open(self._h, int(bool(wire_layout))))
+    def stream_pos_open(self, wire_layout=False, persistent=False):
+        """persistent=True: a resident one-CTA server polls the mailbox (no launch / sync per frame)."""
+        _lib.check(self.lib.hrt_stream_pos_open(self._h, (1 if wire_layout else 0) | (2 if persistent else 0)))
 
     def stream_pos_frame(self, body_np, lhand_np, rhand_np, out_local_q=None, out_dof=None):
         """numpy float32 in / out, one frame of the position path."""

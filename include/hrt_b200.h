@@ -162,13 +162,19 @@ int hrt_stream_close(hrt_ctx* ctx);
 /* Streaming teleop on the POSITION path (what sim_full_body_teleop.py:83-129 runs every frame):
  * VtrdynFullBodyPosRetargeter.retarget on one frame, host in -> host out through mapped pinned
  * mailboxes.  h_body_t (21*3), h_lhand_t / h_rhand_t (20*3) -> h_robot_local_q (31*4)|NULL, h_dof (30)|NULL.
- * wire_layout != 0: the inputs are in the mocap wire layout instead -- h_body_t (23*3) and hands in
- * HandNodes order -- and the 23->21 / hand reorder of sim_full_body_teleop.py:109-112 runs in the
- * kernel prologue. */
+ * HRT_STREAM_WIRE_LAYOUT: the inputs are in the mocap wire layout instead -- h_body_t (23*3) and hands in
+ * HandNodes order -- and the 23->21 / hand reorder of sim_full_body_teleop.py:109-112 is folded into the
+ * kernel's index tables.
+ * HRT_STREAM_PERSISTENT: one CTA stays resident and polls a sequence number in the mailbox; frame() then
+ * is two memcpys and a spin on host memory (no driver call).  The resident kernel leaves by itself after
+ * 20 ms without a frame (and is relaunched by the next frame), so device-wide synchronisation elsewhere in
+ * the process is delayed by at most that. */
 int hrt_retarget_full_body_pos_wire(hrt_ctx* ctx, int64_t B, const float* d_body23_t, const float* d_lhand_t,
                                     const float* d_rhand_t, float* d_robot_local_q, float* d_dof, float* d_body_gq,
                                     void* stream);       /* batched form of the same wire-layout call */
-int hrt_stream_pos_open(hrt_ctx* ctx, int wire_layout);
+#define HRT_STREAM_WIRE_LAYOUT 1   /* inputs in the mocap wire layout (23 body rows, HandNodes finger order) */
+#define HRT_STREAM_PERSISTENT 2    /* resident server kernel polling the mailbox: no launch / sync per frame */
+int hrt_stream_pos_open(hrt_ctx* ctx, int flags);
 int hrt_stream_pos_frame(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
                          float* h_robot_local_q, float* h_dof);
 int hrt_stream_pos_close(hrt_ctx* ctx);

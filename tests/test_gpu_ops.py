@@ -264,3 +264,18 @@ def test_wire_layout_and_position_streaming(hrt, golden):
         eng.stream_pos_frame(body23[i].numpy(), lh_w[i].numpy(), rh_w[i].numpy(), None, o_dof)
         assert np.array_equal(o_dof, dof[i].cpu().numpy())
     eng.stream_pos_close()
+    # resident server kernel: same answers, survives its own idle time-out (20 ms) and a device-wide sync
+    import time
+    for wire in (False, True):
+        eng.stream_pos_open(wire_layout=wire, persistent=True)
+        for i in range(64):
+            if wire:
+                eng.stream_pos_frame(body23[i].numpy(), lh_w[i].numpy(), rh_w[i].numpy(), o_lq, o_dof)
+            else:
+                eng.stream_pos_frame(body[i].numpy(), lh[i].numpy(), rh[i].numpy(), o_lq, o_dof)
+            assert np.array_equal(o_dof, dof[i].cpu().numpy()) and np.array_equal(o_lq, lq[i].cpu().numpy())
+            if i == 20:
+                time.sleep(0.06)                       # the server leaves; the next frame relaunches it
+            if i == 40:
+                torch.cuda.synchronize()               # waits for the server's idle exit, must not dead-lock
+        eng.stream_pos_close()
