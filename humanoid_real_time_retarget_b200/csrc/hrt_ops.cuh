@@ -7,11 +7,11 @@
 // a vector, a 3x3 matrix, a 7-word transform ...) and rows are stored AoS like the reference's tensors.
 //
 // Memory shape.  A warp owns 32 consecutive items, so for every operand and every result the warp's
-// rows are ONE contiguous span of 32*W words.  Spans move global <-> shared with fully coalesced
-// 128-byte warp accesses (W instructions per operand instead of W strided ones per lane) and each lane
-// then picks its own row out of shared memory (odd W: conflict-free; W = 4: one LDS.128).  Operands
-// that broadcast (a single quaternion, or a (J,4) table against (B,J,4)) are read through the
-// read-only path with index i % period.
+// rows are ONE contiguous span of 32*W words.  Quaternion rows (W = 4) are one 16-byte access per lane,
+// coalesced as they are.  Rows of other widths (3, 7, 9 words) move global <-> shared as the warp's
+// contiguous span in 16-byte pieces and each lane then picks its own row out of shared memory (odd W:
+// conflict-free).  Operands that broadcast (a single quaternion, or a (J,4) table against (B,J,4)) are
+// read through the read-only path with index i % period.
 //
 // Numerics.  The fp32 bodies use the exact-order primitives of hrt_math.cuh (one rounded operation per
 // torch op, reference evaluation order), so pure multiply/add chains are bit-identical to torch CPU and
@@ -349,6 +349,26 @@ template <typename Tr, int K> __host__ __device__ constexpr int rot_out_off() {
     return o;
 }
 
+HRT_DEV bool ptr_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// contiguous span of n_words (a multiple of 4 when `vec`) global -> shared / shared -> global by the whole warp
+HRT_DEV void span_load(float* tile, const float* src, int n_words, int lane, bool vec) {
+    if (vec) {
+        for (int w = lane; w < (n_words >> 2); w += 32)
+            *reinterpret_cast<float4*>(tile + w * 4) = __ldcs(reinterpret_cast<const float4*>(src) + w);
+    } else {
+        for (int w = lane; w < n_words; w += 32) tile[w] = __ldcs(src + w);
+    }
+}
+HRT_DEV void span_store(float* dst, const float* tile, int n_words, int lane, bool vec) {
+    if (vec) {
+        for (int w = lane; w < (n_words >> 2); w += 32)
+            __stcs(reinterpret_cast<float4*>(dst) + w, *reinterpret_cast<const float4*>(tile + w * 4));
+    } else {
+        for (int w = lane; w < n_words; w += 32) __stcs(dst + w, tile[w]);
+    }
+}
+
 template <int OP>
 __global__ void __launch_bounds__(ROT_WARPS * 32)
 rot_op_kernel(const RotOpArgs a) {
@@ -358,46 +378,54 @@ rot_op_kernel(const RotOpArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* tile = tiles[warp];
     const long long n_tiles = (a.n + 31) / 32;
+    // 16-byte accesses need 16-byte aligned bases (a warp's span starts at a multiple of 128 bytes from the base)
+    bool al_in[4], al_out[3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) al_in[k] = ptr_aligned16(a.in[k]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) al_out[k] = ptr_aligned16(a.out[k]);
     for (long long t = (long long)blockIdx.x * ROT_WARPS + warp; t < n_tiles; t += (long long)gridDim.x * ROT_WARPS) {
         const long long i0 = t * 32;
         const int cnt = (int)min(32LL, a.n - i0);
         const int row = min(lane, cnt - 1);                 // tail lanes shadow the last row
         const long long i = i0 + row;
         float in[4][9], out[3][9];
-        // 1. operand spans -> shared (coalesced); broadcast operands straight to registers
+        // 1. operands.  Width-4 rows (quaternions) and width-1 rows are coalesced as they are: one LDG.128 / LDG
+        //    per lane.  Other widths: the warp's contiguous span goes through shared memory in 16-byte pieces.
         static_for<0, Tr::NI>([&](auto K) {
             constexpr int k = decltype(K)::value, W = Tr::WI[k], OFF = rot_in_off<Tr, k>();
-            if (a.period[k] == 0) {
-                const float* src = a.in[k] + i0 * W;
-                for (int w = lane; w < cnt * W; w += 32) tile[OFF + w] = __ldcs(src + w);
-            } else {
+            if (a.period[k] != 0) {
                 const float* src = a.in[k] + (i % a.period[k]) * W;
 #pragma unroll
                 for (int c = 0; c < W; ++c) in[k][c] = __ldg(src + c);
+            } else if (W == 4 && al_in[k]) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(a.in[k]) + i);
+                in[k][0] = v.x; in[k][1] = v.y; in[k][2] = v.z; in[k][3] = v.w;
+            } else if (W == 1) {
+                in[k][0] = __ldcs(a.in[k] + i);
+            } else {
+                span_load(tile + OFF, a.in[k] + i0 * W, cnt * W, lane, al_in[k] && ((cnt * W) & 3) == 0);
             }
         });
         __syncwarp();
-        // 2. each lane picks its rows
         static_for<0, Tr::NI>([&](auto K) {
             constexpr int k = decltype(K)::value, W = Tr::WI[k], OFF = rot_in_off<Tr, k>();
-            if (a.period[k] == 0) {
+            if (a.period[k] == 0 && !(W == 4 && al_in[k]) && W != 1) {
                 const float* r = tile + OFF + row * W;
-                if constexpr (W == 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(r);
-                    in[k][0] = v.x; in[k][1] = v.y; in[k][2] = v.z; in[k][3] = v.w;
-                } else {
 #pragma unroll
-                    for (int c = 0; c < W; ++c) in[k][c] = r[c];
-                }
+                for (int c = 0; c < W; ++c) in[k][c] = r[c];
             }
         });
         rot_op_body<OP>(in, out, a.iparam, a.fparam);
-        // 3. result rows -> shared -> global (coalesced)
+        // 2. results, the same way
         static_for<0, Tr::NO>([&](auto K) {
             constexpr int k = decltype(K)::value, W = Tr::WO[k], OFF = rot_out_off<Tr, k>();
-            float* r = tile + OFF + lane * W;
-            if constexpr (W == 4) *reinterpret_cast<float4*>(r) = make_float4(out[k][0], out[k][1], out[k][2], out[k][3]);
-            else {
+            if (W == 4 && al_out[k]) {
+                if (lane < cnt) __stcs(reinterpret_cast<float4*>(a.out[k]) + i, make_float4(out[k][0], out[k][1], out[k][2], out[k][3]));
+            } else if (W == 1) {
+                if (lane < cnt) __stcs(a.out[k] + i, out[k][0]);
+            } else {
+                float* r = tile + OFF + lane * W;
 #pragma unroll
                 for (int c = 0; c < W; ++c) r[c] = out[k][c];
             }
@@ -405,8 +433,8 @@ rot_op_kernel(const RotOpArgs a) {
         __syncwarp();
         static_for<0, Tr::NO>([&](auto K) {
             constexpr int k = decltype(K)::value, W = Tr::WO[k], OFF = rot_out_off<Tr, k>();
-            float* dst = a.out[k] + i0 * W;
-            for (int w = lane; w < cnt * W; w += 32) __stcs(dst + w, tile[OFF + w]);
+            if (!(W == 4 && al_out[k]) && W != 1)
+                span_store(a.out[k] + i0 * W, tile + OFF, cnt * W, lane, al_out[k] && ((cnt * W) & 3) == 0);
         });
         __syncwarp();
     }

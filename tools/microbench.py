@@ -61,7 +61,7 @@ def report(name, n_units, bytes_per_unit, ms_med, ms_min, **extra):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cases", default="fk,bq,elem,jac,stream")
+    ap.add_argument("--cases", default="fk,bq,pos,elem,ops,clip,jac,stream")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--fk-log2", default="16,20,22")
     ap.add_argument("--fk-fast-only", action="store_true")
@@ -107,6 +107,62 @@ def main():
                 continue
             med, mn = timeit(lambda: eng.retarget_body_quat(raw, flags=flags, ik_iters=iters_ik, out=outs), args.iters, flush=True)
             report(name, B, nbytes, med, mn)
+
+    if "pos" in cases:
+        from oracle import retarget_oracle as oc            # input synthesis only (SURVEY 8(d) config 3p recipe)
+        sk = oc.load_skeletons()
+        chunks = []
+        for sd in range(4):
+            gg = torch.Generator().manual_seed(sd)
+            n = 1 << 18
+            em = 0.4 * torch.randn(n, 59, 3, generator=gg)
+            root = torch.zeros(n, 3)
+            root[:, 2] = 1.0
+            _, gt = oc.cal_forward_kinematics(oc.exp_map_to_quat(em), root, sk["vtrdyn_full_zero_pose/parents"].tolist(),
+                                              torch.from_numpy(sk["vtrdyn_full_zero_pose/offsets"]))
+            chunks.append(gt)
+        gt = torch.cat(chunks)
+        B = gt.shape[0]
+        full2body = [0, 4, 5, 6, 1, 2, 3, 7, 8, 9, 10, 34, 35, 36, 37, 38, 39, 11, 12, 13, 14]
+        body, lh, rh = gt[:, full2body].contiguous().cuda(), gt[:, 14:34].contiguous().cuda(), gt[:, 39:59].contiguous().cuda()
+        dof = torch.empty(B, 30, device="cuda")
+        lq = torch.empty(B, 31, 4, device="cuda")
+        bq = torch.empty(B, 59, 4, device="cuda")
+        med, mn = timeit(lambda: eng.retarget_full_body_pos(body, lh, rh, out=(None, dof, None)), args.iters, flush=True)
+        report("pos_full_body_pos_dof_only", B, 732 + 120, med, mn)
+        med, mn = timeit(lambda: eng.retarget_full_body_pos(body, lh, rh, out=(lq, dof, bq)), args.iters, flush=True)
+        report("pos_full_body_pos_all_outputs (reference's 3 returns)", B, 732 + 120 + 496 + 944, med, mn)
+        med, mn = timeit(lambda: eng.retarget_upper_body(body, want_local_q=False), args.iters, flush=True)
+        report("pos_upper_body_dof_only (incl. torch.empty)", B, 252 + 120, med, mn)
+        del body, lh, rh, dof, lq, bq, gt
+
+    if "ops" in cases:
+        from humanoid_real_time_retarget_b200 import rotation3d as r3d
+        n = 1 << 24
+        a = torch.nn.functional.normalize(torch.randn(n, 4, device="cuda", generator=gen), dim=-1)
+        b = torch.nn.functional.normalize(torch.randn(n, 4, device="cuda", generator=gen), dim=-1)
+        v = torch.randn(n, 3, device="cuda", generator=gen)
+        o4, o3 = torch.empty(n, 4, device="cuda"), torch.empty(n, 3, device="cuda")
+        for name, op, ins, outs, nbytes in [("op_quat_mul", r3d.OP_QUAT_MUL, [a, b], [o4], 48), ("op_quat_mul_norm", r3d.OP_QUAT_MUL_NORM, [a, b], [o4], 48),
+                                            ("op_quat_rotate", r3d.OP_QUAT_ROTATE, [a, v], [o3], 40), ("op_quat_normalize", r3d.OP_QUAT_NORMALIZE, [a], [o4], 32),
+                                            ("op_quat_to_exp_map", r3d.OP_QUAT_TO_EXP_MAP, [a], [o3], 28), ("op_exp_map_to_quat", r3d.OP_EXP_MAP_TO_QUAT, [v], [o4], 28)]:
+            med, mn = timeit(lambda: eng.rot_op(op, n, ins, [0] * len(ins), outs), args.iters, flush=False)
+            report(name, n, nbytes, med, mn)
+        del a, b, v, o4, o3
+
+    if "clip" in cases:
+        T = 1 << 20
+        gt = torch.randn(T, 21, 3, device="cuda", generator=gen)
+        gq = torch.nn.functional.normalize(torch.randn(T, 21, 4, device="cuda", generator=gen), dim=-1)
+        med, mn = timeit(lambda: eng.rescale_motion(hrt.TREE_SOURCE, gt, dir=[-1.0, -1.0, 1.0]), args.iters, flush=True)
+        report("rescale_motion_21 (incl. torch.empty)", T, 504, med, mn)
+        med, mn = timeit(lambda: eng.rebuild_global_rotation(hrt.TREE_SOURCE, gt), args.iters, flush=True)
+        report("rebuild_global_rotation_21 (2 launches, incl. torch.empty)", T, 252 * 2 + 336, med, mn)
+        med, mn = timeit(lambda: eng.motion_velocity(gt, 1 / 30), args.iters, flush=True)
+        report("motion_velocity_21 (2 launches + scratch)", T, 252 * 4, med, mn)
+        med, mn = timeit(lambda: eng.motion_angular_velocity(gq, 1 / 30), args.iters, flush=True)
+        report("motion_angular_velocity_21 (2 launches + scratch)", T, 336 + 252 * 3, med, mn)
+        del gt, gq
 
     if "elem" in cases:
         B = 1 << 20
