@@ -274,7 +274,7 @@ int hrt_ctx_create(int device, hrt_ctx** out) {
     c->device = device;
     HRT_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     // these kernels need more than the default 48 KB of dynamic shared memory
-    HRT_CUDA(cudaFuncSetAttribute(jacobian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(jacobian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_ik2_kernel<BQ2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -441,8 +441,11 @@ int hrt_fk_jacobian(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, co
     FkArgs a{};
     a.B = B; a.angles = d_angles; a.root_t = d_root_t; a.root_q = d_root_q; a.out_jac = d_jac; a.clip = clip;
     const int D = t->tp.J - 1;
-    const size_t smem = (size_t)JAC_WARPS_PER_CTA * 32 * (6 * D + 1) * sizeof(float);
-    const long long groups = (B + 31) / 32;
+    if ((6 * D) % 4 != 0) return fail(HRT_E_UNSUPPORTED_TREE, "the Jacobian kernel needs 6*(J-1) to be a multiple of 4");
+    if (!aligned16(d_jac)) return fail(HRT_E_ALIGNMENT, "d_jac must be 16-byte aligned");
+    const int cpw = 32 / jac_lanes_per_cfg(K);
+    const size_t smem = (size_t)JAC_WARPS_PER_CTA * cpw * jac_row_words(K, D) * sizeof(float);
+    const long long groups = (B + cpw - 1) / cpw;
     const long long ctas = (groups + JAC_WARPS_PER_CTA - 1) / JAC_WARPS_PER_CTA;
     int grid = 1;
     if ((rc = grid_for(ctx, jacobian_kernel, JAC_WARPS_PER_CTA * 32, smem, ctas, &grid))) return rc;
