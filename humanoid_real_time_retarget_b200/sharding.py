@@ -44,3 +44,55 @@ def retarget_clip_sharded(engine, raw_global_q_full, flags, ik_iters=10, damping
     if gather and world > 1:
         dof = all_gather_frames(dof, n, group)
     return dof, lp
+
+
+# ---------------------------------------------------------------------------------------------------
+# Block-cyclic sharding: the all-gather of block c lands in final frame order, so it can run on a second
+# stream while block c+1 is still being computed ("chunked and overlapped").
+# ---------------------------------------------------------------------------------------------------
+def block_cyclic_ranges(n_frames, rank, world, n_blocks):
+    """Frames of the clip are cut into n_blocks super-blocks of world*blk frames; rank r owns the r-th slice of
+    every super-block.  Returns (blk, [(lo, hi) per block]) with blk a multiple of 16; the clip is padded up to
+    n_blocks*world*blk frames by the caller's buffers (tail ranges may be short or empty)."""
+    blk = -(-n_frames // (n_blocks * world))
+    blk = max(16, -(-blk // 16) * 16)
+    spans = []
+    for c in range(n_blocks):
+        lo = min(n_frames, (c * world + rank) * blk)
+        spans.append((lo, min(n_frames, lo + blk)))
+    return blk, spans
+
+
+def retarget_clip_overlapped(engine, raw_blocks, n_frames, flags, ik_iters=10, damping=0.1, rot_weight=0.2, n_blocks=4,
+                             group=None, comm_stream=None, out=None):
+    """raw_blocks: this rank's frames as a (n_blocks, blk, Js, 4) device tensor (block-cyclic slices, zero padded).
+    Launches the fused kernel block by block on the current stream; as soon as a block is done its dof_pos is
+    all-gathered on `comm_stream` straight into its final position of the (n_blocks*world*blk, 30) result, while
+    the next block computes.  Returns the reassembled dof_pos trimmed to n_frames (valid after the returned event)."""
+    world = dist.get_world_size(group)
+    nb, blk = raw_blocks.shape[0], raw_blocks.shape[1]
+    assert nb == n_blocks
+    dev = raw_blocks.device
+    if out is None:
+        out = torch.empty((n_blocks * world * blk, 30), dtype=torch.float32, device=dev)
+    local = torch.empty((n_blocks, blk, 30), dtype=torch.float32, device=dev)
+    cuda = dev.type == "cuda"
+    comm_stream = comm_stream or (torch.cuda.Stream(dev) if cuda else None)
+    for c in range(n_blocks):
+        engine.retarget_body_quat(raw_blocks[c], flags=flags, ik_iters=ik_iters, damping=damping, rot_weight=rot_weight,
+                                  out=(None, local[c], None))
+        dst = out[c * world * blk:(c + 1) * world * blk]
+        if cuda:
+            done = torch.cuda.Event()
+            done.record()
+            comm_stream.wait_event(done)
+            with torch.cuda.stream(comm_stream):
+                dist.all_gather_into_tensor(dst, local[c], group=group)
+        else:
+            dist.all_gather_into_tensor(dst, local[c], group=group)
+    finished = None
+    if cuda:
+        finished = torch.cuda.Event()
+        finished.record(comm_stream)
+        torch.cuda.current_stream(dev).wait_event(finished)
+    return out[:n_frames], finished

@@ -47,3 +47,40 @@ def test_all_gather_reassembles_ragged_shards_gloo():
     mp.spawn(_worker, args=(world, _free_port(), n_frames, ret), nprocs=world, join=True)
     assert ret[0][2] and ret[1][2]
     assert ret[0][0] == 0 and ret[0][1] == ret[1][0] and ret[1][1] == n_frames
+
+
+class _FakeEngine:
+    """Stands in for the CUDA engine on the CPU: dof_pos[f] = 2 * (first 30 words of frame f)."""
+
+    def retarget_body_quat(self, raw, flags=0, ik_iters=0, damping=0.0, rot_weight=0.0, out=None):
+        out[1].copy_(raw.reshape(raw.shape[0], -1)[:, :30] * 2.0)
+        return out
+
+
+def _worker_cyclic(rank, world, port, n_frames, n_blocks, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from humanoid_real_time_retarget_b200.sharding import block_cyclic_ranges, retarget_clip_overlapped
+    full = torch.arange(n_frames * 84, dtype=torch.float32).reshape(n_frames, 21, 4)
+    blk, spans = block_cyclic_ranges(n_frames, rank, world, n_blocks)
+    mine = torch.zeros(n_blocks, blk, 21, 4)
+    for c, (lo, hi) in enumerate(spans):
+        mine[c, : hi - lo] = full[lo:hi]
+    dof, _ = retarget_clip_overlapped(_FakeEngine(), mine, n_frames, flags=0, n_blocks=n_blocks)
+    ret[rank] = bool(torch.equal(dof, full.reshape(n_frames, -1)[:, :30] * 2.0))
+    dist.destroy_process_group()
+
+
+def test_block_cyclic_overlapped_gather_lands_in_frame_order_gloo():
+    from humanoid_real_time_retarget_b200.sharding import block_cyclic_ranges
+    for n, w, nb in ((1000, 2, 4), (1 << 20, 8, 4), (17, 4, 2)):
+        blk, _ = block_cyclic_ranges(n, 0, w, nb)
+        covered = sorted(s for r in range(w) for s in block_cyclic_ranges(n, r, w, nb)[1] if s[1] > s[0])
+        assert covered[0][0] == 0 and covered[-1][1] == n and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+        assert blk % 16 == 0
+    world, n_frames, n_blocks = 2, 1000 + 7, 4
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_cyclic, args=(world, _free_port(), n_frames, n_blocks, ret), nprocs=world, join=True)
+    assert ret[0] and ret[1]
