@@ -2,7 +2,7 @@
 retarget hot path of shuoshuof/Humanoid-Real-Time-Retarget.  See DESIGN.md / INTEGRATION.md."""
 from . import robot_config
 from ._lib import HrtError, LIB_PATH, EXPORTED_SYMBOLS
-from .engine import (BQ_CLAMP, BQ_IK, BQ_PACKED_IK, BQ_PRE_TRANSFORMED, FK_EXACT, TREE_ROBOT, TREE_SOURCE, TREE_SOURCE_FULL,
+from .engine import (BQ_ACTIVE_SET, BQ_CLAMP, BQ_IK, BQ_PACKED_IK, BQ_PRE_TRANSFORMED, POS_CLAMP, POS_IK, FK_EXACT, TREE_ROBOT, TREE_SOURCE, TREE_SOURCE_FULL,
                      Engine, default_engine)
 from .kinematics import (BaseForwardModel, HuForwardModel, RobotZeroPose, cal_forward_kinematics, cal_local_rotation)
 from .retarget_solver import (BaseHumanoidRetargeter, HuUpperBodyFromMocapRetarget, Mocap2HuBodyRetargeter,

@@ -149,7 +149,9 @@ size_t body_quat_smem(const hrt_ctx* ctx, const BodyQuatArgs& a);
 // is ~4 % SLOWER end to end than the one-arm-per-thread kernel (profiles/r01_notes.md, "packed fp32x2"): the
 // packed iteration is 17 % faster, but 168-246 registers per thread leave 8-12 warps per SM and the
 // latency-bound closed-form phase loses more than the refinement gains.  Kept selectable, off by default.
-bool use_packed_ik(const BodyQuatArgs& a) { return (a.flags & BQ_IK) && (a.flags & BQ_PACKED_IK) && !a.out_local_q; }
+bool use_packed_ik(const BodyQuatArgs& a) {
+    return (a.flags & BQ_IK) && (a.flags & BQ_PACKED_IK) && !(a.flags & BQ_ACTIVE_SET) && !a.out_local_q;
+}
 
 int launch_body_quat(hrt_ctx* ctx, const BodyQuatArgs& a, cudaStream_t st, int force_grid = 0) {
     if (use_packed_ik(a)) {
@@ -236,7 +238,8 @@ int fill_body_quat_args(hrt_ctx* ctx, int64_t B, const float* src, unsigned flag
     a->B = B;
     a->src_gq = src;
     a->pre_transformed = (flags & HRT_BQ_PRE_TRANSFORMED) ? 1 : 0;
-    a->flags = (flags & HRT_BQ_CLAMP ? BQ_CLAMP : 0u) | (flags & HRT_BQ_IK ? BQ_IK : 0u) | (flags & HRT_BQ_PACKED_IK ? BQ_PACKED_IK : 0u);
+    a->flags = (flags & HRT_BQ_CLAMP ? BQ_CLAMP : 0u) | (flags & HRT_BQ_IK ? BQ_IK : 0u) | (flags & HRT_BQ_PACKED_IK ? BQ_PACKED_IK : 0u) |
+               (flags & HRT_BQ_ACTIVE_SET ? BQ_ACTIVE_SET : 0u);
     a->ik_iters = ik_iters;
     a->damping = damping;
     a->rot_weight = rot_weight;
@@ -711,6 +714,20 @@ int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const 
         }
         pp.orig_x = sum / 5.f;
     }
+    {
+        // robot-side arm tables for the limit-aware refinement: zero-pose positions p_j = off_j + p_parent
+        const TreeParams& rt = r->tp;
+        std::vector<float> pos(rt.J * 3, 0.f);
+        for (int j = 1; j < rt.J; ++j)
+            for (int k = 0; k < 3; ++k) pos[j * 3 + k] = rt.jr[j].off[k] + pos[rt.parent[j] * 3 + k];
+        for (int side = 0; side < 2; ++side) {
+            const int f = rob_first[side];
+            for (int c = 0; c < 9; ++c)
+                for (int k = 0; k < 3; ++k) pp.ik[side].off[c][k] = rt.jr[f + c].off[k];
+            for (int c = 0; c < 7; ++c) { pp.ik[side].lower[c] = rt.lim[f + c][0]; pp.ik[side].upper[c] = rt.lim[f + c][1]; }
+            for (int k = 0; k < 3; ++k) pp.ik[side].p_sh[k] = pos[f * 3 + k];
+        }
+    }
     ctx->pos_set[mode] = true;
     if (mode == POS_FULL_BODY_POS) {
         // the same solver reading the mocap wire layout (sim_full_body_teleop.py:109-112): body rows
@@ -744,8 +761,7 @@ static int launch_pos(hrt_ctx* ctx, int slot, const PosArgs& a, cudaStream_t st,
         if (!aligned16(p)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
     const PosParams& pp = ctx->pos[slot];
     const bool with_bq = mode == POS_FULL_BODY_POS && a.out_body_gq;
-    const int const_words = (2 * (int)sizeof(PosArm) / 4 + 8 + 3) / 4 * 4;
-    const size_t smem = ((size_t)const_words + (size_t)POS_WARPS * pos_tile_words(pp, a.out_local_q != nullptr, with_bq)) * sizeof(float);
+    const size_t smem = ((size_t)pos_const_words() + (size_t)POS_WARPS * pos_tile_words(pp, a.out_local_q != nullptr, with_bq)) * sizeof(float);
     const long long groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
     const long long ctas = (groups + POS_WARPS - 1) / POS_WARPS;
     const int grid = force_grid ? force_grid : (int)std::max(1LL, std::min(ctas, (long long)ctx->sm_count));
@@ -770,6 +786,21 @@ int hrt_retarget_full_body_pos(hrt_ctx* ctx, int64_t B, const float* d_body_t, c
     PosArgs a{};
     a.B = B; a.body_t = d_body_t; a.lhand_t = d_lhand_t; a.rhand_t = d_rhand_t;
     a.out_local_q = d_robot_local_q; a.out_dof = d_dof; a.out_body_gq = d_body_gq;
+    return launch_pos(ctx, POS_FULL_BODY_POS, a, (cudaStream_t)stream);
+}
+
+int hrt_retarget_full_body_pos_ex(hrt_ctx* ctx, int64_t B, const float* d_body_t, const float* d_lhand_t, const float* d_rhand_t,
+                                  unsigned flags, int ik_iters, float damping, float rot_weight, float* d_robot_local_q,
+                                  float* d_dof, float* d_body_gq, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (B > 0 && (!d_body_t || !d_lhand_t || !d_rhand_t)) return fail(HRT_E_INVALID_ARG, "null input");
+    if ((flags & HRT_POS_IK) && (ik_iters < 0 || ik_iters > 1000)) return fail(HRT_E_INVALID_ARG, "ik_iters out of range");
+    PosArgs a{};
+    a.B = B; a.body_t = d_body_t; a.lhand_t = d_lhand_t; a.rhand_t = d_rhand_t;
+    a.out_local_q = d_robot_local_q; a.out_dof = d_dof; a.out_body_gq = d_body_gq;
+    a.flags = (flags & HRT_POS_CLAMP ? POS_CLAMP : 0u) | (flags & HRT_POS_IK ? POS_IK : 0u);
+    a.ik_iters = ik_iters; a.damping = damping; a.rot_weight = rot_weight;
     return launch_pos(ctx, POS_FULL_BODY_POS, a, (cudaStream_t)stream);
 }
 
@@ -870,8 +901,7 @@ constexpr unsigned long long kServerIdleNs = 20ull * 1000 * 1000;     // the res
 
 size_t pos_smem_bytes(const PosParams& pp, const PosArgs& a) {
     const bool with_bq = pp.mode == POS_FULL_BODY_POS && a.out_body_gq;
-    const int const_words = (2 * (int)sizeof(PosArm) / 4 + 8 + 3) / 4 * 4;
-    return ((size_t)const_words + (size_t)POS_WARPS * pos_tile_words(pp, a.out_local_q != nullptr, with_bq)) * sizeof(float);
+    return ((size_t)pos_const_words() + (size_t)POS_WARPS * pos_tile_words(pp, a.out_local_q != nullptr, with_bq)) * sizeof(float);
 }
 
 int launch_pos_server(hrt_ctx* ctx) {

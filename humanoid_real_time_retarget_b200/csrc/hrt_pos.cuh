@@ -36,6 +36,16 @@ struct PosArm {
     float zwrist[5][3];            // zero-pose offsets paired with the 5 finger points
 };
 
+// robot-side tables of one arm for the limit-aware refinement (flags POS_CLAMP / POS_IK)
+struct ArmIkParams {
+    float off[9][3];               // robot offsets of the 7 arm hinges + 2 gripper links
+    float lower[7], upper[7];
+    float p_sh[3];                 // shoulder-pitch link position at the zero pose (root frame)
+};
+
+constexpr unsigned POS_CLAMP = 1u; // clamp the 7 arm hinge angles of each arm to the robot limits
+constexpr unsigned POS_IK = 2u;    // + damped-least-squares steps towards the pose of the UNCLAMPED closed form
+
 struct PosParams {
     int mode;
     int J_rob;                     // 31
@@ -51,7 +61,12 @@ struct PosParams {
     float orig_x;                  // mean zero-pose finger-tip x extent
     int precise_gripper;
     PosArm arm[2];
+    ArmIkParams ik[2];
 };
+// CTA-shared constants in shared memory: [2 x PosArm][8 zero-pose angles][2 x ArmIkParams]
+HRT_HD inline int pos_zero_ang_word() { return 2 * (int)sizeof(PosArm) / 4; }
+HRT_HD inline int pos_ik_word() { return (pos_zero_ang_word() + 8 + 3) / 4 * 4; }
+HRT_HD inline int pos_const_words() { return (pos_ik_word() + 2 * (int)sizeof(ArmIkParams) / 4 + 3) / 4 * 4; }
 
 struct PosArgs {
     long long B;
@@ -62,6 +77,9 @@ struct PosArgs {
     float* __restrict__ out_local_q;     // (B, 31, 4) or nullptr
     float* __restrict__ out_dof;         // (B, 30) or nullptr
     float* __restrict__ out_body_gq;     // (B, 59, 4) or nullptr (mode POS)
+    unsigned flags;                      // POS_CLAMP | POS_IK
+    int ik_iters;
+    float damping, rot_weight;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -302,9 +320,11 @@ HRT_DEV void pos_align(int warp) {
 // CTA-shared constants: both PosArm tables + the zero-pose bone angles (once per CTA)
 HRT_DEV void pos_setup(const PosParams& pp, float* smem) {
     PosArm* arms_s = reinterpret_cast<PosArm*>(smem);
-    float* zero_ang = smem + 2 * sizeof(PosArm) / 4;      // [side][4] = theta0_sh, phi0_sh, theta0_el, phi0_el
+    float* zero_ang = smem + pos_zero_ang_word();         // [side][4] = theta0_sh, phi0_sh, theta0_el, phi0_el
     const float* src = reinterpret_cast<const float*>(&pp.arm[0]);
     for (int i = threadIdx.x; i < 2 * (int)sizeof(PosArm) / 4; i += blockDim.x) smem[i] = src[i];
+    const float* iks = reinterpret_cast<const float*>(&pp.ik[0]);
+    for (int i = threadIdx.x; i < 2 * (int)sizeof(ArmIkParams) / 4; i += blockDim.x) smem[pos_ik_word() + i] = iks[i];
     __syncthreads();
     if (threadIdx.x < 2) {
         const PosArm& ar = arms_s[threadIdx.x];
@@ -327,9 +347,10 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
     constexpr bool HANDS = MODE == POS_FULL_BODY_POS || MODE == POS_FULL_BODY;
     constexpr bool QUATS = MODE == POS_FULL_BODY || MODE == POS_MAIN;
     const PosArm* arms_s = reinterpret_cast<const PosArm*>(smem);
-    const float* zero_ang = smem + 2 * sizeof(PosArm) / 4;
+    const float* zero_ang = smem + pos_zero_ang_word();
+    const ArmIkParams& ik = reinterpret_cast<const ArmIkParams*>(smem + pos_ik_word())[side];
     const PosArm& ap = arms_s[side];
-    const int const_words = (2 * (int)sizeof(PosArm) / 4 + 8 + 3) / 4 * 4;
+    const int const_words = pos_const_words();
     const bool with_lq = a.out_local_q != nullptr;
     const bool with_bq = (MODE == POS_FULL_BODY_POS) && a.out_body_gq != nullptr;
     float* tile = smem + const_words + warp * pos_tile_words(pp, with_lq, with_bq);
@@ -498,6 +519,31 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
                 th[7] = closed ? 0.f : 0.044f;
                 th[8] = closed ? 0.f : -0.044f;
             }
+        }
+        // ---- 5b. joint limits / limit-aware refinement (builder-specified) ----------
+        if (a.flags & (POS_CLAMP | POS_IK)) {
+            const vec3 p_sh = make_vec3(ik.p_sh[0], ik.p_sh[1], ik.p_sh[2]);
+            float thc[7];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) thc[c] = fminf(fmaxf(th[c], ik.lower[c]), ik.upper[c]);
+            if (a.flags & POS_IK) {
+                // targets: elbow / wrist positions and wrist orientation of the UNCLAMPED closed-form pose
+                vec3 ax[7], pc[7];
+                float4 G;
+                arm_chain_f(th, p_sh, ik.off, ax, pc, G);
+                const vec3 pe_t = pc[3], pw_t = pc[6];
+                const float4 Rh = quat_normalize_f(G);
+                const float lam2 = a.damping * a.damping;
+                for (int it = 0; it < a.ik_iters; ++it) {
+                    pos_align<SYSMEM>(warp);
+                    ik_step_f(thc, p_sh, ik.off, ik.lower, ik.upper, pe_t, pw_t, Rh, lam2, a.rot_weight, true);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 7; ++c) th[c] = thc[c];
+            rl[0] = arm_local_quat<0>(th[0]); rl[1] = arm_local_quat<1>(th[1]); rl[2] = arm_local_quat<2>(th[2]);
+            rl[3] = arm_local_quat<3>(th[3]); rl[4] = arm_local_quat<4>(th[4]); rl[5] = arm_local_quat<5>(th[5]);
+            rl[6] = arm_local_quat<6>(th[6]);
         }
         __syncwarp();                                  // every lane is done with the input rows
 

@@ -58,6 +58,7 @@ local_from_global_kernel(const float4* __restrict__ gq, const int* __restrict__ 
 constexpr unsigned BQ_CLAMP = 1u;     // clamp hinge angles to the robot limits
 constexpr unsigned BQ_IK = 2u;        // run the damped-least-squares refinement (implies clamp)
 constexpr unsigned BQ_PACKED_IK = 8u; // refinement on packed fp32x2 registers, two arms per thread (experimental)
+constexpr unsigned BQ_ACTIVE_SET = 16u; // freeze hinges that sit on a limit with the gradient pushing outwards
 
 constexpr int BQ_FRAMES_PER_WARP = 16;
 // One CTA per SM.  16 warps when only dof / link positions are published (the headline path),
@@ -140,6 +141,79 @@ HRT_DEV void chol_solve7(float* A, float* b) {
     }
 }
 
+// the 7-hinge arm chain at angles th: world axis and position of every hinge, final orientation G (not normalised)
+HRT_DEV void arm_chain_f(const float th[7], const vec3 p_sh, const float (*off)[3], vec3 ax[7], vec3 pc[7], float4& G) {
+    G = make_float4(0.f, 0.f, 0.f, 1.f);
+    vec3 p = p_sh;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        ax[c] = (HRT_ARM_AXIS(c) == 0) ? quat_axis_f<0>(G) : (HRT_ARM_AXIS(c) == 1) ? quat_axis_f<1>(G) : quat_axis_f<2>(G);
+        pc[c] = p;
+        float s, cs;
+        sincos_half_nf(0.5f * th[c], &s, &cs);
+        // products of unit quaternions: renormalising once, where G is used, is enough
+        G = quat_mul_axis_f(G, HRT_ARM_AXIS(c), s, cs);
+        if (c < 6) p = add3(p, quat_rotate_f(G, make_vec3(off[c + 1][0], off[c + 1][1], off[c + 1][2])));
+    }
+}
+
+// one damped-least-squares step: e = [pe* - p_elbow; pw* - p_wrist; w_o rotvec(qw* qw^-1)],
+// dtheta = (J^T J + lambda^2 I)^-1 J^T e (7x7 Cholesky in registers), theta <- clamp(theta + dtheta).
+// active_set: a hinge that sits on a limit while the gradient J^T e pushes it further out is frozen for this
+// step (its row / column leave the system), which makes the clamped iteration a descent method.
+HRT_DEV void ik_step_f(float th[7], const vec3 p_sh, const float (*off)[3], const float* lower, const float* upper,
+                       const vec3 pe_t, const vec3 pw_t, const float4 Rh, const float lam2, const float wo, const bool active_set) {
+    vec3 ax[7], pc[7];
+    float4 G;
+    arm_chain_f(th, p_sh, off, ax, pc, G);
+    float e[9];
+    e[0] = pe_t.x - pc[3].x; e[1] = pe_t.y - pc[3].y; e[2] = pe_t.z - pc[3].z;
+    e[3] = pw_t.x - pc[6].x; e[4] = pw_t.y - pc[6].y; e[5] = pw_t.z - pc[6].z;
+    {
+        const float4 qe = quat_normalize_f(quat_mul_f(Rh, quat_conj(G)));
+        const float n = sqrtf(qe.x * qe.x + qe.y * qe.y + qe.z * qe.z);
+        const float sc = wo * rotvec_scale_f(n, qe.w);
+        e[6] = qe.x * sc; e[7] = qe.y * sc; e[8] = qe.z * sc;
+    }
+    vec3 je[3], jw[6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) je[c] = cross3_f(ax[c], sub3(pc[3], pc[c]));
+#pragma unroll
+    for (int c = 0; c < 6; ++c) jw[c] = cross3_f(ax[c], sub3(pc[6], pc[c]));
+    float A[28], g[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        float gi = wo * (ax[i].x * e[6] + ax[i].y * e[7] + ax[i].z * e[8]);
+        if (i < 6) gi += jw[i].x * e[3] + jw[i].y * e[4] + jw[i].z * e[5];
+        if (i < 3) gi += je[i].x * e[0] + je[i].y * e[1] + je[i].z * e[2];
+        g[i] = gi;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            float s = wo * wo * dot3_f(ax[i], ax[j]);
+            if (i < 6) s += dot3_f(jw[i], jw[j]);
+            if (i < 3) s += dot3_f(je[i], je[j]);
+            if (i == j) s += lam2;
+            A[i * (i + 1) / 2 + j] = s;
+        }
+    }
+    if (active_set) {
+        float m[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const bool blocked = (th[i] >= upper[i] && g[i] > 0.f) || (th[i] <= lower[i] && g[i] < 0.f);
+            m[i] = blocked ? 0.f : 1.f;
+            g[i] *= m[i];
+        }
+#pragma unroll
+        for (int i = 1; i < 7; ++i)
+#pragma unroll
+            for (int j = 0; j < i; ++j) A[i * (i + 1) / 2 + j] *= m[i] * m[j];
+    }
+    chol_solve7(A, g);
+#pragma unroll
+    for (int c = 0; c < 7; ++c) th[c] = fminf(fmaxf(th[c] + g[c], lower[c]), upper[c]);
+}
+
 // Warps that share a scheduler (warp % 4) re-align at the top of every IK iteration with a named
 // barrier: the unrolled iteration body is ~16 KB of SASS, far more than an SMSP's L0 instruction
 // cache, and ncu showed "no instruction" as the top stall (2.4 warps per issue) when the warps
@@ -147,6 +221,7 @@ HRT_DEV void chol_solve7(float* A, float* b) {
 #ifndef HRT_BQ_ALIGN
 #define HRT_BQ_ALIGN 1
 #endif
+
 template <int WARPS>
 HRT_DEV void smsp_align(int warp) {
 #if HRT_BQ_ALIGN
@@ -282,55 +357,7 @@ body_quat_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a
             const float wo = a.rot_weight;
             for (int it = 0; it < a.ik_iters; ++it) {
                 smsp_align<BQ_WARPS_PER_CTA>(warp);
-                vec3 ax[7], pc[7];
-                float4 G = make_float4(0.f, 0.f, 0.f, 1.f);
-                vec3 p = p_sh;
-#pragma unroll
-                for (int c = 0; c < 7; ++c) {
-                    constexpr int dummy = 0; (void)dummy;
-                    ax[c] = (HRT_ARM_AXIS(c) == 0) ? quat_axis_f<0>(G) : (HRT_ARM_AXIS(c) == 1) ? quat_axis_f<1>(G) : quat_axis_f<2>(G);
-                    pc[c] = p;
-                    float s, cs;
-                    sincos_half_nf(0.5f * th[c], &s, &cs);
-                    // products of unit quaternions: renormalising once, below, is enough inside the loop
-                    G = quat_mul_axis_f(G, HRT_ARM_AXIS(c), s, cs);
-                    if (c < 6) p = add3(p, quat_rotate_f(G, make_vec3(ap.off[c + 1][0], ap.off[c + 1][1], ap.off[c + 1][2])));
-                }
-                // residual
-                float e[9];
-                e[0] = pe_t.x - pc[3].x; e[1] = pe_t.y - pc[3].y; e[2] = pe_t.z - pc[3].z;
-                e[3] = pw_t.x - pc[6].x; e[4] = pw_t.y - pc[6].y; e[5] = pw_t.z - pc[6].z;
-                {
-                    const float4 qe = quat_normalize_f(quat_mul_f(Rh, quat_conj(G)));
-                    const float n = sqrtf(qe.x * qe.x + qe.y * qe.y + qe.z * qe.z);
-                    const float sc = wo * rotvec_scale_f(n, qe.w);
-                    e[6] = qe.x * sc; e[7] = qe.y * sc; e[8] = qe.z * sc;
-                }
-                // Jacobian blocks
-                vec3 je[3], jw[6];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) je[c] = cross3_f(ax[c], sub3(pc[3], pc[c]));
-#pragma unroll
-                for (int c = 0; c < 6; ++c) jw[c] = cross3_f(ax[c], sub3(pc[6], pc[c]));
-                float A[28], g[7];
-#pragma unroll
-                for (int i = 0; i < 7; ++i) {
-                    float gi = wo * (ax[i].x * e[6] + ax[i].y * e[7] + ax[i].z * e[8]);
-                    if (i < 6) gi += jw[i].x * e[3] + jw[i].y * e[4] + jw[i].z * e[5];
-                    if (i < 3) gi += je[i].x * e[0] + je[i].y * e[1] + je[i].z * e[2];
-                    g[i] = gi;
-#pragma unroll
-                    for (int j = 0; j <= i; ++j) {
-                        float s = wo * wo * dot3_f(ax[i], ax[j]);
-                        if (i < 6) s += dot3_f(jw[i], jw[j]);
-                        if (i < 3) s += dot3_f(je[i], je[j]);
-                        if (i == j) s += lam2;
-                        A[i * (i + 1) / 2 + j] = s;
-                    }
-                }
-                chol_solve7(A, g);
-#pragma unroll
-                for (int c = 0; c < 7; ++c) th[c] = fminf(fmaxf(th[c] + g[c], ap.lower[c]), ap.upper[c]);
+                ik_step_f(th, p_sh, ap.off, ap.lower, ap.upper, pe_t, pw_t, Rh, lam2, wo, (a.flags & BQ_ACTIVE_SET) != 0);
             }
         }
         if (do_clamp) {

@@ -10,8 +10,9 @@ from . import robot_config as cfg
 
 TREE_ROBOT, TREE_SOURCE, TREE_SOURCE_FULL = 0, 1, 2
 FK_EXACT = 1
-BQ_CLAMP, BQ_IK, BQ_PRE_TRANSFORMED, BQ_PACKED_IK = 1, 2, 4, 8
+BQ_CLAMP, BQ_IK, BQ_PRE_TRANSFORMED, BQ_PACKED_IK, BQ_ACTIVE_SET = 1, 2, 4, 8, 16
 POS_FULL_BODY_POS, POS_UPPER_BODY, POS_FULL_BODY, POS_MAIN = 0, 1, 2, 3
+POS_CLAMP, POS_IK = 1, 2
 
 
 def _ptr(t):
@@ -186,14 +187,20 @@ class Engine:
         bq = torch.empty((B, 59, 4), device=self.device, dtype=torch.float32) if want_body_gq else None
         return lq, dof, bq
 
-    def retarget_full_body_pos(self, body_t, lhand_t, rhand_t, want_local_q=True, want_dof=True, want_body_gq=True, out=None):
-        """VtrdynFullBodyPosRetargeter.retarget on (B,21,3), (B,20,3), (B,20,3) device tensors."""
+    def retarget_full_body_pos(self, body_t, lhand_t, rhand_t, want_local_q=True, want_dof=True, want_body_gq=True, out=None,
+                               flags=0, ik_iters=10, damping=0.1, rot_weight=0.2):
+        """VtrdynFullBodyPosRetargeter.retarget on (B,21,3), (B,20,3), (B,20,3) device tensors.  flags: POS_CLAMP |
+        POS_IK add the joint limits / the fused limit-aware refinement (ours)."""
         body_t, lhand_t, rhand_t = (_f32c(x, self.device) for x in (body_t, lhand_t, rhand_t))
         B = body_t.numel() // 63
         assert lhand_t.numel() == B * 60 and rhand_t.numel() == B * 60
         lq, dof, bq = out if out is not None else self._pos_outputs(B, want_local_q, want_dof, want_body_gq)
-        _lib.check(self.lib.hrt_retarget_full_body_pos(self._h, B, _ptr(body_t), _ptr(lhand_t), _ptr(rhand_t),
-                                                       _ptr(lq), _ptr(dof), _ptr(bq), self._stream()))
+        if flags:
+            _lib.check(self.lib.hrt_retarget_full_body_pos_ex(self._h, B, _ptr(body_t), _ptr(lhand_t), _ptr(rhand_t), flags, ik_iters,
+                                                              damping, rot_weight, _ptr(lq), _ptr(dof), _ptr(bq), self._stream()))
+        else:
+            _lib.check(self.lib.hrt_retarget_full_body_pos(self._h, B, _ptr(body_t), _ptr(lhand_t), _ptr(rhand_t),
+                                                           _ptr(lq), _ptr(dof), _ptr(bq), self._stream()))
         return lq, dof, bq
 
     def retarget_upper_body(self, body_t, want_local_q=True, want_dof=True):

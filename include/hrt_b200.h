@@ -51,6 +51,7 @@ extern "C" {
 #define HRT_BQ_CLAMP 1u       /* clamp hinge angles to the joint limits */
 #define HRT_BQ_IK 2u          /* fused damped-least-squares refinement (implies clamp) */
 #define HRT_BQ_PRE_TRANSFORMED 4u /* input already zero-pose re-referenced: skip the a24 step */
+#define HRT_BQ_ACTIVE_SET 16u /* refinement: freeze hinges sitting on a limit while the gradient pushes outwards (always on in the position path) */
 #define HRT_BQ_PACKED_IK 8u   /* experimental: refinement on packed fp32x2 (FFMA2), two arms per thread; dof / link-position outputs only */
 
 typedef struct hrt_ctx hrt_ctx;
@@ -141,6 +142,17 @@ int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const 
 int hrt_retarget_full_body_pos(hrt_ctx* ctx, int64_t B, const float* d_body_t, const float* d_lhand_t,
                                const float* d_rhand_t, float* d_robot_local_q, float* d_dof, float* d_body_gq,
                                void* stream);
+
+/* The same with joint limits and the fused limit-aware refinement (builder-specified, no reference counterpart:
+ * DESIGN.md section 5).  HRT_POS_CLAMP: the 7 hinge angles of each arm are clamped to the robot limits.
+ * HRT_POS_IK (implies clamp): ik_iters damped-least-squares steps pull the clamped arm towards the elbow / wrist
+ * positions and wrist orientation of the UNCLAMPED closed-form pose (a frame inside the limits is a fixed point). */
+#define HRT_POS_CLAMP 1u
+#define HRT_POS_IK 2u
+int hrt_retarget_full_body_pos_ex(hrt_ctx* ctx, int64_t B, const float* d_body_t, const float* d_lhand_t,
+                                  const float* d_rhand_t, unsigned flags, int ik_iters, float damping,
+                                  float rot_weight, float* d_robot_local_q, float* d_dof, float* d_body_gq,
+                                  void* stream);
 
 /* HuUpperBodyFromMocapRetarget.retarget_from_global_translation: d_body_t (B,21,3), flipped by
  * coord_transform(dir=[-1,-1,1]) inside (retarget_solver.py:41) -> d_robot_local_q (B,31,4), d_dof (B,30). */

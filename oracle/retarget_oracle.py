@@ -620,12 +620,13 @@ def geometric_jacobian(angles, root_t, root_q, parents, offsets, dof_axis, lower
 ARM_AXIS = [1, 0, 2, 1, 0, 1, 2]          # Hu_DOF_AXIS[11:18] == Hu_DOF_AXIS[20:27]
 
 
-def ik_refine_arm(theta0, p_sh, offs, lower, upper, pe_t, pw_t, qw_t, iters, damping, rot_weight):
+def ik_refine_arm(theta0, p_sh, offs, lower, upper, pe_t, pw_t, qw_t, iters, damping, rot_weight, active_set=False):
     """DESIGN.md section 5.  theta0 (B,7) warm start (already clamped); offs (9,3) offsets of the 7 arm
     hinges + 2 gripper links; targets in the robot root frame.  Each step:
       FK of the 7-hinge chain; e = [pe* - p_elbow; pw* - p_wrist; w_o * rotvec(qw* qw^-1)];
       dtheta = (J^T J + lambda^2 I)^-1 J^T e;  theta <- clamp(theta + dtheta, lower, upper).
-    Exactly `iters` steps, no early exit."""
+    Exactly `iters` steps, no early exit.  active_set: a hinge sitting on a limit while its gradient component
+    (J^T e)_i pushes further out is frozen for that step (row / column removed from the system)."""
     B = theta0.shape[0]
     th = theta0.clone()
     eye = torch.eye(3)
@@ -652,15 +653,59 @@ def ik_refine_arm(theta0, p_sh, offs, lower, upper, pe_t, pw_t, qw_t, iters, dam
             if c < 6:
                 Jm[:, 3:6, c] = torch.cross(ax[c], pc[6] - pc[c], dim=-1)
             Jm[:, 6:9, c] = rot_weight * ax[c]
-        A = Jm.transpose(1, 2) @ Jm + (damping * damping) * torch.eye(7)
         g = (Jm.transpose(1, 2) @ e.unsqueeze(-1))
+        if active_set:
+            blocked = ((th >= hi) & (g.squeeze(-1) > 0)) | ((th <= lo) & (g.squeeze(-1) < 0))
+            m = (~blocked).float()
+            Jm = Jm * m.unsqueeze(1)
+            g = g * m.unsqueeze(-1)
+        A = Jm.transpose(1, 2) @ Jm + (damping * damping) * torch.eye(7)
         L = torch.linalg.cholesky(A)
         d = torch.cholesky_solve(g, L).squeeze(-1)
         th = torch.minimum(torch.maximum(th + d, lo), hi)
     return th
 
 
-def body_quat_pipeline(raw_gq, sk, clamp=True, ik_iters=10, damping=0.1, rot_weight=0.2, pre_transformed=False):
+def arm_chain(th, p_sh, offs):
+    """FK of the 7-hinge arm chain at angles th (B,7): hinge positions pc[0..6] and the final orientation."""
+    B = th.shape[0]
+    G = quat_identity((B,))
+    p = p_sh.expand(B, 3)
+    pc = []
+    for c in range(7):
+        pc.append(p)
+        G = quat_normalize(quat_mul(G, _axis_quat(th[:, c], ARM_AXIS[c])))
+        if c < 6:
+            p = p + quat_rotate(G, offs[c + 1].expand(B, 3))
+    return pc, G
+
+
+def refine_pos_dof(dof, sk, clamp=True, ik_iters=10, damping=0.1, rot_weight=0.2):
+    """Limit-aware refinement of the position path (builder-specified; no reference
+    counterpart): per arm, the 7 closed-form hinge angles are clamped to the Hu v5 limits and, with ik_iters > 0,
+    pulled by damped-least-squares steps towards the elbow / wrist positions and wrist orientation of the
+    UNCLAMPED closed-form pose (active-set steps).  dof (B,30) from retarget_full_body_pos; returns the refined copy."""
+    T = torch.from_numpy
+    rob_par = sk["hu_v5_zero_pose/parents"].tolist()
+    rob_off = T(sk["hu_v5_zero_pose/offsets"])
+    pos = torch.zeros(31, 3)
+    for j in range(1, 31):
+        pos[j] = rob_off[j] + pos[rob_par[j]]
+    out = dof.clone()
+    lo, hi = torch.tensor(HU_V5_DOF_LOWER), torch.tensor(HU_V5_DOF_UPPER)
+    for first in (12, 21):
+        d0 = first - 1
+        th_u = dof[:, d0:d0 + 7]
+        th = torch.minimum(torch.maximum(th_u, lo[d0:d0 + 7]), hi[d0:d0 + 7]) if (clamp or ik_iters > 0) else th_u
+        if ik_iters > 0:
+            pc, G = arm_chain(th_u, pos[first], rob_off[first:first + 9])
+            th = ik_refine_arm(th, pos[first], rob_off[first:first + 9], HU_V5_DOF_LOWER[d0:d0 + 7], HU_V5_DOF_UPPER[d0:d0 + 7],
+                               pc[3], pc[6], G, ik_iters, damping, rot_weight, active_set=True)
+        out[:, d0:d0 + 7] = th
+    return out
+
+
+def body_quat_pipeline(raw_gq, sk, clamp=True, ik_iters=10, damping=0.1, rot_weight=0.2, pre_transformed=False, active_set=False):
     """The fused config-3q pipeline: a24 -> a21 -> a30 (+a16, a17) -> [limits -> IK] -> FK.
     Returns robot_local_q (B,31,4), dof (B,30), link_pos (B,31,3).  With clamp=False, ik_iters=0 the
     first two are exactly the reference's retarget_from_pose outputs."""
@@ -692,7 +737,7 @@ def body_quat_pipeline(raw_gq, sk, clamp=True, ik_iters=10, damping=0.1, rot_wei
                 pe_t = p_sh + quat_rotate(Ru, (pos[first + 3] - pos[first]).expand(B, 3))
                 pw_t = pe_t + quat_rotate(Rf, (pos[first + 6] - pos[first + 3]).expand(B, 3))
                 th = ik_refine_arm(th, p_sh, rob_off[first:first + 9], HU_V5_DOF_LOWER[d0:d0 + 7],
-                                   HU_V5_DOF_UPPER[d0:d0 + 7], pe_t, pw_t, Rh, ik_iters, damping, rot_weight)
+                                   HU_V5_DOF_UPPER[d0:d0 + 7], pe_t, pw_t, Rh, ik_iters, damping, rot_weight, active_set)
             dof[:, d0:d0 + 7] = th
             for c in range(7):
                 rl[:, first + c] = _axis_quat(th[:, c], ARM_AXIS[c])

@@ -183,6 +183,25 @@ def test_body_quat_with_clamp_and_ik_vs_oracle(hrt, eng, oc, skeletons):
     assert float(r1.mean()) < 0.7 * float(r0.mean())
 
 
+def test_body_quat_active_set_refinement(hrt, eng, oc, skeletons):
+    """HRT_BQ_ACTIVE_SET: same refinement with blocked hinges frozen; kernel vs oracle, and it must be a descent
+    method (the IK objective never increases, and ends lower than without the active set)."""
+    B = 8192
+    raw = oc.synth_clip_3q(B, seed=23, sk=skeletons)
+    flags = hrt.BQ_CLAMP | hrt.BQ_IK
+    _, dof_a, lp_a = eng.retarget_body_quat(raw, flags=flags | hrt.BQ_ACTIVE_SET, ik_iters=10)
+    _, dof_o, lp_o = oc.body_quat_pipeline(raw, skeletons, clamp=True, ik_iters=10, active_set=True)
+    err = (dof_a.cpu() - dof_o).abs().max(dim=-1).values
+    print(f"active-set IK parity: {float((err <= ANGLE_TOL).float().mean()):.4f} within 1e-5; p99.9 {float(np.quantile(err.numpy(), 0.999)):.2e} max {float(err.max()):.2e}")
+    assert float((err <= ANGLE_TOL).float().mean()) >= 0.95 and float(np.quantile(err.numpy(), 0.99)) <= 1e-4
+    zq = oc.zero_pose_transform(raw, T(skeletons["t2z/vtrdyn"]))
+    _, dof_c, _ = eng.retarget_body_quat(raw, flags=hrt.BQ_CLAMP)
+    _, dof_p, _ = eng.retarget_body_quat(raw, flags=flags, ik_iters=10)
+    r_c, r_p, r_a = (oc.ik_residual(d.cpu(), zq, skeletons) for d in (dof_c, dof_p, dof_a))
+    assert float((r_a > r_c + 1e-5).float().mean()) <= 0.001
+    assert float(r_a.mean()) < float(r_p.mean()) < float(r_c.mean())
+
+
 def test_packed_ik_variant_matches_scalar(hrt, eng, oc, skeletons):
     """The FFMA2 (two arms per thread) refinement is the same algorithm with a different rounding sequence:
     it must agree with the default kernel like the default kernel agrees with the oracle, on ragged sizes too."""
@@ -434,6 +453,47 @@ def test_full_body_pos_vs_oracle_large(hrt, eng, oc, skeletons):
     perr = (gt_k[:, arm] - gt_o[:, arm]).norm(dim=-1).amax(dim=-1).cpu()
     print(f"FK link-position error of kernel angles vs oracle angles: p99 {float(np.quantile(perr[ok].numpy(), 0.99)):.2e} max {float(perr[ok].max()):.2e}")
     assert float(np.quantile(perr[ok].numpy(), 0.99)) <= 5e-5
+
+
+def test_full_body_pos_limits_and_refinement_vs_oracle(hrt, eng, oc, skeletons, golden):
+    """Position path + joint limits + fused limit-aware refinement (builder-specified: kernel vs own oracle, the
+    refinement applied by the oracle to the KERNEL's closed-form angles so that only the refinement is compared)."""
+    g = golden("full_body_pos")
+    body, lh, rh = T(g["body_t"]), T(g["lhand_t"]), T(g["rhand_t"])
+    lq0, dof0, _ = eng.retarget_full_body_pos(body, lh, rh)
+    dof0 = dof0.cpu()
+    # clamp only
+    lq1, dof1, _ = eng.retarget_full_body_pos(body, lh, rh, flags=hrt.POS_CLAMP)
+    ref1 = oc.refine_pos_dof(dof0, skeletons, clamp=True, ik_iters=0)
+    assert torch.equal(dof1.cpu(), ref1)
+    arm = list(range(11, 18)) + list(range(20, 27))
+    lo5, hi5 = torch.tensor(oc.HU_V5_DOF_LOWER), torch.tensor(oc.HU_V5_DOF_UPPER)
+    assert bool(((dof1.cpu()[:, arm] >= lo5[arm]) & (dof1.cpu()[:, arm] <= hi5[arm])).all())
+    assert torch.equal(dof1.cpu()[:, [18, 19, 27, 28]], dof0[:, [18, 19, 27, 28]])            # gripper DOFs untouched
+    # clamp + 10 refinement steps
+    lq2, dof2, _ = eng.retarget_full_body_pos(body, lh, rh, flags=hrt.POS_CLAMP | hrt.POS_IK, ik_iters=10)
+    ref2 = oc.refine_pos_dof(dof0, skeletons, clamp=True, ik_iters=10)
+    err = (dof2.cpu() - ref2).abs().max(dim=-1).values
+    print(f"pos refinement vs oracle: within 1e-5 {float((err <= ANGLE_TOL).float().mean()):.4f}; p99 {float(np.quantile(err.numpy(), 0.99)):.2e} max {float(err.max()):.2e}")
+    assert float((err <= ANGLE_TOL).float().mean()) >= 0.97 and float(err.max()) <= 1e-3
+    assert bool(((dof2.cpu()[:, arm] >= lo5[arm]) & (dof2.cpu()[:, arm] <= hi5[arm])).all())
+    # a frame whose closed form is inside the limits is a fixed point of the refinement
+    inside = ((dof0[:, arm] >= lo5[arm]) & (dof0[:, arm] <= hi5[arm])).all(dim=-1)
+    if bool(inside.any()):
+        assert float((dof2.cpu()[inside] - dof0[inside]).abs().max()) <= 2e-6
+    # where limits bite, the refinement brings the wrist closer to the unclamped pose than clamping alone
+    _, gt_u = eng.fk_angles(hrt.TREE_ROBOT, dof0, clip=False)
+    _, gt_c = eng.fk_angles(hrt.TREE_ROBOT, dof1, clip=False)
+    _, gt_r = eng.fk_angles(hrt.TREE_ROBOT, dof2, clip=False)
+    wr = [18, 27]
+    d_c = (gt_c[:, wr] - gt_u[:, wr]).norm(dim=-1).sum(-1)
+    d_r = (gt_r[:, wr] - gt_u[:, wr]).norm(dim=-1).sum(-1)
+    bite = ~inside.cuda()
+    assert bool(bite.any()) and float(d_r[bite].mean()) < 0.9 * float(d_c[bite].mean())
+    # published local rotations are those of the refined angles
+    ax = torch.eye(3)[oc.HU_V5_DOF_AXIS]
+    q = oc.quat_from_angle_axis(dof2.cpu()[:, 11:18].reshape(-1), ax[11:18].repeat(dof2.shape[0], 1))
+    assert maxdiff(lq2[:, 12:19].reshape(-1, 4), q) <= 2e-6
 
 
 def test_upper_body_and_full_body_vs_reference_golden(hrt, eng, golden):
