@@ -78,6 +78,11 @@ struct hrt_ctx {
     float *mb_in_d = nullptr, *mb_out_d = nullptr;
     cudaStream_t ss = nullptr;
     BodyQuatArgs stream_args;
+    bool stream_persistent = false;    // resident server kernel for the quaternion path
+    bool bserver_launched = false;
+    unsigned bseq = 0;
+    volatile unsigned* bctrl = nullptr;
+    unsigned* bctrl_d = nullptr;
     // position-path streaming
     bool pstream_open = false;
     int pstream_mode = 0;
@@ -97,6 +102,46 @@ int check_ctx(hrt_ctx* ctx) {
     if (!ctx) return fail(HRT_E_INVALID_ARG, "null context");
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return fail((int)e, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+    return 0;
+}
+
+constexpr unsigned long long kServerIdleNs = 20ull * 1000 * 1000;     // a resident kernel leaves after 20 ms without a frame
+
+// Post one request to a resident server kernel and spin on its answer.  ctrl words (mapped pinned memory):
+// [0] seq_in, [1] stop (host writes) / [16] seq_out, [17] exited (device writes).  `launch(served)` (re)starts the
+// kernel with the last sequence number it must consider served.
+template <typename Launch>
+int server_roundtrip(volatile unsigned* ctrl, unsigned* seq_io, bool* launched, cudaStream_t st, Launch&& launch) {
+    if (!*launched || ctrl[17] != 0u) {
+        ctrl[17] = 0u;
+        std::atomic_thread_fence(std::memory_order_seq_cst);
+        int rc = launch(*seq_io);
+        if (rc) return rc;
+        *launched = true;
+    }
+    unsigned seq = *seq_io + 1u;
+    if (seq == 0u) seq = 1u;
+    std::atomic_thread_fence(std::memory_order_seq_cst);      // inputs first, then the sequence number (x86 keeps store order)
+    ctrl[0] = seq;
+    *seq_io = seq;
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (ctrl[16] != seq) {
+        if (ctrl[17] != 0u) {                                  // the server timed out just before this request was posted
+            ctrl[17] = 0u;
+            std::atomic_thread_fence(std::memory_order_seq_cst);
+            int rc = launch(seq - 1u);                         // it will see `seq` as new
+            if (rc) return rc;
+        }
+        if ((++spins & 0xfffu) == 0u) {
+            cudaError_t e = cudaStreamQuery(st);
+            if (e != cudaSuccess && e != cudaErrorNotReady)
+                return fail((int)e, "stream server failed: %s", cudaGetErrorString(e));
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2))
+                return fail(HRT_E_INVALID_ARG, "stream server did not answer within 2 s");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_seq_cst);
     return 0;
 }
 
@@ -831,6 +876,7 @@ int hrt_stream_open(hrt_ctx* ctx, unsigned flags, int ik_iters, float damping, f
     BodyQuatArgs a;
     if ((rc = fill_body_quat_args(ctx, 1, nullptr, flags, ik_iters, damping, rot_weight, nullptr, nullptr, nullptr, &a)))
         return rc;
+    a.flags &= ~BQ_PACKED_IK;
     const int JS = ctx->bq.J_src, JR = ctx->bq.J_rob;
     const size_t in_w = (size_t)JS * 4;
     const size_t out_w = (size_t)JR * 4 + 32 + (size_t)JR * 3 + 3;   // local_q | dof (padded to 32) | link pos
@@ -844,6 +890,17 @@ int hrt_stream_open(hrt_ctx* ctx, unsigned flags, int ik_iters, float damping, f
     a.out_dof = ctx->mb_out_d + JR * 4;
     a.out_link_pos = ctx->mb_out_d + JR * 4 + 32;
     ctx->stream_args = a;
+    ctx->stream_persistent = (flags & HRT_BQ_PERSISTENT) != 0;
+    ctx->bserver_launched = false;
+    ctx->bseq = 0;
+    if (ctx->stream_persistent) {
+        unsigned* c = nullptr;
+        HRT_CUDA(cudaHostAlloc(&c, 32 * sizeof(unsigned), cudaHostAllocMapped));
+        memset(c, 0, 32 * sizeof(unsigned));
+        ctx->bctrl = c;
+        HRT_CUDA(cudaHostGetDevicePointer(&ctx->bctrl_d, c, 0));
+        HRT_CUDA(cudaFuncSetAttribute(bq_stream_server_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    }
     ctx->stream_open = true;
     return 0;
 }
@@ -854,11 +911,19 @@ int hrt_stream_frame(hrt_ctx* ctx, const float* h_src_gq, float* h_robot_local_q
     if (!h_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
     const int JS = ctx->bq.J_src, JR = ctx->bq.J_rob;
     memcpy(ctx->mb_in, h_src_gq, (size_t)JS * 16);
-    {
+    if (!ctx->stream_persistent) {
         int rc = launch_body_quat(ctx, ctx->stream_args, ctx->ss, 1);
         if (rc) return rc;
+        HRT_CUDA(cudaStreamSynchronize(ctx->ss));
+    } else {
+        const size_t smem = ((size_t)BQ_CONST_WORDS + bq_tile_words(JS, JR, true)) * sizeof(float);
+        int rc = server_roundtrip(ctx->bctrl, &ctx->bseq, &ctx->bserver_launched, ctx->ss, [&](unsigned served) {
+            bq_stream_server_kernel<<<1, 32, smem, ctx->ss>>>(ctx->bq, ctx->stream_args, ctx->bctrl_d, served, kServerIdleNs);
+            HRT_CUDA(cudaGetLastError());
+            return 0;
+        });
+        if (rc) return rc;
     }
-    HRT_CUDA(cudaStreamSynchronize(ctx->ss));
     if (h_robot_local_q) memcpy(h_robot_local_q, ctx->mb_out, (size_t)JR * 16);
     if (h_dof) memcpy(h_dof, ctx->mb_out + JR * 4, (size_t)(JR - 1) * 4);
     if (h_link_pos) memcpy(h_link_pos, ctx->mb_out + JR * 4 + 32, (size_t)JR * 12);
@@ -868,10 +933,13 @@ int hrt_stream_frame(hrt_ctx* ctx, const float* h_src_gq, float* h_robot_local_q
 int hrt_stream_close(hrt_ctx* ctx) {
     if (!ctx || !ctx->stream_open) return 0;
     cudaSetDevice(ctx->device);
+    if (ctx->bctrl) ctx->bctrl[1] = 1u;               // tell a resident server to leave
     if (ctx->ss) { cudaStreamSynchronize(ctx->ss); cudaStreamDestroy(ctx->ss); ctx->ss = nullptr; }
     if (ctx->mb_in) { cudaFreeHost(ctx->mb_in); ctx->mb_in = nullptr; }
     if (ctx->mb_out) { cudaFreeHost(ctx->mb_out); ctx->mb_out = nullptr; }
+    if (ctx->bctrl) { cudaFreeHost(const_cast<unsigned*>(ctx->bctrl)); ctx->bctrl = nullptr; ctx->bctrl_d = nullptr; }
     ctx->stream_open = false;
+    ctx->bserver_launched = false;
     return 0;
 }
 
@@ -897,21 +965,17 @@ int hrt_retarget_main_arms(hrt_ctx* ctx, int64_t B, const float* d_body_q, const
 }
 
 namespace {
-constexpr unsigned long long kServerIdleNs = 20ull * 1000 * 1000;     // the resident kernel leaves after 20 ms without a frame
 
 size_t pos_smem_bytes(const PosParams& pp, const PosArgs& a) {
     const bool with_bq = pp.mode == POS_FULL_BODY_POS && a.out_body_gq;
     return ((size_t)pos_const_words() + (size_t)POS_WARPS * pos_tile_words(pp, a.out_local_q != nullptr, with_bq)) * sizeof(float);
 }
 
-int launch_pos_server(hrt_ctx* ctx) {
+int launch_pos_server(hrt_ctx* ctx, unsigned served) {
     const PosParams& pp = ctx->pos[ctx->pstream_mode];
-    ctx->pctrl[17] = 0u;
-    std::atomic_thread_fence(std::memory_order_seq_cst);
     pos_stream_server_kernel<POS_FULL_BODY_POS><<<1, 32, pos_smem_bytes(pp, ctx->pstream_args), ctx->pss>>>(
-        pp, ctx->pstream_args, ctx->pctrl_d, ctx->pseq, kServerIdleNs);
+        pp, ctx->pstream_args, ctx->pctrl_d, served, kServerIdleNs);
     HRT_CUDA(cudaGetLastError());
-    ctx->pserver_launched = true;
     return 0;
 }
 }  // namespace
@@ -937,6 +1001,8 @@ int hrt_stream_pos_open(hrt_ctx* ctx, int flags) {
     a.rhand_t = a.lhand_t + pp.n_hand * 3;
     a.out_local_q = ctx->pmb_out_d;
     a.out_dof = ctx->pmb_out_d + pp.J_rob * 4;
+    a.flags = ((flags & HRT_STREAM_CLAMP) ? POS_CLAMP : 0u) | ((flags & HRT_STREAM_IK) ? (POS_CLAMP | POS_IK) : 0u);
+    a.ik_iters = 10; a.damping = 0.1f; a.rot_weight = 0.2f;
     ctx->pstream_args = a;
     ctx->pstream_mode = slot;
     ctx->pstream_persistent = (flags & HRT_STREAM_PERSISTENT) != 0;
@@ -968,34 +1034,9 @@ int hrt_stream_pos_frame(hrt_ctx* ctx, const float* h_body_t, const float* h_lha
         if (rc) return rc;
         HRT_CUDA(cudaStreamSynchronize(ctx->pss));
     } else {
-        // post the frame: inputs first, then the sequence number (x86 keeps store order; the fence stops the compiler)
-        if (!ctx->pserver_launched || ctx->pctrl[17] != 0u) {
-            int rc = launch_pos_server(ctx);
-            if (rc) return rc;
-        }
-        unsigned seq = ctx->pseq + 1u;
-        if (seq == 0u) seq = 1u;
-        std::atomic_thread_fence(std::memory_order_seq_cst);
-        ctx->pctrl[0] = seq;
-        ctx->pseq = seq;
-        const auto t0 = std::chrono::steady_clock::now();
-        unsigned spins = 0;
-        while (ctx->pctrl[16] != seq) {
-            if (ctx->pctrl[17] != 0u) {               // the server timed out just before this frame was posted
-                ctx->pseq = seq - 1u;                 // it will see `seq` as new
-                int rc = launch_pos_server(ctx);
-                ctx->pseq = seq;
-                if (rc) return rc;
-            }
-            if ((++spins & 0xfffu) == 0u) {
-                cudaError_t e = cudaStreamQuery(ctx->pss);
-                if (e != cudaSuccess && e != cudaErrorNotReady)
-                    return fail((int)e, "stream server failed: %s", cudaGetErrorString(e));
-                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2))
-                    return fail(HRT_E_INVALID_ARG, "stream server did not answer within 2 s");
-            }
-        }
-        std::atomic_thread_fence(std::memory_order_seq_cst);
+        int rc = server_roundtrip(ctx->pctrl, &ctx->pseq, &ctx->pserver_launched, ctx->pss,
+                                  [&](unsigned served) { return launch_pos_server(ctx, served); });
+        if (rc) return rc;
     }
     if (h_robot_local_q) memcpy(h_robot_local_q, ctx->pmb_out, (size_t)pp.J_rob * 16);
     if (h_dof) memcpy(h_dof, ctx->pmb_out + pp.J_rob * 4, (size_t)(pp.J_rob - 1) * 4);

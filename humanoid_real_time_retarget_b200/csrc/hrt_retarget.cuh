@@ -228,23 +228,29 @@ HRT_DEV void smsp_align(int warp) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(1 + (warp & 3)), "n"(WARPS * 8) : "memory");
 #endif
 }
-template <int BQ_WARPS_PER_CTA>
-__global__ void __launch_bounds__(BQ_WARPS_PER_CTA * 32, 1)
-body_quat_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a) {
-    extern __shared__ __align__(16) float smem[];
+// per-arm tables and rest positions: constant bank -> shared memory once per CTA (the two lanes of a frame
+// index different arms, which would serialise every constant-bank read)
+HRT_DEV void bq_setup(const BodyQuatParams& bp, float* smem) {
+    const float* src = reinterpret_cast<const float*>(&bp.arm[0]);
+    for (int i = threadIdx.x; i < 2 * (int)sizeof(ArmParams) / 4; i += blockDim.x) smem[i] = src[i];
+    float* rp = smem + 2 * sizeof(ArmParams) / 4;
+    for (int i = threadIdx.x; i < bp.J_rob * 3; i += blockDim.x) rp[i] = bp.rest_pos[i];
+    __syncthreads();
+}
+
+// SYSMEM: resident one-warp server reading a frame from mapped host memory (no cross-warp alignment there)
+template <int WARPS, bool SYSMEM>
+HRT_DEV void bq_align(int warp) {
+    if (!SYSMEM) smsp_align<WARPS>(warp);
+}
+
+// all frame groups of `a` that fall to CTA `cta` of `n_ctas`
+template <int BQ_WARPS_PER_CTA, bool SYSMEM>
+HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* smem, int n_ctas, int cta) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int fl = lane >> 1;
     const int side = lane & 1;
-    // per-arm tables and rest positions: constant bank -> shared memory once per CTA (the two lanes of
-    // a frame index different arms, which would serialise every constant-bank read)
-    {
-        const float* src = reinterpret_cast<const float*>(&bp.arm[0]);
-        for (int i = threadIdx.x; i < 2 * (int)sizeof(ArmParams) / 4; i += blockDim.x) smem[i] = src[i];
-        float* rp = smem + 2 * sizeof(ArmParams) / 4;
-        for (int i = threadIdx.x; i < bp.J_rob * 3; i += blockDim.x) rp[i] = bp.rest_pos[i];
-    }
-    __syncthreads();
     const ArmParams& ap = reinterpret_cast<const ArmParams*>(smem)[side];
     const float* rest_s = smem + 2 * sizeof(ArmParams) / 4;
     const bool with_lq = a.out_local_q != nullptr;
@@ -262,10 +268,10 @@ body_quat_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a
 
     // every warp of the CTA runs the same number of rounds (the named barriers below need that);
     // a warp without a group in the last round shadows the last group and publishes nothing
-    const long long total_warps = (long long)gridDim.x * BQ_WARPS_PER_CTA;
+    const long long total_warps = (long long)n_ctas * BQ_WARPS_PER_CTA;
     const long long rounds = (n_groups + total_warps - 1) / total_warps;
     for (long long rnd = 0; rnd < rounds; ++rnd) {
-        const long long grp_raw = rnd * total_warps + (long long)blockIdx.x * BQ_WARPS_PER_CTA + warp;
+        const long long grp_raw = rnd * total_warps + (long long)cta * BQ_WARPS_PER_CTA + warp;
         const bool live = grp_raw < n_groups;
         const long long grp = live ? grp_raw : n_groups - 1;
         const long long f0 = grp * BQ_FRAMES_PER_WARP;
@@ -280,7 +286,17 @@ body_quat_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a
             pending_store = false;
         }
         // ---- 1. stage the group's input rows (one contiguous span) ----------------------------
-        warp_span_g2s(tile, a.src_gq + f0 * JS * 4, nld * JS * 4, lane);
+        if (SYSMEM) {
+            // one frame in mapped host memory: all PCIe reads in flight together, caches bypassed
+            const int n_words = nld * JS * 4;
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = (lane + 32 * k < n_words) ? __ldcv(a.src_gq + f0 * JS * 4 + lane + 32 * k) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (lane + 32 * k < n_words) tile[lane + 32 * k] = v[k];
+        } else {
+            warp_span_g2s(tile, a.src_gq + f0 * JS * 4, nld * JS * 4, lane);
+        }
         cp_async_commit();
         // while the copy is in flight: pre-fill the output images with their constant parts
         if (a.out_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
@@ -300,7 +316,7 @@ body_quat_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a
                 for (int i = lane; i < W; i += 32) lp_t[r * W + i] = rest_s[i];
 
         // ---- 2. zero-pose re-referencing (a24), exact rounding order -------------------------
-        smsp_align<BQ_WARPS_PER_CTA>(warp);
+        bq_align<BQ_WARPS_PER_CTA, SYSMEM>(warp);
         if (!a.pre_transformed) {
             const float4 rot = make_float4(bp.rot_z90[0], bp.rot_z90[1], bp.rot_z90[2], bp.rot_z90[3]);
 #define HRT_ZPT(q, n) q = quat_mul_norm_x(quat_mul_norm_x(q, rot), \
@@ -316,11 +332,11 @@ body_quat_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a
         float4 rl[7];
         {
             double eS[3], eE[3];
-            smsp_align<BQ_WARPS_PER_CTA>(warp);
+            bq_align<BQ_WARPS_PER_CTA, SYSMEM>(warp);
             euler_intrinsic_f64<1, 0, 2>(lU, eS);      // 'YXZ': pitch, roll, yaw
-            smsp_align<BQ_WARPS_PER_CTA>(warp);
+            bq_align<BQ_WARPS_PER_CTA, SYSMEM>(warp);
             euler_intrinsic_f64<2, 1, 0>(lL, eE);      // 'ZYX': yaw, pitch, roll
-            smsp_align<BQ_WARPS_PER_CTA>(warp);
+            bq_align<BQ_WARPS_PER_CTA, SYSMEM>(warp);
             rl[0] = axis_quat_from_f64(eS[0], 1);
             rl[1] = axis_quat_from_f64(eS[1], 0);
             rl[2] = quat_mul_norm_x(axis_quat_from_f64(eE[0], 2), axis_quat_from_f64(eS[2], 2));
@@ -330,7 +346,7 @@ body_quat_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a
             rl[6] = make_float4(0.f, 0.f, 0.f, 1.f);
         }
         // ---- 5. hinge angles (a17) ------------------------------------------------------------
-        smsp_align<BQ_WARPS_PER_CTA>(warp);
+        bq_align<BQ_WARPS_PER_CTA, SYSMEM>(warp);
         float th[7];
         th[0] = quat_to_dof_x(rl[0], 1);
         th[1] = quat_to_dof_x(rl[1], 0);
@@ -356,7 +372,7 @@ body_quat_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a
             const float lam2 = a.damping * a.damping;
             const float wo = a.rot_weight;
             for (int it = 0; it < a.ik_iters; ++it) {
-                smsp_align<BQ_WARPS_PER_CTA>(warp);
+                bq_align<BQ_WARPS_PER_CTA, SYSMEM>(warp);
                 ik_step_f(th, p_sh, ap.off, ap.lower, ap.upper, pe_t, pw_t, Rh, lam2, wo, (a.flags & BQ_ACTIVE_SET) != 0);
             }
         }
@@ -415,6 +431,58 @@ body_quat_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a
         }
     }
     if (pending_store && lane == 0) bulk_wait_read_all();
+}
+
+
+template <int BQ_WARPS_PER_CTA>
+__global__ void __launch_bounds__(BQ_WARPS_PER_CTA * 32, 1)
+body_quat_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    bq_setup(bp, smem);
+    bq_process<BQ_WARPS_PER_CTA, false>(bp, a, smem, (int)gridDim.x, (int)blockIdx.x);
+}
+
+// Resident single-frame server of the quaternion path (same protocol as pos_stream_server_kernel in hrt_pos.cuh:
+// ctrl words [0] seq_in, [1] stop (host) / [16] seq_out, [17] exited (device); one warp, one frame per request).
+HRT_DEV unsigned bq_ld_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+HRT_DEV void bq_st_sys(unsigned* p, unsigned v) { asm volatile("st.volatile.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
+HRT_DEV unsigned long long bq_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(32, 1)
+bq_stream_server_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a, unsigned* ctrl, unsigned served,
+                        unsigned long long idle_ns) {
+    extern __shared__ __align__(16) float smem[];
+    bq_setup(bp, smem);
+    for (;;) {
+        unsigned cmd = 0;
+        if (threadIdx.x == 0) {
+            const unsigned long long t0 = bq_timer_ns();
+            for (;;) {
+                const unsigned s = bq_ld_sys(ctrl);
+                if (s != served) { cmd = s; break; }
+                if (bq_ld_sys(ctrl + 1) != 0u || bq_timer_ns() - t0 > idle_ns) break;
+            }
+        }
+        cmd = __shfl_sync(0xffffffffu, cmd, 0);
+        if (cmd == 0u) break;
+        bq_process<1, true>(bp, a, smem, 1, 0);
+        __threadfence_system();
+        __syncwarp();
+        if (threadIdx.x == 0) bq_st_sys(ctrl + 16, cmd);
+        served = cmd;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        bq_st_sys(ctrl + 17, 1u);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

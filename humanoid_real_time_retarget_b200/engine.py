@@ -313,9 +313,11 @@ class Engine:
                                                self._stream()))
         return out
 
-    def stream_pos_open(self, wire_layout=False, persistent=False):
-        """persistent=True: a resident one-CTA server polls the mailbox (no launch / sync per frame)."""
-        _lib.check(self.lib.hrt_stream_pos_open(self._h, (1 if wire_layout else 0) | (2 if persistent else 0)))
+    def stream_pos_open(self, wire_layout=False, persistent=False, clamp=False, ik=False):
+        """persistent=True: a resident one-warp server polls the mailbox (no launch / sync per frame);
+        clamp / ik: joint limits / + 10 limit-aware refinement steps, as retarget_full_body_pos(flags=...)."""
+        _lib.check(self.lib.hrt_stream_pos_open(self._h, (1 if wire_layout else 0) | (2 if persistent else 0) |
+                                                (4 if clamp else 0) | (8 if ik else 0)))
 
     def stream_pos_frame(self, body_np, lhand_np, rhand_np, out_local_q=None, out_dof=None):
         """numpy float32 in / out, one frame of the position path."""
@@ -339,8 +341,9 @@ class Engine:
                                                         _ptr(out_local_q), _ptr(out_dof), _ptr(out_link_pos)))
         return out_local_q, out_dof, out_link_pos
 
-    def stream_open(self, flags=0, ik_iters=10, damping=0.1, rot_weight=0.2):
-        _lib.check(self.lib.hrt_stream_open(self._h, flags, ik_iters, damping, rot_weight))
+    def stream_open(self, flags=0, ik_iters=10, damping=0.1, rot_weight=0.2, persistent=False):
+        """persistent=True: a resident one-warp server polls the mailbox (no launch / sync per frame)."""
+        _lib.check(self.lib.hrt_stream_open(self._h, flags | (32 if persistent else 0), ik_iters, damping, rot_weight))
 
     def stream_frame(self, src_gq_np, out_local_q=None, out_dof=None, out_link_pos=None):
         """numpy float32 in / out, one frame."""

@@ -52,6 +52,7 @@ extern "C" {
 #define HRT_BQ_IK 2u          /* fused damped-least-squares refinement (implies clamp) */
 #define HRT_BQ_PRE_TRANSFORMED 4u /* input already zero-pose re-referenced: skip the a24 step */
 #define HRT_BQ_ACTIVE_SET 16u /* refinement: freeze hinges sitting on a limit while the gradient pushes outwards (always on in the position path) */
+#define HRT_BQ_PERSISTENT 32u  /* hrt_stream_open only: resident server kernel polling the mailbox (see hrt_stream_pos_open) */
 #define HRT_BQ_PACKED_IK 8u   /* experimental: refinement on packed fp32x2 (FFMA2), two arms per thread; dof / link-position outputs only */
 
 typedef struct hrt_ctx hrt_ctx;
@@ -186,6 +187,8 @@ int hrt_retarget_full_body_pos_wire(hrt_ctx* ctx, int64_t B, const float* d_body
                                     void* stream);       /* batched form of the same wire-layout call */
 #define HRT_STREAM_WIRE_LAYOUT 1   /* inputs in the mocap wire layout (23 body rows, HandNodes finger order) */
 #define HRT_STREAM_PERSISTENT 2    /* resident server kernel polling the mailbox: no launch / sync per frame */
+#define HRT_STREAM_CLAMP 4         /* joint limits on the arm hinges (HRT_POS_CLAMP) */
+#define HRT_STREAM_IK 8            /* + 10 limit-aware refinement steps (HRT_POS_IK, damping 0.1, rotation weight 0.2) */
 int hrt_stream_pos_open(hrt_ctx* ctx, int flags);
 int hrt_stream_pos_frame(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
                          float* h_robot_local_q, float* h_dof);

@@ -279,3 +279,11 @@ def test_wire_layout_and_position_streaming(hrt, golden):
             if i == 40:
                 torch.cuda.synchronize()               # waits for the server's idle exit, must not dead-lock
         eng.stream_pos_close()
+    # limits + refinement in the streaming call = the batched call with the same flags
+    _, dof_ik, _ = eng.retarget_full_body_pos(body, lh, rh, flags=hrt.POS_CLAMP | hrt.POS_IK)
+    for persistent in (False, True):
+        eng.stream_pos_open(persistent=persistent, ik=True)
+        for i in range(16):
+            eng.stream_pos_frame(body[i].numpy(), lh[i].numpy(), rh[i].numpy(), None, o_dof)
+            assert np.array_equal(o_dof, dof_ik[i].cpu().numpy())
+        eng.stream_pos_close()

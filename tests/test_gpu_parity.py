@@ -308,6 +308,17 @@ def test_host_call_and_streaming_match_device_call(hrt, eng, oc, skeletons):
         eng.stream_frame(raw_np[i], None, o_dof, o_lp)
         assert np.array_equal(o_dof, dof[i].cpu().numpy()) and np.array_equal(o_lp, lp[i].cpu().numpy())
     eng.stream_close()
+    # resident server kernel (no launch / sync per frame): same answers, survives its idle time-out
+    import time
+    eng.stream_open(flags=flags, persistent=True)
+    o_lq = np.empty((31, 4), np.float32)
+    for i in range(64):
+        eng.stream_frame(raw_np[i], o_lq, o_dof, o_lp)
+        assert np.array_equal(o_dof, dof[i].cpu().numpy()) and np.array_equal(o_lp, lp[i].cpu().numpy())
+        assert np.array_equal(o_lq, lq[i].cpu().numpy())
+        if i == 30:
+            time.sleep(0.06)
+    eng.stream_close()
 
 
 # ------------------------------------------------------------------------------- full-size properties

@@ -182,8 +182,9 @@ def main():
     if "stream" in cases:
         from oracle import retarget_oracle as oc
         raw = oc.synth_clip_3q(4096, seed=3).numpy()
-        for name, flags in [("stream_closed_form", 0), ("stream_ik10", hrt.BQ_CLAMP | hrt.BQ_IK)]:
-            eng.stream_open(flags=flags)
+        for name, flags, persistent in [("stream_closed_form", 0, False), ("stream_ik10", hrt.BQ_CLAMP | hrt.BQ_IK, False),
+                                        ("stream_closed_form_resident", 0, True), ("stream_ik10_resident", hrt.BQ_CLAMP | hrt.BQ_IK, True)]:
+            eng.stream_open(flags=flags, persistent=persistent)
             o_dof = np.empty(30, np.float32)
             o_lp = np.empty((31, 3), np.float32)
             for i in range(2000):
