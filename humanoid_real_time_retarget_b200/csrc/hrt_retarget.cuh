@@ -75,8 +75,10 @@ HRT_HD inline int bq_dof_words(int JR) { return (BQ_FRAMES_PER_WARP * (JR - 1) +
 HRT_HD inline int bq_tile_words(int JS, int JR, bool with_lq) {
     return bq_io_words(JS, JR) + bq_dof_words(JR) + (with_lq ? BQ_FRAMES_PER_WARP * JR * 4 : 0);
 }
-// CTA-shared constants: both ArmParams + the robot's rest positions
-constexpr int BQ_CONST_WORDS = (2 * (int)sizeof(ArmParams) / 4 + HRT_MAX_JOINTS * 3 + 3) / 4 * 4;
+// CTA-shared constants: both ArmParams, the robot's rest positions, and a 16-frame image of them (the link-position
+// tile of every group starts as a 16-byte-wise copy of it)
+constexpr int BQ_REST_IMG_WORD = (2 * (int)sizeof(ArmParams) / 4 + HRT_MAX_JOINTS * 3 + 3) / 4 * 4;
+constexpr int BQ_CONST_WORDS = BQ_REST_IMG_WORD + (BQ_FRAMES_PER_WARP * 31 * 3 + 3) / 4 * 4;
 
 struct BodyQuatArgs {
     long long B;
@@ -235,6 +237,8 @@ HRT_DEV void bq_setup(const BodyQuatParams& bp, float* smem) {
     for (int i = threadIdx.x; i < 2 * (int)sizeof(ArmParams) / 4; i += blockDim.x) smem[i] = src[i];
     float* rp = smem + 2 * sizeof(ArmParams) / 4;
     for (int i = threadIdx.x; i < bp.J_rob * 3; i += blockDim.x) rp[i] = bp.rest_pos[i];
+    const int W = bp.J_rob * 3;
+    for (int i = threadIdx.x; i < BQ_FRAMES_PER_WARP * W; i += blockDim.x) smem[BQ_REST_IMG_WORD + i] = bp.rest_pos[i % W];
     __syncthreads();
 }
 
@@ -311,9 +315,12 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
         float4 zL = *reinterpret_cast<const float4*>(row + ap.src_lower * 4);
         float4 zH = *reinterpret_cast<const float4*>(row + ap.src_hand * 4);
         __syncwarp();                              // the input rows may now be overwritten:
-        if (a.out_link_pos)                        // link-position image starts as the robot's rest pose
-            for (int r = 0; r < nfr; ++r)
-                for (int i = lane; i < W; i += 32) lp_t[r * W + i] = rest_s[i];
+        if (a.out_link_pos) {                      // link-position image starts as the robot's rest pose
+            const float* img = smem + BQ_REST_IMG_WORD;
+            const int n4 = (nfr * W) >> 2;
+            for (int i = lane; i < n4; i += 32) reinterpret_cast<float4*>(lp_t)[i] = reinterpret_cast<const float4*>(img)[i];
+            for (int i = (n4 << 2) + lane; i < nfr * W; i += 32) lp_t[i] = img[i];
+        }
 
         // ---- 2. zero-pose re-referencing (a24), exact rounding order -------------------------
         bq_align<BQ_WARPS_PER_CTA, SYSMEM>(warp);
