@@ -44,8 +44,11 @@ struct FkArgs {
 };
 
 // shared-memory carve-up, in words.  Every region is a multiple of 4 words (16 bytes).
+// angle rows are staged with a padded stride (D rounded up to a multiple of 4, plus 4): 36 for D = 30 and 32, i.e.
+// 4 banks between configurations, so the 8 configurations of a quarter-warp read one joint's angle conflict-free
+HRT_HD inline int fkl_angle_stride(int J) { return ((J - 1) + 3) / 4 * 4 + 4; }
 HRT_HD inline int fkl_in_words(int J, bool from_angles) {
-    return from_angles ? (FKL_CFG * (J - 1) + 3) / 4 * 4 + 32 + 32 : 32;   // angles | root_q | root_t(24, padded)
+    return from_angles ? FKL_CFG * fkl_angle_stride(J) + 32 + 32 : 32;   // angles | root_q | root_t(24, padded)
 }
 HRT_HD inline int fkl_warp_words(int J, bool from_angles) {
     return FKL_CFG * J * 4 + FKL_CFG * J * 3 + 2 * fkl_in_words(J, from_angles);
@@ -57,6 +60,10 @@ HRT_HD inline size_t fkl_smem_bytes(int J, int T, bool from_angles) {
 HRT_DEV void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+HRT_DEV void cp_async8(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
 }
 HRT_DEV void cp_async4(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -87,8 +94,11 @@ fk_limb_kernel(const int J, const FkArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int cfg = lane >> 2;                  // configuration within the warp task
-    const int p = lane & 3;                     // limb lane
+    // a quarter-warp (the unit of a 16-byte shared-memory access) = ONE limb lane over the 8 configurations: with an odd
+    // joint count the 8 rows of the staged images then fall into 8 different bank groups (ncu: the (cfg, limb) =
+    // (lane/4, lane%4) mapping had 8-way conflicts on the quaternion tile, 48 % excess shared wavefronts)
+    const int cfg = lane & 7;                   // configuration within the warp task
+    const int p = lane >> 3;                    // limb lane
     const int D = J - 1;
     const int T = a.T;
 
@@ -101,7 +111,8 @@ fk_limb_kernel(const int J, const FkArgs a) {
     float* qtile = smem + T * HRT_FK_LANES * 8 + warp * fkl_warp_words(J, FROM_ANGLES);
     float* ptile = qtile + FKL_CFG * J * 4;
     float* inbuf = ptile + FKL_CFG * J * 3;
-    const int ang_words = (FKL_CFG * D + 3) / 4 * 4;
+    const int AS = fkl_angle_stride(J);
+    const int ang_words = FKL_CFG * AS;
 
     const long long n_tasks = (a.B + FKL_CFG - 1) / FKL_CFG;
     const long long stride = (long long)gridDim.x * FKL_WARPS_PER_CTA;
@@ -113,7 +124,16 @@ fk_limb_kernel(const int J, const FkArgs a) {
             const long long f0 = tk * FKL_CFG;
             const int rows = (int)min((long long)FKL_CFG, a.B - f0);
             float* in = inbuf + b * in_words;
-            warp_span_g2s(in, a.angles + f0 * D, rows * D, lane);
+            const float* src = a.angles + f0 * D;
+            if ((D & 3) == 0) {
+                const int ppr = D >> 2;                       // 16-byte pieces per row
+                for (int i = lane; i < rows * ppr; i += 32) cp_async16(in + (i / ppr) * AS + (i % ppr) * 4, src + i * 4);
+            } else if ((D & 1) == 0) {
+                const int ppr = D >> 1;                       // rows are only 8-byte aligned
+                for (int i = lane; i < rows * ppr; i += 32) cp_async8(in + (i / ppr) * AS + (i % ppr) * 2, src + i * 2);
+            } else {
+                for (int i = lane; i < rows * D; i += 32) cp_async4(in + (i / D) * AS + (i % D), src + i);
+            }
             if (a.root_q && lane < rows) cp_async16(in + ang_words + lane * 4, a.root_q + (f0 + lane) * 4);
             if (a.root_t) warp_span_g2s(in + ang_words + 32, a.root_t + f0 * 3, rows * 3, lane);
         }
@@ -182,7 +202,7 @@ fk_limb_kernel(const int J, const FkArgs a) {
             const vec3 off = make_vec3(r0.x, r0.y, r0.z);
             float4 gq;
             if (FROM_ANGLES) {
-                float th = in[c * D + (j - 1)];
+                float th = in[c * AS + (j - 1)];
                 if (a.clip) {
                     // forward value of the straight-through clamp: (clamp(x) - x) + x
                     const float cl = fminf(fmaxf(th, lim.x), lim.y);
@@ -194,8 +214,7 @@ fk_limb_kernel(const int J, const FkArgs a) {
                     float s, cs;
                     sincos_half_f(0.5f * th, &s, &cs);
                     if (cs < 0.f) { s = -s; cs = -cs; }                  // quat_normalize's sign flip
-                    const float4 lq = make_float4(k == 0 ? s : 0.f, k == 1 ? s : 0.f, k == 2 ? s : 0.f, cs);
-                    gq = quat_normalize_f(quat_mul_f(pq, lq));
+                    gq = quat_normalize_f(quat_mul_axis_rt_f(pq, k, s, cs));
                 }
             } else {
                 const float4 lq = *reinterpret_cast<const float4*>(qrow + j * 4);
