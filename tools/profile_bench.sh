@@ -11,4 +11,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:body_quat -s 4 -c 2 -f -o gpurun_out/${TAG}_bq_full $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
 tail -3 gpurun_out/${TAG}_bench_full.log
-tail -2 gpurun_out/${TAG}_ncu1.log gpurun_out/${TAG}_ncu2.log
+tail -n 2 gpurun_out/${TAG}_ncu1.log; tail -n 2 gpurun_out/${TAG}_ncu2.log
