@@ -469,7 +469,7 @@ int hrt_fk_jacobian(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, co
     Tree* t;
     if ((rc = get_tree(ctx, tree, &t))) return rc;
     if (!t->has_dof) return fail(HRT_E_NOT_CONFIGURED, "tree %d has no dof_axis table", tree);
-    if (B < 0 || !d_angles || !d_jac || !links) return fail(HRT_E_INVALID_ARG, "bad B / null pointer");
+    if (B < 0 || !links || (B > 0 && (!d_angles || !d_jac))) return fail(HRT_E_INVALID_ARG, "bad B / null pointer");
     if (K < 1 || K > HRT_MAX_LINKS) return fail(HRT_E_INVALID_ARG, "K=%d outside 1..%d", K, HRT_MAX_LINKS);
     if (!aligned16(d_root_q)) return fail(HRT_E_ALIGNMENT, "root_q must be 16-byte aligned");
     JacParams jp;

@@ -523,6 +523,8 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
         // ---- 5b. joint limits / limit-aware refinement (builder-specified) ----------
         if (a.flags & (POS_CLAMP | POS_IK)) {
             const vec3 p_sh = make_vec3(ik.p_sh[0], ik.p_sh[1], ik.p_sh[2]);
+            // fminf / fmaxf swallow NaN: a poisoned frame stays poisoned ("NaN in -> NaN out" also with limits / IK)
+            const float nan_probe = ((th[0] + th[1]) + (th[2] + th[3])) + ((th[4] + th[5]) + th[6]);
             float thc[7];
 #pragma unroll
             for (int c = 0; c < 7; ++c) thc[c] = fminf(fmaxf(th[c], ik.lower[c]), ik.upper[c]);
@@ -540,7 +542,7 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 7; ++c) th[c] = thc[c];
+            for (int c = 0; c < 7; ++c) th[c] = (nan_probe != nan_probe) ? nan_probe : thc[c];
             rl[0] = arm_local_quat<0>(th[0]); rl[1] = arm_local_quat<1>(th[1]); rl[2] = arm_local_quat<2>(th[2]);
             rl[3] = arm_local_quat<3>(th[3]); rl[4] = arm_local_quat<4>(th[4]); rl[5] = arm_local_quat<5>(th[5]);
             rl[6] = arm_local_quat<6>(th[6]);

@@ -363,6 +363,8 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
         th[5] = 0.f;
         th[6] = 0.f;
 
+        // fminf / fmaxf swallow NaN: remember a poisoned frame so that "NaN in -> NaN out" also holds with limits / IK
+        float nan_probe = ((th[0] + th[1]) + (th[2] + th[3])) + th[4];
         if (do_clamp) {
 #pragma unroll
             for (int c = 0; c < 7; ++c) th[c] = fminf(fmaxf(th[c], ap.lower[c]), ap.upper[c]);
@@ -376,6 +378,7 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
             const float4 Rh = quat_mul_norm_f(Tc, zH);
             const vec3 pe_t = add3(p_sh, quat_rotate_f(Ru, make_vec3(ap.seg_elbow[0], ap.seg_elbow[1], ap.seg_elbow[2])));
             const vec3 pw_t = add3(pe_t, quat_rotate_f(Rf, make_vec3(ap.seg_wrist[0], ap.seg_wrist[1], ap.seg_wrist[2])));
+            nan_probe += ((pe_t.x + pe_t.y) + (pe_t.z + pw_t.x)) + ((pw_t.y + pw_t.z) + Rh.w);      // NaN targets poison the frame
             const float lam2 = a.damping * a.damping;
             const float wo = a.rot_weight;
             for (int it = 0; it < a.ik_iters; ++it) {
@@ -384,6 +387,10 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
             }
         }
         if (do_clamp) {
+            if (nan_probe != nan_probe) {
+#pragma unroll
+                for (int c = 0; c < 7; ++c) th[c] = nan_probe;
+            }
             // the published local rotations are those of the final hinge angles
             rl[0] = arm_local_quat<0>(th[0]); rl[1] = arm_local_quat<1>(th[1]); rl[2] = arm_local_quat<2>(th[2]);
             rl[3] = arm_local_quat<3>(th[3]); rl[4] = arm_local_quat<4>(th[4]); rl[5] = arm_local_quat<5>(th[5]);
@@ -656,6 +663,9 @@ body_quat_ik2_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatAr
         q4p Rh;
         Rh.x = pk2[13 * 32]; Rh.y = pk2[14 * 32]; Rh.z = pk2[15 * 32]; Rh.w = pk2[16 * 32];
         const v3p p0 = make_v3p(dup2(p_sh[0]), dup2(p_sh[1]), dup2(p_sh[2]));
+        // a NaN anywhere in the warm start or the targets poisons the frame (clamping would hide it)
+        f2 nan_probe = add2(add2(add2(th[0], th[1]), add2(th[2], th[3])), add2(add2(th[4], Rh.w), add2(pe_t.x, pw_t.x)));
+        nan_probe = add2(nan_probe, add2(add2(pe_t.y, pe_t.z), add2(pw_t.y, pw_t.z)));
         __syncwarp();
         // link-position images start as the robot's rest pose (input rows and parked values are dead now)
         if (a.out_link_pos)
@@ -710,6 +720,11 @@ body_quat_ik2_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatAr
 
         // ---- final FK of the refined angles (packed) and the output images ---------------------------
         smsp_align<WARPS>(warp);
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            if (nan_probe.x != nan_probe.x) th[c].x = nan_probe.x;
+            if (nan_probe.y != nan_probe.y) th[c].y = nan_probe.y;
+        }
         {
             v3p ax[7], pc[9];
             q4p G;

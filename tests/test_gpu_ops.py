@@ -287,3 +287,56 @@ def test_wire_layout_and_position_streaming(hrt, golden):
             eng.stream_pos_frame(body[i].numpy(), lh[i].numpy(), rh[i].numpy(), None, o_dof)
             assert np.array_equal(o_dof, dof_ik[i].cpu().numpy())
         eng.stream_pos_close()
+
+
+def test_edge_cases_of_the_added_entry_points(hrt, golden):
+    """Empty and minimal inputs, NaN propagation and argument errors of the entry points added for the widened scope."""
+    import ctypes as C
+    eng = hrt.default_engine(0)
+    r, t = hrt.rotation3d, hrt.transform3d
+    # empty batches
+    assert r.quat_mul(torch.zeros(0, 4), torch.zeros(0, 4)).shape == (0, 4)
+    assert r.quat_to_exp_map(torch.zeros(0, 4)).shape == (0, 3)
+    assert t.cal_joint_quat(torch.zeros(0, 3, 3), torch.zeros(0, 3, 3)).shape == (0, 4)
+    assert eng.rescale_motion(hrt.TREE_SOURCE, torch.zeros(0, 21, 3)).shape == (0, 21, 3)
+    assert eng.rebuild_global_rotation(hrt.TREE_SOURCE, torch.zeros(0, 21, 3)).shape == (0, 21, 4)
+    lq, dof, bq = eng.retarget_full_body_pos(torch.zeros(0, 21, 3), torch.zeros(0, 20, 3), torch.zeros(0, 20, 3), flags=hrt.POS_CLAMP | hrt.POS_IK)
+    assert lq.shape == (0, 31, 4) and dof.shape == (0, 30) and bq.shape == (0, 59, 4)
+    assert eng.fk_jacobian(hrt.TREE_ROBOT, torch.zeros(0, 30), [18]).shape == (0, 1, 6, 30)
+    # a single row / unbatched shapes of the reference's call sites
+    q = r.quat_from_angle_axis(torch.tensor(0.3), torch.tensor([0., 0., 1.]))
+    assert q.shape == (4,) and abs(float(q[3]) - np.cos(0.15)) < 1e-6
+    assert r.quat_rotate(q, torch.tensor([1., 0., 0.])).shape == (3,)
+    assert r.quat_rotate(q, torch.randn(20, 3)).shape == (20, 3)            # gripper: one quat against 20 finger points
+    assert r.quat_mul(q.reshape(1, 4), q).shape == (1, 4)
+    # NaN in -> NaN out for that row only, never a crash
+    g = golden("full_body_pos")
+    body, lh, rh = T(g["body_t"]).clone(), T(g["lhand_t"]), T(g["rhand_t"])
+    body[3, 19] = float("nan")                                              # left elbow of frame 3
+    _, dof, _ = eng.retarget_full_body_pos(body, lh, rh, flags=hrt.POS_CLAMP | hrt.POS_IK)
+    _, dof_ok, _ = eng.retarget_full_body_pos(T(g["body_t"]), lh, rh, flags=hrt.POS_CLAMP | hrt.POS_IK)
+    others = [i for i in range(body.shape[0]) if i != 3]
+    assert torch.equal(dof[others], dof_ok[others])                         # only the poisoned frame is affected
+    # the reference's angle read-back masks NaN to angle 0 (rotation3d.py:601-605): finite or NaN, never out of limits
+    lo5, hi5 = torch.tensor(hrt.robot_config.Hu_v5_DOF_LOWER).cuda(), torch.tensor(hrt.robot_config.Hu_v5_DOF_UPPER).cuda()
+    bad = dof[3, 11:18]
+    assert bool((torch.isnan(bad) | ((bad >= lo5[11:18]) & (bad <= hi5[11:18]))).all())
+    qs = torch.randn(8, 4)
+    qs[2, 1] = float("nan")
+    out = r.quat_normalize(qs)
+    assert torch.isnan(out[2]).any() and torch.isfinite(out[[0, 1, 3, 4, 5, 6, 7]]).all()
+    # velocities need two frames, like np.gradient
+    with pytest.raises(hrt.HrtError):
+        eng.motion_velocity(torch.zeros(1, 21, 3), 1 / 30)
+    assert eng.motion_velocity(torch.zeros(2, 21, 3), 1 / 30).abs().max() == 0
+    # argument errors of the C ABI
+    bad = C.c_void_p(0)
+    per = (C.c_int64 * 4)(0, 0, 0, 0)
+    ins = (C.c_void_p * 4)(0, 0, 0, 0)
+    outs = (C.c_void_p * 3)(0, 0, 0)
+    assert eng.lib.hrt_rot_op(eng._h, 999, 4, ins, per, 0, 0.0, outs, None) == -1           # unknown op
+    assert eng.lib.hrt_rot_op(eng._h, 0, 4, ins, per, 0, 0.0, outs, None) == -1             # null operand
+    assert eng.lib.hrt_rebuild_global_rotation(eng._h, hrt.TREE_SOURCE, 4, bad, 3, None, None, bad, None) == -1
+    assert eng.lib.hrt_stream_pos_frame(eng._h, None, None, None, None, None) == -2          # not opened
+    e2 = hrt.Engine(0)
+    assert e2.lib.hrt_stream_pos_open(e2._h, 0) == -2                                        # not configured

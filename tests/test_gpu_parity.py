@@ -236,6 +236,14 @@ def test_body_quat_edge_cases(hrt, eng, oc, skeletons):
     raw[5, 18] = float("nan")
     _, dof, _ = eng.retarget_body_quat(raw, flags=0)
     assert torch.isfinite(dof[:5]).all() and torch.isfinite(dof[6:]).all()
+    # The reference's own angle read-back masks NaN to angle 0 (|sin| > 1e-5 is False for NaN, rotation3d.py:601-605), so the
+    # closed form reports 0 for the poisoned arm.  The refinement must not turn NaN targets into clamped garbage: NaN out.
+    _, dof_c, _ = eng.retarget_body_quat(raw, flags=hrt.BQ_CLAMP, want_local_q=False)
+    assert torch.isfinite(dof_c).all() and float(dof_c[5, 11:16].abs().max()) == 0.0
+    for fl in (hrt.BQ_CLAMP | hrt.BQ_IK, hrt.BQ_CLAMP | hrt.BQ_IK | hrt.BQ_PACKED_IK, hrt.BQ_CLAMP | hrt.BQ_IK | hrt.BQ_ACTIVE_SET):
+        _, dof_l, lp_l = eng.retarget_body_quat(raw, flags=fl, want_local_q=False)
+        assert torch.isfinite(dof_l[:5]).all() and torch.isfinite(dof_l[6:]).all() and torch.isnan(dof_l[5, 11:18]).all()
+        assert torch.isfinite(dof_l[5, 20:27]).all() and torch.isnan(lp_l[5, 13:19]).any()
     # quaternion double cover: -q gives the same answer
     raw = oc.synth_clip_3q(64, seed=4, sk=skeletons)
     _, d1, _ = eng.retarget_body_quat(raw, flags=0)
