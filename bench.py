@@ -208,10 +208,58 @@ def side_measurements(eng, hrt, oc, sk, dev):
             times.append(a.elapsed_time(b))
     ms = float(np.median(times))
     peak, _ = hbm_peak()
+    jac = torch.empty((65536, 2, 6, 32), device=dev)
+    jt = []
+    for i in range(13):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng_hu.fk_jacobian(hrt.TREE_ROBOT, ang, [20, 29], clip=True, out=jac)
+        b.record()
+        torch.cuda.synchronize(dev)
+        if i >= 3:
+            jt.append(a.elapsed_time(b))
+    jms = float(np.median(jt))
+    # the same FK on the host cores: the oracle's restatement of HuForwardModel.forward_kinematics (natively batched)
+    ang_h = ang.cpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    oc.hu_forward_kinematics(ang_h.reshape(65536, 32, 1), torch.zeros(65536, 3), oc.quat_identity((65536, 1)),
+                             sk["hu_zero_pose/parents"].tolist(), torch.from_numpy(sk["hu_zero_pose/offsets"]),
+                             oc.HU_DOF_AXIS, oc.HU_DOF_LOWER, oc.HU_DOF_UPPER, True)
+    cpu_s = time.perf_counter() - t0
     out["fk_65536"] = {"workload": "configs[1]: Hu (33 joints) FK with limits, 65,536 configurations, L2 flushed between launches",
                        "ms": ms, "configs_per_s": 65536 / (ms * 1e-3), "algorithmic_bytes_per_config": 1080,
                        "hbm_frac": 65536 * 1080 / (ms * 1e-3) / 1e9 / peak,
+                       "jacobian_2_links_ms": jms, "jacobian_hbm_frac": 65536 * 1664 / (jms * 1e-3) / 1e9 / peak,
+                       "cpu_port_configs_per_s": 65536 / cpu_s,
                        "note": "70.8 MB = 11 us at peak: launch-bound at this size; see profiles/ for 2^20-2^22 configurations"}
+    del jac, gq, gtt, flush
+    # the position-input (teleop) solver batched over a 2^18-frame clip, device-resident
+    n3 = 1 << 18
+    g3 = torch.Generator().manual_seed(3)
+    em = 0.4 * torch.randn(n3, 59, 3, generator=g3)
+    root = torch.zeros(n3, 3)
+    root[:, 2] = 1.0
+    _, gt3 = oc.cal_forward_kinematics(oc.exp_map_to_quat(em), root, sk["vtrdyn_full_zero_pose/parents"].tolist(),
+                                       torch.from_numpy(sk["vtrdyn_full_zero_pose/offsets"]))
+    b3, l3, r3 = gt3[:, full2body].contiguous().to(dev), gt3[:, 14:34].contiguous().to(dev), gt3[:, 39:59].contiguous().to(dev)
+    d3 = torch.empty(n3, 30, device=dev)
+    res = {}
+    for name, fl in (("closed_form", 0), ("limits_and_10_refinement_steps", hrt.POS_CLAMP | hrt.POS_IK)):
+        tt = []
+        for i in range(8):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.retarget_full_body_pos(b3, l3, r3, out=(None, d3, None), flags=fl)
+            b.record()
+            torch.cuda.synchronize(dev)
+            if i >= 3:
+                tt.append(a.elapsed_time(b))
+        m3 = float(np.median(tt))
+        res[name] = {"ms": m3, "frames_per_s": n3 / (m3 * 1e-3), "hbm_frac": n3 * 852 / (m3 * 1e-3) / 1e9 / peak}
+    out["pos_path_2p18"] = {"workload": "config 3p: VtrdynFullBodyPosRetargeter batched, 732 B in + 120 B dof per frame, 2^18 frames (192 MB in)",
+                            **res}
     return out
 
 

@@ -223,6 +223,9 @@ HRT_DEV void ik_step_f(float th[7], const vec3 p_sh, const float (*off)[3], cons
 #ifndef HRT_BQ_ALIGN
 #define HRT_BQ_ALIGN 1
 #endif
+#ifndef HRT_BQ_ALIGN_EULER
+#define HRT_BQ_ALIGN_EULER 1
+#endif
 
 template <int WARPS>
 HRT_DEV void smsp_align(int warp) {
@@ -341,7 +344,9 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
             double eS[3], eE[3];
             bq_align<BQ_WARPS_PER_CTA, SYSMEM>(warp);
             euler_intrinsic_f64<1, 0, 2>(lU, eS);      // 'YXZ': pitch, roll, yaw
+#if HRT_BQ_ALIGN_EULER
             bq_align<BQ_WARPS_PER_CTA, SYSMEM>(warp);
+#endif
             euler_intrinsic_f64<2, 1, 0>(lL, eE);      // 'ZYX': yaw, pitch, roll
             bq_align<BQ_WARPS_PER_CTA, SYSMEM>(warp);
             rl[0] = axis_quat_from_f64(eS[0], 1);
