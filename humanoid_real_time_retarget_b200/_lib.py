@@ -29,6 +29,7 @@ _SIGNATURES = {
     "hrt_configure_pos": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
     "hrt_retarget_full_body_pos": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "hrt_retarget_full_body_pos_ex": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_uint, C.c_int, C.c_float, C.c_float, _P, _P, _P, _P]),
+    "hrt_retarget_full_body_pos_host": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_uint, C.c_int, C.c_float, C.c_float, _P, _P]),
     "hrt_retarget_upper_body": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
     "hrt_retarget_full_body": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "hrt_stream_open": (C.c_int, [_P, C.c_uint, C.c_int, C.c_float, C.c_float]),

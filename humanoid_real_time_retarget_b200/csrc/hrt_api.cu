@@ -849,6 +849,58 @@ int hrt_retarget_full_body_pos_ex(hrt_ctx* ctx, int64_t B, const float* d_body_t
     return launch_pos(ctx, POS_FULL_BODY_POS, a, (cudaStream_t)stream);
 }
 
+int hrt_retarget_full_body_pos_host(hrt_ctx* ctx, int64_t B, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
+                                    unsigned flags, int ik_iters, float damping, float rot_weight, float* h_robot_local_q,
+                                    float* h_dof) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!ctx->pos_set[POS_FULL_BODY_POS]) return fail(HRT_E_NOT_CONFIGURED, "hrt_configure_pos(mode 0) has not been called");
+    if (B < 0) return fail(HRT_E_INVALID_ARG, "negative frame count");
+    if ((flags & HRT_POS_IK) && (ik_iters < 0 || ik_iters > 1000)) return fail(HRT_E_INVALID_ARG, "ik_iters out of range");
+    if (B == 0) return 0;
+    if (!h_body_t || !h_lhand_t || !h_rhand_t) return fail(HRT_E_INVALID_ARG, "null input");
+    const PosParams& pp = ctx->pos[POS_FULL_BODY_POS];
+    const size_t body_b = (size_t)pp.n_body * 12, hand_b = (size_t)pp.n_hand * 12, lq_b = (size_t)pp.J_rob * 16, dof_b = (size_t)(pp.J_rob - 1) * 4;
+    const long long chunk = 1 << 16;                 // frames per pipeline stage (multiple of 16)
+    const size_t need = (body_b + 2 * hand_b + lq_b + dof_b) * chunk;
+    if (ctx->d_stage_bytes < need) {
+        for (int i = 0; i < kHostStreams; ++i) {
+            if (ctx->d_stage[i]) { cudaFree(ctx->d_stage[i]); ctx->d_stage[i] = nullptr; }
+            HRT_CUDA(cudaMalloc(&ctx->d_stage[i], need));
+            if (!ctx->hs[i]) HRT_CUDA(cudaStreamCreateWithFlags(&ctx->hs[i], cudaStreamNonBlocking));
+            if (!ctx->hs_done[i]) HRT_CUDA(cudaEventCreateWithFlags(&ctx->hs_done[i], cudaEventDisableTiming));
+        }
+        ctx->d_stage_bytes = need;
+    }
+    int slot = 0;
+    for (long long f0 = 0; f0 < B; f0 += chunk, slot = (slot + 1) % kHostStreams) {
+        const long long n = std::min(chunk, (long long)B - f0);
+        cudaStream_t st = ctx->hs[slot];
+        char* base = reinterpret_cast<char*>(ctx->d_stage[slot]);
+        float* d_body = reinterpret_cast<float*>(base);
+        float* d_lh = reinterpret_cast<float*>(base + body_b * chunk);
+        float* d_rh = reinterpret_cast<float*>(base + (body_b + hand_b) * chunk);
+        float* d_lq = reinterpret_cast<float*>(base + (body_b + 2 * hand_b) * chunk);
+        float* d_dof = reinterpret_cast<float*>(base + (body_b + 2 * hand_b + lq_b) * chunk);
+        HRT_CUDA(cudaMemcpyAsync(d_body, reinterpret_cast<const char*>(h_body_t) + f0 * body_b, n * body_b, cudaMemcpyHostToDevice, st));
+        HRT_CUDA(cudaMemcpyAsync(d_lh, reinterpret_cast<const char*>(h_lhand_t) + f0 * hand_b, n * hand_b, cudaMemcpyHostToDevice, st));
+        HRT_CUDA(cudaMemcpyAsync(d_rh, reinterpret_cast<const char*>(h_rhand_t) + f0 * hand_b, n * hand_b, cudaMemcpyHostToDevice, st));
+        PosArgs a{};
+        a.B = n; a.body_t = d_body; a.lhand_t = d_lh; a.rhand_t = d_rh;
+        a.out_local_q = h_robot_local_q ? d_lq : nullptr;
+        a.out_dof = h_dof ? d_dof : nullptr;
+        a.flags = (flags & HRT_POS_CLAMP ? POS_CLAMP : 0u) | (flags & HRT_POS_IK ? POS_IK : 0u);
+        a.ik_iters = ik_iters; a.damping = damping; a.rot_weight = rot_weight;
+        if ((rc = launch_pos(ctx, POS_FULL_BODY_POS, a, st))) return rc;
+        if (h_robot_local_q)
+            HRT_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h_robot_local_q) + f0 * lq_b, d_lq, n * lq_b, cudaMemcpyDeviceToHost, st));
+        if (h_dof)
+            HRT_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h_dof) + f0 * dof_b, d_dof, n * dof_b, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < kHostStreams; ++i) HRT_CUDA(cudaStreamSynchronize(ctx->hs[i]));
+    return 0;
+}
+
 int hrt_retarget_upper_body(hrt_ctx* ctx, int64_t B, const float* d_body_t, float* d_robot_local_q, float* d_dof, void* stream) {
     int rc = check_ctx(ctx);
     if (rc) return rc;

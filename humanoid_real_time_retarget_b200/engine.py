@@ -341,6 +341,17 @@ class Engine:
                                                         _ptr(out_local_q), _ptr(out_dof), _ptr(out_link_pos)))
         return out_local_q, out_dof, out_link_pos
 
+    def retarget_full_body_pos_host(self, body_t, lhand_t, rhand_t, flags=0, ik_iters=10, damping=0.1, rot_weight=0.2,
+                                    out_local_q=None, out_dof=None):
+        """Position path on HOST tensors (pinned for full speed); copies are inside the call (chunked, overlapped)."""
+        for t in (body_t, lhand_t, rhand_t, out_local_q, out_dof):
+            assert t is None or (t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous())
+        B = body_t.numel() // 63
+        assert lhand_t.numel() == B * 60 and rhand_t.numel() == B * 60
+        _lib.check(self.lib.hrt_retarget_full_body_pos_host(self._h, B, _ptr(body_t), _ptr(lhand_t), _ptr(rhand_t), flags, ik_iters,
+                                                            damping, rot_weight, _ptr(out_local_q), _ptr(out_dof)))
+        return out_local_q, out_dof
+
     def stream_open(self, flags=0, ik_iters=10, damping=0.1, rot_weight=0.2, persistent=False):
         """persistent=True: a resident one-warp server polls the mailbox (no launch / sync per frame)."""
         _lib.check(self.lib.hrt_stream_open(self._h, flags | (32 if persistent else 0), ik_iters, damping, rot_weight))

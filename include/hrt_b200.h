@@ -155,6 +155,12 @@ int hrt_retarget_full_body_pos_ex(hrt_ctx* ctx, int64_t B, const float* d_body_t
                                   float rot_weight, float* d_robot_local_q, float* d_dof, float* d_body_gq,
                                   void* stream);
 
+/* The same call on HOST buffers (chunked, H2D / kernel / D2H overlapped on three streams; pinned memory for full PCIe
+ * speed).  h_robot_local_q and h_dof may be NULL.  Synchronous. */
+int hrt_retarget_full_body_pos_host(hrt_ctx* ctx, int64_t B, const float* h_body_t, const float* h_lhand_t,
+                                    const float* h_rhand_t, unsigned flags, int ik_iters, float damping,
+                                    float rot_weight, float* h_robot_local_q, float* h_dof);
+
 /* HuUpperBodyFromMocapRetarget.retarget_from_global_translation: d_body_t (B,21,3), flipped by
  * coord_transform(dir=[-1,-1,1]) inside (retarget_solver.py:41) -> d_robot_local_q (B,31,4), d_dof (B,30). */
 int hrt_retarget_upper_body(hrt_ctx* ctx, int64_t B, const float* d_body_t, float* d_robot_local_q, float* d_dof,

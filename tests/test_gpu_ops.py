@@ -279,6 +279,13 @@ def test_wire_layout_and_position_streaming(hrt, golden):
             if i == 40:
                 torch.cuda.synchronize()               # waits for the server's idle exit, must not dead-lock
         eng.stream_pos_close()
+    # host-buffer call (chunked pipeline) = device call, bit for bit, also past one 65,536-frame chunk
+    reps = 70_000 // body.shape[0] + 1
+    hb, hl, hr = (x.repeat(reps, 1, 1)[:70_000].contiguous().pin_memory() for x in (body, lh, rh))
+    h_lq, h_dof = torch.empty(70_000, 31, 4).pin_memory(), torch.empty(70_000, 30).pin_memory()
+    eng.retarget_full_body_pos_host(hb, hl, hr, out_local_q=h_lq, out_dof=h_dof)
+    d_lq, d_dof, _ = eng.retarget_full_body_pos(hb, hl, hr, want_body_gq=False)
+    assert torch.equal(h_dof, d_dof.cpu()) and torch.equal(h_lq, d_lq.cpu())
     # limits + refinement in the streaming call = the batched call with the same flags
     _, dof_ik, _ = eng.retarget_full_body_pos(body, lh, rh, flags=hrt.POS_CLAMP | hrt.POS_IK)
     for persistent in (False, True):
