@@ -5,7 +5,7 @@ from ._lib import HrtError, LIB_PATH, EXPORTED_SYMBOLS
 from .engine import (BQ_ACTIVE_SET, BQ_CLAMP, BQ_IK, BQ_PACKED_IK, BQ_PRE_TRANSFORMED, POS_CLAMP, POS_IK, FK_EXACT, TREE_ROBOT, TREE_SOURCE, TREE_SOURCE_FULL,
                      Engine, default_engine)
 from .kinematics import (BaseForwardModel, HuForwardModel, RobotZeroPose, cal_forward_kinematics, cal_local_rotation)
-from .retarget_solver import (BaseHumanoidRetargeter, HuUpperBodyFromMocapRetarget, Mocap2HuBodyRetargeter,
+from .retarget_solver import (cal_elbowP_and_shoulderY, cal_shoulderPR, BaseHumanoidRetargeter, HuUpperBodyFromMocapRetarget, Mocap2HuBodyRetargeter,
                               VtrdynFullBodyPosRetargeter, VtrdynFullBodyRetargeter, to_numpy, to_torch,
                               vtrdyn_broadcast_zero_pose_transform, vtrdyn_full_zero_pose_transform,
                               vtrdyn_zero_pose_transform)

@@ -1257,7 +1257,8 @@ void rot_op_info(int* ni, int* wi, int* no, int* wo) {
     X(OP_PROJECT_QUAT_TO_AXIS) X(OP_EXTRACT_ROTATION_ALONG_AXIS) X(OP_NORMALIZE_ANGLE) X(OP_QUAT_TO_ANGLE_AXIS)     \
     X(OP_QUAT_TO_EXP_MAP) X(OP_EXP_MAP_TO_ANGLE_AXIS) X(OP_EXP_MAP_TO_QUAT) X(OP_ANGLE_AXIS_TO_EXP_MAP)             \
     X(OP_QUAT_BETWEEN_TWO_VECS) X(OP_PROJ_IN_PLANE) X(OP_RADIANS_BETWEEN_VECS) X(OP_QUAT_SLERP)                     \
-    X(OP_QUAT_TO_DOF_POS) X(OP_EULER_SPLIT) X(OP_EULER_ANGLES_F64) X(OP_COORD_TRANSFORM)
+    X(OP_QUAT_TO_DOF_POS) X(OP_EULER_SPLIT) X(OP_EULER_ANGLES_F64) X(OP_COORD_TRANSFORM)                            \
+    X(OP_CAL_SHOULDER_PR) X(OP_CAL_ELBOWP_SHOULDERY)
 }  // namespace
 }  // extern "C++"
 

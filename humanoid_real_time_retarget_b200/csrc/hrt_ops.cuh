@@ -33,6 +33,7 @@ enum RotOp {
     OP_NORMALIZE_ANGLE, OP_QUAT_TO_ANGLE_AXIS, OP_QUAT_TO_EXP_MAP, OP_EXP_MAP_TO_ANGLE_AXIS, OP_EXP_MAP_TO_QUAT,
     OP_ANGLE_AXIS_TO_EXP_MAP, OP_QUAT_BETWEEN_TWO_VECS, OP_PROJ_IN_PLANE, OP_RADIANS_BETWEEN_VECS,
     OP_QUAT_SLERP, OP_QUAT_TO_DOF_POS, OP_EULER_SPLIT, OP_EULER_ANGLES_F64, OP_COORD_TRANSFORM,
+    OP_CAL_SHOULDER_PR, OP_CAL_ELBOWP_SHOULDERY,
     OP_COUNT
 };
 
@@ -189,6 +190,8 @@ HRT_ROT_TRAITS(OP_QUAT_TO_DOF_POS, 2, 4, 1, 0, 0, 1, 1, 0, 0)
 HRT_ROT_TRAITS(OP_EULER_SPLIT, 1, 4, 0, 0, 0, 3, 4, 4, 4)
 HRT_ROT_TRAITS(OP_EULER_ANGLES_F64, 1, 4, 0, 0, 0, 1, 6, 0, 0)       // three doubles
 HRT_ROT_TRAITS(OP_COORD_TRANSFORM, 2, 3, 3, 0, 0, 1, 3, 0, 0)
+HRT_ROT_TRAITS(OP_CAL_SHOULDER_PR, 3, 3, 3, 4, 0, 2, 4, 4, 0)          // v1, v0, parent quat -> pitch quat, roll quat
+HRT_ROT_TRAITS(OP_CAL_ELBOWP_SHOULDERY, 3, 3, 3, 4, 0, 2, 4, 4, 0)     // v1, v0, parent quat -> yaw quat, elbow-pitch quat
 #undef HRT_ROT_TRAITS
 
 HRT_DEV float4 ld4(const float* p) { return make_float4(p[0], p[1], p[2], p[3]); }
@@ -326,6 +329,17 @@ HRT_DEV void rot_op_body(const float (&in)[4][9], float (&out)[3][9], int ip, fl
     } else if constexpr (OP == OP_COORD_TRANSFORM) {                          // transform3d.py:24-29: p[..., order] * dir
         const int o0 = ip & 3, o1 = (ip >> 2) & 3, o2 = (ip >> 4) & 3;
         out[0][0] = mul_rn(in[0][o0], in[1][0]); out[0][1] = mul_rn(in[0][o1], in[1][1]); out[0][2] = mul_rn(in[0][o2], in[1][2]);
+    }
+    else if constexpr (OP == OP_CAL_SHOULDER_PR || OP == OP_CAL_ELBOWP_SHOULDERY) {
+        // retarget_solver.py:103-158: the measured bone in the parent frame against the zero-pose bone, as angle
+        // differences in the xz- (shoulder) or xy-plane (elbow); the same device code as pos_retarget_kernel
+        constexpr int PLANE = (OP == OP_CAL_SHOULDER_PR) ? 1 : 2;
+        const vec3 v = quat_rotate_x(quat_conj(ld4(in[2])), ld3(in[0]));
+        float t1, p1, t0, p0;
+        bone_angles_x<PLANE>(v, &t1, &p1);
+        bone_angles_x<PLANE>(ld3(in[1]), &t0, &p0);
+        st4(out[0], quat_from_angle_axis_k_x(sub_rn(t1, t0), PLANE == 1 ? 1 : 2));
+        st4(out[1], quat_from_angle_axis_k_x(sub_rn(p1, p0), PLANE == 1 ? 0 : 1));
     }
     (void)fp;
 }

@@ -41,6 +41,29 @@ def vtrdyn_broadcast_zero_pose_transform(global_rotation):
     return _zpt(global_rotation, TREE_SOURCE, 1)
 
 
+def _arm_solve(op, v1, v0, parent_global_rotation):
+    from . import rotation3d as r3d
+    v1, v0, pq = to_torch(v1), to_torch(v0), to_torch(parent_global_rotation)
+    a, b = r3d.run_op(op, [v1, v0, pq], [1, 1, 1], [(4,), (4,)])
+    if v1.dim() == 1 and a.dim() == 2 and a.shape[0] == 1:      # the reference squeezes the (1,4) parent's batch axis
+        a, b = a[0], b[0]
+    return a, b
+
+
+def cal_shoulderPR(v1, v0, parent_global_rotation):
+    """retarget/retarget_solver/retarget_solver.py:127-158 (= full_body_pos_retargeter.py:247-278): shoulder pitch about y and
+    roll about x that carry the zero-pose bone v0 onto the measured bone v1 (world frame).  One kernel launch, the same
+    device code as the fused position solver; rows broadcast."""
+    from . import rotation3d as r3d
+    return _arm_solve(r3d.OP_CAL_SHOULDER_PR, v1, v0, parent_global_rotation)
+
+
+def cal_elbowP_and_shoulderY(v1, v0, parent_global_rotation):
+    """retarget_solver.py:103-125 (= full_body_pos_retargeter.py:221-243): shoulder yaw about z and elbow pitch about y."""
+    from . import rotation3d as r3d
+    return _arm_solve(r3d.OP_CAL_ELBOWP_SHOULDERY, v1, v0, parent_global_rotation)
+
+
 class BaseHumanoidRetargeter:
     def __init__(self, source_zero_pose: RobotZeroPose, target_zero_pose: RobotZeroPose):
         self.source_zero_pose = source_zero_pose

@@ -20,7 +20,8 @@ from . import _lib
  OP_ROT_MATRIX_DET, OP_ROT_MATRIX_FROM_QUATERNION, OP_PROJECT_QUAT_TO_AXIS, OP_EXTRACT_ROTATION_ALONG_AXIS,
  OP_NORMALIZE_ANGLE, OP_QUAT_TO_ANGLE_AXIS, OP_QUAT_TO_EXP_MAP, OP_EXP_MAP_TO_ANGLE_AXIS, OP_EXP_MAP_TO_QUAT,
  OP_ANGLE_AXIS_TO_EXP_MAP, OP_QUAT_BETWEEN_TWO_VECS, OP_PROJ_IN_PLANE, OP_RADIANS_BETWEEN_VECS, OP_QUAT_SLERP,
- OP_QUAT_TO_DOF_POS, OP_EULER_SPLIT, OP_EULER_ANGLES_F64, OP_COORD_TRANSFORM) = range(35)
+ OP_QUAT_TO_DOF_POS, OP_EULER_SPLIT, OP_EULER_ANGLES_F64, OP_COORD_TRANSFORM, OP_CAL_SHOULDER_PR,
+ OP_CAL_ELBOWP_SHOULDERY) = range(37)
 
 _AX = {"x": 0, "y": 1, "z": 2}
 

@@ -271,6 +271,8 @@ enum {
     HRT_OP_EULER_SPLIT,              /* transform3d.py:52-59     (4) -> (4),(4),(4); iparam: sequence code */
     HRT_OP_EULER_ANGLES_F64,         /* rotation3d.py:659-661    (4) -> 3 doubles; iparam: code | 0x80 degrees */
     HRT_OP_COORD_TRANSFORM,          /* transform3d.py:24-29     (3),(3: dir) -> (3); iparam: axis order code */
+    HRT_OP_CAL_SHOULDER_PR,          /* retarget_solver.py:127-158  v1 (3), v0 (3), parent quat (4) -> pitch quat, roll quat */
+    HRT_OP_CAL_ELBOWP_SHOULDERY,     /* retarget_solver.py:103-125  v1 (3), v0 (3), parent quat (4) -> yaw quat, elbow-pitch quat */
     HRT_OP_COUNT
 };
 int hrt_rot_op_info(int op, int* n_in, int* in_width4, int* n_out, int* out_width3);

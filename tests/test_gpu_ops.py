@@ -143,6 +143,14 @@ def test_transform3d(hrt, golden):
     gp = golden("primitives")
     assert md(t.cal_joint_quat(T(gp["Z3"]), T(gp["M3"])), gp["kabsch3"]) <= 1e-3
     assert float(np.median(np.abs(t.cal_joint_quat(T(gp["Z5"]), T(gp["M5"])).numpy() - gp["kabsch5"]))) <= 2e-7
+    # cal_shoulderPR / cal_elbowP_and_shoulderY (module-level functions of retarget_solver.py) against the reference's outputs
+    from humanoid_real_time_retarget_b200 import cal_elbowP_and_shoulderY, cal_shoulderPR
+    pit, rol = cal_shoulderPR(T(gp["v1"]), T(gp["v0_upper"]), T(gp["parent_q"]))
+    yaw, elp = cal_elbowP_and_shoulderY(T(gp["v1"]), T(gp["v0_lower"]), T(gp["parent_q"]))
+    for got, key in ((pit, "sh_pitch"), (rol, "sh_roll"), (yaw, "sh_yaw"), (elp, "el_pitch")):
+        assert float(np.quantile(np.abs(got.numpy() - gp[key]).max(-1), 0.95)) <= 2e-6 and md(got, gp[key]) <= 2e-3, key
+    p1, r1 = cal_shoulderPR(T(gp["v1"][7]), T(gp["v0_upper"]), T(gp["parent_q"][7:8]))       # the reference's call shape
+    assert p1.shape == (4,) and torch.equal(p1, pit[7]) and torch.equal(r1, rol[7])
     # names the reference module re-exports for `from transform3d import *` users
     assert t.torch is torch and t.np is np and callable(t.quat_mul) and callable(t.exp_map_to_quat)
 
