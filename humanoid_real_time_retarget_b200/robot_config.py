@@ -79,3 +79,12 @@ def skeleton_tables():
         z = np.load(_DATA, allow_pickle=False)
         _cache = {k: z[k] for k in z.files}
     return _cache
+
+
+def joint_mappings(robot="Hu_v5"):
+    """The reference's source-joint -> robot-link name tables (retarget/robot_config/Hu.py:27-105, Hu_v5.py:35-113),
+    extracted verbatim by tools/extract_tables.py: {'SMPL2HU_JOINT_MAPPING': {...}, 'NOITOM2HU_...', 'VTRDYN2HU_...',
+    'VTRDYN_LITE2HU_...'}; the argument of SkeletonState.retarget_to."""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "joint_mappings.json")) as f:
+        return json.load(f)[robot]

@@ -116,6 +116,8 @@ def test_compat_shims_and_asset_pickles():
     from retarget.robot_config.Hu import Hu_DOF_AXIS, Hu_DOF_LOWER        # noqa: F401
     assert sk3d.SkeletonState is hrt.SkeletonState and r3d.quat_mul is hrt.rotation3d.quat_mul
     assert t3d.torch is torch and t3d.np is np and len(Hu_DOF_AXIS) == 32 and Hu_DOF_LOWER.shape == (32,)
+    from retarget.robot_config.Hu_v5 import VTRDYN2HU_JOINT_MAPPING, SMPL2HU_JOINT_MAPPING
+    assert len(VTRDYN2HU_JOINT_MAPPING) == 15 and VTRDYN2HU_JOINT_MAPPING['Hips'] == 'pelvis_link' and len(SMPL2HU_JOINT_MAPPING) == 15
     expected = ["quat_mul", "quat_pos", "quat_abs", "quat_unit", "quat_conjugate", "quat_real", "quat_imaginary", "quat_norm_check",
                 "quat_normalize", "quat_from_xyz", "quat_identity", "quat_from_angle_axis", "quat_from_rotation_matrix", "quat_mul_norm",
                 "quat_rotate", "quat_inverse", "quat_identity_like", "quat_angle_axis", "quat_yaw_rotation",
