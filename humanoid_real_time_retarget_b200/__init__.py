@@ -13,6 +13,7 @@ from .retarget_solver import (cal_elbowP_and_shoulderY, cal_shoulderPR, BaseHuma
 from . import rotation3d, transform3d, skeleton3d
 from .skeleton3d import MotionDICT, SkeletonMotion, SkeletonState, SkeletonTree
 from .retarget_main import Retarget, RetargetHuV5fromMocap
+from .teleop import TeleopSession, WireDecoder
 
 import os as _os
 COMPAT_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "compat")
@@ -30,7 +31,7 @@ def enable_compat():
 
 __all__ = [
     "rotation3d", "transform3d", "skeleton3d", "SkeletonTree", "SkeletonState", "SkeletonMotion", "MotionDICT",
-    "Retarget", "RetargetHuV5fromMocap", "enable_compat", "COMPAT_PATH",
+    "Retarget", "RetargetHuV5fromMocap", "TeleopSession", "WireDecoder", "enable_compat", "COMPAT_PATH",
     "Engine", "default_engine", "HrtError", "robot_config",
     "cal_forward_kinematics", "cal_local_rotation", "RobotZeroPose", "BaseForwardModel", "HuForwardModel",
     "BaseHumanoidRetargeter", "Mocap2HuBodyRetargeter", "HuUpperBodyFromMocapRetarget", "VtrdynFullBodyRetargeter",

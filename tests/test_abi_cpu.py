@@ -147,3 +147,28 @@ def test_compat_shims_and_asset_pickles():
         assert np.array_equal(st.skeleton_tree.local_translation.numpy(), sk[f"{key}/offsets"])
         assert st.tensor.shape[-1] == st.num_joints * 4 + 3 and st.is_local in (True, False)
         assert np.array_equal(st.root_translation.numpy(), sk[f"{key}/root_translation"])
+
+
+def test_wire_decoder_round_trip_and_whitelist():
+    """mocap_receiver.py:49-59 framing: incremental decode of a byte stream cut at arbitrary places; only numpy arrays pass."""
+    import pickle
+    from humanoid_real_time_retarget_b200 import WireDecoder
+    rng = np.random.default_rng(0)
+    frames = [{"body_pos": rng.random((23, 3), dtype=np.float32), "body_quat": rng.random((23, 4), dtype=np.float32),
+               "left_hand_pos": rng.random((20, 3), dtype=np.float32), "right_hand_pos": rng.random((20, 3), dtype=np.float32)}
+              for _ in range(5)]
+    stream = b"".join(WireDecoder.encode(f) for f in frames)
+    dec, got = WireDecoder(), []
+    cuts = [0, 3, 4, 100, 101, 1500, len(stream) - 1, len(stream)]
+    for a, b in zip(cuts, cuts[1:]):
+        got += dec.feed(stream[a:b])
+    assert len(got) == 5 and all(np.array_equal(g[k], f[k]) for g, f in zip(got, frames) for k in f)
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("true",))
+    bad = pickle.dumps({"body_pos": Evil()})
+    with pytest.raises(pickle.UnpicklingError):
+        WireDecoder().feed(len(bad).to_bytes(4, "big") + bad)
+    with pytest.raises(ValueError):
+        WireDecoder().feed((1 << 30).to_bytes(4, "big"))

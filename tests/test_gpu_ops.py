@@ -355,3 +355,29 @@ def test_edge_cases_of_the_added_entry_points(hrt, golden):
     assert eng.lib.hrt_stream_pos_frame(eng._h, None, None, None, None, None) == -2          # not opened
     e2 = hrt.Engine(0)
     assert e2.lib.hrt_stream_pos_open(e2._h, 0) == -2                                        # not configured
+
+
+def test_teleop_session_from_wire_bytes(hrt, golden):
+    """Socket bytes in -> dof_pos out, equal to the reference-order preprocessing + batched solver."""
+    g = golden("full_body_pos")
+    eng = hrt.default_engine(0)
+    body, lh, rh = T(g["body_t"][:24]), T(g["lhand_t"][:24]), T(g["rhand_t"][:24])
+    _, dof, _ = eng.retarget_full_body_pos(body, lh, rh)
+    cfg = hrt.robot_config
+    stream = b""
+    for i in range(24):
+        b23 = np.zeros((23, 3), np.float32)
+        b23[cfg.BODY_23_TO_21] = body[i].numpy()
+        lw, rw = np.zeros((20, 3), np.float32), np.zeros((20, 3), np.float32)
+        lw[cfg.HAND_20_REORDER], rw[cfg.HAND_20_REORDER] = lh[i].numpy(), rh[i].numpy()
+        if i == 5:
+            b23[:] = 0                                           # dropped frame: the previous dof_pos is repeated
+        stream += hrt.WireDecoder.encode({"body_pos": b23, "body_quat": np.zeros((23, 4), np.float32), "left_hand_pos": lw, "right_hand_pos": rw})
+    for persistent in (True, False):
+        with hrt.TeleopSession(persistent=persistent) as s:
+            out = []
+            for k in range(0, len(stream), 777):                 # arbitrary recv() sizes
+                out += s.feed_bytes(stream[k:k + 777])
+        assert len(out) == 24
+        for i, d in enumerate(out):
+            assert np.array_equal(d, dof[4 if i == 5 else i].cpu().numpy())
