@@ -311,11 +311,24 @@ HRT_DEV void rot_op_body(const float (&in)[4][9], float (&out)[3][9], int ip, fl
     } else if constexpr (OP == OP_QUAT_TO_DOF_POS) {                          // transform3d.py:176-183; in[1] = hinge axis as a float
         out[0][0] = quat_to_dof_x(ld4(in[0]), (int)in[1][0]);
     } else if constexpr (OP == OP_EULER_SPLIT) {                              // transform3d.py:52-59
-        double e[3];
-        euler_general_f64(ld4(in[0]), ip, e);
-        st4(out[0], axis_quat_from_f64(e[0], ip & 3));
-        st4(out[1], axis_quat_from_f64(e[1], (ip >> 2) & 3));
-        st4(out[2], axis_quat_from_f64(e[2], (ip >> 4) & 3));
+        // the three intrinsic sequences of the fused kernels go through the same half-angle routine they use
+        double hs[3], hc[3];
+        if (ip == (0 | (1 << 2) | (2 << 4))) {                                // 'XYZ'
+            euler_intrinsic_half_sincos_f64<0, 1, 2>(ld4(in[0]), hs, hc);
+            st4(out[0], axis_quat_from_sc(hs[0], hc[0], 0)); st4(out[1], axis_quat_from_sc(hs[1], hc[1], 1)); st4(out[2], axis_quat_from_sc(hs[2], hc[2], 2));
+        } else if (ip == (1 | (0 << 2) | (2 << 4))) {                         // 'YXZ'
+            euler_intrinsic_half_sincos_f64<1, 0, 2>(ld4(in[0]), hs, hc);
+            st4(out[0], axis_quat_from_sc(hs[0], hc[0], 1)); st4(out[1], axis_quat_from_sc(hs[1], hc[1], 0)); st4(out[2], axis_quat_from_sc(hs[2], hc[2], 2));
+        } else if (ip == (2 | (1 << 2) | (0 << 4))) {                         // 'ZYX'
+            euler_intrinsic_half_sincos_f64<2, 1, 0>(ld4(in[0]), hs, hc);
+            st4(out[0], axis_quat_from_sc(hs[0], hc[0], 2)); st4(out[1], axis_quat_from_sc(hs[1], hc[1], 1)); st4(out[2], axis_quat_from_sc(hs[2], hc[2], 0));
+        } else {
+            double e[3];
+            euler_general_f64(ld4(in[0]), ip, e);
+            st4(out[0], axis_quat_from_f64(e[0], ip & 3));
+            st4(out[1], axis_quat_from_f64(e[1], (ip >> 2) & 3));
+            st4(out[2], axis_quat_from_f64(e[2], (ip >> 4) & 3));
+        }
     } else if constexpr (OP == OP_EULER_ANGLES_F64) {                         // rotation3d.py:658-661 (fp64 out)
         double e[3];
         euler_general_f64(ld4(in[0]), ip & 0x7f, e);

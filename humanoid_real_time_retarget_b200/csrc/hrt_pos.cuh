@@ -483,11 +483,11 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
             if (MODE == POS_FULL_BODY) wrist_g = *reinterpret_cast<const float4*>(bodyq_s + (fr * pp.n_bodyq + ap.q_wrist) * 4);
             const float4 wlocal = quat_mul_norm_x(quat_conj(wparent), wrist_g);
             pos_align<SYSMEM>(warp);
-            double e[3];
-            euler_intrinsic_f64<0, 1, 2>(wlocal, e);          // 'XYZ'
-            rl[4] = axis_quat_from_f64(e[0], 0);
-            rl[5] = axis_quat_from_f64(e[1], 1);
-            rl[6] = axis_quat_from_f64(e[2], 2);
+            double es[3], ec[3];
+            euler_intrinsic_half_sincos_f64<0, 1, 2>(wlocal, es, ec);          // 'XYZ'
+            rl[4] = axis_quat_from_sc(es[0], ec[0], 0);
+            rl[5] = axis_quat_from_sc(es[1], ec[1], 1);
+            rl[6] = axis_quat_from_sc(es[2], ec[2], 2);
         }
         // ---- 5. hinge angles + gripper -----------------------------------------------------------------
         pos_align<SYSMEM>(warp);

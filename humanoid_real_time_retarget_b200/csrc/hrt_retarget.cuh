@@ -341,19 +341,19 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
         // ---- 4. intrinsic Euler splits in fp64 (a16) + joint mapping (a30) --------------------
         float4 rl[7];
         {
-            double eS[3], eE[3];
+            double sS[3], cS[3], sE[3], cE[3];
             bq_align<BQ_WARPS_PER_CTA, SYSMEM>(warp);
-            euler_intrinsic_f64<1, 0, 2>(lU, eS);      // 'YXZ': pitch, roll, yaw
+            euler_intrinsic_half_sincos_f64<1, 0, 2>(lU, sS, cS);      // 'YXZ': pitch, roll, yaw
 #if HRT_BQ_ALIGN_EULER
             bq_align<BQ_WARPS_PER_CTA, SYSMEM>(warp);
 #endif
-            euler_intrinsic_f64<2, 1, 0>(lL, eE);      // 'ZYX': yaw, pitch, roll
+            euler_intrinsic_half_sincos_f64<2, 1, 0>(lL, sE, cE);      // 'ZYX': yaw, pitch, roll
             bq_align<BQ_WARPS_PER_CTA, SYSMEM>(warp);
-            rl[0] = axis_quat_from_f64(eS[0], 1);
-            rl[1] = axis_quat_from_f64(eS[1], 0);
-            rl[2] = quat_mul_norm_x(axis_quat_from_f64(eE[0], 2), axis_quat_from_f64(eS[2], 2));
-            rl[3] = axis_quat_from_f64(eE[1], 1);
-            rl[4] = axis_quat_from_f64(eE[2], 0);
+            rl[0] = axis_quat_from_sc(sS[0], cS[0], 1);
+            rl[1] = axis_quat_from_sc(sS[1], cS[1], 0);
+            rl[2] = quat_mul_norm_x(axis_quat_from_sc(sE[0], cE[0], 2), axis_quat_from_sc(sS[2], cS[2], 2));
+            rl[3] = axis_quat_from_sc(sE[1], cE[1], 1);
+            rl[4] = axis_quat_from_sc(sE[2], cE[2], 0);
             rl[5] = make_float4(0.f, 0.f, 0.f, 1.f);
             rl[6] = make_float4(0.f, 0.f, 0.f, 1.f);
         }
@@ -542,17 +542,17 @@ HRT_DEV void bq_closed_form(const BodyQuatParams& bp, const ArmParams& ap, const
     }
     const float4 lU = quat_mul_norm_x(quat_conj(zS), zU);
     const float4 lL = quat_mul_norm_x(quat_conj(zU), zL);
-    double eS[3], eE[3];
+    double sS[3], cS[3], sE[3], cE[3];
     smsp_align<WARPS>(warp);
-    euler_intrinsic_f64<1, 0, 2>(lU, eS);
+    euler_intrinsic_half_sincos_f64<1, 0, 2>(lU, sS, cS);
     smsp_align<WARPS>(warp);
-    euler_intrinsic_f64<2, 1, 0>(lL, eE);
+    euler_intrinsic_half_sincos_f64<2, 1, 0>(lL, sE, cE);
     smsp_align<WARPS>(warp);
-    th[0] = quat_to_dof_x(axis_quat_from_f64(eS[0], 1), 1);
-    th[1] = quat_to_dof_x(axis_quat_from_f64(eS[1], 0), 0);
-    th[2] = quat_to_dof_x(quat_mul_norm_x(axis_quat_from_f64(eE[0], 2), axis_quat_from_f64(eS[2], 2)), 2);
-    th[3] = quat_to_dof_x(axis_quat_from_f64(eE[1], 1), 1);
-    th[4] = quat_to_dof_x(axis_quat_from_f64(eE[2], 0), 0);
+    th[0] = quat_to_dof_x(axis_quat_from_sc(sS[0], cS[0], 1), 1);
+    th[1] = quat_to_dof_x(axis_quat_from_sc(sS[1], cS[1], 0), 0);
+    th[2] = quat_to_dof_x(quat_mul_norm_x(axis_quat_from_sc(sE[0], cE[0], 2), axis_quat_from_sc(sS[2], cS[2], 2)), 2);
+    th[3] = quat_to_dof_x(axis_quat_from_sc(sE[1], cE[1], 1), 1);
+    th[4] = quat_to_dof_x(axis_quat_from_sc(sE[2], cE[2], 0), 0);
     th[5] = 0.f;
     th[6] = 0.f;
     if (do_clamp) {

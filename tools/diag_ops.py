@@ -35,3 +35,8 @@ rep("kabsch n4", t.cal_joint_quat(zero, mot), g2["cal_joint_quat_n4"])
 gp = G("primitives")
 rep("kabsch3", t.cal_joint_quat(T(gp["Z3"]), T(gp["M3"])), gp["kabsch3"])
 rep("kabsch5", t.cal_joint_quat(T(gp["Z5"]), T(gp["M5"])), gp["kabsch5"])
+ge = G("euler")
+for seq in ["XYZ", "YXZ", "ZYX"]:
+    qs = t.quat_in_xyz_axis(T(ge["q"]), seq)
+    for m in range(3):
+        rep(f"euler.npz {seq} {m}", qs[m], ge[f"q{m+1}_{seq}"])
