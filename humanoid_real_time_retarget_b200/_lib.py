@@ -44,6 +44,7 @@ _SIGNATURES = {
     "hrt_rebuild_global_rotation": (C.c_int, [_P, C.c_int, C.c_int64, _P, C.c_int, _P, _P, _P, _P]),
     "hrt_motion_velocity": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_float, C.c_int, _P, _P, _P]),
     "hrt_motion_angular_velocity": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_float, C.c_int, _P, _P, _P]),
+    "hrt_forward_vector": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, _P]),
     "hrt_rot_op_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "hrt_rot_op": (C.c_int, [_P, C.c_int, C.c_int64, C.POINTER(_P), C.POINTER(C.c_int64), C.c_int, C.c_float, C.POINTER(_P), _P]),
     "hrt_max_norm3": (C.c_int, [_P, C.c_int64, _P, C.POINTER(C.c_float), _P]),

@@ -1180,17 +1180,41 @@ int hrt_rebuild_global_rotation(hrt_ctx* ctx, int tree, int64_t B, const float* 
     return 0;
 }
 
-static void gauss_params(GaussParams* gp) {
-    // scipy.ndimage._filters._gaussian_kernel1d(sigma=2, order=0, radius=int(4*2+0.5)=8)
-    const double sigma = 2.0;
-    gp->radius = 8;
-    double sum = 0.0;
-    for (int k = 0; k <= 16; ++k) {
-        const double x = (double)(k - 8);
-        gp->w[k] = std::exp(-0.5 / (sigma * sigma) * x * x);
-        sum += gp->w[k];
+// numpy's pairwise summation (what phi_x.sum() runs): n < 8 sequential; n <= 128 eight partial sums; else split
+static double np_pairwise_sum(const double* a, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r += a[i];
+        return r;
     }
-    for (int k = 0; k <= 16; ++k) gp->w[k] /= sum;
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+}
+
+// scipy.ndimage._filters._gaussian_kernel1d(sigma, order=0, radius=int(4*sigma+0.5)): exp(-0.5/sigma^2 * x^2) / sum
+static int gauss_params(GaussParams* gp, double sigma) {
+    const int radius = (int)(4.0 * sigma + 0.5);
+    if (!(sigma > 0.0) || radius > HRT_GAUSS_MAX_RADIUS) return -1;
+    gp->radius = radius;
+    const int n = 2 * radius + 1;
+    for (int k = 0; k < n; ++k) {
+        const double x = (double)(k - radius);
+        gp->w[k] = std::exp(-0.5 / (sigma * sigma) * (x * x));
+    }
+    const double sum = np_pairwise_sum(gp->w, n);
+    for (int k = 0; k < n; ++k) gp->w[k] /= sum;
+    return 0;
 }
 
 static int ew_grid(hrt_ctx* ctx, long long n) { return (int)std::max(1LL, std::min((n + 255) / 256, (long long)ctx->sm_count * 16)); }
@@ -1207,8 +1231,8 @@ int hrt_motion_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gt, f
     HRT_CUDA(cudaGetLastError());
     if (gaussian) {
         GaussParams gp;
-        gauss_params(&gp);
-        gauss_filter_frames_kernel<<<ew_grid(ctx, n), 256, 0, st>>>(gp, d_scratch, T, C, d_out);
+        gauss_params(&gp, 2.0);
+        gauss_filter_frames_kernel<float, float><<<ew_grid(ctx, n), 256, 0, st>>>(gp, d_scratch, T, C, d_out);
         HRT_CUDA(cudaGetLastError());
     }
     return 0;
@@ -1226,10 +1250,32 @@ int hrt_motion_angular_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float*
     HRT_CUDA(cudaGetLastError());
     if (gaussian) {
         GaussParams gp;
-        gauss_params(&gp);
-        gauss_filter_frames_kernel<<<ew_grid(ctx, n * 3), 256, 0, st>>>(gp, d_scratch, T, J * 3, d_out);
+        gauss_params(&gp, 2.0);
+        gauss_filter_frames_kernel<float, float><<<ew_grid(ctx, n * 3), 256, 0, st>>>(gp, d_scratch, T, J * 3, d_out);
         HRT_CUDA(cudaGetLastError());
     }
+    return 0;
+}
+
+int hrt_forward_vector(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gt, int left_shoulder, int right_shoulder,
+                       int left_hip, int right_hip, double sigma, double* d_scratch, double* d_out, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (T < 0 || J < 1) return fail(HRT_E_INVALID_ARG, "bad T / J");
+    if (T == 0) return 0;
+    if (!d_gt || !d_scratch || !d_out) return fail(HRT_E_INVALID_ARG, "null pointer");
+    const int idx[4] = {left_shoulder, right_shoulder, left_hip, right_hip};
+    for (int k = 0; k < 4; ++k)
+        if (idx[k] < 0 || idx[k] >= J) return fail(HRT_E_INVALID_ARG, "joint index out of range");
+    GaussParams gp;
+    if (gauss_params(&gp, sigma)) return fail(HRT_E_INVALID_ARG, "gaussian width must be in (0, 32)");
+    cudaStream_t st = (cudaStream_t)stream;
+    forward_raw_kernel<<<ew_grid(ctx, T), 256, 0, st>>>(d_gt, T, (int)J, idx[0], idx[1], idx[2], idx[3], d_scratch);
+    HRT_CUDA(cudaGetLastError());
+    gauss_filter_frames_kernel<double, double><<<ew_grid(ctx, T * 3), 256, 0, st>>>(gp, d_scratch, T, 3, d_out);
+    HRT_CUDA(cudaGetLastError());
+    normalize_rows3_f64_kernel<<<ew_grid(ctx, T), 256, 0, st>>>(d_out, T);
+    HRT_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -171,16 +171,18 @@ angular_velocity_raw_kernel(const float4* __restrict__ r, long long T, long long
     }
 }
 
+constexpr int HRT_GAUSS_MAX_RADIUS = 128;
 struct GaussParams {
-    int radius;                 // int(4 * sigma + 0.5) = 8 for sigma = 2
-    double w[33];               // w[k] = weight of offset k - radius (normalised, fp64, as scipy builds it)
+    int radius;                 // int(4 * sigma + 0.5): 8 for sigma = 2 (velocities), 80 for sigma = 20 (forward vector)
+    double w[2 * HRT_GAUSS_MAX_RADIUS + 1];   // w[k] = weight of offset k - radius (normalised, fp64, as scipy builds it)
 };
 
 // scipy.ndimage.gaussian_filter1d along frames, mode="nearest": fp64 accumulation in correlate1d's
-// symmetric order (centre, then the +-j pairs from the outside in), result rounded to fp32
+// symmetric order (centre, then the +-j pairs from the outside in), result rounded to the output type
+template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
-gauss_filter_frames_kernel(const __grid_constant__ GaussParams gp, const float* __restrict__ x, long long T, long long C,
-                           float* __restrict__ out) {
+gauss_filter_frames_kernel(const __grid_constant__ GaussParams gp, const TI* __restrict__ x, long long T, long long C,
+                           TO* __restrict__ out) {
     const long long n = T * C;
     const int R = gp.radius;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -190,7 +192,36 @@ gauss_filter_frames_kernel(const __grid_constant__ GaussParams gp, const float* 
             const long long ta = min(max(t + j, 0LL), T - 1), tb = min(max(t - j, 0LL), T - 1);
             acc += ((double)__ldg(x + ta * C + c) + (double)__ldg(x + tb * C + c)) * gp.w[j + R];
         }
-        out[i] = (float)acc;
+        out[i] = (TO)acc;
+    }
+}
+
+// SkeletonState.compute_forward_vector, poselib/poselib/skeleton/skeleton3d.py:542-566, first half: side direction
+// from shoulders and hips (fp32, numpy's left-to-right order), normalised, crossed with the up vector (0,1,0) in
+// fp64 (numpy promotes float32 x int64 to float64).  One thread per frame.
+__global__ void __launch_bounds__(256)
+forward_raw_kernel(const float* __restrict__ gt, long long T, int J, int ls, int rs, int lh, int rh, double* __restrict__ out) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (long long)gridDim.x * blockDim.x) {
+        const float* f = gt + t * J * 3;
+        float s[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            s[k] = sub_rn(add_rn(sub_rn(__ldg(f + ls * 3 + k), __ldg(f + rs * 3 + k)), __ldg(f + lh * 3 + k)), __ldg(f + rh * 3 + k));
+        const float n = __fsqrt_rn(add_rn(add_rn(mul_rn(s[0], s[0]), mul_rn(s[1], s[1])), mul_rn(s[2], s[2])));
+        const double sx = (double)div_rn(s[0], n), sy = (double)div_rn(s[1], n), sz = (double)div_rn(s[2], n);
+        out[t * 3 + 0] = __dsub_rn(__dmul_rn(sy, 0.0), __dmul_rn(sz, 1.0));
+        out[t * 3 + 1] = __dsub_rn(__dmul_rn(sz, 0.0), __dmul_rn(sx, 0.0));
+        out[t * 3 + 2] = __dsub_rn(__dmul_rn(sx, 1.0), __dmul_rn(sy, 0.0));
+    }
+}
+
+// second half: rows of the smoothed (T,3) array scaled to unit length, fp64, in place
+__global__ void __launch_bounds__(256)
+normalize_rows3_f64_kernel(double* __restrict__ x, long long T) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (long long)gridDim.x * blockDim.x) {
+        const double a = x[t * 3], b = x[t * 3 + 1], c = x[t * 3 + 2];
+        const double n = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(c, c)));
+        x[t * 3] = __ddiv_rn(a, n); x[t * 3 + 1] = __ddiv_rn(b, n); x[t * 3 + 2] = __ddiv_rn(c, n);
     }
 }
 

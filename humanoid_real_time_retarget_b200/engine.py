@@ -283,6 +283,16 @@ class Engine:
                                                         _ptr(scratch), _ptr(out), self._stream()))
         return out
 
+    def forward_vector(self, global_t, left_shoulder, right_shoulder, left_hip, right_hip, sigma=20):
+        """SkeletonState.compute_forward_vector (skeleton3d.py:542-566) on (T,J,3): (T,3) float64 like the reference."""
+        global_t = _f32c(global_t, self.device)
+        T, J = global_t.shape[0], global_t.shape[1]
+        out = torch.empty((T, 3), device=self.device, dtype=torch.float64)
+        scratch = torch.empty_like(out)
+        _lib.check(self.lib.hrt_forward_vector(self._h, T, J, _ptr(global_t), int(left_shoulder), int(right_shoulder), int(left_hip),
+                                               int(right_hip), float(sigma), _ptr(scratch), _ptr(out), self._stream()))
+        return out
+
     # ------------------------------------------------------------------ element-wise rotation algebra
     def rot_op_info(self, op):
         ni, no = C.c_int(), C.c_int()

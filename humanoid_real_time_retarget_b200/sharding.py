@@ -96,3 +96,49 @@ def retarget_clip_overlapped(engine, raw_blocks, n_frames, flags, ik_iters=10, d
         finished.record(comm_stream)
         torch.cuda.current_stream(dev).wait_event(finished)
     return out[:n_frames], finished
+
+
+# ---------------------------------------------------------------------------------------------------
+# Halo exchange: the one temporal stage after retargeting (SkeletonMotion velocities).
+# np.gradient looks 1 frame either side and the sigma = 2 gaussian 8 more, so a shard needs 9 frames of each
+# neighbour; with them the shard's velocities are bit-identical to the ones computed on the whole clip (same
+# central differences, same fp64 filter order; the clip's two real ends keep the reference's one-sided differences
+# and 'nearest' padding because rank 0 / the last rank get no halo there).
+# ---------------------------------------------------------------------------------------------------
+VELOCITY_HALO = 9
+
+
+def exchange_halo(local, halo, group=None):
+    """Neighbour exchange of `halo` leading / trailing frames between consecutive ranks (point-to-point over
+    NCCL / NVLink, gloo in the CPU tests).  Returns (padded, lead): `padded` = [prev rank's tail | local | next
+    rank's head], `lead` = number of frames put in front of the local ones."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if local.shape[0] < halo:
+        raise ValueError(f"shard of {local.shape[0]} frames is shorter than the {halo}-frame halo")
+    prev_buf = torch.empty((halo,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) if rank > 0 else None
+    next_buf = torch.empty((halo,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) if rank < world - 1 else None
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, local[:halo].contiguous(), rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, prev_buf, rank - 1, group))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, local[-halo:].contiguous(), rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, next_buf, rank + 1, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    parts = [p for p in (prev_buf, local, next_buf) if p is not None]
+    return (torch.cat(parts) if len(parts) > 1 else local), (halo if prev_buf is not None else 0)
+
+
+def motion_velocities_sharded(engine, local_global_t, local_global_q, dt, gaussian=True, group=None):
+    """Linear and angular velocities of this rank's contiguous frame range of a clip sharded over the ranks:
+    (n,J,3), (n,J,4) -> (n,J,3), (n,J,3), equal to the same frames of the whole-clip result."""
+    n = local_global_t.shape[0]
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    gt, lead = exchange_halo(local_global_t, VELOCITY_HALO, group) if multi else (local_global_t, 0)
+    gq, _ = exchange_halo(local_global_q, VELOCITY_HALO, group) if multi else (local_global_q, 0)
+    vel = engine.motion_velocity(gt, dt, gaussian)[lead:lead + n]
+    ang = engine.motion_angular_velocity(gq, dt, gaussian)[lead:lead + n]
+    return vel, ang

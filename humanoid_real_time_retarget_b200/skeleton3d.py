@@ -312,6 +312,15 @@ class SkeletonState(Serializable):
     def local_rotation_to_root(self):
         return r3d.quat_mul(r3d.quat_inverse(self.global_root_rotation).unsqueeze(-2), self.global_rotation)
 
+    def compute_forward_vector(self, left_shoulder_index, right_shoulder_index, left_hip_index, right_hip_index,
+                               gaussian_filter_width=20):
+        """skeleton3d.py:542-566: up x (average of the right->left shoulder and hip vectors), smoothed along frames with a
+        gaussian of the given width and normalised; (T,3) float64 like the reference (numpy promotes the cross product)."""
+        gt = self.global_translation
+        eng = r3d._engine(gt.device)
+        out = eng.forward_vector(gt, left_shoulder_index, right_shoulder_index, left_hip_index, right_hip_index, gaussian_filter_width)
+        return out.to(gt.device)
+
     # ---- construction
     @staticmethod
     def _to_state_vector(rot, rt):

@@ -230,6 +230,13 @@ int hrt_motion_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gt, f
 int hrt_motion_angular_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gq, float dt, int gaussian,
                                 float* d_scratch, float* d_out, void* stream);
 
+/* SkeletonState.compute_forward_vector (poselib/poselib/skeleton/skeleton3d.py:542-566): facing direction per frame
+ * from the shoulder and hip positions, smoothed along frames by scipy.ndimage.gaussian_filter1d(sigma,
+ * mode="nearest") and normalised.  d_gt (T, J, 3) fp32; d_scratch, d_out (T, 3) fp64 (numpy promotes the cross
+ * product with the integer up vector to float64 and the reference returns that).  sigma in (0, 32). */
+int hrt_forward_vector(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gt, int left_shoulder, int right_shoulder,
+                       int left_hip, int right_hip, double sigma, double* d_scratch, double* d_out, void* stream);
+
 /* Element-wise rotation algebra: the free functions of poselib/poselib/core/rotation3d.py:15-661 and
  * retarget/spatial_transform/transform3d.py:9-183, one op code each (HRT_OP_*; rows AoS fp32 like the
  * reference's tensors).  Operand k has n rows when period[k] == 0, else period[k] rows that repeat

@@ -588,6 +588,25 @@ def retarget_full_body(body_q, body_t, lhand_t, rhand_t, src_offsets, num_robot_
 # (DESIGN.md section 5).  The linear Jacobian rows are cross-checked against torch.autograd of the
 # reference-pinned FK above (tests/test_oracle_ik.py).
 # ----------------------------------------------------------------------------------------------
+def compute_forward_vector(global_t, left_shoulder, right_shoulder, left_hip, right_hip, gaussian_filter_width=20):
+    """poselib/poselib/skeleton/skeleton3d.py:542-566.  (T,J,3) fp32 -> (T,3) fp64.  The gaussian is restated from
+    scipy.ndimage (un-vendored, unpinned by the reference; goldens from scipy 1.18.1): weights exp(-x^2/(2 s^2))
+    normalised over x = -r..r, r = int(4 s + 0.5); edges repeat the end frames (mode='nearest')."""
+    p = np.asarray(global_t, dtype=np.float32)
+    side = p[:, left_shoulder] - p[:, right_shoulder] + p[:, left_hip] - p[:, right_hip]
+    side = side / np.sqrt((side ** 2).sum(axis=-1))[..., None]
+    fwd = np.stack([-side[:, 2].astype(np.float64), np.zeros(len(side)), side[:, 0].astype(np.float64)], axis=-1)
+    s = float(gaussian_filter_width)
+    r = int(4.0 * s + 0.5)
+    x = np.arange(-r, r + 1)
+    w = np.exp(-0.5 / (s * s) * x ** 2)
+    w = w / w.sum()
+    T = fwd.shape[0]
+    idx = np.clip(np.arange(T)[:, None] + x[None, :], 0, T - 1)        # (T, 2r+1)
+    sm = np.einsum("tkc,k->tc", fwd[idx], w)
+    return sm / np.sqrt((sm ** 2).sum(axis=-1))[..., None]
+
+
 def _axis_quat(theta, k):
     """(.., ) angles about coordinate axis k -> (.., 4); plain (sin, cos) without renormalising."""
     q = torch.zeros(theta.shape + (4,), dtype=theta.dtype)

@@ -381,3 +381,40 @@ def test_teleop_session_from_wire_bytes(hrt, golden):
         assert len(out) == 24
         for i, d in enumerate(out):
             assert np.array_equal(d, dof[4 if i == 5 else i].cpu().numpy())
+
+
+def test_forward_vector(hrt, golden):
+    """SkeletonState.compute_forward_vector (skeleton3d.py:542-566): fp64 (T,3), smoothed with sigma = 20 frames."""
+    g = golden("forward_vector")
+    idx = [int(i) for i in g["idx"]]
+    tree = hrt.RobotZeroPose.from_asset("vtrdyn_t_pose").skeleton_tree
+    st = hrt.SkeletonState.from_rotation_and_root_translation(tree, T(g["local_q"]), T(g["root_t"]), is_local=True)
+    assert exact(st.global_translation, g["global_translation"])
+    fwd = st.compute_forward_vector(*idx)
+    assert fwd.dtype == torch.float64 and tuple(fwd.shape) == (300, 3)
+    assert md(fwd, g["fwd_default"]) <= 1e-13
+    assert md(st.compute_forward_vector(*idx, gaussian_filter_width=5), g["fwd_width5"]) <= 1e-13
+    short = hrt.SkeletonState.from_rotation_and_root_translation(tree, T(g["local_q"][:30]), T(g["root_t"][:30]), is_local=True)
+    assert md(short.compute_forward_vector(*idx), g["fwd_short"]) <= 1e-13       # clip shorter than the filter radius
+    with pytest.raises(RuntimeError):
+        st.compute_forward_vector(*idx, gaussian_filter_width=40)                 # radius 160 > the kernel's table
+    with pytest.raises(RuntimeError):
+        st.compute_forward_vector(21, 13, 4, 1)
+
+
+def test_velocity_shards_with_halo_equal_whole_clip(hrt, golden):
+    """with 9 frames of each neighbour (sharding.VELOCITY_HALO) a shard's velocities are
+    bit-identical to the whole-clip kernels' (checked on one GPU by cutting the clip by hand)."""
+    from humanoid_real_time_retarget_b200.sharding import VELOCITY_HALO as H
+    g = golden("forward_vector")
+    eng = hrt.default_engine(0)
+    gt = T(g["global_translation"])
+    tree = hrt.RobotZeroPose.from_asset("vtrdyn_t_pose").skeleton_tree
+    gq = hrt.SkeletonState.from_rotation_and_root_translation(tree, T(g["local_q"]), T(g["root_t"]), is_local=True).global_rotation
+    whole_v, whole_w = eng.motion_velocity(gt, 1 / 30).cpu(), eng.motion_angular_velocity(gq, 1 / 30).cpu()
+    n = gt.shape[0]
+    for lo, hi in ((0, 112), (112, 208), (208, n)):
+        a, b = max(0, lo - H), min(n, hi + H)
+        v = eng.motion_velocity(gt[a:b], 1 / 30).cpu()[lo - a:lo - a + hi - lo]
+        w = eng.motion_angular_velocity(gq[a:b], 1 / 30).cpu()[lo - a:lo - a + hi - lo]
+        assert torch.equal(v, whole_v[lo:hi]) and torch.equal(w, whole_w[lo:hi]), (lo, hi)

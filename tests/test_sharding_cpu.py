@@ -84,3 +84,48 @@ def test_block_cyclic_overlapped_gather_lands_in_frame_order_gloo():
     ret = mgr.dict()
     mp.spawn(_worker_cyclic, args=(world, _free_port(), n_frames, n_blocks, ret), nprocs=world, join=True)
     assert ret[0] and ret[1]
+
+
+class _ScipyEngine:
+    """CPU stand-in with the reference's arithmetic (np.gradient + gaussian_filter1d, skeleton3d.py:1126-1135)."""
+
+    def motion_velocity(self, gt, dt, gaussian=True):
+        import numpy as np
+        from scipy.ndimage import gaussian_filter1d
+        v = np.gradient(gt.numpy(), axis=-3) / dt
+        return torch.from_numpy(gaussian_filter1d(v, 2, axis=-3, mode="nearest") if gaussian else v)
+
+    def motion_angular_velocity(self, gq, dt, gaussian=True):
+        return self.motion_velocity(gq[..., :3], dt, gaussian)            # any frame-local map + the same stencil
+
+
+def _worker_halo(rank, world, port, n_frames, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from humanoid_real_time_retarget_b200.sharding import exchange_halo, motion_velocities_sharded, shard_range
+    g = torch.Generator().manual_seed(5)
+    gt = torch.cumsum(torch.randn(n_frames, 4, 3, generator=g), dim=0)
+    gq = torch.randn(n_frames, 4, 4, generator=g)
+    lo, hi = shard_range(n_frames, rank, world)
+    padded, lead = exchange_halo(gt[lo:hi], 9)
+    ok_halo = torch.equal(padded, gt[max(0, lo - 9):min(n_frames, hi + 9)]) and lead == (9 if rank else 0)
+    eng = _ScipyEngine()
+    vel, ang = motion_velocities_sharded(eng, gt[lo:hi], gq[lo:hi], 1 / 30)
+    ok_vel = torch.equal(vel, eng.motion_velocity(gt, 1 / 30)[lo:hi]) and torch.equal(ang, eng.motion_angular_velocity(gq, 1 / 30)[lo:hi])
+    try:
+        exchange_halo(gt[:4], 9)
+        short = False
+    except ValueError:
+        short = True
+    ret[rank] = (bool(ok_halo), bool(ok_vel), short)
+    dist.destroy_process_group()
+
+
+def test_velocity_halo_exchange_matches_whole_clip_gloo():
+    """a 9-frame halo from each neighbour makes the sharded velocities equal the whole-clip ones."""
+    world, n_frames = 2, 203
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_halo, args=(world, _free_port(), n_frames, ret), nprocs=world, join=True)
+    assert all(all(ret[r]) for r in range(world)), dict(ret)

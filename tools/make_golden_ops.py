@@ -1,4 +1,4 @@
-"""Generate tests/golden/{rotation_ops2,skeleton_state,main_path}.npz by running the UNMODIFIED reference
+"""Generate tests/golden/{rotation_ops2,skeleton_state,main_path,forward_vector}.npz by running the UNMODIFIED reference
 (dev container only; same shim as tools/make_golden.py).
 
     python tools/make_golden_ops.py
@@ -168,9 +168,30 @@ def main_path(ref):
          robot_tensor=retargeted.tensor)
 
 
+def forward_vector(ref):
+    """SkeletonState.compute_forward_vector (skeleton3d.py:542-566) on a turning, walking vtrdyn clip; a clip shorter
+    than the filter radius (80 frames at the default width 20) and a narrower filter as edge cases."""
+    sk3d, r3d = ref.sk3d, ref.r3d
+    g = torch.Generator().manual_seed(78)
+    tree = ref_shim.load_asset(ref, "asset/t_pose/vtrdyn_t_pose.pkl").skeleton_tree
+    J = tree.num_joints
+    T = 300
+    lq = r3d.exp_map_to_quat(0.2 * torch.randn(T, J, 3, generator=g) + torch.cumsum(0.03 * torch.randn(T, J, 3, generator=g), dim=0))
+    rt = torch.cumsum(0.02 * torch.randn(T, 3, generator=g), dim=0)
+    st = sk3d.SkeletonState.from_rotation_and_root_translation(tree, lq, rt, is_local=True)
+    idx = (17, 13, 4, 1)                       # vtrdyn: left / right shoulder, left / right hip (VTRDYN.py:2-26)
+    out = dict(local_q=lq, root_t=rt, idx=np.asarray(idx), global_translation=st.global_translation,
+               fwd_default=st.compute_forward_vector(*idx), fwd_width5=st.compute_forward_vector(*idx, gaussian_filter_width=5))
+    short = sk3d.SkeletonState.from_rotation_and_root_translation(tree, lq[:30], rt[:30], is_local=True)
+    out["fwd_short"] = short.compute_forward_vector(*idx)
+    save("forward_vector", **out)
+
+
 if __name__ == "__main__":
     ref = ref_shim.load()
-    which = sys.argv[1:] or ["ops", "skeleton", "main"]
+    which = sys.argv[1:] or ["ops", "skeleton", "main", "forward"]
+    if "forward" in which:
+        forward_vector(ref)
     if "ops" in which:
         ops(ref)
     if "skeleton" in which:
