@@ -284,7 +284,11 @@ def run_ours(args):
     flags = hrt.BQ_CLAMP | hrt.BQ_IK
     sk = oc.load_skeletons()
     # synthetic clip (SURVEY 8(d) config 3q recipe), per-rank seed; built on the host in chunks
-    raw_h = torch.empty((B, 21, 4), dtype=torch.float32).pin_memory()
+    from humanoid_real_time_retarget_b200.sharding import gpu_local_host_memory
+    with gpu_local_host_memory(dev) as numa:               # pinned staging buffers on this GPU's NUMA node
+        raw_h = torch.empty((B, 21, 4), dtype=torch.float32).pin_memory()
+        h_dof = torch.empty((B, 30)).pin_memory()
+        h_lp = torch.empty((B, 31, 3)).pin_memory()
     chunk = 1 << 18
     for i, f0 in enumerate(range(0, B, chunk)):
         n = min(chunk, B - f0)
@@ -293,8 +297,6 @@ def run_ours(args):
     lq_d = None                                            # the headline path publishes dof + link positions
     dof_d = torch.empty((B, 30), device=dev)
     lp_d = torch.empty((B, 31, 3), device=dev)
-    h_dof = torch.empty((B, 30)).pin_memory()
-    h_lp = torch.empty((B, 31, 3)).pin_memory()
 
     def step_dev():
         eng.retarget_body_quat(raw_d, flags=flags, ik_iters=IK_ITERS, damping=DAMPING, rot_weight=ROT_WEIGHT,
@@ -416,7 +418,8 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (+f64 Euler split)", "data": "synthetic",
             "config": {"workload": "configs[2]: full quaternion-path pipeline, vtrdyn (21 joints) -> Hu v5 (31 joints), "
                                    f"{IK_ITERS}-iter IK + FK", "frames_per_gpu_per_step": B, "ik_iters": IK_ITERS,
-                       "l2": "input clip 336 MB/GPU > 126 MB L2, streamed once per step", "parallelism": f"frames x{world}"},
+                       "l2": "input clip 336 MB/GPU > 126 MB L2, streamed once per step", "parallelism": f"frames x{world}",
+                       "host_staging": numa.info},
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": "frames/s",
                     "h2d_bytes_per_step": B * 21 * 16, "d2h_bytes_per_step": B * (30 * 4 + 31 * 12)},
             "gpu_launches": args.steps,

@@ -167,15 +167,16 @@ int launch_fk_variant(hrt_ctx* ctx, Tree* t, FkArgs a, cudaStream_t st) {
     const int J = t->tp.J;
     a.sched = t->d_sched;
     a.T = t->T;
-    const size_t smem = fkl_smem_bytes(J, t->T, FROM_ANGLES);
+    constexpr int cfgs = FKL_GROUP * fkl_cpl(FROM_ANGLES, EXACT), warps = fkl_warps(FROM_ANGLES, EXACT);
+    const size_t smem = fkl_smem_bytes(J, t->T, FROM_ANGLES, cfgs, warps);
     auto kern = fk_limb_kernel<FROM_ANGLES, EXACT>;
     if (smem > 48 * 1024) HRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long tasks = (a.B + FKL_CFG - 1) / FKL_CFG;
-    const long long ctas = (tasks + FKL_WARPS_PER_CTA - 1) / FKL_WARPS_PER_CTA;
+    const long long tasks = (a.B + cfgs - 1) / cfgs;
+    const long long ctas = (tasks + warps - 1) / warps;
     int grid = 1;
-    int rc = grid_for(ctx, kern, FKL_WARPS_PER_CTA * 32, smem, ctas, &grid);
+    int rc = grid_for(ctx, kern, warps * 32, smem, ctas, &grid);
     if (rc) return rc;
-    kern<<<grid, FKL_WARPS_PER_CTA * 32, smem, st>>>(J, a);
+    kern<<<grid, warps * 32, smem, st>>>(J, a);
     HRT_CUDA(cudaGetLastError());
     return 0;
 }

@@ -11,8 +11,8 @@
 // Here FOUR lanes cooperate on one configuration, each walking one limb (the host list-schedules
 // the tree's chains onto the four lanes: sched[step][lane], 10 steps for Hu instead of 32), so
 //   * the dependent chain per warp is 3x shorter,
-//   * a warp owns 8 WHOLE configurations, whose outputs are ONE contiguous span of HBM each
-//     (8*J*16 B of quats, 8*J*12 B of positions): they are staged in a warp-private shared-memory
+//   * a warp owns 16 WHOLE configurations, whose outputs are ONE contiguous span of HBM each
+//     (16*J*16 B of quats, 16*J*12 B of positions): they are staged in a warp-private shared-memory
 //     image of that span and leave with two TMA bulk stores (cp.async.bulk.global.shared::cta,
 //     SASS UBLKCP) -- no per-row address math, no partially written sectors,
 //   * a child finds its parent's global transform in that same staged image (one LDS.128 + three
@@ -26,8 +26,14 @@
 
 namespace hrt {
 
-constexpr int FKL_CFG = 32 / HRT_FK_LANES;        // 8 configurations per warp task
-constexpr int FKL_WARPS_PER_CTA = 4;
+// A lane can walk its limb for CPL configurations at once (c, c + 8, ...): the per-step schedule decode is paid once
+// for CPL joint updates and the lane has CPL independent dependency chains in flight.  Measured (profiles/r01_notes.md):
+// CPL = 2 lifts the local-quaternion variant from 0.86 to 0.95 of the HBM peak; the joint-angle variant (sin / cos, clamp
+// and angle fetch per update, 135 instructions per lane-step of which ~60 are FP) is issue-bound and fastest with CPL = 1
+// and twice the resident warps.
+constexpr int FKL_GROUP = 32 / HRT_FK_LANES;      // 8 lanes share a limb
+HRT_HD constexpr int fkl_cpl(bool from_angles, bool exact) { return (!from_angles && !exact) ? 2 : 1; }
+HRT_HD constexpr int fkl_warps(bool from_angles, bool exact) { return (!from_angles && !exact) ? 3 : 4; }
 
 struct FkArgs {
     long long B;
@@ -43,18 +49,18 @@ struct FkArgs {
     int clip;
 };
 
-// shared-memory carve-up, in words.  Every region is a multiple of 4 words (16 bytes).
+// shared-memory carve-up, in words (cfgs = configurations per warp task).  Every region is a multiple of 4 words.
 // angle rows are staged with a padded stride (D rounded up to a multiple of 4, plus 4): 36 for D = 30 and 32, i.e.
 // 4 banks between configurations, so the 8 configurations of a quarter-warp read one joint's angle conflict-free
 HRT_HD inline int fkl_angle_stride(int J) { return ((J - 1) + 3) / 4 * 4 + 4; }
-HRT_HD inline int fkl_in_words(int J, bool from_angles) {
-    return from_angles ? FKL_CFG * fkl_angle_stride(J) + 32 + 32 : 32;   // angles | root_q | root_t(24, padded)
+HRT_HD inline int fkl_in_words(int J, bool from_angles, int cfgs) {
+    return from_angles ? cfgs * fkl_angle_stride(J) + cfgs * 4 + cfgs * 4 : 32;   // angles | root_q | root_t (padded)
 }
-HRT_HD inline int fkl_warp_words(int J, bool from_angles) {
-    return FKL_CFG * J * 4 + FKL_CFG * J * 3 + 2 * fkl_in_words(J, from_angles);
+HRT_HD inline int fkl_warp_words(int J, bool from_angles, int cfgs) {
+    return cfgs * J * 4 + cfgs * J * 3 + 2 * fkl_in_words(J, from_angles, cfgs);
 }
-HRT_HD inline size_t fkl_smem_bytes(int J, int T, bool from_angles) {
-    return (size_t)T * HRT_FK_LANES * 32 + (size_t)FKL_WARPS_PER_CTA * fkl_warp_words(J, from_angles) * 4;
+HRT_HD inline size_t fkl_smem_bytes(int J, int T, bool from_angles, int cfgs, int warps) {
+    return (size_t)T * HRT_FK_LANES * 32 + (size_t)warps * fkl_warp_words(J, from_angles, cfgs) * 4;
 }
 
 HRT_DEV void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -89,15 +95,18 @@ HRT_DEV void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 
 HRT_DEV void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 template <bool FROM_ANGLES, bool EXACT>
-__global__ void __launch_bounds__(FKL_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(fkl_warps(FROM_ANGLES, EXACT) * 32)
 fk_limb_kernel(const int J, const FkArgs a) {
+    constexpr int FKL_CPL = fkl_cpl(FROM_ANGLES, EXACT);
+    constexpr int FKL_CFG = FKL_GROUP * FKL_CPL;           // configurations per warp task
+    constexpr int FKL_WARPS_PER_CTA = fkl_warps(FROM_ANGLES, EXACT);
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    // a quarter-warp (the unit of a 16-byte shared-memory access) = ONE limb lane over the 8 configurations: with an odd
+    // a quarter-warp (the unit of a 16-byte shared-memory access) = ONE limb lane over 8 configurations: with an odd
     // joint count the 8 rows of the staged images then fall into 8 different bank groups (ncu: the (cfg, limb) =
     // (lane/4, lane%4) mapping had 8-way conflicts on the quaternion tile, 48 % excess shared wavefronts)
-    const int cfg = lane & 7;                   // configuration within the warp task
+    const int cfg = lane & 7;                   // first configuration of this lane within the warp task
     const int p = lane >> 3;                    // limb lane
     const int D = J - 1;
     const int T = a.T;
@@ -107,8 +116,8 @@ fk_limb_kernel(const int J, const FkArgs a) {
     for (int i = threadIdx.x; i < T * HRT_FK_LANES * 2; i += blockDim.x) sched_s[i] = __ldg(a.sched + i);
     __syncthreads();
 
-    const int in_words = fkl_in_words(J, FROM_ANGLES);
-    float* qtile = smem + T * HRT_FK_LANES * 8 + warp * fkl_warp_words(J, FROM_ANGLES);
+    const int in_words = fkl_in_words(J, FROM_ANGLES, FKL_CFG);
+    float* qtile = smem + T * HRT_FK_LANES * 8 + warp * fkl_warp_words(J, FROM_ANGLES, FKL_CFG);
     float* ptile = qtile + FKL_CFG * J * 4;
     float* inbuf = ptile + FKL_CFG * J * 3;
     const int AS = fkl_angle_stride(J);
@@ -118,6 +127,13 @@ fk_limb_kernel(const int J, const FkArgs a) {
     const long long stride = (long long)gridDim.x * FKL_WARPS_PER_CTA;
     long long task = (long long)blockIdx.x * FKL_WARPS_PER_CTA + warp;
 
+    // angle rows arrive in pieces of `pw` words (16 / 8 / 4 bytes, what the row alignment allows); a lane's pieces are
+    // 32 apart, so their (row, column) advance by constants: no division inside the task loop
+    const int pw = (D & 3) == 0 ? 4 : ((D & 1) == 0 ? 2 : 1);
+    const int ppr = D > 0 ? D / pw : 1;           // pieces per row
+    const int row_step = 32 / ppr, col_step = 32 % ppr;
+    const int row0 = lane / ppr, col0 = lane % ppr;
+
     // issue the asynchronous input copies of `tk` into buffer `b`
     auto stage_inputs = [&](long long tk, int b) {
         if (FROM_ANGLES && tk < n_tasks) {
@@ -125,17 +141,18 @@ fk_limb_kernel(const int J, const FkArgs a) {
             const int rows = (int)min((long long)FKL_CFG, a.B - f0);
             float* in = inbuf + b * in_words;
             const float* src = a.angles + f0 * D;
-            if ((D & 3) == 0) {
-                const int ppr = D >> 2;                       // 16-byte pieces per row
-                for (int i = lane; i < rows * ppr; i += 32) cp_async16(in + (i / ppr) * AS + (i % ppr) * 4, src + i * 4);
-            } else if ((D & 1) == 0) {
-                const int ppr = D >> 1;                       // rows are only 8-byte aligned
-                for (int i = lane; i < rows * ppr; i += 32) cp_async8(in + (i / ppr) * AS + (i % ppr) * 2, src + i * 2);
-            } else {
-                for (int i = lane; i < rows * D; i += 32) cp_async4(in + (i / D) * AS + (i % D), src + i);
+            int row = row0, col = col0;
+            const int n_pieces = D > 0 ? rows * ppr : 0;
+            for (int i = lane; i < n_pieces; i += 32) {
+                float* dst = in + row * AS + col * pw;
+                if (pw == 4) cp_async16(dst, src + i * 4);
+                else if (pw == 2) cp_async8(dst, src + i * 2);
+                else cp_async4(dst, src + i);
+                row += row_step; col += col_step;
+                if (col >= ppr) { col -= ppr; ++row; }
             }
-            if (a.root_q && lane < rows) cp_async16(in + ang_words + lane * 4, a.root_q + (f0 + lane) * 4);
-            if (a.root_t) warp_span_g2s(in + ang_words + 32, a.root_t + f0 * 3, rows * 3, lane);
+            if (a.root_q) for (int i = lane; i < rows; i += 32) cp_async16(in + ang_words + i * 4, a.root_q + (f0 + i) * 4);
+            if (a.root_t) warp_span_g2s(in + ang_words + FKL_CFG * 4, a.root_t + f0 * 3, rows * 3, lane);
         }
         cp_async_commit();
     };
@@ -147,10 +164,16 @@ fk_limb_kernel(const int J, const FkArgs a) {
     for (; task < n_tasks; task += stride, buf ^= 1) {
         const long long f0 = task * FKL_CFG;
         const int rows = (int)min((long long)FKL_CFG, a.B - f0);
-        const bool cfg_ok = cfg < rows;
-        const int c = cfg_ok ? cfg : rows - 1;            // tail lanes shadow the last valid configuration
-        float* qrow = qtile + c * J * 4;
-        float* prow = ptile + c * J * 3;
+        bool cfg_ok[FKL_CPL];
+        int c[FKL_CPL];
+        float *qrow[FKL_CPL], *prow[FKL_CPL];
+#pragma unroll
+        for (int u = 0; u < FKL_CPL; ++u) {
+            cfg_ok[u] = cfg + u * FKL_GROUP < rows;
+            c[u] = cfg_ok[u] ? cfg + u * FKL_GROUP : rows - 1;      // tail lanes shadow the last valid configuration
+            qrow[u] = qtile + c[u] * J * 4;
+            prow[u] = ptile + c[u] * J * 3;
+        }
 
         // the previous task's bulk stores must have finished READING the tiles before we overwrite them
         if (pending_store) {
@@ -172,17 +195,16 @@ fk_limb_kernel(const int J, const FkArgs a) {
         const float* in = inbuf + buf * in_words;
 
         // ---- root (joint 0): G_r[0] = l[0] as given (NOT normalised), G_t[0] = root translation
-        if (p == 0 && cfg_ok) {
-            if (FROM_ANGLES) {
-                const float4 rq = a.root_q ? *reinterpret_cast<const float4*>(in + ang_words + c * 4) : make_float4(0.f, 0.f, 0.f, 1.f);
-                *reinterpret_cast<float4*>(qrow) = rq;
-            }
+        for (int r = lane; r < rows; r += 32) {
+            float* qr = qtile + r * J * 4;
+            float* pr = ptile + r * J * 3;
+            if (FROM_ANGLES)
+                *reinterpret_cast<float4*>(qr) = a.root_q ? *reinterpret_cast<const float4*>(in + ang_words + r * 4) : make_float4(0.f, 0.f, 0.f, 1.f);
             if (a.root_t) {
-                const float* rt = FROM_ANGLES ? in + ang_words + 32 + c * 3 : nullptr;
-                if (FROM_ANGLES) { prow[0] = rt[0]; prow[1] = rt[1]; prow[2] = rt[2]; }
-                else { const float* g = a.root_t + (f0 + c) * 3; prow[0] = __ldg(g); prow[1] = __ldg(g + 1); prow[2] = __ldg(g + 2); }
+                if (FROM_ANGLES) { const float* rt = in + ang_words + FKL_CFG * 4 + r * 3; pr[0] = rt[0]; pr[1] = rt[1]; pr[2] = rt[2]; }
+                else { const float* g = a.root_t + (f0 + r) * 3; pr[0] = __ldg(g); pr[1] = __ldg(g + 1); pr[2] = __ldg(g + 2); }
             } else {
-                prow[0] = 0.f; prow[1] = 0.f; prow[2] = 0.f;
+                pr[0] = 0.f; pr[1] = 0.f; pr[2] = 0.f;
             }
         }
         __syncwarp();
@@ -193,43 +215,49 @@ fk_limb_kernel(const int J, const FkArgs a) {
             const float2 lim = *reinterpret_cast<const float2*>(&sched_s[(t * HRT_FK_LANES + p) * 2 + 1]);
             const uint32_t meta = __float_as_uint(r0.w);
             const int jraw = (int)(meta & 0xFFu);
-            const bool active = (jraw != 0xFF) && cfg_ok;
-            const int j = (jraw != 0xFF) ? jraw : 1;
-            const int par = (jraw != 0xFF) ? (int)((meta >> 8) & 0xFFu) : 0;
+            const bool joint_ok = jraw != 0xFF;
+            const int j = joint_ok ? jraw : 1;
+            const int par = joint_ok ? (int)((meta >> 8) & 0xFFu) : 0;
             const int k = (int)((meta >> 16) & 3u);
-            const float4 pq = *reinterpret_cast<const float4*>(qrow + par * 4);
-            const vec3 pp = make_vec3(prow[par * 3], prow[par * 3 + 1], prow[par * 3 + 2]);
             const vec3 off = make_vec3(r0.x, r0.y, r0.z);
-            float4 gq;
-            if (FROM_ANGLES) {
-                float th = in[c * AS + (j - 1)];
-                if (a.clip) {
-                    // forward value of the straight-through clamp: (clamp(x) - x) + x
-                    const float cl = fminf(fmaxf(th, lim.x), lim.y);
-                    th = add_rn(sub_rn(cl, th), th);
+            float4 gq[FKL_CPL];
+            vec3 gp[FKL_CPL];
+#pragma unroll
+            for (int u = 0; u < FKL_CPL; ++u) {
+                const float4 pq = *reinterpret_cast<const float4*>(qrow[u] + par * 4);
+                const vec3 pp = make_vec3(prow[u][par * 3], prow[u][par * 3 + 1], prow[u][par * 3 + 2]);
+                if (FROM_ANGLES) {
+                    float th = in[c[u] * AS + (j - 1)];
+                    if (a.clip) {
+                        // forward value of the straight-through clamp: (clamp(x) - x) + x
+                        const float cl = fminf(fmaxf(th, lim.x), lim.y);
+                        th = add_rn(sub_rn(cl, th), th);
+                    }
+                    if (EXACT) {
+                        gq[u] = quat_mul_norm_x(pq, quat_from_angle_axis_k_x(th, k));
+                    } else {
+                        float sn, cs;
+                        sincos_half_f(0.5f * th, &sn, &cs);
+                        if (cs < 0.f) { sn = -sn; cs = -cs; }                // quat_normalize's sign flip
+                        gq[u] = quat_normalize_f(quat_mul_axis_rt_f(pq, k, sn, cs));
+                    }
+                } else {
+                    const float4 lq = *reinterpret_cast<const float4*>(qrow[u] + j * 4);
+                    gq[u] = EXACT ? quat_mul_norm_x(pq, lq) : quat_mul_norm_f(pq, lq);
                 }
                 if (EXACT) {
-                    gq = quat_mul_norm_x(pq, quat_from_angle_axis_k_x(th, k));
+                    const vec3 r = quat_rotate_x(pq, off);
+                    gp[u] = make_vec3(add_rn(r.x, pp.x), add_rn(r.y, pp.y), add_rn(r.z, pp.z));
                 } else {
-                    float s, cs;
-                    sincos_half_f(0.5f * th, &s, &cs);
-                    if (cs < 0.f) { s = -s; cs = -cs; }                  // quat_normalize's sign flip
-                    gq = quat_normalize_f(quat_mul_axis_rt_f(pq, k, s, cs));
+                    gp[u] = add3(quat_rotate_f(pq, off), pp);
                 }
-            } else {
-                const float4 lq = *reinterpret_cast<const float4*>(qrow + j * 4);
-                gq = EXACT ? quat_mul_norm_x(pq, lq) : quat_mul_norm_f(pq, lq);
             }
-            vec3 gp;
-            if (EXACT) {
-                const vec3 r = quat_rotate_x(pq, off);
-                gp = make_vec3(add_rn(r.x, pp.x), add_rn(r.y, pp.y), add_rn(r.z, pp.z));
-            } else {
-                gp = add3(quat_rotate_f(pq, off), pp);
-            }
-            if (active) {
-                *reinterpret_cast<float4*>(qrow + j * 4) = gq;
-                prow[j * 3] = gp.x; prow[j * 3 + 1] = gp.y; prow[j * 3 + 2] = gp.z;
+#pragma unroll
+            for (int u = 0; u < FKL_CPL; ++u) {
+                if (joint_ok && cfg_ok[u]) {
+                    *reinterpret_cast<float4*>(qrow[u] + j * 4) = gq[u];
+                    prow[u][j * 3] = gp[u].x; prow[u][j * 3 + 1] = gp[u].y; prow[u][j * 3 + 2] = gp[u].z;
+                }
             }
             __syncwarp();
         }

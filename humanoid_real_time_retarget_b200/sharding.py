@@ -142,3 +142,49 @@ def motion_velocities_sharded(engine, local_global_t, local_global_q, dt, gaussi
     vel = engine.motion_velocity(gt, dt, gaussian)[lead:lead + n]
     ang = engine.motion_angular_velocity(gq, dt, gaussian)[lead:lead + n]
     return vel, ang
+
+
+# ---------------------------------------------------------------------------------------------------
+# Host side of a rank: staging buffers next to the GPU.  The host-buffer entry points move ~830 B per frame over
+# PCIe; pinned pages on the other socket cross the inter-socket link on every copy and ranks then share that link.
+# ---------------------------------------------------------------------------------------------------
+class gpu_local_host_memory:
+    """Context manager: while active the calling thread runs on the CPUs NVML reports as closest to `device`, so
+    pinned buffers allocated inside land on that GPU's NUMA node; the previous affinity is restored on exit.
+    `info` says what was done ({"cpus": n, "numa_node": k} or {"skipped": reason}); never raises."""
+
+    def __init__(self, device):
+        self.device = device
+        self.info = {}
+        self._saved = None
+
+    def __enter__(self):
+        import os
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            props = torch.cuda.get_device_properties(self.device)
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(props.uuid)).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(torch.device(self.device).index or 0)
+            self._saved = os.sched_getaffinity(0)
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+            now = os.sched_getaffinity(0)
+            self.info = {"cpus": len(now), "of": len(self._saved)}
+            try:
+                self.info["numa_node"] = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+            except Exception:
+                pass
+        except Exception as e:                                  # no NVML / no permission: keep the default placement
+            self.info = {"skipped": f"{type(e).__name__}: {e}"[:120]}
+        return self
+
+    def __exit__(self, *exc):
+        import os
+        if self._saved is not None:
+            try:
+                os.sched_setaffinity(0, self._saved)
+            except Exception:
+                pass
+        return False
