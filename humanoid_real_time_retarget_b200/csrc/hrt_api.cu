@@ -493,7 +493,7 @@ int hrt_fk_jacobian(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, co
     if ((6 * D) % 4 != 0) return fail(HRT_E_UNSUPPORTED_TREE, "the Jacobian kernel needs 6*(J-1) to be a multiple of 4");
     if (!aligned16(d_jac)) return fail(HRT_E_ALIGNMENT, "d_jac must be 16-byte aligned");
     const int cpw = 32 / jac_lanes_per_cfg(K);
-    const size_t smem = (size_t)JAC_WARPS_PER_CTA * cpw * jac_row_words(K, D) * sizeof(float);
+    const size_t smem = (size_t)JAC_WARPS_PER_CTA * jac_tile_words(K, D, cpw) * sizeof(float);
     const long long groups = (B + cpw - 1) / cpw;
     const long long ctas = (groups + JAC_WARPS_PER_CTA - 1) / JAC_WARPS_PER_CTA;
     int grid = 1;
