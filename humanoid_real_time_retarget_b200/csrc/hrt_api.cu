@@ -47,6 +47,7 @@ struct Tree {
     bool has_dof = false;
     TreeParams tp;
     int T = 0;                    // steps of the limb-parallel FK schedule
+    bool angles_bounded = false;  // every hinge has finite limits within +-3pi/2: clipped angles need no sin/cos fallback
     float4* d_sched = nullptr;    // T * 4 entries of 32 bytes
     std::vector<float> t2z;       // host copy (J*4) or empty
     float* d_t2z = nullptr;       // device copy
@@ -162,14 +163,14 @@ int grid_for(hrt_ctx* ctx, K kernel, int threads, size_t smem, long long n_ctas_
     return 0;
 }
 
-template <bool FROM_ANGLES, bool EXACT>
+template <bool FROM_ANGLES, bool EXACT, bool BOUNDED>
 int launch_fk_variant(hrt_ctx* ctx, Tree* t, FkArgs a, cudaStream_t st) {
     const int J = t->tp.J;
     a.sched = t->d_sched;
     a.T = t->T;
     constexpr int cfgs = FKL_GROUP * fkl_cpl(FROM_ANGLES, EXACT), warps = fkl_warps(FROM_ANGLES, EXACT);
     const size_t smem = fkl_smem_bytes(J, t->T, FROM_ANGLES, cfgs, warps);
-    auto kern = fk_limb_kernel<FROM_ANGLES, EXACT>;
+    auto kern = fk_limb_kernel<FROM_ANGLES, EXACT, BOUNDED>;
     if (smem > 48 * 1024) HRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long tasks = (a.B + cfgs - 1) / cfgs;
     const long long ctas = (tasks + warps - 1) / warps;
@@ -183,8 +184,10 @@ int launch_fk_variant(hrt_ctx* ctx, Tree* t, FkArgs a, cudaStream_t st) {
 
 template <bool FROM_ANGLES>
 int launch_fk(hrt_ctx* ctx, Tree* t, const FkArgs& a, unsigned flags, cudaStream_t st) {
-    return (flags & HRT_FK_EXACT) ? launch_fk_variant<FROM_ANGLES, true>(ctx, t, a, st)
-                                  : launch_fk_variant<FROM_ANGLES, false>(ctx, t, a, st);
+    if (flags & HRT_FK_EXACT) return launch_fk_variant<FROM_ANGLES, true, false>(ctx, t, a, st);
+    // clipped angles of a tree whose limits are all finite stay inside the half-angle polynomials' range
+    if (FROM_ANGLES && a.clip && t->angles_bounded) return launch_fk_variant<FROM_ANGLES, false, FROM_ANGLES>(ctx, t, a, st);
+    return launch_fk_variant<FROM_ANGLES, false, false>(ctx, t, a, st);
 }
 
 int body_quat_warps(const BodyQuatArgs& a) { return a.out_local_q ? BQ_WARPS_NARROW : BQ_WARPS_WIDE; }
@@ -256,17 +259,26 @@ int build_schedule(const TreeParams& tp, std::vector<float>* out, int* T_out) {
             }
         for (int p = 0; p < HRT_FK_LANES; ++p) {
             const int j = pick[p];
+            // 32-byte record: offset xyz | w3 || limits | w6 | w7, the w words carrying the BYTE offsets the kernel adds to
+            // its row bases: w3 = live << 31 | axis << 16 | (j - 1) * 4  (angle row), w6 = par * 16 | par * 12 << 16 (parent in the
+            // quaternion / position image), w7 = j * 16 | j * 12 << 16 (this joint's slots).  An idle lane-step reads joint 1
+            // and parent 0 and stores nothing.
             float rec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            uint32_t meta = 0xFFu;
+            const int jj = j >= 0 ? j : 1, par = j >= 0 ? tp.parent[j] : 0;
+            uint32_t w3 = (uint32_t)((jj - 1) * 4) | ((uint32_t)jr_axis(tp.jr[jj].meta) << 16);
+            const uint32_t w6 = (uint32_t)(par * 16) | ((uint32_t)(par * 12) << 16);
+            const uint32_t w7 = (uint32_t)(jj * 16) | ((uint32_t)(jj * 12) << 16);
             if (j >= 0) {
-                meta = (uint32_t)j | ((uint32_t)tp.parent[j] << 8) | ((uint32_t)jr_axis(tp.jr[j].meta) << 16);
+                w3 |= 0x80000000u;
                 rec[0] = tp.jr[j].off[0]; rec[1] = tp.jr[j].off[1]; rec[2] = tp.jr[j].off[2];
                 rec[4] = tp.lim[j][0]; rec[5] = tp.lim[j][1];
                 scheduled[j] = 1;
                 done[j] = T;
                 --remaining;
             }
-            memcpy(&rec[3], &meta, 4);
+            memcpy(&rec[3], &w3, 4);
+            memcpy(&rec[6], &w6, 4);
+            memcpy(&rec[7], &w7, 4);
             out->insert(out->end(), rec, rec + 8);
             last[p] = j;
         }
@@ -408,6 +420,9 @@ int hrt_set_tree(hrt_ctx* ctx, int tree, int J, const int32_t* parents, const fl
     }
     tp.n_slots = n_slots;
     t.has_dof = dof_axis != nullptr;
+    t.angles_bounded = lower && upper;
+    for (int j = 1; j < J && t.angles_bounded; ++j)
+        t.angles_bounded = std::fabs(tp.lim[j][0]) <= 4.7f && std::fabs(tp.lim[j][1]) <= 4.7f;      // NaN fails too
     if (t.d_t2z) { cudaFree(t.d_t2z); t.d_t2z = nullptr; }
     if (t.d_parents) { cudaFree(t.d_parents); t.d_parents = nullptr; }
     if (t.d_sched) { cudaFree(t.d_sched); t.d_sched = nullptr; }
