@@ -17,8 +17,8 @@
 //     SASS UBLKCP) -- no per-row address math, no partially written sectors,
 //   * a child finds its parent's global transform in that same staged image (one LDS.128 + three
 //     LDS), so no transform is kept in registers across steps and there is no branch on topology,
-//   * inputs (8*D angles, 8 root quats, 8 root translations: contiguous too) arrive by cp.async
-//     (LDGSTS) into a double buffer one task ahead of their use.
+//   * inputs (angles, root quats, root translations, or the local quaternions: contiguous spans too) arrive by
+//     cp.async (LDGSTS) into a double buffer one task ahead of their use.
 // All control flow is warp-uniform; idle lane-steps (18 % for Hu) are predicated off.
 #pragma once
 #include "hrt_math.cuh"
@@ -32,8 +32,14 @@ namespace hrt {
 // and angle fetch per update, 135 instructions per lane-step of which ~60 are FP) is issue-bound and fastest with CPL = 1
 // and twice the resident warps.
 constexpr int FKL_GROUP = 32 / HRT_FK_LANES;      // 8 lanes share a limb
-HRT_HD constexpr int fkl_cpl(bool from_angles, bool exact) { return (!from_angles && !exact) ? 2 : 1; }
-HRT_HD constexpr int fkl_warps(bool from_angles, bool exact) { return (!from_angles && !exact) ? 3 : 4; }
+#ifndef HRT_FKL_LOCAL_CPL
+#define HRT_FKL_LOCAL_CPL 2
+#endif
+#ifndef HRT_FKL_LOCAL_WARPS
+#define HRT_FKL_LOCAL_WARPS 3
+#endif
+HRT_HD constexpr int fkl_cpl(bool from_angles, bool exact) { return (!from_angles && !exact) ? HRT_FKL_LOCAL_CPL : 1; }
+HRT_HD constexpr int fkl_warps(bool from_angles, bool exact) { return (!from_angles && !exact) ? HRT_FKL_LOCAL_WARPS : 4; }
 
 struct FkArgs {
     long long B;
@@ -54,7 +60,8 @@ struct FkArgs {
 // 4 banks between configurations, so the 8 configurations of a quarter-warp read one joint's angle conflict-free
 HRT_HD inline int fkl_angle_stride(int J) { return ((J - 1) + 3) / 4 * 4 + 4; }
 HRT_HD inline int fkl_in_words(int J, bool from_angles, int cfgs) {
-    return from_angles ? cfgs * fkl_angle_stride(J) + cfgs * 4 + cfgs * 4 : 32;   // angles | root_q | root_t (padded)
+    return from_angles ? cfgs * fkl_angle_stride(J) + cfgs * 4 + cfgs * 4    // angles | root_q | root_t (padded)
+                       : cfgs * J * 4;                                       // local quaternions
 }
 HRT_HD inline int fkl_warp_words(int J, bool from_angles, int cfgs) {
     return cfgs * J * 4 + cfgs * J * 3 + 2 * fkl_in_words(J, from_angles, cfgs);
@@ -165,6 +172,11 @@ fk_limb_kernel(const int J, const FkArgs a) {
 
     // issue the asynchronous input copies of `tk` into buffer `b`
     auto stage_inputs = [&](long long tk, int b) {
+        if (!FROM_ANGLES && tk < n_tasks) {
+            const long long f0 = tk * FKL_CFG;
+            const int rows = (int)min((long long)FKL_CFG, a.B - f0);
+            warp_span_g2s(inbuf + b * in_words, a.local_q + f0 * J * 4, rows * J * 4, lane);
+        }
         if (FROM_ANGLES && tk < n_tasks) {
             const long long f0 = tk * FKL_CFG;
             const int rows = (int)min((long long)FKL_CFG, a.B - f0);
@@ -213,21 +225,17 @@ fk_limb_kernel(const int J, const FkArgs a) {
             __syncwarp();
             pending_store = false;
         }
-        if (FROM_ANGLES) {
-            stage_inputs(task + stride, buf ^ 1);         // next task's inputs, one task ahead
-            cp_async_wait<1>();                           // ... and this task's have landed
-        } else {
-            // local quats are staged IN PLACE in the quat tile (a joint's slot is rewritten with its
-            // global quat by the only lane that read it)
-            warp_span_g2s(qtile, a.local_q + f0 * J * 4, rows * J * 4, lane);
-            cp_async_commit();
-            cp_async_wait<0>();
-        }
+        stage_inputs(task + stride, buf ^ 1);             // next task's inputs, one task ahead
+        cp_async_wait<1>();                               // ... and this task's have landed
         __syncwarp();
         const float* in = inbuf + buf * in_words;
-        unsigned arow[FKL_CPL];
+        unsigned arow[FKL_CPL];                         // angle rows (shared-window addresses) / local-quaternion rows
+        const char* lrow_g[FKL_CPL];
 #pragma unroll
-        for (int u = 0; u < FKL_CPL; ++u) arow[u] = smem_addr(in + c[u] * AS);
+        for (int u = 0; u < FKL_CPL; ++u) {
+            arow[u] = smem_addr(in + c[u] * AS);
+            lrow_g[u] = reinterpret_cast<const char*>(in + c[u] * J * 4);
+        }
 
         // ---- root (joint 0): G_r[0] = l[0] as given (NOT normalised), G_t[0] = root translation
         for (int r = lane; r < rows; r += 32) {
@@ -235,6 +243,8 @@ fk_limb_kernel(const int J, const FkArgs a) {
             float* pr = ptile + r * J * 3;
             if (FROM_ANGLES)
                 *reinterpret_cast<float4*>(qr) = a.root_q ? *reinterpret_cast<const float4*>(in + ang_words + r * 4) : make_float4(0.f, 0.f, 0.f, 1.f);
+            else
+                *reinterpret_cast<float4*>(qr) = *reinterpret_cast<const float4*>(in + r * J * 4);
             if (a.root_t) {
                 if (FROM_ANGLES) { const float* rt = in + ang_words + FKL_CFG * 4 + r * 3; pr[0] = rt[0]; pr[1] = rt[1]; pr[2] = rt[2]; }
                 else { const float* g = a.root_t + (f0 + r) * 3; pr[0] = __ldg(g); pr[1] = __ldg(g + 1); pr[2] = __ldg(g + 2); }
@@ -247,7 +257,7 @@ fk_limb_kernel(const int J, const FkArgs a) {
         // ---- the scheduled walk: step t, lane p -> joint sched[t][p] ---------------------------
         // The joint-angle variant is issue-bound and takes the explicit shared-window accesses (135 -> 113 instructions per
         // lane-step together with the byte offsets: 0.72 -> 0.83 of the HBM peak); the local-quaternion variant (two chains
-        // per lane, exposed input latency: its tile is staged in place) keeps plain generic accesses.
+        // per lane, 0.90 of the peak) keeps plain generic accesses, which measured the same.
         auto ld_q = [&](int u, unsigned o) {
             return FROM_ANGLES ? lds128(qrow[u] + o) : *reinterpret_cast<const float4*>(qrow_g[u] + o);
         };
@@ -286,7 +296,7 @@ fk_limb_kernel(const int J, const FkArgs a) {
                 pq[u] = ld_q(u, qpar_o);
                 pp[u] = ld_p(u, ppar_o);
                 if (FROM_ANGLES) th[u] = lds32(arow[u] + ang_o);
-                else lq[u] = ld_q(u, qj_o);
+                else lq[u] = *reinterpret_cast<const float4*>(lrow_g[u] + qj_o);
             }
 #pragma unroll
             for (int u = 0; u < FKL_CPL; ++u) {
