@@ -339,10 +339,15 @@ int hrt_ctx_create(int device, hrt_ctx** out) {
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_ik2_kernel<BQ2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_FULL_BODY_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_UPPER_BODY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_FULL_BODY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<POS_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define HRT_POS_ATTR(MODE)                                                                                                          \
+    HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<MODE, POS_WARPS_MIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<MODE, POS_WARPS_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<MODE, POS_WARPS_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HRT_POS_ATTR(POS_FULL_BODY_POS)
+    HRT_POS_ATTR(POS_UPPER_BODY)
+    HRT_POS_ATTR(POS_FULL_BODY)
+    HRT_POS_ATTR(POS_MAIN)
+#undef HRT_POS_ATTR
     HRT_CUDA(cudaFuncSetAttribute(rescale_motion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(rebuild_rotation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     HRT_CUDA(cudaMalloc(&c->d_scalars, (HRT_MAX_JOINTS + 2) * sizeof(unsigned)));
@@ -822,19 +827,30 @@ static int launch_pos(hrt_ctx* ctx, int slot, const PosArgs& a, cudaStream_t st,
         if (!aligned16(p)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
     const PosParams& pp = ctx->pos[slot];
     const bool with_bq = mode == POS_FULL_BODY_POS && a.out_body_gq;
-    const size_t smem = ((size_t)pos_const_words() + (size_t)POS_WARPS * pos_tile_words(pp, a.out_local_q != nullptr, with_bq)) * sizeof(float);
+    const size_t tile_bytes = (size_t)pos_tile_words(pp, a.out_local_q != nullptr, with_bq) * sizeof(float);
+    const size_t const_bytes = (size_t)pos_const_words() * sizeof(float);
     const long long groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
-    const long long ctas = (groups + POS_WARPS - 1) / POS_WARPS;
-    const int grid = force_grid ? force_grid : (int)std::max(1LL, std::min(ctas, (long long)ctx->sm_count));
-    if (mode == POS_MAIN) {
-        pos_retarget_kernel<POS_MAIN><<<grid, POS_WARPS * 32, smem, st>>>(pp, a);
-    } else if (mode == POS_FULL_BODY_POS) {
-        pos_retarget_kernel<POS_FULL_BODY_POS><<<grid, POS_WARPS * 32, smem, st>>>(pp, a);
-    } else if (mode == POS_UPPER_BODY) {
-        pos_retarget_kernel<POS_UPPER_BODY><<<grid, POS_WARPS * 32, smem, st>>>(pp, a);
-    } else {
-        pos_retarget_kernel<POS_FULL_BODY><<<grid, POS_WARPS * 32, smem, st>>>(pp, a);
+    // the most warps per CTA whose staging tiles fit (a latency-bound kernel: see POS_WARPS_* in hrt_pos.cuh); a call
+    // that cannot fill one small CTA per SM (single frames, short clips) stays with the small CTA
+    int warps = POS_WARPS_MIN;
+    if (groups > (long long)ctx->sm_count * POS_WARPS_MIN) {
+        if (const_bytes + POS_WARPS_MAX * tile_bytes <= 226 * 1024) warps = POS_WARPS_MAX;
+        else if (const_bytes + POS_WARPS_MID * tile_bytes <= 226 * 1024) warps = POS_WARPS_MID;
     }
+    const size_t smem = const_bytes + (size_t)warps * tile_bytes;
+    const long long ctas = (groups + warps - 1) / warps;
+    const int grid = force_grid ? force_grid : (int)std::max(1LL, std::min(ctas, (long long)ctx->sm_count));
+#define HRT_POS_LAUNCH(MODE)                                                                                             \
+    do {                                                                                                                 \
+        if (warps == POS_WARPS_MAX) pos_retarget_kernel<MODE, POS_WARPS_MAX><<<grid, POS_WARPS_MAX * 32, smem, st>>>(pp, a);      \
+        else if (warps == POS_WARPS_MID) pos_retarget_kernel<MODE, POS_WARPS_MID><<<grid, POS_WARPS_MID * 32, smem, st>>>(pp, a); \
+        else pos_retarget_kernel<MODE, POS_WARPS_MIN><<<grid, POS_WARPS_MIN * 32, smem, st>>>(pp, a);                             \
+    } while (0)
+    if (mode == POS_MAIN) HRT_POS_LAUNCH(POS_MAIN);
+    else if (mode == POS_FULL_BODY_POS) HRT_POS_LAUNCH(POS_FULL_BODY_POS);
+    else if (mode == POS_UPPER_BODY) HRT_POS_LAUNCH(POS_UPPER_BODY);
+    else HRT_POS_LAUNCH(POS_FULL_BODY);
+#undef HRT_POS_LAUNCH
     HRT_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1036,7 +1052,7 @@ namespace {
 
 size_t pos_smem_bytes(const PosParams& pp, const PosArgs& a) {
     const bool with_bq = pp.mode == POS_FULL_BODY_POS && a.out_body_gq;
-    return ((size_t)pos_const_words() + (size_t)POS_WARPS * pos_tile_words(pp, a.out_local_q != nullptr, with_bq)) * sizeof(float);
+    return ((size_t)pos_const_words() + (size_t)pos_tile_words(pp, a.out_local_q != nullptr, with_bq)) * sizeof(float);   // one warp
 }
 
 int launch_pos_server(hrt_ctx* ctx, unsigned served) {

@@ -291,7 +291,13 @@ HRT_HD inline int pos_tile_words(const PosParams& pp, bool with_lq, bool with_bq
     int io = in > bq ? in : bq;                         // body_global_rotation image reuses the input rows
     return (io + 3) / 4 * 4 + bq_dof_words(pp.J_rob) + (with_lq ? BQ_FRAMES_PER_WARP * pp.J_rob * 4 : 0);
 }
-constexpr int POS_WARPS = 8;
+// Warps per CTA (one CTA per SM).  The closed form is a chain of fp64 Jacobi sweeps and fp32 libm calls: latency-bound
+// with 8 warps (ncu: issue slots 34 % busy, 2.2 warps per issue in fixed-latency waits); 12 / 16 warps measured
+// 1.30x / 1.47x on the dof-only batch (184 / 164 / 128 registers per thread).  The host picks the largest count whose
+// staging tiles fit in shared memory (all three outputs requested: 8).
+constexpr int POS_WARPS_MIN = 8;
+constexpr int POS_WARPS_MID = 12;
+constexpr int POS_WARPS_MAX = 16;
 
 // host-visible (mapped, pinned) inputs must bypass the caches when a resident kernel re-reads them per frame
 template <bool SYSMEM>
@@ -312,9 +318,9 @@ HRT_DEV void pos_stage_span(float* dst, const float* src, int n_words, int lane)
     }
 }
 // the resident server runs ONE warp: no cross-warp instruction-fetch alignment there
-template <bool SYSMEM>
+template <bool SYSMEM, int WARPS>
 HRT_DEV void pos_align(int warp) {
-    if (!SYSMEM) smsp_align<POS_WARPS>(warp);
+    if (!SYSMEM) smsp_align<WARPS>(warp);
 }
 
 // CTA-shared constants: both PosArm tables + the zero-pose bone angles (once per CTA)
@@ -338,7 +344,7 @@ HRT_DEV void pos_setup(const PosParams& pp, float* smem) {
 }
 
 // all frame groups of `a` that fall to CTA `cta` of `n_ctas`
-template <int MODE, bool SYSMEM>
+template <int MODE, bool SYSMEM, int WARPS>
 HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int n_ctas, int cta) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -367,10 +373,10 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
     bool pending_store = false;
 
     const long long n_groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
-    const long long total_warps = (long long)n_ctas * POS_WARPS;
+    const long long total_warps = (long long)n_ctas * WARPS;
     const long long rounds = (n_groups + total_warps - 1) / total_warps;
     for (long long rnd = 0; rnd < rounds; ++rnd) {
-        const long long grp_raw = rnd * total_warps + (long long)cta * POS_WARPS + warp;
+        const long long grp_raw = rnd * total_warps + (long long)cta * WARPS + warp;
         const bool live = grp_raw < n_groups;
         const long long grp = live ? grp_raw : n_groups - 1;
         const long long f0 = grp * BQ_FRAMES_PER_WARP;
@@ -427,7 +433,7 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
         if (QUATS) {
             parent = *reinterpret_cast<const float4*>(bodyq_s + (fr * pp.n_bodyq + ap.q_parent) * 4);
         } else {
-            pos_align<SYSMEM>(warp);
+            pos_align<SYSMEM, WARPS>(warp);
             // the torso fit and (full_body_pos) this arm's wrist fit are independent: solved together
             double A[2][3][3];
             {
@@ -459,7 +465,7 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
             parent = torso;
         }
         // ---- 3. shoulder pitch / roll, shoulder yaw / elbow pitch ----------------------------------
-        pos_align<SYSMEM>(warp);
+        pos_align<SYSMEM, WARPS>(warp);
         float4 rl[7];
         {
             const vec3 v_up = sub3_x(bpt(ap.b_el), bpt(ap.b_sh));
@@ -476,13 +482,13 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
         rl[4] = rl[5] = rl[6] = make_float4(0.f, 0.f, 0.f, 1.f);
         // ---- 4. wrist -------------------------------------------------------------------------------
         if (HANDS) {
-            pos_align<SYSMEM>(warp);
+            pos_align<SYSMEM, WARPS>(warp);
             const float4 chain = quat_mul_x(quat_mul_x(quat_mul_x(rl[0], rl[1]), rl[2]), rl[3]);
             const float4 base = (MODE == POS_FULL_BODY) ? parent : torso;
             const float4 wparent = quat_mul_norm_x(base, chain);
             if (MODE == POS_FULL_BODY) wrist_g = *reinterpret_cast<const float4*>(bodyq_s + (fr * pp.n_bodyq + ap.q_wrist) * 4);
             const float4 wlocal = quat_mul_norm_x(quat_conj(wparent), wrist_g);
-            pos_align<SYSMEM>(warp);
+            pos_align<SYSMEM, WARPS>(warp);
             double es[3], ec[3];
             euler_intrinsic_half_sincos_f64<0, 1, 2>(wlocal, es, ec);          // 'XYZ'
             rl[4] = axis_quat_from_sc(es[0], ec[0], 0);
@@ -490,7 +496,7 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
             rl[6] = axis_quat_from_sc(es[2], ec[2], 2);
         }
         // ---- 5. hinge angles + gripper -----------------------------------------------------------------
-        pos_align<SYSMEM>(warp);
+        pos_align<SYSMEM, WARPS>(warp);
         float th[9];
         th[0] = quat_to_dof_x(rl[0], 1); th[1] = quat_to_dof_x(rl[1], 0); th[2] = quat_to_dof_x(rl[2], 2);
         th[3] = quat_to_dof_x(rl[3], 1);
@@ -537,7 +543,7 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
                 const float4 Rh = quat_normalize_f(G);
                 const float lam2 = a.damping * a.damping;
                 for (int it = 0; it < a.ik_iters; ++it) {
-                    pos_align<SYSMEM>(warp);
+                    pos_align<SYSMEM, WARPS>(warp);
                     ik_step_f(thc, p_sh, ik.off, ik.lower, ik.upper, pe_t, pw_t, Rh, lam2, a.rot_weight, true);
                 }
             }
@@ -589,12 +595,12 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
     if (pending_store && lane == 0) bulk_wait_read_all();
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(POS_WARPS * 32, 1)
+template <int MODE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 pos_retarget_kernel(const __grid_constant__ PosParams pp, const PosArgs a) {
     extern __shared__ __align__(16) float smem[];
     pos_setup(pp, smem);
-    pos_process<MODE, false>(pp, a, smem, (int)gridDim.x, (int)blockIdx.x);
+    pos_process<MODE, false, WARPS>(pp, a, smem, (int)gridDim.x, (int)blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -640,7 +646,7 @@ pos_stream_server_kernel(const __grid_constant__ PosParams pp, const PosArgs a, 
         const unsigned cmd = s_cmd;
         __syncthreads();
         if (cmd == 0u) break;
-        pos_process<MODE, true>(pp, a, smem, 1, 0);
+        pos_process<MODE, true, 1>(pp, a, smem, 1, 0);
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) st_sys(ctrl + 16, cmd);
