@@ -154,7 +154,7 @@ def side_measurements(eng, hrt, oc, sk, dev):
     out = {}
     # configs[3]: one frame at a time, pinned mapped mailboxes, host-visible in -> host-visible dof_pos
     g = torch.Generator().manual_seed(0)
-    n = 20000
+    n = 100000                                             # 1000 warm-up + >= 100 k timed frames
     em = 0.4 * torch.randn(2048, 59, 3, generator=g)
     root = torch.zeros(2048, 3)
     root[:, 2] = 1.0

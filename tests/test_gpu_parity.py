@@ -487,6 +487,45 @@ def test_full_body_pos_vs_oracle_large(hrt, eng, oc, skeletons):
     assert float(np.quantile(perr[ok].numpy(), 0.99)) <= 5e-5
 
 
+def test_pos_path_cta_shapes_agree(hrt, eng, oc, skeletons):
+    """The position kernels are instantiated for 8 / 12 / 16 warps per CTA and the host picks by what the requested
+    outputs need in shared memory (all three outputs: 8, dof + body quats: 12, dof only: 16) and by clip length
+    (short clips: 8).  Same device code, so the same angles, whichever shape runs."""
+    B = 40_000
+    g = torch.Generator().manual_seed(3)
+    em = 0.4 * torch.randn(B, 59, 3, generator=g)
+    root = torch.zeros(B, 3)
+    root[:, 2] = 1.0
+    _, gt = oc.cal_forward_kinematics(oc.exp_map_to_quat(em), root, skeletons["vtrdyn_full_zero_pose/parents"].tolist(),
+                                      T(skeletons["vtrdyn_full_zero_pose/offsets"]))
+    full2body = [0, 4, 5, 6, 1, 2, 3, 7, 8, 9, 10, 34, 35, 36, 37, 38, 39, 11, 12, 13, 14]
+    body, lh, rh = gt[:, full2body].contiguous().cuda(), gt[:, 14:34].contiguous().cuda(), gt[:, 39:59].contiguous().cuda()
+    dev = body.device
+    lq8, dof8, bq8 = eng.retarget_full_body_pos(body, lh, rh)                                            # 8 warps
+    dof16 = torch.empty(B, 30, device=dev)
+    eng.retarget_full_body_pos(body, lh, rh, out=(None, dof16, None))                                    # 16 warps
+    dof12, bq12 = torch.empty(B, 30, device=dev), torch.empty(B, 59, 4, device=dev)
+    eng.retarget_full_body_pos(body, lh, rh, out=(None, dof12, bq12))                                    # 12 warps
+    ok = torch.isfinite(dof8).all(dim=-1)
+    assert float(ok.float().mean()) > 0.999
+    for name, d in (("16 warps", dof16), ("12 warps", dof12)):
+        diff = (d - dof8)[ok].abs().max().item()
+        print(f"[pos cta shapes] {name} vs 8 warps: max |d dof| = {diff:.3e}")
+        assert diff <= 1e-6, name
+        assert torch.equal(torch.isfinite(d).all(dim=-1), ok)
+    assert (bq12 - bq8)[ok].abs().max().item() <= 1e-6
+    # short clip (8 warps) = the same frames of the long one
+    dof_s = torch.empty(1000, 30, device=dev)
+    eng.retarget_full_body_pos(body[:1000], lh[:1000], rh[:1000], out=(None, dof_s, None))
+    assert (dof_s - dof16[:1000])[ok[:1000]].abs().max().item() <= 1e-6
+    # upper-body path, long clip (16 warps) against its oracle on a sample
+    _, dof_u = eng.retarget_upper_body(body)
+    rl_o, dof_o = oc.retarget_upper_body(body[:4096].cpu(), T(skeletons["vtrdyn_zero_pose/offsets"]))
+    err = (dof_u[:4096].cpu() - dof_o).abs().max(dim=-1).values
+    fin = torch.isfinite(err)
+    assert float(np.quantile(err[fin].numpy(), 0.80)) <= ANGLE_TOL and float(fin.float().mean()) > 0.999
+
+
 def test_full_body_pos_limits_and_refinement_vs_oracle(hrt, eng, oc, skeletons, golden):
     """Position path + joint limits + fused limit-aware refinement (builder-specified: kernel vs own oracle, the
     refinement applied by the oracle to the KERNEL's closed-form angles so that only the refinement is compared)."""
