@@ -21,6 +21,7 @@
 //     cp.async (LDGSTS) into a double buffer one task ahead of their use.
 // All control flow is warp-uniform; idle lane-steps (18 % for Hu) are predicated off.
 #pragma once
+#include <type_traits>
 #include "hrt_math.cuh"
 #include "hrt_params.h"
 
@@ -276,62 +277,82 @@ fk_limb_kernel(const int J, const FkArgs a) {
                 d[0] = v.x; d[1] = v.y; d[2] = v.z;
             }
         };
-        for (int t = 0; t < T; ++t) {
-            const float4 r0 = sched_s[(t * HRT_FK_LANES + p) * 2];
-            const float4 r1 = sched_s[(t * HRT_FK_LANES + p) * 2 + 1];
-            const float2 lim = make_float2(r1.x, r1.y);
-            const uint32_t w3 = __float_as_uint(r0.w), w6 = __float_as_uint(r1.z), w7 = __float_as_uint(r1.w);
-            const bool joint_ok = (int)w3 < 0;
-            const int k = (int)((w3 >> 16) & 3u);
-            const unsigned ang_o = w3 & 0xFFFFu;                   // byte offsets into the angle row / the staged images
-            const unsigned qpar_o = w6 & 0xFFFFu, ppar_o = w6 >> 16;
-            const unsigned qj_o = w7 & 0xFFFFu, pj_o = w7 >> 16;
-            const vec3 off = make_vec3(r0.x, r0.y, r0.z);
-            float4 gq[FKL_CPL], pq[FKL_CPL], lq[FKL_CPL];
-            vec3 gp[FKL_CPL], pp[FKL_CPL];
-            float th[FKL_CPL];
-            // all of the step's loads first (the lane's chains are independent), then the arithmetic
-#pragma unroll
-            for (int u = 0; u < FKL_CPL; ++u) {
-                pq[u] = ld_q(u, qpar_o);
-                pp[u] = ld_p(u, ppar_o);
-                if (FROM_ANGLES) th[u] = lds32(arow[u] + ang_o);
-                else lq[u] = *reinterpret_cast<const float4*>(lrow_g[u] + qj_o);
-            }
-#pragma unroll
-            for (int u = 0; u < FKL_CPL; ++u) {
-                if (FROM_ANGLES) {
-                    if (a.clip) {
-                        // forward value of the straight-through clamp: (clamp(x) - x) + x
-                        const float cl = fminf(fmaxf(th[u], lim.x), lim.y);
-                        th[u] = add_rn(sub_rn(cl, th[u]), th[u]);
+        bool wild = false;
+        auto walk = [&](auto tame) {
+            for (int t = 0; t < T; ++t) {
+                const float4 r0 = sched_s[(t * HRT_FK_LANES + p) * 2];
+                const float4 r1 = sched_s[(t * HRT_FK_LANES + p) * 2 + 1];
+                const float2 lim = make_float2(r1.x, r1.y);
+                const uint32_t w3 = __float_as_uint(r0.w), w6 = __float_as_uint(r1.z), w7 = __float_as_uint(r1.w);
+                const bool joint_ok = (int)w3 < 0;
+                const int k = (int)((w3 >> 16) & 3u);
+                const unsigned ang_o = w3 & 0xFFFFu;                   // byte offsets into the angle row / the staged images
+                const unsigned qpar_o = w6 & 0xFFFFu, ppar_o = w6 >> 16;
+                const unsigned qj_o = w7 & 0xFFFFu, pj_o = w7 >> 16;
+                const vec3 off = make_vec3(r0.x, r0.y, r0.z);
+                float4 gq[FKL_CPL], pq[FKL_CPL], lq[FKL_CPL];
+                vec3 gp[FKL_CPL], pp[FKL_CPL];
+                float th[FKL_CPL];
+                // all of the step's loads first (the lane's chains are independent), then the arithmetic
+    #pragma unroll
+                for (int u = 0; u < FKL_CPL; ++u) {
+                    pq[u] = ld_q(u, qpar_o);
+                    pp[u] = ld_p(u, ppar_o);
+                    if (FROM_ANGLES) th[u] = lds32(arow[u] + ang_o);
+                    else lq[u] = *reinterpret_cast<const float4*>(lrow_g[u] + qj_o);
+                }
+    #pragma unroll
+                for (int u = 0; u < FKL_CPL; ++u) {
+                    if (FROM_ANGLES) {
+                        if (a.clip) {
+                            // forward value of the straight-through clamp: (clamp(x) - x) + x
+                            const float cl = fminf(fmaxf(th[u], lim.x), lim.y);
+                            th[u] = add_rn(sub_rn(cl, th[u]), th[u]);
+                        }
+                        if (EXACT) {
+                            gq[u] = quat_mul_norm_x(pq[u], quat_from_angle_axis_k_x(th[u], k));
+                        } else {
+                            float sn, cs;
+                            if (decltype(tame)::value) {
+                                wild |= fabsf(th[u]) > 4.7f;
+                                sincos_half_nf(0.5f * th[u], &sn, &cs);
+                            } else {
+                                sincos_half_f(0.5f * th[u], &sn, &cs);
+                            }
+                            if (cs < 0.f) { sn = -sn; cs = -cs; }                // quat_normalize's sign flip
+                            gq[u] = quat_normalize_f(quat_mul_axis_rt_f(pq[u], k, sn, cs));
+                        }
+                    } else {
+                        gq[u] = EXACT ? quat_mul_norm_x(pq[u], lq[u]) : quat_mul_norm_f(pq[u], lq[u]);
                     }
                     if (EXACT) {
-                        gq[u] = quat_mul_norm_x(pq[u], quat_from_angle_axis_k_x(th[u], k));
+                        const vec3 r = quat_rotate_x(pq[u], off);
+                        gp[u] = make_vec3(add_rn(r.x, pp[u].x), add_rn(r.y, pp[u].y), add_rn(r.z, pp[u].z));
                     } else {
-                        float sn, cs;
-                        if (BOUNDED) sincos_half_nf(0.5f * th[u], &sn, &cs);
-                        else sincos_half_f(0.5f * th[u], &sn, &cs);
-                        if (cs < 0.f) { sn = -sn; cs = -cs; }                // quat_normalize's sign flip
-                        gq[u] = quat_normalize_f(quat_mul_axis_rt_f(pq[u], k, sn, cs));
+                        gp[u] = add3(quat_rotate_f(pq[u], off), pp[u]);
                     }
-                } else {
-                    gq[u] = EXACT ? quat_mul_norm_x(pq[u], lq[u]) : quat_mul_norm_f(pq[u], lq[u]);
                 }
-                if (EXACT) {
-                    const vec3 r = quat_rotate_x(pq[u], off);
-                    gp[u] = make_vec3(add_rn(r.x, pp[u].x), add_rn(r.y, pp[u].y), add_rn(r.z, pp[u].z));
-                } else {
-                    gp[u] = add3(quat_rotate_f(pq[u], off), pp[u]);
+    #pragma unroll
+                for (int u = 0; u < FKL_CPL; ++u) {
+                    if (joint_ok && cfg_ok[u]) {
+                        st_qp(u, qj_o, pj_o, gq[u], gp[u]);
+                    }
                 }
+                __syncwarp();
             }
-#pragma unroll
-            for (int u = 0; u < FKL_CPL; ++u) {
-                if (joint_ok && cfg_ok[u]) {
-                    st_qp(u, qj_o, pj_o, gq[u], gp[u]);
-                }
+        };
+        if constexpr (FROM_ANGLES && !EXACT && BOUNDED) {
+            // Every limit of the tree is finite, so a clipped angle is inside the half-angle polynomials' range -- unless the
+            // input is so large (|x| > ~1e7 rad) that (clamp(x) - x) + x loses the clamp to rounding.  The walk runs without
+            // the per-update range test and branch and only accumulates "an angle was out of range" in a predicate (one
+            // FSETP per update); one warp vote per task sends such a task through the generic walk again.
+            walk(std::true_type{});
+            if (__any_sync(0xffffffffu, wild)) {
+                wild = false;
+                walk(std::false_type{});
             }
-            __syncwarp();
+        } else {
+            walk(std::false_type{});
         }
 
         // ---- results leave as whole contiguous spans ---------------------------------------------

@@ -65,6 +65,27 @@ def test_fk_angles_vs_reference_golden(hrt, eng_hu, golden):
     assert maxdiff(gt[0], zero) <= 1e-6
 
 
+def test_fk_clip_of_wild_angles_matches_the_reference_arithmetic(hrt, eng_hu, oc, skeletons):
+    """hu_forward_model.py:27-33: the forward value of the clamp is (clamp(x) - x) + x, which LOSES the clamp to rounding
+    for huge inputs (|x| > ~1e7 rad: the result is a multiple of ulp(x), not the limit).  The kernel's fast path for
+    trees with finite limits must notice such angles (warp vote) and still agree with the reference arithmetic."""
+    g = torch.Generator().manual_seed(9)
+    B = 64
+    ang = (torch.rand(B, 32, generator=g) - 0.5) * 2.0
+    wild = torch.tensor([1.0e7, -3.0e7, 5.0e7, 1.3e8, -7.7e8, 3.0e4, -2.0e5, 1.0e30])
+    for i, w in enumerate(wild):
+        ang[i * 3 % B, (7 * i) % 32] = w
+        ang[(i * 5 + 1) % B, (11 * i + 3) % 32] = -w
+    root_t = torch.zeros(B, 3)
+    root_q = torch.zeros(B, 1, 4)
+    root_q[..., 3] = 1.0
+    gq_o, gt_o = oc.hu_forward_kinematics(ang.reshape(B, 32, 1), root_t, root_q, skeletons["hu_zero_pose/parents"].tolist(),
+                                          T(skeletons["hu_zero_pose/offsets"]), oc.HU_DOF_AXIS, oc.HU_DOF_LOWER, oc.HU_DOF_UPPER, True)
+    for exact in (False, True):
+        gq, gt = eng_hu.fk_angles(hrt.TREE_ROBOT, ang, root_t, root_q.reshape(B, 4), clip=True, exact=exact)
+        assert maxdiff(gt, gt_o) <= POS_TOL and maxdiff(gq, gq_o) <= 3e-6, exact
+
+
 @pytest.mark.parametrize("name,tree", [("hu_v5_zero_pose", 0), ("vtrdyn_t_pose", 1), ("vtrdyn_full_zero_pose", 2)])
 def test_fk_local_quats_and_local_rotation_vs_golden(hrt, eng, golden, name, tree):
     g = golden(f"fk_{name}")
