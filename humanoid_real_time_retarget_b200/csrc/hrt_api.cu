@@ -665,7 +665,12 @@ int hrt_retarget_body_quat_host(hrt_ctx* ctx, int64_t B, const float* h_src_gq, 
     if (!h_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
     const int JS = ctx->bq.J_src, JR = ctx->bq.J_rob;
     const size_t in_b = (size_t)JS * 16, lq_b = (size_t)JR * 16, dof_b = (size_t)(JR - 1) * 4, lp_b = (size_t)JR * 12;
-    const long long chunk = 1 << 16;                 // frames per pipeline stage (multiple of 16)
+    // frames per pipeline stage (multiple of 16); HRT_HOST_CHUNK_LOG2 overrides it for tuning runs
+    static const long long chunk = [] {
+        const char* e = std::getenv("HRT_HOST_CHUNK_LOG2");
+        const int lg = e ? std::atoi(e) : 16;
+        return 1LL << (lg < 10 ? 10 : (lg > 20 ? 20 : lg));
+    }();
     const size_t per_frame = in_b + lq_b + dof_b + lp_b;
     const size_t need = per_frame * chunk;
     if (ctx->d_stage_bytes < need) {
@@ -893,7 +898,12 @@ int hrt_retarget_full_body_pos_host(hrt_ctx* ctx, int64_t B, const float* h_body
     if (!h_body_t || !h_lhand_t || !h_rhand_t) return fail(HRT_E_INVALID_ARG, "null input");
     const PosParams& pp = ctx->pos[POS_FULL_BODY_POS];
     const size_t body_b = (size_t)pp.n_body * 12, hand_b = (size_t)pp.n_hand * 12, lq_b = (size_t)pp.J_rob * 16, dof_b = (size_t)(pp.J_rob - 1) * 4;
-    const long long chunk = 1 << 16;                 // frames per pipeline stage (multiple of 16)
+    // frames per pipeline stage (multiple of 16); HRT_HOST_CHUNK_LOG2 overrides it for tuning runs
+    static const long long chunk = [] {
+        const char* e = std::getenv("HRT_HOST_CHUNK_LOG2");
+        const int lg = e ? std::atoi(e) : 16;
+        return 1LL << (lg < 10 ? 10 : (lg > 20 ? 20 : lg));
+    }();
     const size_t need = (body_b + 2 * hand_b + lq_b + dof_b) * chunk;
     if (ctx->d_stage_bytes < need) {
         for (int i = 0; i < kHostStreams; ++i) {
