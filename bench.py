@@ -51,6 +51,28 @@ def ncu_traffic():
         return None
 
 
+def issue_roofline(kern_ms, clocks, n_sms):
+    """The bound that actually holds for the fused kernel: warp instructions issued per second against 4 schedulers per SM
+    at the SM clock sampled during the run.  Instruction count per launch from the committed ncu capture."""
+    n = ncu_warp_instructions()
+    mhz = (clocks or {}).get("sm_mhz") or 0
+    if not n or not mhz:
+        return None
+    peak = 4.0 * n_sms * mhz * 1e6
+    achieved = n / (kern_ms * 1e-3)
+    return {"bound": "issue", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "G warp-instructions/s",
+            "frac": achieved / peak, "warp_instructions_per_launch": n}
+
+
+def ncu_warp_instructions():
+    """smsp__inst_executed.sum per launch of the fused kernel from the same committed capture, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return float(json.load(open(p))["body_quat_kernel"]["warp_instructions_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -427,7 +449,8 @@ def run_ours(args):
                          "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "body_quat_kernel",
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_frame": ALG_BYTES_PER_FRAME,
                          "note": "with 10 IK iterations the kernel is issue-bound by construction (~0.4 Mflop/frame); "
-                                 "see profiles/ for issue-slot utilisation"},
+                                 "see profiles/ for issue-slot utilisation",
+                         "issue": issue_roofline(kern_ms, clocks, torch.cuda.get_device_properties(dev).multi_processor_count)},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
