@@ -210,6 +210,22 @@ def side_measurements(eng, hrt, oc, sk, dev):
         lat[mode] = {"back_to_back": {"frames": n, "p50": float(np.percentile(ts, 50)) / 1e3, "p99": float(np.percentile(ts, 99)) / 1e3,
                                       "p999": float(np.percentile(ts, 99.9)) / 1e3},
                      "paced_120hz": {"frames": 240, "p50": float(np.percentile(paced, 50)) / 1e3, "p99": float(np.percentile(paced, 99)) / 1e3}}
+    # the same frames through the reference-named class, called the way sim_full_body_teleop.py:115 calls it (CPU tensors)
+    solver = hrt.VtrdynFullBodyPosRetargeter(hrt.RobotZeroPose.from_asset("vtrdyn_full_zero_pose"),
+                                             hrt.RobotZeroPose.from_asset("hu_v5_zero_pose"), precise_gripper=True,
+                                             device=dev.index or 0)
+    tb, tl, tr = torch.from_numpy(body), torch.from_numpy(lh), torch.from_numpy(rh)
+    for i in range(1000):
+        solver.retarget(tb[i % 2048], tl[i % 2048], tr[i % 2048], record=False)
+    tc = np.empty(20000)
+    for i in range(20000):
+        k = i % 2048
+        t0 = time.perf_counter_ns()
+        solver.retarget(tb[k], tl[k], tr[k], record=False)
+        tc[i] = time.perf_counter_ns() - t0
+    solver._eng.stream_pos_close()
+    lat["reference_class_call"] = {"call": "VtrdynFullBodyPosRetargeter.retarget(body, lhand, rhand) -> (local_q, dof_pos, body_q), CPU tensors",
+                                   "frames": 20000, "p50": float(np.percentile(tc, 50)) / 1e3, "p99": float(np.percentile(tc, 99)) / 1e3}
     out["latency_us"] = lat
     # configs[1]: 65,536 Hu (33-joint) configurations, FK with joint limits; L2 flushed between launches
     eng_hu = hrt.default_engine(dev.index or 0, robot="hu")

@@ -1082,7 +1082,8 @@ int hrt_stream_pos_open(hrt_ctx* ctx, int flags) {
     if (ctx->pstream_open) hrt_stream_pos_close(ctx);
     const PosParams& pp = ctx->pos[slot];
     const size_t in_w = (size_t)(pp.n_body * 3 + 3) / 4 * 4 + 2 * (size_t)pp.n_hand * 3;   // body | lhand | rhand (16-byte aligned parts)
-    const size_t out_w = (size_t)pp.J_rob * 4 + 32;                                       // local_q | dof (padded)
+    const bool want_bq = (flags & HRT_STREAM_BODY_GQ) != 0;
+    const size_t out_w = (size_t)pp.J_rob * 4 + 32 + (want_bq ? (size_t)pp.J_bq * 4 : 0);   // local_q | dof (padded) | body_gq
     HRT_CUDA(cudaHostAlloc(&ctx->pmb_in, in_w * sizeof(float), cudaHostAllocMapped));
     HRT_CUDA(cudaHostAlloc(&ctx->pmb_out, out_w * sizeof(float), cudaHostAllocMapped));
     HRT_CUDA(cudaHostGetDevicePointer(&ctx->pmb_in_d, ctx->pmb_in, 0));
@@ -1095,6 +1096,7 @@ int hrt_stream_pos_open(hrt_ctx* ctx, int flags) {
     a.rhand_t = a.lhand_t + pp.n_hand * 3;
     a.out_local_q = ctx->pmb_out_d;
     a.out_dof = ctx->pmb_out_d + pp.J_rob * 4;
+    a.out_body_gq = want_bq ? ctx->pmb_out_d + pp.J_rob * 4 + 32 : nullptr;
     a.flags = ((flags & HRT_STREAM_CLAMP) ? POS_CLAMP : 0u) | ((flags & HRT_STREAM_IK) ? (POS_CLAMP | POS_IK) : 0u);
     a.ik_iters = 10; a.damping = 0.1f; a.rot_weight = 0.2f;
     ctx->pstream_args = a;
@@ -1116,8 +1118,14 @@ int hrt_stream_pos_open(hrt_ctx* ctx, int flags) {
 
 int hrt_stream_pos_frame(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
                          float* h_robot_local_q, float* h_dof) {
+    return hrt_stream_pos_frame_bq(ctx, h_body_t, h_lhand_t, h_rhand_t, h_robot_local_q, h_dof, nullptr);
+}
+
+int hrt_stream_pos_frame_bq(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
+                            float* h_robot_local_q, float* h_dof, float* h_body_gq) {
     if (!ctx || !ctx->pstream_open) return fail(HRT_E_NOT_CONFIGURED, "hrt_stream_pos_open has not been called");
     if (!h_body_t || !h_lhand_t || !h_rhand_t) return fail(HRT_E_INVALID_ARG, "null input");
+    if (h_body_gq && !ctx->pstream_args.out_body_gq) return fail(HRT_E_INVALID_ARG, "stream opened without HRT_STREAM_BODY_GQ");
     const PosParams& pp = ctx->pos[ctx->pstream_mode];
     const size_t body_w = (size_t)pp.n_body * 3, hand_w = (size_t)pp.n_hand * 3;
     memcpy(ctx->pmb_in, h_body_t, body_w * 4);
@@ -1134,6 +1142,7 @@ int hrt_stream_pos_frame(hrt_ctx* ctx, const float* h_body_t, const float* h_lha
     }
     if (h_robot_local_q) memcpy(h_robot_local_q, ctx->pmb_out, (size_t)pp.J_rob * 16);
     if (h_dof) memcpy(h_dof, ctx->pmb_out + pp.J_rob * 4, (size_t)(pp.J_rob - 1) * 4);
+    if (h_body_gq) memcpy(h_body_gq, ctx->pmb_out + pp.J_rob * 4 + 32, (size_t)pp.J_bq * 16);
     return 0;
 }
 

@@ -41,6 +41,8 @@ class Engine:
         _lib.check(self.lib.hrt_ctx_create(self.device.index, C.byref(h)))
         self._h = h
         self._trees = {}
+        self._pos_stream_cfg = None        # what the position / quaternion streaming mailboxes are currently opened for
+        self._bq_stream_cfg = None
         self.sm_count = self.lib.hrt_ctx_sm_count(h)
 
     def close(self):
@@ -323,19 +325,30 @@ class Engine:
                                                self._stream()))
         return out
 
-    def stream_pos_open(self, wire_layout=False, persistent=False, clamp=False, ik=False):
+    def stream_pos_open(self, wire_layout=False, persistent=False, clamp=False, ik=False, body_gq=False):
         """persistent=True: a resident one-warp server polls the mailbox (no launch / sync per frame);
-        clamp / ik: joint limits / + 10 limit-aware refinement steps, as retarget_full_body_pos(flags=...)."""
+        clamp / ik: joint limits / + 10 limit-aware refinement steps, as retarget_full_body_pos(flags=...);
+        body_gq=True: the mailbox also carries the (59,4) body quaternions (stream_pos_frame_tensors)."""
         _lib.check(self.lib.hrt_stream_pos_open(self._h, (1 if wire_layout else 0) | (2 if persistent else 0) |
-                                                (4 if clamp else 0) | (8 if ik else 0)))
+                                                (4 if clamp else 0) | (8 if ik else 0) | (16 if body_gq else 0)))
+        self._pos_stream_cfg = (bool(wire_layout), bool(persistent), bool(clamp), bool(ik), bool(body_gq))
 
     def stream_pos_frame(self, body_np, lhand_np, rhand_np, out_local_q=None, out_dof=None):
         """numpy float32 in / out, one frame of the position path."""
         _lib.check(self.lib.hrt_stream_pos_frame(self._h, _np_ptr(body_np), _np_ptr(lhand_np), _np_ptr(rhand_np),
                                                  _np_ptr(out_local_q), _np_ptr(out_dof)))
 
+    def stream_pos_frame_tensors(self, body, lhand, rhand, out_local_q, out_dof, out_body_gq=None):
+        """The same on contiguous float32 CPU tensors (data_ptr() is several microseconds cheaper than numpy's ctypes
+        view on the per-frame path); out_body_gq needs stream_pos_open(body_gq=True)."""
+        _lib.check(self.lib.hrt_stream_pos_frame_bq(self._h, body.data_ptr(), lhand.data_ptr(), rhand.data_ptr(),
+                                                    out_local_q.data_ptr() if out_local_q is not None else None,
+                                                    out_dof.data_ptr() if out_dof is not None else None,
+                                                    out_body_gq.data_ptr() if out_body_gq is not None else None))
+
     def stream_pos_close(self):
         _lib.check(self.lib.hrt_stream_pos_close(self._h))
+        self._pos_stream_cfg = None
 
     # ------------------------------------------------------------------ host-buffer (reference-facing) calls
     def retarget_body_quat_host(self, src_gq, flags=0, ik_iters=10, damping=0.1, rot_weight=0.2,
@@ -365,14 +378,23 @@ class Engine:
     def stream_open(self, flags=0, ik_iters=10, damping=0.1, rot_weight=0.2, persistent=False):
         """persistent=True: a resident one-warp server polls the mailbox (no launch / sync per frame)."""
         _lib.check(self.lib.hrt_stream_open(self._h, flags | (32 if persistent else 0), ik_iters, damping, rot_weight))
+        self._bq_stream_cfg = (int(flags), int(ik_iters), float(damping), float(rot_weight), bool(persistent))
 
     def stream_frame(self, src_gq_np, out_local_q=None, out_dof=None, out_link_pos=None):
         """numpy float32 in / out, one frame."""
         _lib.check(self.lib.hrt_stream_frame(self._h, _np_ptr(src_gq_np), _np_ptr(out_local_q), _np_ptr(out_dof),
                                              _np_ptr(out_link_pos)))
 
+    def stream_frame_tensors(self, src_gq, out_local_q=None, out_dof=None, out_link_pos=None):
+        """The same on contiguous float32 CPU tensors."""
+        _lib.check(self.lib.hrt_stream_frame(self._h, src_gq.data_ptr(),
+                                             out_local_q.data_ptr() if out_local_q is not None else None,
+                                             out_dof.data_ptr() if out_dof is not None else None,
+                                             out_link_pos.data_ptr() if out_link_pos is not None else None))
+
     def stream_close(self):
         _lib.check(self.lib.hrt_stream_close(self._h))
+        self._bq_stream_cfg = None
 
 
 _default = {}

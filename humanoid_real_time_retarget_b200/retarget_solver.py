@@ -114,6 +114,18 @@ class Mocap2HuBodyRetargeter(BaseHumanoidRetargeter):
     def retarget_from_pose(self, source_global_rotation, record=True):
         g = to_torch(source_global_rotation)
         single = g.dim() == 2
+        if single and not g.is_cuda and g.dtype == torch.float32:
+            # the teleop call: one CPU frame.  It goes through the pinned mailbox of the streaming entry point (one launch,
+            # no torch allocation or copy kernels on the way) instead of the batched device path.
+            cfg_ = (BQ_PRE_TRANSFORMED, 0, 0.0, 0.0, False)
+            if self._eng._bq_stream_cfg != cfg_:
+                self._eng.stream_open(flags=BQ_PRE_TRANSFORMED, ik_iters=0, damping=0.0, rot_weight=0.0)
+            lq, dof = torch.empty((31, 4)), torch.empty((30,))
+            self._eng.stream_frame_tensors(g.contiguous(), lq, dof, None)
+            if record:
+                self._motion_local_rotation.append(lq)
+                self._motion_dof_pos.append(dof)
+            return lq, dof
         lq, dof, _ = self._eng.retarget_body_quat(g.reshape(-1, 21, 4), flags=BQ_PRE_TRANSFORMED, want_link_pos=False)
         lq, dof = lq.to(g.device), dof.to(g.device)
         if single:
@@ -156,9 +168,12 @@ class VtrdynFullBodyPosRetargeter(_PosRetargeterBase):
     the reference, or a batch with a leading frame axis.  Returns (robot_local_rotation, dof_pos,
     body_global_rotation)."""
 
-    def __init__(self, mocap_zero_pose, target_zero_pose, precise_gripper=False, device=0):
+    def __init__(self, mocap_zero_pose, target_zero_pose, precise_gripper=False, device=0, resident=False):
+        """resident=True (additive): single CPU frames are served by a resident one-warp kernel polling the pinned mailbox
+        (no launch or stream synchronisation per frame, ~28 us instead of ~46 us; it leaves after 20 ms without a frame)."""
         super().__init__(mocap_zero_pose, target_zero_pose, device)
         self.precise_gripper = precise_gripper
+        self.resident = bool(resident)
         from . import robot_config as _cfg
         self._eng.configure_pos(POS_FULL_BODY_POS, TREE_SOURCE_FULL, TREE_ROBOT,
                                 _cfg.skeleton_tables()["vtrdyn_full_zero_pose/global_translation"], precise_gripper)
@@ -166,6 +181,20 @@ class VtrdynFullBodyPosRetargeter(_PosRetargeterBase):
     def retarget(self, body_global_translation, left_hand_global_translation, right_hand_global_translation, record=True):
         b = to_torch(body_global_translation)
         single = b.dim() == 2
+        if single and not b.is_cuda:
+            # the teleop call (sim_full_body_teleop.py:115): one CPU frame through the pinned mailbox of the streaming entry
+            # point -- one launch, no torch allocation or copy kernels on the way
+            lh, rh = to_torch(left_hand_global_translation), to_torch(right_hand_global_translation)
+            if b.dtype == lh.dtype == rh.dtype == torch.float32 and b.shape == (21, 3) and lh.shape == rh.shape == (20, 3):
+                cfg_ = (False, self.resident, False, False, True)
+                if self._eng._pos_stream_cfg != cfg_:
+                    self._eng.stream_pos_open(persistent=self.resident, body_gq=True)
+                lq, dof, bq = torch.empty((31, 4)), torch.empty((30,)), torch.empty((59, 4))
+                self._eng.stream_pos_frame_tensors(b.contiguous(), lh.contiguous(), rh.contiguous(), lq, dof, bq)
+                if record:
+                    self._motion_local_rotation.append(lq)
+                    self._motion_dof_pos.append(dof)
+                return lq, dof, bq
         lq, dof, bq = self._eng.retarget_full_body_pos(b.reshape(-1, 21, 3), to_torch(left_hand_global_translation).reshape(-1, 20, 3),
                                                        to_torch(right_hand_global_translation).reshape(-1, 20, 3))
         return self._finish(b, lq, dof, single, record, bq)

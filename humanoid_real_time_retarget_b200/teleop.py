@@ -62,6 +62,7 @@ class TeleopSession:
 
     def __init__(self, device=0, persistent=True, clamp=False, ik=False, engine=None):
         self._eng = engine or default_engine(device)
+        self._cfg = (True, bool(persistent), bool(clamp), bool(ik), False)
         self._eng.stream_pos_open(wire_layout=True, persistent=persistent, clamp=clamp, ik=ik)
         self._dof = np.zeros(30, np.float32)
         self.last_dof_pos = np.zeros(30, np.float32)
@@ -77,6 +78,8 @@ class TeleopSession:
         rh = np.ascontiguousarray(data_dict["right_hand_pos"], dtype=np.float32)
         if lh.shape != (20, 3) or rh.shape != (20, 3):
             raise ValueError("left_hand_pos / right_hand_pos must be (20, 3)")
+        if self._eng._pos_stream_cfg != self._cfg:      # another user of this engine re-opened the mailbox in between
+            self._eng.stream_pos_open(wire_layout=True, persistent=self._cfg[1], clamp=self._cfg[2], ik=self._cfg[3])
         self._eng.stream_pos_frame(body, lh, rh, None, self._dof)
         self.last_dof_pos = self._dof.copy()
         return self.last_dof_pos.copy()
@@ -86,7 +89,8 @@ class TeleopSession:
         return [self.step(d) for d in self.decoder.feed(chunk)]
 
     def close(self):
-        self._eng.stream_pos_close()
+        if self._eng._pos_stream_cfg == self._cfg:
+            self._eng.stream_pos_close()
 
     def __enter__(self):
         return self

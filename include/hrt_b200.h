@@ -195,9 +195,13 @@ int hrt_retarget_full_body_pos_wire(hrt_ctx* ctx, int64_t B, const float* d_body
 #define HRT_STREAM_PERSISTENT 2    /* resident server kernel polling the mailbox: no launch / sync per frame */
 #define HRT_STREAM_CLAMP 4         /* joint limits on the arm hinges (HRT_POS_CLAMP) */
 #define HRT_STREAM_IK 8            /* + 10 limit-aware refinement steps (HRT_POS_IK, damping 0.1, rotation weight 0.2) */
+#define HRT_STREAM_BODY_GQ 16      /* also publish the third return of VtrdynFullBodyPosRetargeter.retarget (59 x 4 body quats) */
 int hrt_stream_pos_open(hrt_ctx* ctx, int flags);
 int hrt_stream_pos_frame(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
                          float* h_robot_local_q, float* h_dof);
+/* the same with the (J_bq, 4) body global rotations (full_body_pos_retargeter.py:217, third return); needs HRT_STREAM_BODY_GQ */
+int hrt_stream_pos_frame_bq(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
+                            float* h_robot_local_q, float* h_dof, float* h_body_gq);
 int hrt_stream_pos_close(hrt_ctx* ctx);
 
 /* RetargetHuV5fromMocap (retarget/main.py:51-279), mode 3 of the position solvers: arms from joint

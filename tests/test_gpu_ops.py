@@ -418,3 +418,52 @@ def test_velocity_shards_with_halo_equal_whole_clip(hrt, golden):
         v = eng.motion_velocity(gt[a:b], 1 / 30).cpu()[lo - a:lo - a + hi - lo]
         w = eng.motion_angular_velocity(gq[a:b], 1 / 30).cpu()[lo - a:lo - a + hi - lo]
         assert torch.equal(v, whole_v[lo:hi]) and torch.equal(w, whole_w[lo:hi]), (lo, hi)
+
+
+def test_single_frame_calls_of_the_reference_classes_use_the_mailbox(hrt, golden):
+    """One CPU frame through VtrdynFullBodyPosRetargeter.retarget / Mocap2HuBodyRetargeter.retarget_from_pose (what the
+    teleop scripts do) takes the streaming mailbox; results must equal the batched device path bit for bit, the three
+    returns must be fresh tensors, and a TeleopSession sharing the engine must keep working."""
+    g = golden("full_body_pos")
+    src = hrt.RobotZeroPose.from_asset("vtrdyn_full_zero_pose")
+    tgt = hrt.RobotZeroPose.from_asset("hu_v5_zero_pose")
+    solver = hrt.VtrdynFullBodyPosRetargeter(src, tgt, precise_gripper=True)
+    eng = solver._eng
+    body, lh, rh = T(g["body_t"]), T(g["lhand_t"]), T(g["rhand_t"])
+    lq_b, dof_b, bq_b = eng.retarget_full_body_pos(body, lh, rh)
+    outs = []
+    for i in range(6):
+        lq, dof, bq = solver.retarget(body[i], lh[i], rh[i])
+        assert lq.shape == (31, 4) and dof.shape == (30,) and bq.shape == (59, 4) and dof.device.type == "cpu"
+        assert torch.equal(dof, dof_b[i].cpu()) and torch.equal(lq, lq_b[i].cpu()) and torch.equal(bq, bq_b[i].cpu())
+        outs.append(dof)
+    assert eng._pos_stream_cfg == (False, False, False, False, True)
+    assert len({o.data_ptr() for o in outs}) == 6 and solver.motion_length == 6          # new tensors, recorded like the reference
+    # a teleop session on the same engine re-opens the mailbox for the wire layout, then the solver takes it back
+    wire_body = torch.zeros(23, 3)
+    wire_body[[0, 1, 2, 3, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22]] = body[0]
+    inv = [0, 4, 5, 6, 7, 8, 9, 10, 11, 16, 17, 18, 19, 12, 13, 14, 15, 1, 2, 3]
+    wl, wr = torch.zeros(20, 3), torch.zeros(20, 3)
+    wl[inv], wr[inv] = lh[0], rh[0]
+    with hrt.TeleopSession(engine=eng, persistent=False) as sess:
+        d0 = sess.step({"body_pos": wire_body.numpy(), "left_hand_pos": wl.numpy(), "right_hand_pos": wr.numpy()})
+        assert np.array_equal(d0, dof_b[0].cpu().numpy())
+        _, dof1, _ = solver.retarget(body[1], lh[1], rh[1], record=False)
+        assert torch.equal(dof1, dof_b[1].cpu())
+        d0b = sess.step({"body_pos": wire_body.numpy(), "left_hand_pos": wl.numpy(), "right_hand_pos": wr.numpy()})
+        assert np.array_equal(d0b, d0)
+    # resident server behind the same call
+    rsolver = hrt.VtrdynFullBodyPosRetargeter(src, tgt, precise_gripper=True, resident=True)
+    for i in range(3):
+        lq, dof, bq = rsolver.retarget(body[i], lh[i], rh[i], record=False)
+        assert md(dof, dof_b[i].cpu()) <= 1e-6 and md(bq, bq_b[i].cpu()) <= 1e-6 and md(lq, lq_b[i].cpu()) <= 1e-6
+    eng.stream_pos_close()
+    # quaternion path
+    gq = golden("body_quat")
+    mocap = hrt.RobotZeroPose.from_asset("vtrdyn_zero_pose")
+    bsolver = hrt.Mocap2HuBodyRetargeter(mocap, tgt)
+    zq = T(gq["zero_pose_q"])
+    lq_bb, dof_bb, _ = bsolver._eng.retarget_body_quat(zq, flags=hrt.BQ_PRE_TRANSFORMED, want_link_pos=False)
+    for i in range(4):
+        lq, dof = bsolver.retarget_from_pose(zq[i])
+        assert torch.equal(dof, dof_bb[i].cpu()) and torch.equal(lq, lq_bb[i].cpu())
