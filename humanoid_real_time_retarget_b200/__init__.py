@@ -2,7 +2,8 @@
 retarget hot path of shuoshuof/Humanoid-Real-Time-Retarget.  See DESIGN.md / INTEGRATION.md."""
 from . import robot_config
 from ._lib import HrtError, LIB_PATH, EXPORTED_SYMBOLS
-from .engine import (BQ_ACTIVE_SET, BQ_CLAMP, BQ_IK, BQ_PACKED_IK, BQ_PRE_TRANSFORMED, POS_CLAMP, POS_IK, FK_EXACT, TREE_ROBOT, TREE_SOURCE, TREE_SOURCE_FULL,
+from .engine import (BQ_ACTIVE_SET, BQ_CLAMP, BQ_IK, BQ_PACKED_IK, BQ_PRE_TRANSFORMED, POS_CLAMP, POS_IK, POS_FULL_BODY, POS_FULL_BODY_POS,
+                     POS_MAIN, POS_UPPER_BODY, FK_EXACT, TREE_ROBOT, TREE_SOURCE, TREE_SOURCE_FULL,
                      Engine, default_engine)
 from .kinematics import (BaseForwardModel, HuForwardModel, RobotZeroPose, cal_forward_kinematics, cal_local_rotation)
 from .retarget_solver import (cal_elbowP_and_shoulderY, cal_shoulderPR, BaseHumanoidRetargeter, HuUpperBodyFromMocapRetarget, Mocap2HuBodyRetargeter,

@@ -38,7 +38,7 @@ _SIGNATURES = {
     "hrt_retarget_full_body_pos_wire": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "hrt_stream_pos_open": (C.c_int, [_P, C.c_int]),
     "hrt_stream_pos_frame": (C.c_int, [_P, _P, _P, _P, _P, _P]),
-    "hrt_stream_pos_frame_bq": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "hrt_stream_pos_frame_ex": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "hrt_stream_pos_close": (C.c_int, [_P]),
     "hrt_retarget_main_arms": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
     "hrt_rescale_motion": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, _P]),

@@ -1077,11 +1077,19 @@ int launch_pos_server(hrt_ctx* ctx, unsigned served) {
 int hrt_stream_pos_open(hrt_ctx* ctx, int flags) {
     int rc = check_ctx(ctx);
     if (rc) return rc;
-    const int slot = (flags & HRT_STREAM_WIRE_LAYOUT) ? 4 : 0;
-    if (!ctx->pos_set[slot]) return fail(HRT_E_NOT_CONFIGURED, "hrt_configure_pos(mode 0) has not been called");
+    const int mode = (flags >> HRT_STREAM_MODE_SHIFT) & 3;
+    const bool wire = (flags & HRT_STREAM_WIRE_LAYOUT) != 0;
+    if (mode == POS_MAIN) return fail(HRT_E_INVALID_ARG, "streaming serves modes 0 (full_body_pos), 1 (upper_body), 2 (full_body)");
+    if (mode != POS_FULL_BODY_POS && (flags & (HRT_STREAM_WIRE_LAYOUT | HRT_STREAM_PERSISTENT | HRT_STREAM_BODY_GQ)))
+        return fail(HRT_E_INVALID_ARG, "wire layout, resident server and body quaternions exist for mode 0 only");
+    const int slot = wire ? 4 : mode;
+    if (!ctx->pos_set[slot]) return fail(HRT_E_NOT_CONFIGURED, "hrt_configure_pos(mode %d) has not been called", mode);
     if (ctx->pstream_open) hrt_stream_pos_close(ctx);
     const PosParams& pp = ctx->pos[slot];
-    const size_t in_w = (size_t)(pp.n_body * 3 + 3) / 4 * 4 + 2 * (size_t)pp.n_hand * 3;   // body | lhand | rhand (16-byte aligned parts)
+    const bool hands = mode != POS_UPPER_BODY, quats = mode == POS_FULL_BODY;
+    // mailbox in: body | lhand | rhand | body_q (16-byte aligned parts, a part a mode does not read stays unused)
+    const size_t body_w = (size_t)(pp.n_body * 3 + 3) / 4 * 4, hand_w = (size_t)(pp.n_hand * 3 + 3) / 4 * 4;
+    const size_t in_w = body_w + 2 * hand_w + (size_t)pp.n_bodyq * 4;
     const bool want_bq = (flags & HRT_STREAM_BODY_GQ) != 0;
     const size_t out_w = (size_t)pp.J_rob * 4 + 32 + (want_bq ? (size_t)pp.J_bq * 4 : 0);   // local_q | dof (padded) | body_gq
     HRT_CUDA(cudaHostAlloc(&ctx->pmb_in, in_w * sizeof(float), cudaHostAllocMapped));
@@ -1092,8 +1100,11 @@ int hrt_stream_pos_open(hrt_ctx* ctx, int flags) {
     PosArgs a{};
     a.B = 1;
     a.body_t = ctx->pmb_in_d;
-    a.lhand_t = ctx->pmb_in_d + (pp.n_body * 3 + 3) / 4 * 4;
-    a.rhand_t = a.lhand_t + pp.n_hand * 3;
+    if (hands) {
+        a.lhand_t = ctx->pmb_in_d + body_w;
+        a.rhand_t = a.lhand_t + hand_w;
+    }
+    if (quats) a.body_q = ctx->pmb_in_d + body_w + 2 * hand_w;
     a.out_local_q = ctx->pmb_out_d;
     a.out_dof = ctx->pmb_out_d + pp.J_rob * 4;
     a.out_body_gq = want_bq ? ctx->pmb_out_d + pp.J_rob * 4 + 32 : nullptr;
@@ -1118,19 +1129,23 @@ int hrt_stream_pos_open(hrt_ctx* ctx, int flags) {
 
 int hrt_stream_pos_frame(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
                          float* h_robot_local_q, float* h_dof) {
-    return hrt_stream_pos_frame_bq(ctx, h_body_t, h_lhand_t, h_rhand_t, h_robot_local_q, h_dof, nullptr);
+    return hrt_stream_pos_frame_ex(ctx, h_body_t, h_lhand_t, h_rhand_t, nullptr, h_robot_local_q, h_dof, nullptr);
 }
 
-int hrt_stream_pos_frame_bq(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
-                            float* h_robot_local_q, float* h_dof, float* h_body_gq) {
+int hrt_stream_pos_frame_ex(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
+                            const float* h_body_q, float* h_robot_local_q, float* h_dof, float* h_body_gq) {
     if (!ctx || !ctx->pstream_open) return fail(HRT_E_NOT_CONFIGURED, "hrt_stream_pos_open has not been called");
-    if (!h_body_t || !h_lhand_t || !h_rhand_t) return fail(HRT_E_INVALID_ARG, "null input");
-    if (h_body_gq && !ctx->pstream_args.out_body_gq) return fail(HRT_E_INVALID_ARG, "stream opened without HRT_STREAM_BODY_GQ");
+    const PosArgs& a = ctx->pstream_args;
+    if (!h_body_t || (a.lhand_t && (!h_lhand_t || !h_rhand_t)) || (a.body_q && !h_body_q)) return fail(HRT_E_INVALID_ARG, "null input");
+    if (h_body_gq && !a.out_body_gq) return fail(HRT_E_INVALID_ARG, "stream opened without HRT_STREAM_BODY_GQ");
     const PosParams& pp = ctx->pos[ctx->pstream_mode];
-    const size_t body_w = (size_t)pp.n_body * 3, hand_w = (size_t)pp.n_hand * 3;
-    memcpy(ctx->pmb_in, h_body_t, body_w * 4);
-    memcpy(ctx->pmb_in + (body_w + 3) / 4 * 4, h_lhand_t, hand_w * 4);
-    memcpy(ctx->pmb_in + (body_w + 3) / 4 * 4 + hand_w, h_rhand_t, hand_w * 4);
+    const size_t body_w = (size_t)(pp.n_body * 3 + 3) / 4 * 4, hand_w = (size_t)(pp.n_hand * 3 + 3) / 4 * 4;
+    memcpy(ctx->pmb_in, h_body_t, (size_t)pp.n_body * 12);
+    if (a.lhand_t) {
+        memcpy(ctx->pmb_in + body_w, h_lhand_t, (size_t)pp.n_hand * 12);
+        memcpy(ctx->pmb_in + body_w + hand_w, h_rhand_t, (size_t)pp.n_hand * 12);
+    }
+    if (a.body_q) memcpy(ctx->pmb_in + body_w + 2 * hand_w, h_body_q, (size_t)pp.n_bodyq * 16);
     if (!ctx->pstream_persistent) {
         int rc = launch_pos(ctx, ctx->pstream_mode, ctx->pstream_args, ctx->pss, 1);
         if (rc) return rc;

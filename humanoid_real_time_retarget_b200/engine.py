@@ -325,26 +325,26 @@ class Engine:
                                                self._stream()))
         return out
 
-    def stream_pos_open(self, wire_layout=False, persistent=False, clamp=False, ik=False, body_gq=False):
+    def stream_pos_open(self, wire_layout=False, persistent=False, clamp=False, ik=False, body_gq=False, mode=POS_FULL_BODY_POS):
         """persistent=True: a resident one-warp server polls the mailbox (no launch / sync per frame);
         clamp / ik: joint limits / + 10 limit-aware refinement steps, as retarget_full_body_pos(flags=...);
-        body_gq=True: the mailbox also carries the (59,4) body quaternions (stream_pos_frame_tensors)."""
+        body_gq=True: the mailbox also carries the (59,4) body quaternions (stream_pos_frame_tensors);
+        mode: POS_FULL_BODY_POS, POS_UPPER_BODY or POS_FULL_BODY (the last two: launch per frame only)."""
         _lib.check(self.lib.hrt_stream_pos_open(self._h, (1 if wire_layout else 0) | (2 if persistent else 0) |
-                                                (4 if clamp else 0) | (8 if ik else 0) | (16 if body_gq else 0)))
-        self._pos_stream_cfg = (bool(wire_layout), bool(persistent), bool(clamp), bool(ik), bool(body_gq))
+                                                (4 if clamp else 0) | (8 if ik else 0) | (16 if body_gq else 0) | (int(mode) << 8)))
+        self._pos_stream_cfg = (bool(wire_layout), bool(persistent), bool(clamp), bool(ik), bool(body_gq), int(mode))
 
     def stream_pos_frame(self, body_np, lhand_np, rhand_np, out_local_q=None, out_dof=None):
         """numpy float32 in / out, one frame of the position path."""
         _lib.check(self.lib.hrt_stream_pos_frame(self._h, _np_ptr(body_np), _np_ptr(lhand_np), _np_ptr(rhand_np),
                                                  _np_ptr(out_local_q), _np_ptr(out_dof)))
 
-    def stream_pos_frame_tensors(self, body, lhand, rhand, out_local_q, out_dof, out_body_gq=None):
+    def stream_pos_frame_tensors(self, body, lhand, rhand, out_local_q, out_dof, out_body_gq=None, body_q=None):
         """The same on contiguous float32 CPU tensors (data_ptr() is several microseconds cheaper than numpy's ctypes
-        view on the per-frame path); out_body_gq needs stream_pos_open(body_gq=True)."""
-        _lib.check(self.lib.hrt_stream_pos_frame_bq(self._h, body.data_ptr(), lhand.data_ptr(), rhand.data_ptr(),
-                                                    out_local_q.data_ptr() if out_local_q is not None else None,
-                                                    out_dof.data_ptr() if out_dof is not None else None,
-                                                    out_body_gq.data_ptr() if out_body_gq is not None else None))
+        view on the per-frame path); out_body_gq needs stream_pos_open(body_gq=True), body_q is mode POS_FULL_BODY's input."""
+        p = lambda t: t.data_ptr() if t is not None else None
+        _lib.check(self.lib.hrt_stream_pos_frame_ex(self._h, p(body), p(lhand), p(rhand), p(body_q), p(out_local_q), p(out_dof),
+                                                    p(out_body_gq)))
 
     def stream_pos_close(self):
         _lib.check(self.lib.hrt_stream_pos_close(self._h))

@@ -8,7 +8,8 @@ import numpy as np
 import torch
 
 from . import robot_config as cfg
-from .engine import (BQ_CLAMP, BQ_IK, BQ_PRE_TRANSFORMED, POS_FULL_BODY_POS, TREE_ROBOT, TREE_SOURCE, TREE_SOURCE_FULL,
+from .engine import (BQ_CLAMP, BQ_IK, BQ_PRE_TRANSFORMED, POS_FULL_BODY, POS_FULL_BODY_POS, POS_UPPER_BODY, TREE_ROBOT, TREE_SOURCE,
+                     TREE_SOURCE_FULL,
                      default_engine)
 from .kinematics import RobotZeroPose, cal_forward_kinematics
 
@@ -186,7 +187,7 @@ class VtrdynFullBodyPosRetargeter(_PosRetargeterBase):
             # point -- one launch, no torch allocation or copy kernels on the way
             lh, rh = to_torch(left_hand_global_translation), to_torch(right_hand_global_translation)
             if b.dtype == lh.dtype == rh.dtype == torch.float32 and b.shape == (21, 3) and lh.shape == rh.shape == (20, 3):
-                cfg_ = (False, self.resident, False, False, True)
+                cfg_ = (False, self.resident, False, False, True, POS_FULL_BODY_POS)
                 if self._eng._pos_stream_cfg != cfg_:
                     self._eng.stream_pos_open(persistent=self.resident, body_gq=True)
                 lq, dof, bq = torch.empty((31, 4)), torch.empty((30,)), torch.empty((59, 4))
@@ -206,6 +207,17 @@ class HuUpperBodyFromMocapRetarget(_PosRetargeterBase):
     def retarget_from_global_translation(self, source_global_translation, record=True):
         b = to_torch(source_global_translation)
         single = b.dim() == 2
+        if single and not b.is_cuda and b.dtype == torch.float32 and b.shape == (21, 3):
+            # the teleop call (sim_teleop.py:86-108): one CPU frame through the pinned streaming mailbox
+            cfg_ = (False, False, False, False, False, POS_UPPER_BODY)
+            if self._eng._pos_stream_cfg != cfg_:
+                self._eng.stream_pos_open(mode=POS_UPPER_BODY)
+            lq, dof = torch.empty((31, 4)), torch.empty((30,))
+            self._eng.stream_pos_frame_tensors(b.contiguous(), None, None, lq, dof)
+            if record:
+                self._motion_local_rotation.append(lq)
+                self._motion_dof_pos.append(dof)
+            return lq, dof
         lq, dof = self._eng.retarget_upper_body(b.reshape(-1, 21, 3))
         return self._finish(b, lq, dof, single, record)
 
@@ -218,6 +230,19 @@ class VtrdynFullBodyRetargeter(_PosRetargeterBase):
                  left_hand_global_translation, right_hand_global_rotation, right_hand_global_translation, record=True):
         b = to_torch(body_global_translation)
         single = b.dim() == 2
+        if single and not b.is_cuda:
+            q, lh, rh = to_torch(body_global_rotation), to_torch(left_hand_global_translation), to_torch(right_hand_global_translation)
+            if (b.dtype == q.dtype == lh.dtype == rh.dtype == torch.float32 and b.shape == (21, 3) and q.shape == (21, 4)
+                    and lh.shape == rh.shape == (20, 3)):
+                cfg_ = (False, False, False, False, False, POS_FULL_BODY)
+                if self._eng._pos_stream_cfg != cfg_:
+                    self._eng.stream_pos_open(mode=POS_FULL_BODY)
+                lq, dof = torch.empty((31, 4)), torch.empty((30,))
+                self._eng.stream_pos_frame_tensors(b.contiguous(), lh.contiguous(), rh.contiguous(), lq, dof, None, q.contiguous())
+                if record:
+                    self._motion_local_rotation.append(lq)
+                    self._motion_dof_pos.append(dof)
+                return lq, dof
         lq, dof = self._eng.retarget_full_body(to_torch(body_global_rotation).reshape(-1, 21, 4), b.reshape(-1, 21, 3),
                                                to_torch(left_hand_global_translation).reshape(-1, 20, 3),
                                                to_torch(right_hand_global_translation).reshape(-1, 20, 3))

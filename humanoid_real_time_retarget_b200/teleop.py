@@ -62,7 +62,7 @@ class TeleopSession:
 
     def __init__(self, device=0, persistent=True, clamp=False, ik=False, engine=None):
         self._eng = engine or default_engine(device)
-        self._cfg = (True, bool(persistent), bool(clamp), bool(ik), False)
+        self._cfg = (True, bool(persistent), bool(clamp), bool(ik), False, 0)
         self._eng.stream_pos_open(wire_layout=True, persistent=persistent, clamp=clamp, ik=ik)
         self._dof = np.zeros(30, np.float32)
         self.last_dof_pos = np.zeros(30, np.float32)

@@ -196,12 +196,16 @@ int hrt_retarget_full_body_pos_wire(hrt_ctx* ctx, int64_t B, const float* d_body
 #define HRT_STREAM_CLAMP 4         /* joint limits on the arm hinges (HRT_POS_CLAMP) */
 #define HRT_STREAM_IK 8            /* + 10 limit-aware refinement steps (HRT_POS_IK, damping 0.1, rotation weight 0.2) */
 #define HRT_STREAM_BODY_GQ 16      /* also publish the third return of VtrdynFullBodyPosRetargeter.retarget (59 x 4 body quats) */
+#define HRT_STREAM_MODE_SHIFT 8    /* bits 8-9: position solver served (0 full_body_pos, 1 upper_body, 2 full_body) */
 int hrt_stream_pos_open(hrt_ctx* ctx, int flags);
 int hrt_stream_pos_frame(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
                          float* h_robot_local_q, float* h_dof);
-/* the same with the (J_bq, 4) body global rotations (full_body_pos_retargeter.py:217, third return); needs HRT_STREAM_BODY_GQ */
-int hrt_stream_pos_frame_bq(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
-                            float* h_robot_local_q, float* h_dof, float* h_body_gq);
+/* General form.  The stream serves the position solver selected at open time: flags | (mode << HRT_STREAM_MODE_SHIFT) with
+ * mode 0 = VtrdynFullBodyPosRetargeter (body, hands), 1 = HuUpperBodyFromMocapRetarget (body only; hands / body_q ignored),
+ * 2 = VtrdynFullBodyRetargeter (body_q (21,4), body, hands).  h_body_gq (third return of mode 0) needs HRT_STREAM_BODY_GQ.
+ * Wire layout, resident server and body quaternions exist for mode 0 only. */
+int hrt_stream_pos_frame_ex(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
+                            const float* h_body_q, float* h_robot_local_q, float* h_dof, float* h_body_gq);
 int hrt_stream_pos_close(hrt_ctx* ctx);
 
 /* RetargetHuV5fromMocap (retarget/main.py:51-279), mode 3 of the position solvers: arms from joint

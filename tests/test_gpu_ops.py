@@ -437,7 +437,7 @@ def test_single_frame_calls_of_the_reference_classes_use_the_mailbox(hrt, golden
         assert lq.shape == (31, 4) and dof.shape == (30,) and bq.shape == (59, 4) and dof.device.type == "cpu"
         assert torch.equal(dof, dof_b[i].cpu()) and torch.equal(lq, lq_b[i].cpu()) and torch.equal(bq, bq_b[i].cpu())
         outs.append(dof)
-    assert eng._pos_stream_cfg == (False, False, False, False, True)
+    assert eng._pos_stream_cfg == (False, False, False, False, True, hrt.POS_FULL_BODY_POS)
     assert len({o.data_ptr() for o in outs}) == 6 and solver.motion_length == 6          # new tensors, recorded like the reference
     # a teleop session on the same engine re-opens the mailbox for the wire layout, then the solver takes it back
     wire_body = torch.zeros(23, 3)
@@ -458,6 +458,29 @@ def test_single_frame_calls_of_the_reference_classes_use_the_mailbox(hrt, golden
         lq, dof, bq = rsolver.retarget(body[i], lh[i], rh[i], record=False)
         assert md(dof, dof_b[i].cpu()) <= 1e-6 and md(bq, bq_b[i].cpu()) <= 1e-6 and md(lq, lq_b[i].cpu()) <= 1e-6
     eng.stream_pos_close()
+    # the other two position solvers, one CPU frame each (sim_teleop.py and the full-body variant)
+    gu = golden("upper_body")
+    mocap21 = hrt.RobotZeroPose.from_asset("vtrdyn_zero_pose")
+    us = hrt.HuUpperBodyFromMocapRetarget(mocap21, tgt)
+    lq_u, dof_u = us._eng.retarget_upper_body(T(gu["global_t"]))
+    for i in range(4):
+        lq, dof = us.retarget_from_global_translation(T(gu["global_t"][i]))
+        assert lq.shape == (31, 4) and torch.equal(dof, dof_u[i].cpu()) and torch.equal(lq, lq_u[i].cpu())
+    assert us._eng._pos_stream_cfg[-1] == hrt.POS_UPPER_BODY
+    gf = golden("full_body")
+    fs = hrt.VtrdynFullBodyRetargeter(src, tgt)
+    lq_f, dof_f = fs._eng.retarget_full_body(T(gf["body_q"]), T(gf["body_t"]), T(gf["lhand_t"]), T(gf["rhand_t"]))
+    for i in range(4):
+        lq, dof = fs.retarget(T(gf["body_q"][i]), T(gf["body_t"][i]), None, T(gf["lhand_t"][i]), None, T(gf["rhand_t"][i]))
+        assert torch.equal(dof, dof_f[i].cpu()) and torch.equal(lq, lq_f[i].cpu())
+    # error behaviour of the general entry point
+    e = fs._eng
+    assert e.lib.hrt_stream_pos_open(e._h, (1 << 8) | 2) == -1                      # resident server: mode 0 only
+    assert e.lib.hrt_stream_pos_open(e._h, 3 << 8) == -1                            # no streaming for the clip-level "main" mode
+    e.stream_pos_open(mode=hrt.POS_FULL_BODY)
+    with pytest.raises(RuntimeError):
+        e.stream_pos_frame_tensors(T(gf["body_t"][0]), T(gf["lhand_t"][0]), T(gf["rhand_t"][0]), None, torch.empty(30))   # body_q missing
+    e.stream_pos_close()
     # quaternion path
     gq = golden("body_quat")
     mocap = hrt.RobotZeroPose.from_asset("vtrdyn_zero_pose")

@@ -48,3 +48,14 @@ for i in range(5000):
     ts[i] = time.perf_counter_ns() - t0
 print("Mocap2HuBodyRetargeter.retarget_from_pose per frame (CPU tensors in/out): p50 %.1f us  p99 %.1f us" %
       (np.percentile(ts, 50) / 1e3, np.percentile(ts, 99) / 1e3))
+
+us = hrt.HuUpperBodyFromMocapRetarget(mocap, tgt)
+for i in range(200):
+    us.retarget_from_global_translation(body[i], record=False)
+for i in range(5000):
+    k = i % n
+    t0 = time.perf_counter_ns()
+    us.retarget_from_global_translation(body[k], record=False)
+    ts[i] = time.perf_counter_ns() - t0
+print("HuUpperBodyFromMocapRetarget.retarget_from_global_translation per frame: p50 %.1f us  p99 %.1f us" %
+      (np.percentile(ts, 50) / 1e3, np.percentile(ts, 99) / 1e3))
