@@ -403,6 +403,55 @@ def test_full_size_properties(hrt, eng, eng_hu, oc, skeletons):
     assert float(np.quantile(err.numpy(), 0.98)) <= ANGLE_TOL and float(err.max()) <= 1e-3
 
 
+def test_full_size_properties_position_path(hrt, eng, oc, skeletons):
+    """Config 3p size: 2^20 frames through the position solver (16-warp CTAs).  Size-independent properties: frames are
+    independent (any sub-range run on its own gives the same bits), the gripper DOFs take only their defined values, the
+    limit-aware refinement keeps every arm hinge inside its limits, and a strided sample agrees with the oracle."""
+    B = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(5)
+    em = 0.4 * torch.randn(B, 59, 3, device="cuda", generator=g)
+    lq = hrt.rotation3d.exp_map_to_quat(em)
+    root = torch.zeros(B, 3, device="cuda")
+    root[:, 2] = 1.0
+    _, gt = eng.fk_local_quats(hrt.TREE_SOURCE_FULL, lq, root, exact=True)            # the clip, built on the device
+    full2body = [0, 4, 5, 6, 1, 2, 3, 7, 8, 9, 10, 34, 35, 36, 37, 38, 39, 11, 12, 13, 14]
+    body, lh, rh = gt[:, full2body].contiguous(), gt[:, 14:34].contiguous(), gt[:, 39:59].contiguous()
+    del gt, lq, em
+    dof = torch.empty(B, 30, device="cuda")
+    eng.retarget_full_body_pos(body, lh, rh, out=(None, dof, None))
+    fin = torch.isfinite(dof).all(dim=-1)
+    assert float(fin.float().mean()) > 0.9995
+    for lo, hi in ((0, 1 << 16), (B - (1 << 16) - 48, B - 48), (123_456, 123_456 + 30_000)):
+        part = torch.empty(hi - lo, 30, device="cuda")
+        eng.retarget_full_body_pos(body[lo:hi], lh[lo:hi], rh[lo:hi], out=(None, part, None))
+        same = (part == dof[lo:hi]) | (torch.isnan(part) & torch.isnan(dof[lo:hi]))
+        assert bool(same.all()), (lo, hi)
+    small = torch.empty(4096, 30, device="cuda")                                      # 8-warp CTAs
+    eng.retarget_full_body_pos(body[5000:9096], lh[5000:9096], rh[5000:9096], out=(None, small, None))
+    assert bool(((small == dof[5000:9096]) | torch.isnan(small)).all())
+    grip = dof[fin][:, [18, 19, 27, 28]].abs()
+    assert float(grip.max()) <= 0.044 + 1e-7                                          # full_body_pos_retargeter.py:199-215
+    rest = [i for i in range(30) if i not in list(range(11, 20)) + list(range(20, 29))]
+    assert float(dof[fin][:, rest].abs().max()) == 0.0
+    # limits + refinement on the whole clip
+    dof_r = torch.empty(B, 30, device="cuda")
+    eng.retarget_full_body_pos(body, lh, rh, out=(None, dof_r, None), flags=hrt.POS_CLAMP | hrt.POS_IK)
+    arm = list(range(11, 18)) + list(range(20, 27))
+    lo5, hi5 = torch.tensor(oc.HU_V5_DOF_LOWER).cuda(), torch.tensor(oc.HU_V5_DOF_UPPER).cuda()
+    ok = torch.isfinite(dof_r).all(dim=-1)
+    assert float(ok.float().mean()) > 0.9995
+    assert bool(((dof_r[ok][:, arm] >= lo5[arm]) & (dof_r[ok][:, arm] <= hi5[arm])).all())
+    # strided sample against the oracle
+    idx = torch.arange(0, B, 509)
+    off = T(skeletons["vtrdyn_full_zero_pose/offsets"])
+    zgt = T(skeletons["vtrdyn_full_zero_pose/global_translation"])
+    _, dof_o, _ = oc.retarget_full_body_pos(body[idx].cpu(), lh[idx].cpu(), rh[idx].cpu(), off, zgt, True)
+    err = (dof[idx].cpu() - dof_o).abs().max(dim=-1).values
+    f2 = torch.isfinite(err)
+    _pos_report("full_body_pos 2^20 (strided sample) vs oracle", err[f2])
+    assert float(np.quantile(err[f2].numpy(), 0.80)) <= ANGLE_TOL
+
+
 # ------------------------------------------------------------------------------- position-input paths
 def _pos_report(name, err, self_delta=None):
     e = err.numpy() if torch.is_tensor(err) else err
