@@ -190,7 +190,13 @@ int launch_fk(hrt_ctx* ctx, Tree* t, const FkArgs& a, unsigned flags, cudaStream
     return launch_fk_variant<FROM_ANGLES, false, false>(ctx, t, a, st);
 }
 
-int body_quat_warps(const BodyQuatArgs& a) { return a.out_local_q ? BQ_WARPS_NARROW : BQ_WARPS_WIDE; }
+int body_quat_warps(const hrt_ctx* ctx, const BodyQuatArgs& a) {
+    if (a.flags & BQ_IK) return a.out_local_q ? BQ_WARPS_NARROW : BQ_WARPS_WIDE;
+    // no refinement: the instantiation without the IK loop; single frames and short clips keep the small CTA
+    const long long groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
+    if (groups <= (long long)ctx->sm_count * BQ_WARPS_NARROW) return BQ_WARPS_NARROW;
+    return a.out_local_q ? BQ_WARPS_NOIK_NARROW : BQ_WARPS_NOIK;
+}
 
 size_t body_quat_smem(const hrt_ctx* ctx, const BodyQuatArgs& a);
 
@@ -214,12 +220,20 @@ int launch_body_quat(hrt_ctx* ctx, const BodyQuatArgs& a, cudaStream_t st, int f
         return 0;
     }
     const size_t smem = body_quat_smem(ctx, a);
-    const int warps = body_quat_warps(a);
+    const int warps = body_quat_warps(ctx, a);
     const long long groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
     const long long ctas = (groups + warps - 1) / warps;
     const int grid = force_grid ? force_grid : (int)std::max(1LL, std::min(ctas, (long long)ctx->sm_count));
-    if (warps == BQ_WARPS_WIDE) body_quat_kernel<BQ_WARPS_WIDE><<<grid, BQ_WARPS_WIDE * 32, smem, st>>>(ctx->bq, a);
-    else body_quat_kernel<BQ_WARPS_NARROW><<<grid, BQ_WARPS_NARROW * 32, smem, st>>>(ctx->bq, a);
+    if (a.flags & BQ_IK) {
+        if (a.out_local_q) body_quat_kernel<BQ_WARPS_NARROW><<<grid, BQ_WARPS_NARROW * 32, smem, st>>>(ctx->bq, a);
+        else body_quat_kernel<BQ_WARPS_WIDE><<<grid, BQ_WARPS_WIDE * 32, smem, st>>>(ctx->bq, a);
+    } else if (warps == BQ_WARPS_NARROW) {
+        body_quat_kernel<BQ_WARPS_NARROW, false><<<grid, BQ_WARPS_NARROW * 32, smem, st>>>(ctx->bq, a);
+    } else if (warps == BQ_WARPS_NOIK_NARROW) {
+        body_quat_kernel<BQ_WARPS_NOIK_NARROW, false><<<grid, BQ_WARPS_NOIK_NARROW * 32, smem, st>>>(ctx->bq, a);
+    } else {
+        body_quat_kernel<BQ_WARPS_NOIK, false><<<grid, BQ_WARPS_NOIK * 32, smem, st>>>(ctx->bq, a);
+    }
     HRT_CUDA(cudaGetLastError());
     return 0;
 }
@@ -312,7 +326,7 @@ int fill_body_quat_args(hrt_ctx* ctx, int64_t B, const float* src, unsigned flag
 namespace {
 size_t body_quat_smem(const hrt_ctx* ctx, const BodyQuatArgs& a) {
     return ((size_t)BQ_CONST_WORDS +
-            (size_t)body_quat_warps(a) * bq_tile_words(ctx->bq.J_src, ctx->bq.J_rob, a.out_local_q != nullptr)) * sizeof(float);
+            (size_t)body_quat_warps(ctx, a) * bq_tile_words(ctx->bq.J_src, ctx->bq.J_rob, a.out_local_q != nullptr)) * sizeof(float);
 }
 }  // namespace
 
@@ -338,6 +352,9 @@ int hrt_ctx_create(int device, hrt_ctx** out) {
     HRT_CUDA(cudaFuncSetAttribute(jacobian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NOIK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NOIK_NARROW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NARROW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_ik2_kernel<BQ2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 #define HRT_POS_ATTR(MODE)                                                                                                          \
     HRT_CUDA(cudaFuncSetAttribute(pos_retarget_kernel<MODE, POS_WARPS_MIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \

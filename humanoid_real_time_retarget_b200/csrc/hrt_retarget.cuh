@@ -67,6 +67,15 @@ constexpr int BQ_FRAMES_PER_WARP = 16;
 #define HRT_BQ_WARPS_WIDE 16
 #endif
 constexpr int BQ_WARPS_WIDE = HRT_BQ_WARPS_WIDE;
+// calls without the refinement run an instantiation with the IK loop compiled out: fewer registers, more warps per SM for
+// the latency-bound closed form (exact-order libm chains, fp64 Euler split)
+// (94 registers instead of 124).  Measured on 2^20 frames, dof + link positions: 0.385 ms (IK instantiation, 16 warps) ->
+// 0.347 (16) / 0.333 (20) / 0.323 (24) / 0.312 ms (28 warps, 72 registers, 4 B spill).
+#ifndef HRT_BQ_WARPS_NOIK
+#define HRT_BQ_WARPS_NOIK 28
+#endif
+constexpr int BQ_WARPS_NOIK = HRT_BQ_WARPS_NOIK;
+constexpr int BQ_WARPS_NOIK_NARROW = 12;          // with the local-rotation tile staged as well
 constexpr int BQ_WARPS_NARROW = 8;
 // warp-private staging, in words: [input rows, later the link-position image] [dof image]
 // [local-rotation image, only when that output is requested]
@@ -252,7 +261,7 @@ HRT_DEV void bq_align(int warp) {
 }
 
 // all frame groups of `a` that fall to CTA `cta` of `n_ctas`
-template <int BQ_WARPS_PER_CTA, bool SYSMEM>
+template <int BQ_WARPS_PER_CTA, bool SYSMEM, bool WITH_IK = true>
 HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* smem, int n_ctas, int cta) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -376,7 +385,7 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
         }
 
         // ---- 6. fused damped-least-squares refinement (never leaves the SM) -------------------
-        if (do_ik) {
+        if (WITH_IK && do_ik) {
             const float4 Tc = quat_conj(zT);
             const float4 Ru = quat_mul_norm_f(Tc, zU);
             const float4 Rf = quat_mul_norm_f(Tc, zL);
@@ -453,12 +462,12 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
 }
 
 
-template <int BQ_WARPS_PER_CTA>
+template <int BQ_WARPS_PER_CTA, bool WITH_IK = true>
 __global__ void __launch_bounds__(BQ_WARPS_PER_CTA * 32, 1)
 body_quat_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a) {
     extern __shared__ __align__(16) float smem[];
     bq_setup(bp, smem);
-    bq_process<BQ_WARPS_PER_CTA, false>(bp, a, smem, (int)gridDim.x, (int)blockIdx.x);
+    bq_process<BQ_WARPS_PER_CTA, false, WITH_IK>(bp, a, smem, (int)gridDim.x, (int)blockIdx.x);
 }
 
 // Resident single-frame server of the quaternion path (same protocol as pos_stream_server_kernel in hrt_pos.cuh:

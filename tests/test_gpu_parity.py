@@ -238,6 +238,26 @@ def test_packed_ik_variant_matches_scalar(hrt, eng, oc, skeletons):
         assert float(d1[:, rest].abs().max()) == 0.0
 
 
+def test_body_quat_cta_shapes_agree(hrt, eng, oc, skeletons):
+    """Calls without the refinement run the instantiation with the IK loop compiled out, at 28 warps per CTA (dof / link
+    positions only), 12 (local rotations staged too) or 8 (short clips); with the refinement 16 / 8.  Same device code
+    for the closed form, so the same bits whichever shape runs."""
+    B = 40_000
+    raw = oc.synth_clip_3q(B, seed=21, sk=skeletons).cuda()
+    lq12, dof12, lp12 = eng.retarget_body_quat(raw, flags=0)                                     # 12 warps (local_q staged)
+    _, dof28, lp28 = eng.retarget_body_quat(raw, flags=0, want_local_q=False)                   # 28 warps
+    _, dof8, lp8 = eng.retarget_body_quat(raw[:4000], flags=0, want_local_q=False)              # 8 warps (short clip)
+    assert torch.equal(dof28, dof12) and torch.equal(lp28, lp12)
+    assert torch.equal(dof8, dof28[:4000]) and torch.equal(lp8, lp28[:4000])
+    _, dofc, _ = eng.retarget_body_quat(raw, flags=hrt.BQ_CLAMP, want_local_q=False)            # clamp only: no-IK instantiation too
+    _, dofi, _ = eng.retarget_body_quat(raw, flags=hrt.BQ_CLAMP | hrt.BQ_IK, ik_iters=0, want_local_q=False)   # IK instantiation, 0 steps
+    assert (dofc - dofi).abs().max().item() <= 1e-6
+    # and against the oracle on a sample
+    idx = torch.arange(0, B, 97)
+    _, dof_o, lp_o = oc.body_quat_pipeline(raw[idx].cpu(), skeletons, clamp=False, ik_iters=0)
+    assert maxdiff(dof28[idx], dof_o) <= 2e-6 and maxdiff(lp28[idx], lp_o) <= POS_TOL
+
+
 def test_body_quat_edge_cases(hrt, eng, oc, skeletons):
     # empty, single, ragged (not a multiple of the 16-frame warp group)
     for B in (0, 1, 15, 17, 33):
