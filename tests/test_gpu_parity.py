@@ -258,6 +258,35 @@ def test_body_quat_cta_shapes_agree(hrt, eng, oc, skeletons):
     assert maxdiff(dof28[idx], dof_o) <= 2e-6 and maxdiff(lp28[idx], lp_o) <= POS_TOL
 
 
+def test_ragged_clip_lengths_around_the_cta_shape_thresholds(hrt, eng, oc, skeletons):
+    """Clip lengths just below / above the point where the host switches to the large CTAs (one small CTA per SM = 148 * 8
+    warps * 16 frames = 18,944 frames), none a multiple of the 16-frame warp group: every length must reproduce the
+    frames of the longest run bit for bit, and nothing may be written past the end of the outputs."""
+    n_max = 18_944 + 16 * 28 * 3 + 5
+    raw = oc.synth_clip_3q(n_max, seed=33, sk=skeletons).cuda()
+    _, dof_ref, lp_ref = eng.retarget_body_quat(raw, flags=0, want_local_q=False)
+    g = torch.Generator(device="cuda").manual_seed(8)
+    em = 0.4 * torch.randn(n_max, 59, 3, device="cuda", generator=g)
+    root = torch.zeros(n_max, 3, device="cuda")
+    root[:, 2] = 1.0
+    _, gt = eng.fk_local_quats(hrt.TREE_SOURCE_FULL, hrt.rotation3d.exp_map_to_quat(em), root, exact=True)
+    full2body = [0, 4, 5, 6, 1, 2, 3, 7, 8, 9, 10, 34, 35, 36, 37, 38, 39, 11, 12, 13, 14]
+    body, lh, rh = gt[:, full2body].contiguous(), gt[:, 14:34].contiguous(), gt[:, 39:59].contiguous()
+    pdof_ref = torch.empty(n_max, 30, device="cuda")
+    eng.retarget_full_body_pos(body, lh, rh, out=(None, pdof_ref, None))
+    for n in (18_943, 18_944, 18_945, 18_961, 18_944 + 16 * 28 + 7, n_max - 1):
+        guard = 4
+        dof = torch.full((n + guard, 30), 7.0, device="cuda")
+        lp = torch.full((n + guard, 31, 3), 7.0, device="cuda")
+        eng.retarget_body_quat(raw[:n], flags=0, out=(None, dof[:n], lp[:n]))
+        assert torch.equal(dof[:n], dof_ref[:n]) and torch.equal(lp[:n], lp_ref[:n]), n
+        assert bool((dof[n:] == 7.0).all()) and bool((lp[n:] == 7.0).all()), n
+        pdof = torch.full((n + guard, 30), 7.0, device="cuda")
+        eng.retarget_full_body_pos(body[:n], lh[:n], rh[:n], out=(None, pdof[:n], None))
+        same = (pdof[:n] == pdof_ref[:n]) | (torch.isnan(pdof[:n]) & torch.isnan(pdof_ref[:n]))
+        assert bool(same.all()) and bool((pdof[n:] == 7.0).all()), n
+
+
 def test_body_quat_edge_cases(hrt, eng, oc, skeletons):
     # empty, single, ragged (not a multiple of the 16-frame warp group)
     for B in (0, 1, 15, 17, 33):
