@@ -349,7 +349,8 @@ int hrt_ctx_create(int device, hrt_ctx** out) {
     c->device = device;
     HRT_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     // these kernels need more than the default 48 KB of dynamic shared memory
-    HRT_CUDA(cudaFuncSetAttribute(jacobian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(jacobian_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    HRT_CUDA(cudaFuncSetAttribute(jacobian_kernel<HRT_MAX_CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NOIK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -534,8 +535,15 @@ int hrt_fk_jacobian(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, co
     const long long groups = (B + cpw - 1) / cpw;
     const long long ctas = (groups + JAC_WARPS_PER_CTA - 1) / JAC_WARPS_PER_CTA;
     int grid = 1;
-    if ((rc = grid_for(ctx, jacobian_kernel, JAC_WARPS_PER_CTA * 32, smem, ctas, &grid))) return rc;
-    jacobian_kernel<<<grid, JAC_WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(t->tp, jp, a);
+    int max_depth = 0;
+    for (int k = 0; k < K; ++k) max_depth = std::max(max_depth, jp.depth[k]);
+    if (max_depth <= 8) {
+        if ((rc = grid_for(ctx, jacobian_kernel<8>, JAC_WARPS_PER_CTA * 32, smem, ctas, &grid))) return rc;
+        jacobian_kernel<8><<<grid, JAC_WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(t->tp, jp, a);
+    } else {
+        if ((rc = grid_for(ctx, jacobian_kernel<HRT_MAX_CHAIN>, JAC_WARPS_PER_CTA * 32, smem, ctas, &grid))) return rc;
+        jacobian_kernel<HRT_MAX_CHAIN><<<grid, JAC_WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(t->tp, jp, a);
+    }
     HRT_CUDA(cudaGetLastError());
     return 0;
 }

@@ -27,7 +27,12 @@ HRT_HD inline int jac_bundle_words(int K, int D) { return JAC_BUNDLE * K * 6 * D
 HRT_HD inline int jac_tile_words(int K, int D, int cpw) { return cpw / JAC_BUNDLE * jac_bundle_words(K, D); }
 HRT_HD inline int jac_lanes_per_cfg(int K) { return K <= 1 ? 1 : (K <= 2 ? 2 : 4); }   // K <= HRT_MAX_LINKS = 4
 
-// lanes of a warp = (configuration, link): the K chains of a configuration are walked in parallel
+// lanes of a warp = (configuration, link): the K chains of a configuration are walked in parallel.
+// MAXC = unroll bound of the chain loops (8 or HRT_MAX_CHAIN): the walk keeps every chain joint's axis and position in
+// registers, so the loops are fully unrolled; the host takes the small instantiation when every requested chain fits
+// (Hu wrists: 8 joints) -- half the code (the 16-step body missed the instruction cache: 0.8 warps per issue without an
+// instruction) and 96 registers fewer.
+template <int MAXC>
 __global__ void __launch_bounds__(JAC_WARPS_PER_CTA * 32)
 jacobian_kernel(const __grid_constant__ TreeParams tp, const __grid_constant__ JacParams jp, const FkArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -48,9 +53,9 @@ jacobian_kernel(const __grid_constant__ TreeParams tp, const __grid_constant__ J
     const int kk = has_link ? k : 0;
     const int depth = jp.depth[kk];
     // this lane's chain, packed four joints to a word (the per-lane index into the constant bank is loop invariant)
-    uint32_t chain_w[HRT_MAX_CHAIN / 4];
+    uint32_t chain_w[MAXC / 4];
 #pragma unroll
-    for (int w = 0; w < HRT_MAX_CHAIN / 4; ++w) {
+    for (int w = 0; w < MAXC / 4; ++w) {
         uint32_t v = 0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) v |= (uint32_t)(uint8_t)jp.chain[kk][w * 4 + b] << (8 * b);
@@ -63,13 +68,13 @@ jacobian_kernel(const __grid_constant__ TreeParams tp, const __grid_constant__ J
     // A tile's inputs (the chain's angles, root transform) are fetched one tile ahead, all loads in flight together:
     // ncu showed the first version latency-bound (issue slots 25 % busy, 3.2 warps per issue waiting on global loads,
     // 8 resident warps per SM) with one dependent load per chain step.
-    struct TileIn { float th[HRT_MAX_CHAIN]; float4 rq; vec3 rt; };
+    struct TileIn { float th[MAXC]; float4 rq; vec3 rt; };
     auto fetch = [&](long long grp, TileIn& in) {
         const long long f0 = grp * cpw;
         const int rows = (int)min((long long)cpw, a.B - f0);
         const long long fc = f0 + min(ci, rows - 1);
 #pragma unroll
-        for (int c = 0; c < HRT_MAX_CHAIN; ++c) in.th[c] = (c < depth) ? __ldg(a.angles + fc * D + (chain_joint(c) - 1)) : 0.f;
+        for (int c = 0; c < MAXC; ++c) in.th[c] = (c < depth) ? __ldg(a.angles + fc * D + (chain_joint(c) - 1)) : 0.f;
         in.rq = a.root_q ? __ldg(reinterpret_cast<const float4*>(a.root_q) + fc) : make_float4(0.f, 0.f, 0.f, 1.f);
         in.rt = make_vec3(0.f, 0.f, 0.f);
         if (a.root_t) in.rt = make_vec3(__ldg(a.root_t + fc * 3), __ldg(a.root_t + fc * 3 + 1), __ldg(a.root_t + fc * 3 + 2));
@@ -84,9 +89,9 @@ jacobian_kernel(const __grid_constant__ TreeParams tp, const __grid_constant__ J
         vec3 gp = cur.rt;
         // walk this lane's chain, remember world axis and position of every chain joint
         float4 gq = cur.rq;
-        vec3 ax[HRT_MAX_CHAIN], pj[HRT_MAX_CHAIN];
+        vec3 ax[MAXC], pj[MAXC];
 #pragma unroll
-        for (int c = 0; c < HRT_MAX_CHAIN; ++c) {
+        for (int c = 0; c < MAXC; ++c) {
             if (c < depth) {
                 const int j = chain_joint(c);
                 const float4 rec = *reinterpret_cast<const float4*>(&tp.jr[j]);
@@ -113,7 +118,7 @@ jacobian_kernel(const __grid_constant__ TreeParams tp, const __grid_constant__ J
         if (has_link) {
             float* r = row + k * blk;
 #pragma unroll
-            for (int c = 0; c < HRT_MAX_CHAIN; ++c) {
+            for (int c = 0; c < MAXC; ++c) {
                 if (c < depth) {
                     const int col = chain_joint(c) - 1;
                     const vec3 jv = cross3_f(ax[c], sub3(pk, pj[c]));

@@ -355,6 +355,14 @@ def test_jacobian_vs_oracle(hrt, eng_hu, oc, skeletons):
                                True, links)
     assert J.shape == (B, 4, 6, 32)
     assert maxdiff(J, Jo) <= 5e-6
+    # chains longer than 8 joints (gripper links: torso + 7 arm hinges + finger) take the 16-step instantiation, the wrists
+    # alone the 8-step one; K = 1, 2 and 3 exercise the three lane layouts
+    for links in ([21, 31], [20, 29], [22], [6, 21, 12]):
+        J = eng_hu.fk_jacobian(hrt.TREE_ROBOT, ang, links, root_t, root_q, clip=True)
+        Jo = oc.geometric_jacobian(ang, root_t, root_q, skeletons["hu_zero_pose/parents"].tolist(),
+                                   T(skeletons["hu_zero_pose/offsets"]), oc.HU_DOF_AXIS, oc.HU_DOF_LOWER, oc.HU_DOF_UPPER,
+                                   True, links)
+        assert maxdiff(J, Jo) <= 5e-6, links
 
 
 # ------------------------------------------------------------------------------- host / streaming calls
