@@ -191,11 +191,11 @@ int launch_fk(hrt_ctx* ctx, Tree* t, const FkArgs& a, unsigned flags, cudaStream
 }
 
 int body_quat_warps(const hrt_ctx* ctx, const BodyQuatArgs& a) {
-    if (a.flags & BQ_IK) return a.out_local_q ? BQ_WARPS_NARROW : BQ_WARPS_WIDE;
-    // no refinement: the instantiation without the IK loop; single frames and short clips keep the small CTA
+    // single frames and short clips keep the small CTA; long clips: 16 warps with the refinement (issue-bound, 127 registers),
+    // 28 without (the instantiation with the IK loop compiled out: latency-bound closed form, 72 registers)
     const long long groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
     if (groups <= (long long)ctx->sm_count * BQ_WARPS_NARROW) return BQ_WARPS_NARROW;
-    return a.out_local_q ? BQ_WARPS_NOIK_NARROW : BQ_WARPS_NOIK;
+    return (a.flags & BQ_IK) ? BQ_WARPS_WIDE : BQ_WARPS_NOIK;
 }
 
 size_t body_quat_smem(const hrt_ctx* ctx, const BodyQuatArgs& a);
@@ -225,14 +225,11 @@ int launch_body_quat(hrt_ctx* ctx, const BodyQuatArgs& a, cudaStream_t st, int f
     const long long ctas = (groups + warps - 1) / warps;
     const int grid = force_grid ? force_grid : (int)std::max(1LL, std::min(ctas, (long long)ctx->sm_count));
     if (a.flags & BQ_IK) {
-        if (a.out_local_q) body_quat_kernel<BQ_WARPS_NARROW><<<grid, BQ_WARPS_NARROW * 32, smem, st>>>(ctx->bq, a);
+        if (warps == BQ_WARPS_NARROW) body_quat_kernel<BQ_WARPS_NARROW><<<grid, BQ_WARPS_NARROW * 32, smem, st>>>(ctx->bq, a);
         else body_quat_kernel<BQ_WARPS_WIDE><<<grid, BQ_WARPS_WIDE * 32, smem, st>>>(ctx->bq, a);
-    } else if (warps == BQ_WARPS_NARROW) {
-        body_quat_kernel<BQ_WARPS_NARROW, false><<<grid, BQ_WARPS_NARROW * 32, smem, st>>>(ctx->bq, a);
-    } else if (warps == BQ_WARPS_NOIK_NARROW) {
-        body_quat_kernel<BQ_WARPS_NOIK_NARROW, false><<<grid, BQ_WARPS_NOIK_NARROW * 32, smem, st>>>(ctx->bq, a);
     } else {
-        body_quat_kernel<BQ_WARPS_NOIK, false><<<grid, BQ_WARPS_NOIK * 32, smem, st>>>(ctx->bq, a);
+        if (warps == BQ_WARPS_NARROW) body_quat_kernel<BQ_WARPS_NARROW, false><<<grid, BQ_WARPS_NARROW * 32, smem, st>>>(ctx->bq, a);
+        else body_quat_kernel<BQ_WARPS_NOIK, false><<<grid, BQ_WARPS_NOIK * 32, smem, st>>>(ctx->bq, a);
     }
     HRT_CUDA(cudaGetLastError());
     return 0;
@@ -354,7 +351,6 @@ int hrt_ctx_create(int device, hrt_ctx** out) {
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NOIK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NOIK_NARROW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_kernel<BQ_WARPS_NARROW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HRT_CUDA(cudaFuncSetAttribute(body_quat_ik2_kernel<BQ2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 #define HRT_POS_ATTR(MODE)                                                                                                          \

@@ -284,17 +284,18 @@ HRT_DEV vec3 ld3(const float* p) { return make_vec3(p[0], p[1], p[2]); }
 HRT_HD inline int pos_in_words(int n_body, int n_hand, bool hands, bool quats) {
     return BQ_FRAMES_PER_WARP * (n_body * 3 + (hands ? 2 * n_hand * 3 : 0) + (quats ? 21 * 4 : 0));
 }
-HRT_HD inline int pos_tile_words(const PosParams& pp, bool with_lq, bool with_bq) {
+// The local rotations and the body quaternions are identity except for a few rows per frame: they are written straight to
+// HBM (coalesced identity fill, then each lane patches its own rows), not staged, so the tile is inputs + dof for every
+// combination of outputs and the large CTAs fit whatever the caller asks for.
+HRT_HD inline int pos_tile_words(const PosParams& pp, bool /*with_lq*/, bool /*with_bq*/) {
     const bool hands = pp.mode == POS_FULL_BODY_POS || pp.mode == POS_FULL_BODY;
     int in = pos_in_words(pp.n_body, pp.n_hand, hands, pp.mode == POS_FULL_BODY || pp.mode == POS_MAIN);
-    int bq = with_bq ? BQ_FRAMES_PER_WARP * pp.J_bq * 4 : 0;
-    int io = in > bq ? in : bq;                         // body_global_rotation image reuses the input rows
-    return (io + 3) / 4 * 4 + bq_dof_words(pp.J_rob) + (with_lq ? BQ_FRAMES_PER_WARP * pp.J_rob * 4 : 0);
+    return (in + 3) / 4 * 4 + bq_dof_words(pp.J_rob);
 }
 // Warps per CTA (one CTA per SM).  The closed form is a chain of fp64 Jacobi sweeps and fp32 libm calls: latency-bound
 // with 8 warps (ncu: issue slots 34 % busy, 2.2 warps per issue in fixed-latency waits); 12 / 16 warps measured
 // 1.30x / 1.47x on the dof-only batch (184 / 164 / 128 registers per thread).  The host picks the largest count whose
-// staging tiles fit in shared memory (all three outputs requested: 8).
+// staging tiles fit in shared memory.
 constexpr int POS_WARPS_MIN = 8;
 constexpr int POS_WARPS_MID = 12;
 constexpr int POS_WARPS_MAX = 16;
@@ -362,9 +363,7 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
     float* tile = smem + const_words + warp * pos_tile_words(pp, with_lq, with_bq);
     const int NB = pp.n_body, NH = pp.n_hand, JR = pp.J_rob, D = JR - 1;
     const int in_words = pos_in_words(NB, NH, HANDS, QUATS);
-    const int bq_words = with_bq ? BQ_FRAMES_PER_WARP * pp.J_bq * 4 : 0;
-    float* dof_t = tile + ((in_words > bq_words ? in_words : bq_words) + 3) / 4 * 4;
-    float* lq_t = dof_t + bq_dof_words(JR);
+    float* dof_t = tile + (in_words + 3) / 4 * 4;
     // input sub-regions (each a contiguous image of 16 rows)
     float* body_s = tile;
     float* lh_s = body_s + BQ_FRAMES_PER_WARP * NB * 3;
@@ -414,8 +413,6 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
         if (QUATS) pos_stage_span<SYSMEM>(bodyq_s, a.body_q + f0 * pp.n_bodyq * 4, nld * pp.n_bodyq * 4, lane);
         cp_async_commit();
         if (a.out_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
-        if (with_lq)
-            for (int i = lane; i < nfr * JR; i += 32) *reinterpret_cast<float4*>(lq_t + i * 4) = make_float4(0.f, 0.f, 0.f, 1.f);
         cp_async_wait<0>();
         __syncwarp();
 
@@ -561,34 +558,37 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
 #pragma unroll
             for (int c = 0; c < 9; ++c) r[c] = th[c];
         }
-        if (with_lq && fl < nfr) {
-            float* r = lq_t + (fl * JR + ap.rob_first) * 4;
+        // local rotations / body quaternions: identity fill of the group's contiguous span (one 512-byte store per warp
+        // instruction), then every lane overwrites its own hinges (a warp barrier orders the two stores to the same rows)
+        const float4 ident = make_float4(0.f, 0.f, 0.f, 1.f);
+        float4* lq_g = with_lq ? reinterpret_cast<float4*>(a.out_local_q + f0 * JR * 4) : nullptr;
+        float4* bq_g = with_bq ? reinterpret_cast<float4*>(a.out_body_gq + f0 * pp.J_bq * 4) : nullptr;
+        if (with_lq) for (int i = lane; i < nfr * JR; i += 32) lq_g[i] = ident;
+        if (with_bq) for (int i = lane; i < nfr * pp.J_bq; i += 32) bq_g[i] = ident;
+        if (with_lq || with_bq) __syncwarp();
+        if (fl < nfr) {
+            if (with_lq) {
 #pragma unroll
-            for (int c = 0; c < 7; ++c) *reinterpret_cast<float4*>(r + c * 4) = rl[c];
-        }
-        if (with_bq) {
-            for (int i = lane; i < nfr * pp.J_bq; i += 32) *reinterpret_cast<float4*>(tile + i * 4) = make_float4(0.f, 0.f, 0.f, 1.f);
-            __syncwarp();
-            if (fl < nfr) {
-                if (side == 0) *reinterpret_cast<float4*>(tile + (fl * pp.J_bq + pp.bq_torso) * 4) = torso;
-                *reinterpret_cast<float4*>(tile + (fl * pp.J_bq + ap.bq_wrist) * 4) = wrist_g;
+                for (int c = 0; c < 7; ++c) lq_g[fl * JR + ap.rob_first + c] = rl[c];
+            }
+            if (with_bq) {
+                if (side == 0) bq_g[fl * pp.J_bq + pp.bq_torso] = torso;
+                bq_g[fl * pp.J_bq + ap.bq_wrist] = wrist_g;
             }
         }
         if (nfr == BQ_FRAMES_PER_WARP) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                if (a.out_dof) bulk_store_s2g(a.out_dof + f0 * D, dof_t, (unsigned)(BQ_FRAMES_PER_WARP * D * 4));
-                if (with_lq) bulk_store_s2g(a.out_local_q + f0 * JR * 4, lq_t, (unsigned)(BQ_FRAMES_PER_WARP * JR * 16));
-                if (with_bq) bulk_store_s2g(a.out_body_gq + f0 * pp.J_bq * 4, tile, (unsigned)(BQ_FRAMES_PER_WARP * pp.J_bq * 16));
-                bulk_commit();
+            if (a.out_dof) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_store_s2g(a.out_dof + f0 * D, dof_t, (unsigned)(BQ_FRAMES_PER_WARP * D * 4));
+                    bulk_commit();
+                }
+                pending_store = true;
             }
-            pending_store = true;
         } else if (nfr > 0) {
             __syncwarp();
             if (a.out_dof) warp_store_span(a.out_dof + f0 * D, dof_t, nfr * D, lane);
-            if (with_lq) warp_store_span(a.out_local_q + f0 * JR * 4, lq_t, nfr * JR * 4, lane);
-            if (with_bq) warp_store_span(a.out_body_gq + f0 * pp.J_bq * 4, tile, nfr * pp.J_bq * 4, lane);
             __syncwarp();
         }
     }

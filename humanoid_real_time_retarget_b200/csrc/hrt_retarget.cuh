@@ -75,14 +75,15 @@ constexpr int BQ_WARPS_WIDE = HRT_BQ_WARPS_WIDE;
 #define HRT_BQ_WARPS_NOIK 28
 #endif
 constexpr int BQ_WARPS_NOIK = HRT_BQ_WARPS_NOIK;
-constexpr int BQ_WARPS_NOIK_NARROW = 12;          // with the local-rotation tile staged as well
 constexpr int BQ_WARPS_NARROW = 8;
 // warp-private staging, in words: [input rows, later the link-position image] [dof image]
 // [local-rotation image, only when that output is requested]
 HRT_HD inline int bq_io_words(int JS, int JR) { return BQ_FRAMES_PER_WARP * (JS * 4 > JR * 3 ? JS * 4 : JR * 3); }
 HRT_HD inline int bq_dof_words(int JR) { return (BQ_FRAMES_PER_WARP * (JR - 1) + 3) / 4 * 4; }
-HRT_HD inline int bq_tile_words(int JS, int JR, bool with_lq) {
-    return bq_io_words(JS, JR) + bq_dof_words(JR) + (with_lq ? BQ_FRAMES_PER_WARP * JR * 4 : 0);
+// (the local rotations are identity except for the arm hinges: they go straight to HBM -- coalesced identity fill, then each
+// lane patches its own rows -- so the tile does not depend on the outputs requested)
+HRT_HD inline int bq_tile_words(int JS, int JR, bool /*with_lq*/) {
+    return bq_io_words(JS, JR) + bq_dof_words(JR);
 }
 // CTA-shared constants: both ArmParams, the robot's rest positions, and a 16-frame image of them (the link-position
 // tile of every group starts as a 16-byte-wise copy of it)
@@ -273,7 +274,6 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
     float* tile = smem + BQ_CONST_WORDS + warp * bq_tile_words(bp.J_src, bp.J_rob, with_lq);
     float* lp_t = tile;                                   // input rows, later the link-position image
     float* dof_t = tile + bq_io_words(bp.J_src, bp.J_rob);
-    float* lq_t = dof_t + bq_dof_words(bp.J_rob);
     bool pending_store = false;
     const long long n_groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
     const int JS = bp.J_src, JR = bp.J_rob;
@@ -316,8 +316,6 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
         cp_async_commit();
         // while the copy is in flight: pre-fill the output images with their constant parts
         if (a.out_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
-        if (with_lq)
-            for (int i = lane; i < nfr * JR; i += 32) *reinterpret_cast<float4*>(lq_t + i * 4) = make_float4(0.f, 0.f, 0.f, 1.f);
         cp_async_wait<0>();
         __syncwarp();
         const float* row = tile + fr * JS * 4;
@@ -417,10 +415,14 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
 #pragma unroll
             for (int c = 0; c < 7; ++c) r[c] = th[c];
         }
-        if (with_lq && fl < nfr) {
-            float* r = lq_t + (fl * JR + ap.rob_first) * 4;
+        if (with_lq) {
+            float4* lq_g = reinterpret_cast<float4*>(a.out_local_q + f0 * JR * 4);
+            for (int i = lane; i < nfr * JR; i += 32) lq_g[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+            __syncwarp();                                  // orders the fill before the patches of other lanes' rows
+            if (fl < nfr) {
 #pragma unroll
-            for (int c = 0; c < 7; ++c) *reinterpret_cast<float4*>(r + c * 4) = rl[c];
+                for (int c = 0; c < 7; ++c) lq_g[fl * JR + ap.rob_first + c] = rl[c];
+            }
         }
         if (a.out_link_pos && fl < nfr) {
             float* r = lp_t + fl * W + ap.rob_first * 3;
@@ -445,7 +447,6 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
             __syncwarp();
             if (lane == 0) {
                 if (a.out_dof) bulk_store_s2g(a.out_dof + f0 * D, dof_t, (unsigned)(BQ_FRAMES_PER_WARP * D * 4));
-                if (with_lq) bulk_store_s2g(a.out_local_q + f0 * JR * 4, lq_t, (unsigned)(BQ_FRAMES_PER_WARP * JR * 16));
                 if (a.out_link_pos) bulk_store_s2g(a.out_link_pos + f0 * W, lp_t, (unsigned)(BQ_FRAMES_PER_WARP * W * 4));
                 bulk_commit();
             }
@@ -453,7 +454,6 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
         } else if (nfr > 0) {
             __syncwarp();
             if (a.out_dof) warp_store_span(a.out_dof + f0 * D, dof_t, nfr * D, lane);
-            if (with_lq) warp_store_span(a.out_local_q + f0 * JR * 4, lq_t, nfr * JR * 4, lane);
             if (a.out_link_pos) warp_store_span(a.out_link_pos + f0 * W, lp_t, nfr * W, lane);
             __syncwarp();
         }

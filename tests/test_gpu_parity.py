@@ -239,12 +239,12 @@ def test_packed_ik_variant_matches_scalar(hrt, eng, oc, skeletons):
 
 
 def test_body_quat_cta_shapes_agree(hrt, eng, oc, skeletons):
-    """Calls without the refinement run the instantiation with the IK loop compiled out, at 28 warps per CTA (dof / link
-    positions only), 12 (local rotations staged too) or 8 (short clips); with the refinement 16 / 8.  Same device code
-    for the closed form, so the same bits whichever shape runs."""
+    """Calls without the refinement run the instantiation with the IK loop compiled out, at 28 warps per CTA or 8 (short
+    clips); with the refinement 16 / 8.  Same device code for the closed form, so the same bits whichever shape runs and
+    whichever outputs are requested (the local rotations go straight to HBM, the rest through staged images)."""
     B = 40_000
     raw = oc.synth_clip_3q(B, seed=21, sk=skeletons).cuda()
-    lq12, dof12, lp12 = eng.retarget_body_quat(raw, flags=0)                                     # 12 warps (local_q staged)
+    lq12, dof12, lp12 = eng.retarget_body_quat(raw, flags=0)                                     # all three outputs
     _, dof28, lp28 = eng.retarget_body_quat(raw, flags=0, want_local_q=False)                   # 28 warps
     _, dof8, lp8 = eng.retarget_body_quat(raw[:4000], flags=0, want_local_q=False)              # 8 warps (short clip)
     assert torch.equal(dof28, dof12) and torch.equal(lp28, lp12)
@@ -615,9 +615,9 @@ def test_full_body_pos_vs_oracle_large(hrt, eng, oc, skeletons):
 
 
 def test_pos_path_cta_shapes_agree(hrt, eng, oc, skeletons):
-    """The position kernels are instantiated for 8 / 12 / 16 warps per CTA and the host picks by what the requested
-    outputs need in shared memory (all three outputs: 8, dof + body quats: 12, dof only: 16) and by clip length
-    (short clips: 8).  Same device code, so the same angles, whichever shape runs."""
+    """The position kernels are instantiated for 8 / 12 / 16 warps per CTA and the host picks by what fits in shared memory
+    and by clip length (short clips: 8).  Same device code, so the same angles, whichever shape runs and whichever outputs
+    are requested (local rotations and body quaternions are written straight to HBM, only dof_pos is staged)."""
     B = 40_000
     g = torch.Generator().manual_seed(3)
     em = 0.4 * torch.randn(B, 59, 3, generator=g)
