@@ -75,9 +75,8 @@ constexpr int BQ_WARPS_WIDE = HRT_BQ_WARPS_WIDE;
 #define HRT_BQ_WARPS_NOIK 28
 #endif
 constexpr int BQ_WARPS_NOIK = HRT_BQ_WARPS_NOIK;
-constexpr int BQ_WARPS_NARROW = 8;
+constexpr int BQ_WARPS_NARROW = 8;                // single frames and short clips
 // warp-private staging, in words: [input rows, later the link-position image] [dof image]
-// [local-rotation image, only when that output is requested]
 HRT_HD inline int bq_io_words(int JS, int JR) { return BQ_FRAMES_PER_WARP * (JS * 4 > JR * 3 ? JS * 4 : JR * 3); }
 HRT_HD inline int bq_dof_words(int JR) { return (BQ_FRAMES_PER_WARP * (JR - 1) + 3) / 4 * 4; }
 // (the local rotations are identity except for the arm hinges: they go straight to HBM -- coalesced identity fill, then each
