@@ -153,11 +153,27 @@ int get_tree(hrt_ctx* ctx, int tree, Tree** out) {
     return 0;
 }
 
+// Occupancy of (kernel, block size, dynamic shared memory) and the kernel's shared-memory attribute are queried / set once per
+// device and cached per call site: both are driver calls of a few microseconds, which is a third of a 65,536-configuration
+// FK launch when they sit between the caller's events.
+struct LaunchCache {
+    size_t occ_smem[16] = {};
+    int occ_threads[16] = {};
+    int per_sm[16] = {};
+    size_t attr_smem[16] = {};
+};
+
 template <typename K>
-int grid_for(hrt_ctx* ctx, K kernel, int threads, size_t smem, long long n_ctas_wanted, int* grid) {
+int grid_for(hrt_ctx* ctx, K kernel, int threads, size_t smem, long long n_ctas_wanted, int* grid, LaunchCache* cache = nullptr) {
+    const int d = ctx->device & 15;
     int per_sm = 0;
-    HRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
-    if (per_sm < 1) per_sm = 1;
+    if (cache && cache->per_sm[d] > 0 && cache->occ_smem[d] == smem && cache->occ_threads[d] == threads) {
+        per_sm = cache->per_sm[d];
+    } else {
+        HRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+        if (per_sm < 1) per_sm = 1;
+        if (cache) { cache->per_sm[d] = per_sm; cache->occ_smem[d] = smem; cache->occ_threads[d] = threads; }
+    }
     long long cap = (long long)ctx->sm_count * per_sm;
     *grid = (int)std::max(1LL, std::min(n_ctas_wanted, cap));
     return 0;
@@ -171,11 +187,16 @@ int launch_fk_variant(hrt_ctx* ctx, Tree* t, FkArgs a, cudaStream_t st) {
     constexpr int cfgs = FKL_GROUP * fkl_cpl(FROM_ANGLES, EXACT), warps = fkl_warps(FROM_ANGLES, EXACT);
     const size_t smem = fkl_smem_bytes(J, t->T, FROM_ANGLES, cfgs, warps);
     auto kern = fk_limb_kernel<FROM_ANGLES, EXACT, BOUNDED>;
-    if (smem > 48 * 1024) HRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static LaunchCache cache;                              // one per instantiation
+    const int d = ctx->device & 15;
+    if (smem > 48 * 1024 && cache.attr_smem[d] < smem) {
+        HRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cache.attr_smem[d] = smem;
+    }
     const long long tasks = (a.B + cfgs - 1) / cfgs;
     const long long ctas = (tasks + warps - 1) / warps;
     int grid = 1;
-    int rc = grid_for(ctx, kern, warps * 32, smem, ctas, &grid);
+    int rc = grid_for(ctx, kern, warps * 32, smem, ctas, &grid, &cache);
     if (rc) return rc;
     kern<<<grid, warps * 32, smem, st>>>(J, a);
     HRT_CUDA(cudaGetLastError());
@@ -533,11 +554,12 @@ int hrt_fk_jacobian(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, co
     int grid = 1;
     int max_depth = 0;
     for (int k = 0; k < K; ++k) max_depth = std::max(max_depth, jp.depth[k]);
+    static LaunchCache jc8, jc16;
     if (max_depth <= 8) {
-        if ((rc = grid_for(ctx, jacobian_kernel<8>, JAC_WARPS_PER_CTA * 32, smem, ctas, &grid))) return rc;
+        if ((rc = grid_for(ctx, jacobian_kernel<8>, JAC_WARPS_PER_CTA * 32, smem, ctas, &grid, &jc8))) return rc;
         jacobian_kernel<8><<<grid, JAC_WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(t->tp, jp, a);
     } else {
-        if ((rc = grid_for(ctx, jacobian_kernel<HRT_MAX_CHAIN>, JAC_WARPS_PER_CTA * 32, smem, ctas, &grid))) return rc;
+        if ((rc = grid_for(ctx, jacobian_kernel<HRT_MAX_CHAIN>, JAC_WARPS_PER_CTA * 32, smem, ctas, &grid, &jc16))) return rc;
         jacobian_kernel<HRT_MAX_CHAIN><<<grid, JAC_WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(t->tp, jp, a);
     }
     HRT_CUDA(cudaGetLastError());
