@@ -129,3 +129,12 @@ def test_velocity_halo_exchange_matches_whole_clip_gloo():
     ret = mgr.dict()
     mp.spawn(_worker_halo, args=(world, _free_port(), n_frames, ret), nprocs=world, join=True)
     assert all(all(ret[r]) for r in range(world)), dict(ret)
+
+
+def test_gpu_local_host_memory_never_raises_without_a_gpu():
+    """The NUMA helper is best effort: without NVML / a GPU it reports why it did nothing and leaves the affinity alone."""
+    from humanoid_real_time_retarget_b200.sharding import gpu_local_host_memory
+    before = os.sched_getaffinity(0)
+    with gpu_local_host_memory(0) as h:
+        assert isinstance(h.info, dict) and ("skipped" in h.info or "cpus" in h.info)
+    assert os.sched_getaffinity(0) == before
