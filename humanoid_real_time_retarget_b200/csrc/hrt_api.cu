@@ -99,12 +99,33 @@ struct hrt_ctx {
 
 namespace {
 
-int check_ctx(hrt_ctx* ctx) {
-    if (!ctx) return fail(HRT_E_INVALID_ARG, "null context");
-    cudaError_t e = cudaSetDevice(ctx->device);
-    if (e != cudaSuccess) return fail((int)e, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
-    return 0;
-}
+// Every entry point runs on the context's device and puts the caller's current device back on return (a caller with
+// engines on several GPUs, or torch with another current device, must not see its device change under it).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    int enter_device(int device) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return fail((int)e, "cudaGetDevice: %s", cudaGetErrorString(e));
+        if (prev != device) {
+            e = cudaSetDevice(device);
+            if (e != cudaSuccess) return fail((int)e, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+            switched = true;
+        }
+        return 0;
+    }
+    int enter(const hrt_ctx* ctx) {
+        if (!ctx) return fail(HRT_E_INVALID_ARG, "null context");
+        return enter_device(ctx->device);
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+#define HRT_ENTER(ctx)         \
+    DeviceGuard dev_guard_;    \
+    int rc = dev_guard_.enter(ctx); \
+    if (rc) return rc
 
 constexpr unsigned long long kServerIdleNs = 20ull * 1000 * 1000;     // a resident kernel leaves after 20 ms without a frame
 
@@ -361,7 +382,11 @@ int hrt_ctx_create(int device, hrt_ctx** out) {
     if (e != cudaSuccess || n == 0)
         return fail(HRT_E_NO_DEVICE, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
     if (device < 0 || device >= n) return fail(HRT_E_INVALID_ARG, "device %d out of range (0..%d)", device, n - 1);
-    HRT_CUDA(cudaSetDevice(device));
+    DeviceGuard dev_guard_;
+    {
+        int rc = dev_guard_.enter_device(device);
+        if (rc) return rc;
+    }
     hrt_ctx* c = new (std::nothrow) hrt_ctx();
     if (!c) return fail(HRT_E_INVALID_ARG, "out of host memory");
     c->device = device;
@@ -392,7 +417,8 @@ int hrt_ctx_create(int device, hrt_ctx** out) {
 
 int hrt_ctx_destroy(hrt_ctx* ctx) {
     if (!ctx) return 0;
-    cudaSetDevice(ctx->device);
+    DeviceGuard dev_guard_;
+    dev_guard_.enter(ctx);
     hrt_stream_close(ctx);
     hrt_stream_pos_close(ctx);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
@@ -414,8 +440,10 @@ int hrt_ctx_sm_count(const hrt_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 int hrt_set_tree(hrt_ctx* ctx, int tree, int J, const int32_t* parents, const float* offsets,
                  const uint8_t* dof_axis, const float* lower, const float* upper, const float* t2z) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
+    // streams (and a resident server kernel) hold the previous tables by value: stop them, the caller re-opens
+    hrt_stream_close(ctx);
+    hrt_stream_pos_close(ctx);
     if (tree < 0 || tree >= HRT_MAX_TREES) return fail(HRT_E_INVALID_ARG, "tree id %d out of range", tree);
     if (J < 1 || J > HRT_MAX_JOINTS) return fail(HRT_E_UNSUPPORTED_TREE, "J=%d outside 1..%d", J, HRT_MAX_JOINTS);
     if (!parents || !offsets) return fail(HRT_E_INVALID_ARG, "parents/offsets are required");
@@ -424,6 +452,7 @@ int hrt_set_tree(hrt_ctx* ctx, int tree, int J, const int32_t* parents, const fl
         if (parents[j] < 0 || parents[j] >= j)
             return fail(HRT_E_UNSUPPORTED_TREE, "parents[%d]=%d: parents must precede children, single root", j, parents[j]);
     Tree& t = ctx->trees[tree];
+    t.set = false;                     // an early return below must not leave a half-installed tree usable
     TreeParams& tp = t.tp;
     memset(&tp, 0, sizeof(tp));
     tp.J = J;
@@ -488,8 +517,7 @@ int hrt_set_tree(hrt_ctx* ctx, int tree, int J, const int32_t* parents, const fl
 
 int hrt_fk_local_quats(hrt_ctx* ctx, int tree, int64_t B, const float* d_local_q, const float* d_root_t,
                        float* d_gq, float* d_gt, unsigned flags, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     Tree* t;
     if ((rc = get_tree(ctx, tree, &t))) return rc;
     if (B == 0) return 0;
@@ -503,8 +531,7 @@ int hrt_fk_local_quats(hrt_ctx* ctx, int tree, int64_t B, const float* d_local_q
 
 int hrt_fk_angles(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, const float* d_root_t,
                   const float* d_root_q, int clip, float* d_gq, float* d_gt, unsigned flags, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     Tree* t;
     if ((rc = get_tree(ctx, tree, &t))) return rc;
     if (!t->has_dof) return fail(HRT_E_NOT_CONFIGURED, "tree %d has no dof_axis table", tree);
@@ -520,8 +547,7 @@ int hrt_fk_angles(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, cons
 
 int hrt_fk_jacobian(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, const float* d_root_t,
                     const float* d_root_q, int clip, const int32_t* links, int K, float* d_jac, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     Tree* t;
     if ((rc = get_tree(ctx, tree, &t))) return rc;
     if (!t->has_dof) return fail(HRT_E_NOT_CONFIGURED, "tree %d has no dof_axis table", tree);
@@ -567,8 +593,7 @@ int hrt_fk_jacobian(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, co
 }
 
 int hrt_local_from_global(hrt_ctx* ctx, int tree, int64_t B, const float* d_gq, float* d_lq, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     Tree* t;
     if ((rc = get_tree(ctx, tree, &t))) return rc;
     if (B == 0) return 0;
@@ -595,8 +620,7 @@ static void rot_quat(int variant, float out[4]) {
 
 int hrt_zero_pose_transform(hrt_ctx* ctx, int tree, int64_t B, const float* d_gq, int variant, float* d_out,
                             void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     Tree* t;
     if ((rc = get_tree(ctx, tree, &t))) return rc;
     if (!t->d_t2z) return fail(HRT_E_NOT_CONFIGURED, "tree %d has no T2Z table", tree);
@@ -617,8 +641,8 @@ int hrt_zero_pose_transform(hrt_ctx* ctx, int tree, int64_t B, const float* d_gq
 
 int hrt_configure_body_quat(hrt_ctx* ctx, int src_tree, int rob_tree, const int32_t* src_joints,
                             const int32_t* rob_first) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
+    hrt_stream_close(ctx);             // a stream opened before keeps the old wiring by value
     Tree *s, *r;
     if ((rc = get_tree(ctx, src_tree, &s))) return rc;
     if ((rc = get_tree(ctx, rob_tree, &r))) return rc;
@@ -649,6 +673,11 @@ int hrt_configure_body_quat(hrt_ctx* ctx, int src_tree, int rob_tree, const int3
         const int32_t* sj = src_joints + side * 5;
         for (int n = 0; n < 5; ++n)
             if (sj[n] < 0 || sj[n] >= s->tp.J) return fail(HRT_E_INVALID_ARG, "src_joints[%d][%d]=%d out of range", side, n, sj[n]);
+        // the fused kernel takes the upper / lower arm's local rotation against the listed shoulder / upper arm joint:
+        // that is cal_local_rotation (kinematics.py:41-63) only if those ARE the tree parents
+        if (s->tp.parent[sj[2]] != sj[1] || s->tp.parent[sj[3]] != sj[2])
+            return fail(HRT_E_UNSUPPORTED_TREE, "src_joints[%d]: joint %d must be the parent of %d and %d the parent of %d in the source tree",
+                        side, sj[1], sj[2], sj[2], sj[3]);
         ap.src_torso = sj[0]; ap.src_shoulder = sj[1]; ap.src_upper = sj[2]; ap.src_lower = sj[3]; ap.src_hand = sj[4];
         const int f = rob_first[side];
         if (f < 1 || f + 8 >= rt.J) return fail(HRT_E_INVALID_ARG, "rob_first[%d]=%d out of range", side, f);
@@ -683,8 +712,7 @@ int hrt_configure_body_quat(hrt_ctx* ctx, int src_tree, int rob_tree, const int3
 int hrt_retarget_body_quat(hrt_ctx* ctx, int64_t B, const float* d_src_gq, unsigned flags, int ik_iters,
                            float damping, float rot_weight, float* d_robot_local_q, float* d_dof,
                            float* d_link_pos, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     BodyQuatArgs a;
     if ((rc = fill_body_quat_args(ctx, B, d_src_gq, flags, ik_iters, damping, rot_weight, d_robot_local_q, d_dof,
                                   d_link_pos, &a)))
@@ -699,8 +727,7 @@ int hrt_retarget_body_quat(hrt_ctx* ctx, int64_t B, const float* d_src_gq, unsig
 int hrt_retarget_body_quat_host(hrt_ctx* ctx, int64_t B, const float* h_src_gq, unsigned flags, int ik_iters,
                                 float damping, float rot_weight, float* h_robot_local_q, float* h_dof,
                                 float* h_link_pos) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     BodyQuatArgs proto;
     if ((rc = fill_body_quat_args(ctx, B, nullptr, flags, ik_iters, damping, rot_weight, nullptr, nullptr, nullptr, &proto)))
         return rc;
@@ -755,8 +782,8 @@ int hrt_retarget_body_quat_host(hrt_ctx* ctx, int64_t B, const float* h_src_gq, 
 }
 
 int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const float* src_global_t, int precise_gripper) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
+    hrt_stream_pos_close(ctx);         // a stream (or resident server) opened before keeps the old PosParams by value
     if (mode < 0 || mode > 3) return fail(HRT_E_INVALID_ARG, "mode must be 0 (full_body_pos), 1 (upper_body), 2 (full_body) or 3 (main)");
     Tree *s, *r;
     if ((rc = get_tree(ctx, src_tree, &s))) return rc;
@@ -905,8 +932,7 @@ static int launch_pos(hrt_ctx* ctx, int slot, const PosArgs& a, cudaStream_t st,
 
 int hrt_retarget_full_body_pos(hrt_ctx* ctx, int64_t B, const float* d_body_t, const float* d_lhand_t, const float* d_rhand_t,
                                float* d_robot_local_q, float* d_dof, float* d_body_gq, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     if (B > 0 && (!d_body_t || !d_lhand_t || !d_rhand_t)) return fail(HRT_E_INVALID_ARG, "null input");
     PosArgs a{};
     a.B = B; a.body_t = d_body_t; a.lhand_t = d_lhand_t; a.rhand_t = d_rhand_t;
@@ -917,8 +943,7 @@ int hrt_retarget_full_body_pos(hrt_ctx* ctx, int64_t B, const float* d_body_t, c
 int hrt_retarget_full_body_pos_ex(hrt_ctx* ctx, int64_t B, const float* d_body_t, const float* d_lhand_t, const float* d_rhand_t,
                                   unsigned flags, int ik_iters, float damping, float rot_weight, float* d_robot_local_q,
                                   float* d_dof, float* d_body_gq, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     if (B > 0 && (!d_body_t || !d_lhand_t || !d_rhand_t)) return fail(HRT_E_INVALID_ARG, "null input");
     if ((flags & HRT_POS_IK) && (ik_iters < 0 || ik_iters > 1000)) return fail(HRT_E_INVALID_ARG, "ik_iters out of range");
     PosArgs a{};
@@ -932,8 +957,7 @@ int hrt_retarget_full_body_pos_ex(hrt_ctx* ctx, int64_t B, const float* d_body_t
 int hrt_retarget_full_body_pos_host(hrt_ctx* ctx, int64_t B, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
                                     unsigned flags, int ik_iters, float damping, float rot_weight, float* h_robot_local_q,
                                     float* h_dof) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     if (!ctx->pos_set[POS_FULL_BODY_POS]) return fail(HRT_E_NOT_CONFIGURED, "hrt_configure_pos(mode 0) has not been called");
     if (B < 0) return fail(HRT_E_INVALID_ARG, "negative frame count");
     if ((flags & HRT_POS_IK) && (ik_iters < 0 || ik_iters > 1000)) return fail(HRT_E_INVALID_ARG, "ik_iters out of range");
@@ -987,8 +1011,7 @@ int hrt_retarget_full_body_pos_host(hrt_ctx* ctx, int64_t B, const float* h_body
 }
 
 int hrt_retarget_upper_body(hrt_ctx* ctx, int64_t B, const float* d_body_t, float* d_robot_local_q, float* d_dof, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     if (B > 0 && !d_body_t) return fail(HRT_E_INVALID_ARG, "null input");
     PosArgs a{};
     a.B = B; a.body_t = d_body_t; a.out_local_q = d_robot_local_q; a.out_dof = d_dof;
@@ -997,8 +1020,7 @@ int hrt_retarget_upper_body(hrt_ctx* ctx, int64_t B, const float* d_body_t, floa
 
 int hrt_retarget_full_body(hrt_ctx* ctx, int64_t B, const float* d_body_q, const float* d_body_t, const float* d_lhand_t,
                            const float* d_rhand_t, float* d_robot_local_q, float* d_dof, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     if (B > 0 && (!d_body_q || !d_body_t || !d_lhand_t || !d_rhand_t)) return fail(HRT_E_INVALID_ARG, "null input");
     PosArgs a{};
     a.B = B; a.body_q = d_body_q; a.body_t = d_body_t; a.lhand_t = d_lhand_t; a.rhand_t = d_rhand_t;
@@ -1007,8 +1029,7 @@ int hrt_retarget_full_body(hrt_ctx* ctx, int64_t B, const float* d_body_q, const
 }
 
 int hrt_stream_open(hrt_ctx* ctx, unsigned flags, int ik_iters, float damping, float rot_weight) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     if (ctx->stream_open) hrt_stream_close(ctx);
     BodyQuatArgs a;
     if ((rc = fill_body_quat_args(ctx, 1, nullptr, flags, ik_iters, damping, rot_weight, nullptr, nullptr, nullptr, &a)))
@@ -1046,6 +1067,11 @@ int hrt_stream_frame(hrt_ctx* ctx, const float* h_src_gq, float* h_robot_local_q
                      float* h_link_pos) {
     if (!ctx || !ctx->stream_open) return fail(HRT_E_NOT_CONFIGURED, "hrt_stream_open has not been called");
     if (!h_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
+    DeviceGuard dev_guard_;                      // the launch on ctx->ss needs the context's device current
+    if (!ctx->stream_persistent) {
+        int rc = dev_guard_.enter(ctx);
+        if (rc) return rc;
+    }
     const int JS = ctx->bq.J_src, JR = ctx->bq.J_rob;
     memcpy(ctx->mb_in, h_src_gq, (size_t)JS * 16);
     if (!ctx->stream_persistent) {
@@ -1069,7 +1095,8 @@ int hrt_stream_frame(hrt_ctx* ctx, const float* h_src_gq, float* h_robot_local_q
 
 int hrt_stream_close(hrt_ctx* ctx) {
     if (!ctx || !ctx->stream_open) return 0;
-    cudaSetDevice(ctx->device);
+    DeviceGuard dev_guard_;
+    dev_guard_.enter(ctx);
     if (ctx->bctrl) ctx->bctrl[1] = 1u;               // tell a resident server to leave
     if (ctx->ss) { cudaStreamSynchronize(ctx->ss); cudaStreamDestroy(ctx->ss); ctx->ss = nullptr; }
     if (ctx->mb_in) { cudaFreeHost(ctx->mb_in); ctx->mb_in = nullptr; }
@@ -1082,8 +1109,7 @@ int hrt_stream_close(hrt_ctx* ctx) {
 
 int hrt_retarget_full_body_pos_wire(hrt_ctx* ctx, int64_t B, const float* d_body23_t, const float* d_lhand_t, const float* d_rhand_t,
                                     float* d_robot_local_q, float* d_dof, float* d_body_gq, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     if (B > 0 && (!d_body23_t || !d_lhand_t || !d_rhand_t)) return fail(HRT_E_INVALID_ARG, "null input");
     PosArgs a{};
     a.B = B; a.body_t = d_body23_t; a.lhand_t = d_lhand_t; a.rhand_t = d_rhand_t;
@@ -1093,8 +1119,7 @@ int hrt_retarget_full_body_pos_wire(hrt_ctx* ctx, int64_t B, const float* d_body
 
 int hrt_retarget_main_arms(hrt_ctx* ctx, int64_t B, const float* d_body_q, const float* d_body_t,
                            float* d_robot_local_q, float* d_dof, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     if (B > 0 && (!d_body_q || !d_body_t)) return fail(HRT_E_INVALID_ARG, "null input");
     PosArgs a{};
     a.B = B; a.body_q = d_body_q; a.body_t = d_body_t; a.out_local_q = d_robot_local_q; a.out_dof = d_dof;
@@ -1118,8 +1143,7 @@ int launch_pos_server(hrt_ctx* ctx, unsigned served) {
 }  // namespace
 
 int hrt_stream_pos_open(hrt_ctx* ctx, int flags) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     const int mode = (flags >> HRT_STREAM_MODE_SHIFT) & 3;
     const bool wire = (flags & HRT_STREAM_WIRE_LAYOUT) != 0;
     if (mode == POS_MAIN) return fail(HRT_E_INVALID_ARG, "streaming serves modes 0 (full_body_pos), 1 (upper_body), 2 (full_body)");
@@ -1178,6 +1202,11 @@ int hrt_stream_pos_frame(hrt_ctx* ctx, const float* h_body_t, const float* h_lha
 int hrt_stream_pos_frame_ex(hrt_ctx* ctx, const float* h_body_t, const float* h_lhand_t, const float* h_rhand_t,
                             const float* h_body_q, float* h_robot_local_q, float* h_dof, float* h_body_gq) {
     if (!ctx || !ctx->pstream_open) return fail(HRT_E_NOT_CONFIGURED, "hrt_stream_pos_open has not been called");
+    DeviceGuard dev_guard_;                      // the launch on ctx->pss needs the context's device current
+    if (!ctx->pstream_persistent) {
+        int rc = dev_guard_.enter(ctx);
+        if (rc) return rc;
+    }
     const PosArgs& a = ctx->pstream_args;
     if (!h_body_t || (a.lhand_t && (!h_lhand_t || !h_rhand_t)) || (a.body_q && !h_body_q)) return fail(HRT_E_INVALID_ARG, "null input");
     if (h_body_gq && !a.out_body_gq) return fail(HRT_E_INVALID_ARG, "stream opened without HRT_STREAM_BODY_GQ");
@@ -1206,7 +1235,8 @@ int hrt_stream_pos_frame_ex(hrt_ctx* ctx, const float* h_body_t, const float* h_
 
 int hrt_stream_pos_close(hrt_ctx* ctx) {
     if (!ctx || !ctx->pstream_open) return 0;
-    cudaSetDevice(ctx->device);
+    DeviceGuard dev_guard_;
+    dev_guard_.enter(ctx);
     if (ctx->pctrl) ctx->pctrl[1] = 1u;               // tell a resident server to leave
     if (ctx->pss) { cudaStreamSynchronize(ctx->pss); cudaStreamDestroy(ctx->pss); ctx->pss = nullptr; }
     if (ctx->pmb_in) { cudaFreeHost(ctx->pmb_in); ctx->pmb_in = nullptr; }
@@ -1218,8 +1248,7 @@ int hrt_stream_pos_close(hrt_ctx* ctx) {
 }
 
 int hrt_rescale_motion(hrt_ctx* ctx, int tree, int64_t B, const float* d_gt, const float* dir3, float* d_out, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     Tree* t;
     if ((rc = get_tree(ctx, tree, &t))) return rc;
     if (B == 0) return 0;
@@ -1242,8 +1271,7 @@ int hrt_rescale_motion(hrt_ctx* ctx, int tree, int64_t B, const float* d_gt, con
 
 int hrt_rebuild_global_rotation(hrt_ctx* ctx, int tree, int64_t B, const float* d_gt, int n_kabsch,
                                 const int32_t* kabsch_joint, const int32_t* kabsch_pts, float* d_out_gq, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     Tree* t;
     if ((rc = get_tree(ctx, tree, &t))) return rc;
     if (n_kabsch < 0 || n_kabsch > 2 || (n_kabsch && (!kabsch_joint || !kabsch_pts)))
@@ -1330,8 +1358,7 @@ static int ew_grid(hrt_ctx* ctx, long long n) { return (int)std::max(1LL, std::m
 
 int hrt_motion_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gt, float dt, int gaussian,
                         float* d_scratch, float* d_out, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     if (T < 2) return fail(HRT_E_INVALID_ARG, "np.gradient needs at least 2 frames");
     if (J < 1 || !d_gt || !d_out || (gaussian && !d_scratch)) return fail(HRT_E_INVALID_ARG, "bad J / null pointer");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1349,8 +1376,7 @@ int hrt_motion_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gt, f
 
 int hrt_motion_angular_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gq, float dt, int gaussian,
                                 float* d_scratch, float* d_out, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     if (T < 1 || J < 1 || !d_gq || !d_out || (gaussian && !d_scratch)) return fail(HRT_E_INVALID_ARG, "bad T / J / null pointer");
     if (!aligned16(d_gq)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1368,8 +1394,7 @@ int hrt_motion_angular_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float*
 
 int hrt_forward_vector(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gt, int left_shoulder, int right_shoulder,
                        int left_hip, int right_hip, double sigma, double* d_scratch, double* d_out, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     if (T < 0 || J < 1) return fail(HRT_E_INVALID_ARG, "bad T / J");
     if (T == 0) return 0;
     if (!d_gt || !d_scratch || !d_out) return fail(HRT_E_INVALID_ARG, "null pointer");
@@ -1429,8 +1454,7 @@ int hrt_rot_op_info(int op, int* n_in, int* in_width4, int* n_out, int* out_widt
 
 int hrt_rot_op(hrt_ctx* ctx, int op, int64_t n, const float* const* d_in4, const int64_t* period4, int iparam,
                float fparam, float* const* d_out3, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     int ni, wi[4], no, wo[3];
     if ((rc = hrt_rot_op_info(op, &ni, wi, &no, wo))) return rc;
     if (n < 0 || !d_in4 || !period4 || !d_out3) return fail(HRT_E_INVALID_ARG, "bad n / null pointer");
@@ -1459,8 +1483,7 @@ int hrt_rot_op(hrt_ctx* ctx, int op, int64_t n, const float* const* d_in4, const
 }
 
 int hrt_max_norm3(hrt_ctx* ctx, int64_t n, const float* d_v, float* h_out, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     if (n < 0 || !h_out || (n > 0 && !d_v)) return fail(HRT_E_INVALID_ARG, "bad n / null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned* slot = ctx->d_scalars + HRT_MAX_JOINTS;
@@ -1478,8 +1501,7 @@ int hrt_max_norm3(hrt_ctx* ctx, int64_t n, const float* d_v, float* h_out, void*
 
 int hrt_cal_joint_quat(hrt_ctx* ctx, int64_t n, int n_points, const float* d_zero, int64_t zero_period,
                        const float* d_motion, float* d_out_q, void* stream) {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HRT_ENTER(ctx);
     if (n < 0 || n_points < 1 || zero_period < 0) return fail(HRT_E_INVALID_ARG, "bad n / n_points / zero_period");
     if (n == 0) return 0;
     if (!d_zero || !d_motion || !d_out_q) return fail(HRT_E_INVALID_ARG, "null pointer");

@@ -68,11 +68,13 @@ class Engine:
         tz = None if t2z is None else np.ascontiguousarray(np.asarray(t2z, dtype=np.float32).reshape(J, 4))
         for a in (ax, lo, hi):
             assert a is None or a.shape[0] == J - 1
+        self._trees.pop(tree, None)
+        self._pos_stream_cfg = self._bq_stream_cfg = None
         _lib.check(self.lib.hrt_set_tree(self._h, tree, J, _np_ptr(parents), _np_ptr(offsets), _np_ptr(ax),
                                          _np_ptr(lo), _np_ptr(hi), _np_ptr(tz)))
         self._trees[tree] = J
 
-    def set_standard_trees(self, robot="hu_v5"):
+    def set_standard_trees(self, robot="hu_v5", precise_gripper=True):
         """Hu v5 (or Hu) robot + vtrdyn / vtrdyn_full sources from the bundled tables, and the fused
         quaternion-path wiring of body_retargeter.py:40-73."""
         sk = cfg.skeleton_tables()
@@ -89,7 +91,7 @@ class Engine:
                       t2z=sk["t2z/vtrdyn_full"])
         if robot == "hu_v5":
             self.configure_body_quat(TREE_SOURCE, TREE_ROBOT, cfg.VTRDYN_ARM_JOINTS, cfg.HU_V5_ARM_FIRST)
-            self.configure_pos(POS_FULL_BODY_POS, TREE_SOURCE_FULL, TREE_ROBOT, sk["vtrdyn_full_zero_pose/global_translation"], True)
+            self.configure_pos(POS_FULL_BODY_POS, TREE_SOURCE_FULL, TREE_ROBOT, sk["vtrdyn_full_zero_pose/global_translation"], precise_gripper)
             self.configure_pos(POS_UPPER_BODY, TREE_SOURCE, TREE_ROBOT)
             self.configure_pos(POS_FULL_BODY, TREE_SOURCE_FULL, TREE_ROBOT)
             self.configure_pos(POS_MAIN, TREE_SOURCE, TREE_ROBOT)
@@ -100,10 +102,12 @@ class Engine:
         rf = np.ascontiguousarray(np.asarray(rob_first, dtype=np.int32).reshape(2))
         _lib.check(self.lib.hrt_configure_body_quat(self._h, src_tree, rob_tree, _np_ptr(sj), _np_ptr(rf)))
         self._bq = (self._trees[src_tree], self._trees[rob_tree])
+        self._bq_stream_cfg = None         # the C side closed the stream: it held the previous wiring by value
 
     def configure_pos(self, mode, src_tree, rob_tree, src_global_t=None, precise_gripper=False):
         gt = None if src_global_t is None else np.ascontiguousarray(np.asarray(src_global_t, dtype=np.float32))
         _lib.check(self.lib.hrt_configure_pos(self._h, mode, src_tree, rob_tree, _np_ptr(gt), int(bool(precise_gripper))))
+        self._pos_stream_cfg = None        # the C side closed the stream (and stopped a resident server)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -395,6 +399,44 @@ class Engine:
     def stream_close(self):
         _lib.check(self.lib.hrt_stream_close(self._h))
         self._bq_stream_cfg = None
+
+
+def _zp_arrays(zero_pose):
+    """(parents int32 (J,), offsets float32 (J,3), global translations float32 (J,3)) of a RobotZeroPose-like object."""
+    def arr(x, dt):
+        x = x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)
+        return np.ascontiguousarray(x, dtype=dt)
+    parents = arr(zero_pose.parent_indices, np.int32).reshape(-1)
+    off = arr(zero_pose.local_translation, np.float32).reshape(-1, 3)
+    glob = arr(zero_pose.global_translation, np.float32).reshape(-1, 3)
+    if off.shape[0] != parents.shape[0] or glob.shape[0] != parents.shape[0]:
+        raise ValueError(f"zero pose tables disagree: {parents.shape[0]} parents, {off.shape[0]} offsets, {glob.shape[0]} positions")
+    return parents, off, glob
+
+
+def engine_from_zero_poses(source_zero_pose, target_zero_pose, device=0):
+    """A NEW context whose trees are the zero poses a solver was constructed with -- the reference's solvers read every
+    offset from those objects (full_body_pos_retargeter.py:69-107,139,162,184; retarget_solver.py:49-86;
+    full_body_retargeter.py:59-99,152; body_retargeter.py:35,38), never from module-level tables.  The robot must be the
+    31-joint Hu v5 the reference's solvers hard-code (`Hu_DOF_AXIS` of Hu_v5.py, robot_local_rotation[12..27]); the source
+    is the 21-joint vtrdyn or the 59-joint vtrdyn_full skeleton.  Returns (engine, source tree slot, source tables)."""
+    sp, so, sg = _zp_arrays(source_zero_pose)
+    tp, to, _ = _zp_arrays(target_zero_pose)
+    if tp.shape[0] != 31:
+        raise ValueError(f"target zero pose has {tp.shape[0]} joints: the retarget solvers write Hu v5 joints 12-29 and "
+                         "decompose with the 30-entry Hu_DOF_AXIS (retarget/robot_config/Hu_v5.py:12-18)")
+    if sp.shape[0] not in (21, 59):
+        raise ValueError(f"source zero pose has {sp.shape[0]} joints: expected the 21-joint vtrdyn or the 59-joint vtrdyn_full skeleton")
+    eng = Engine(device)
+    eng.set_tree(TREE_ROBOT, tp, to, cfg.Hu_v5_DOF_AXIS, cfg.Hu_v5_DOF_LOWER, cfg.Hu_v5_DOF_UPPER)
+    sk = cfg.skeleton_tables()
+    if sp.shape[0] == 21:
+        slot, t2z = TREE_SOURCE, sk["t2z/vtrdyn"]
+    else:
+        slot, t2z = TREE_SOURCE_FULL, sk["t2z/vtrdyn_full"]
+    # T2Z (parse_mocap.py:71-78,97-104) is built from rotations only: it does not depend on the offsets
+    eng.set_tree(slot, sp, so, t2z=t2z)
+    return eng, slot, (sp, so, sg)
 
 
 _default = {}

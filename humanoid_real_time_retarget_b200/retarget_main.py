@@ -10,7 +10,7 @@ the clip (frames are independent except for the velocity smoothing at the very e
 The reference plots the two motions and returns nothing; this returns them."""
 import torch
 
-from .engine import TREE_SOURCE, default_engine
+from .engine import POS_MAIN, TREE_ROBOT, engine_from_zero_poses
 from .kinematics import RobotZeroPose
 from .skeleton3d import SkeletonMotion, SkeletonState
 
@@ -35,12 +35,16 @@ class Retarget:
 class RetargetHuV5fromMocap(Retarget):
     def __init__(self, mocap_zero_pose: RobotZeroPose, target_zero_pose: RobotZeroPose, device=0):
         super().__init__(mocap_zero_pose, target_zero_pose)
-        self._eng = default_engine(device)
+        # this instance's own context, built from ITS zero poses (main.py:37-47,118-152,203-240 read every offset from them)
+        self._eng, self._src, (parents, _, _) = engine_from_zero_poses(mocap_zero_pose, target_zero_pose, device)
+        if parents.shape[0] != 21:
+            raise ValueError(f"RetargetHuV5fromMocap needs the 21-joint vtrdyn zero pose, got {parents.shape[0]} joints")
+        self._eng.configure_pos(POS_MAIN, self._src, TREE_ROBOT)
 
     def _rebuild_with_vtrdyn_zero_pose(self, motion_global_translation, fps=30) -> SkeletonMotion:
         """main.py:116-165"""
         g = motion_global_translation
-        gq = self._eng.rebuild_global_rotation(TREE_SOURCE, g).to(g.device)
+        gq = self._eng.rebuild_global_rotation(self._src, g).to(g.device)
         state = SkeletonState.from_rotation_and_root_translation(self.mocap_zero_pose.skeleton_tree, gq, g[:, 0, :].clone(),
                                                                  is_local=False)
         motion = SkeletonMotion.from_skeleton_state(state, fps=fps)
@@ -50,7 +54,7 @@ class RetargetHuV5fromMocap(Retarget):
     def retarget_from_global_translation(self, global_translation, fps=30):
         """main.py:169-279.  global_translation (L,21,3).  Returns (mocap_motion, retargeted_motion)."""
         g = torch.as_tensor(global_translation, dtype=torch.float32)
-        scaled = self._eng.rescale_motion(TREE_SOURCE, g, dir=[-1.0, -1.0, 1.0]).to(g.device)     # main.py:170-172
+        scaled = self._eng.rescale_motion(self._src, g, dir=[-1.0, -1.0, 1.0]).to(g.device)     # main.py:170-172
         mocap_motion = self._rebuild_with_vtrdyn_zero_pose(scaled, fps=fps)
         lq, _ = self._eng.retarget_main_arms(mocap_motion.global_rotation, mocap_motion.global_translation, want_dof=False)
         retargeted_state = SkeletonState.from_rotation_and_root_translation(

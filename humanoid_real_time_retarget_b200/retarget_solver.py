@@ -1,16 +1,22 @@
-"""Drop-in for the quaternion-input retargeter and its helpers.
+"""Drop-in for the retarget solvers and their helpers.
 
   BaseHumanoidRetargeter            retarget/retarget_solver/base_retargeter.py:15-58
   Mocap2HuBodyRetargeter            retarget/retarget_solver/body_retargeter.py:30-99
+  VtrdynFullBodyPosRetargeter       retarget/retarget_solver/full_body_pos_retargeter.py:17-217
+  HuUpperBodyFromMocapRetarget      retarget/retarget_solver/retarget_solver.py:27-99
+  VtrdynFullBodyRetargeter          retarget/retarget_solver/full_body_retargeter.py:15-177
   vtrdyn_zero_pose_transform & co.  retarget/utils/parse_mocap.py:81-89,106-114,126-134
+
+Every solver instance owns its own hrt_ctx, built from the zero poses handed to its constructor (the reference reads
+every offset from those objects); nothing here touches a process-wide engine, so instances with different skeletons or
+different `precise_gripper` never see each other.
 """
 import numpy as np
 import torch
 
 from . import robot_config as cfg
 from .engine import (BQ_CLAMP, BQ_IK, BQ_PRE_TRANSFORMED, POS_FULL_BODY, POS_FULL_BODY_POS, POS_UPPER_BODY, TREE_ROBOT, TREE_SOURCE,
-                     TREE_SOURCE_FULL,
-                     default_engine)
+                     TREE_SOURCE_FULL, Engine, engine_from_zero_poses)
 from .kinematics import RobotZeroPose, cal_forward_kinematics
 
 
@@ -24,9 +30,20 @@ def to_torch(tensor):
     return tensor if torch.is_tensor(tensor) else torch.from_numpy(tensor).to(torch.float32)
 
 
+_bundled = {}
+
+
+def _bundled_engine(device):
+    """Private context holding the BUNDLED vtrdyn tables for the module-level transforms below: the reference builds their
+    T2Z table at import from its own asset files (parse_mocap.py:65-78,91-104), not from a caller's zero pose."""
+    if device not in _bundled:
+        _bundled[device] = Engine(device).set_standard_trees()
+    return _bundled[device]
+
+
 def _zpt(global_rotation, tree, variant):
     g = to_torch(global_rotation)
-    eng = default_engine(g.device.index or 0 if g.is_cuda else 0)
+    eng = _bundled_engine(g.device.index or 0 if g.is_cuda else 0)
     return eng.zero_pose_transform(tree, g, variant).reshape(g.shape).to(g.device)
 
 
@@ -104,52 +121,24 @@ class BaseHumanoidRetargeter:
         return sum(x.reshape(-1, *x.shape[-2:]).shape[0] for x in self._motion_local_rotation)
 
 
-class Mocap2HuBodyRetargeter(BaseHumanoidRetargeter):
-    """retarget_from_pose takes ONE frame (21,4) of zero-pose re-referenced global quats, like the
-    reference, or a batch (B,21,4).  Returns new tensors (robot_local_rotation, dof_pos)."""
-
-    def __init__(self, mocap_zero_pose: RobotZeroPose, target_zero_pose: RobotZeroPose, device=0):
-        super().__init__(mocap_zero_pose, target_zero_pose)
-        self._eng = default_engine(device)
-
-    def retarget_from_pose(self, source_global_rotation, record=True):
-        g = to_torch(source_global_rotation)
-        single = g.dim() == 2
-        if single and not g.is_cuda and g.dtype == torch.float32:
-            # the teleop call: one CPU frame.  It goes through the pinned mailbox of the streaming entry point (one launch,
-            # no torch allocation or copy kernels on the way) instead of the batched device path.
-            cfg_ = (BQ_PRE_TRANSFORMED, 0, 0.0, 0.0, False)
-            if self._eng._bq_stream_cfg != cfg_:
-                self._eng.stream_open(flags=BQ_PRE_TRANSFORMED, ik_iters=0, damping=0.0, rot_weight=0.0)
-            lq, dof = torch.empty((31, 4)), torch.empty((30,))
-            self._eng.stream_frame_tensors(g.contiguous(), lq, dof, None)
-            if record:
-                self._motion_local_rotation.append(lq)
-                self._motion_dof_pos.append(dof)
-            return lq, dof
-        lq, dof, _ = self._eng.retarget_body_quat(g.reshape(-1, 21, 4), flags=BQ_PRE_TRANSFORMED, want_link_pos=False)
-        lq, dof = lq.to(g.device), dof.to(g.device)
-        if single:
-            lq, dof = lq[0], dof[0]
-        if record:
-            self._motion_local_rotation.append(lq)
-            self._motion_dof_pos.append(dof)
-        return lq, dof
-
-    def retarget_clip(self, raw_global_rotation, clamp=True, ik_iters=10, damping=0.1, rot_weight=0.2):
-        """Whole pipeline on a (B,21,4) clip of RAW mocap quats: zero-pose transform, mapping, angle
-        decomposition, limits, IK refinement, FK.  Returns (robot_local_rotation, dof_pos, link_pos)."""
-        g = to_torch(raw_global_rotation)
-        flags = (BQ_CLAMP if clamp else 0) | (BQ_IK if ik_iters > 0 else 0)
-        out = self._eng.retarget_body_quat(g.reshape(-1, 21, 4), flags=flags, ik_iters=ik_iters, damping=damping,
-                                           rot_weight=rot_weight)
-        return tuple(o.to(g.device) for o in out)
+def _require_parents(parents, pairs, what):
+    for child, parent in pairs:
+        if int(parents[child]) != parent:
+            raise ValueError(f"{what}: source joint {child} must hang off joint {parent} (got parent {int(parents[child])}); "
+                             "the solver's hard-coded joint indices are those of the vtrdyn skeleton")
 
 
-class _PosRetargeterBase(BaseHumanoidRetargeter):
+class _OwnedEngineRetargeter(BaseHumanoidRetargeter):
+    """Builds this instance's own context from the constructor's zero poses."""
+    _SOURCE_JOINTS = None
+
     def __init__(self, mocap_zero_pose, target_zero_pose, device=0):
         super().__init__(mocap_zero_pose, target_zero_pose)
-        self._eng = default_engine(device)
+        self._eng, self._src_slot, (self._src_parents, self._src_offsets, self._src_global_t) = engine_from_zero_poses(
+            mocap_zero_pose, target_zero_pose, device)
+        if self._SOURCE_JOINTS is not None and self._src_parents.shape[0] != self._SOURCE_JOINTS:
+            raise ValueError(f"{type(self).__name__} needs a {self._SOURCE_JOINTS}-joint source zero pose, "
+                             f"got {self._src_parents.shape[0]} joints")
 
     def _finish(self, ref, lq, dof, single, record, extra=None):
         lq, dof = lq.to(ref.device), dof.to(ref.device)
@@ -163,11 +152,57 @@ class _PosRetargeterBase(BaseHumanoidRetargeter):
         extra = extra.to(ref.device)
         return lq, dof, (extra[0] if single else extra)
 
+    def _record(self, lq, dof, record):
+        if record:
+            self._motion_local_rotation.append(lq)
+            self._motion_dof_pos.append(dof)
 
-class VtrdynFullBodyPosRetargeter(_PosRetargeterBase):
+
+class Mocap2HuBodyRetargeter(_OwnedEngineRetargeter):
+    """retarget_from_pose takes ONE frame (21,4) of zero-pose re-referenced global quats, like the
+    reference, or a batch (B,21,4).  Returns new tensors (robot_local_rotation, dof_pos).  The reference reads the
+    source zero pose's parent_indices (cal_local_rotation, body_retargeter.py:35) and the target's joint count (:38)."""
+    _SOURCE_JOINTS = 21
+
+    def __init__(self, mocap_zero_pose: RobotZeroPose, target_zero_pose: RobotZeroPose, device=0):
+        super().__init__(mocap_zero_pose, target_zero_pose, device)
+        # local rotations 18, 19 / 14, 15 are taken relative to the source tree's own parents (body_retargeter.py:35,40-53)
+        arms = cfg.VTRDYN_ARM_JOINTS
+        _require_parents(self._src_parents, [(a[2], a[1]) for a in arms] + [(a[3], a[2]) for a in arms], type(self).__name__)
+        self._eng.configure_body_quat(self._src_slot, TREE_ROBOT, arms, cfg.HU_V5_ARM_FIRST)
+
+    def retarget_from_pose(self, source_global_rotation, record=True):
+        g = to_torch(source_global_rotation)
+        single = g.dim() == 2
+        if single and not g.is_cuda and g.dtype == torch.float32:
+            # the teleop call: one CPU frame.  It goes through the pinned mailbox of the streaming entry point (one launch,
+            # no torch allocation or copy kernels on the way) instead of the batched device path.
+            cfg_ = (BQ_PRE_TRANSFORMED, 0, 0.0, 0.0, False)
+            if self._eng._bq_stream_cfg != cfg_:
+                self._eng.stream_open(flags=BQ_PRE_TRANSFORMED, ik_iters=0, damping=0.0, rot_weight=0.0)
+            lq, dof = torch.empty((31, 4)), torch.empty((30,))
+            self._eng.stream_frame_tensors(g.contiguous(), lq, dof, None)
+            self._record(lq, dof, record)
+            return lq, dof
+        lq, dof, _ = self._eng.retarget_body_quat(g.reshape(-1, 21, 4), flags=BQ_PRE_TRANSFORMED, want_link_pos=False)
+        return self._finish(g, lq, dof, single, record)
+
+    def retarget_clip(self, raw_global_rotation, clamp=True, ik_iters=10, damping=0.1, rot_weight=0.2):
+        """Whole pipeline on a (B,21,4) clip of RAW mocap quats: zero-pose transform, mapping, angle
+        decomposition, limits, IK refinement, FK.  Returns (robot_local_rotation, dof_pos, link_pos)."""
+        g = to_torch(raw_global_rotation)
+        flags = (BQ_CLAMP if clamp else 0) | (BQ_IK if ik_iters > 0 else 0)
+        out = self._eng.retarget_body_quat(g.reshape(-1, 21, 4), flags=flags, ik_iters=ik_iters, damping=damping,
+                                           rot_weight=rot_weight)
+        return tuple(o.to(g.device) for o in out)
+
+
+class VtrdynFullBodyPosRetargeter(_OwnedEngineRetargeter):
     """retarget/retarget_solver/full_body_pos_retargeter.py:17-217.  One frame ((21,3), (20,3), (20,3)) like
     the reference, or a batch with a leading frame axis.  Returns (robot_local_rotation, dof_pos,
-    body_global_rotation)."""
+    body_global_rotation).  Offsets [11,36,34], [13],[14],[38],[39], [16,20,24,28,32], [41,45,49,53,56] and the global
+    translations [18,22,26,30,33],[14] come from `mocap_zero_pose` (:69-107,139,162,184)."""
+    _SOURCE_JOINTS = 59
 
     def __init__(self, mocap_zero_pose, target_zero_pose, precise_gripper=False, device=0, resident=False):
         """resident=True (additive): single CPU frames are served by a resident one-warp kernel polling the pinned mailbox
@@ -175,9 +210,7 @@ class VtrdynFullBodyPosRetargeter(_PosRetargeterBase):
         super().__init__(mocap_zero_pose, target_zero_pose, device)
         self.precise_gripper = precise_gripper
         self.resident = bool(resident)
-        from . import robot_config as _cfg
-        self._eng.configure_pos(POS_FULL_BODY_POS, TREE_SOURCE_FULL, TREE_ROBOT,
-                                _cfg.skeleton_tables()["vtrdyn_full_zero_pose/global_translation"], precise_gripper)
+        self._eng.configure_pos(POS_FULL_BODY_POS, self._src_slot, TREE_ROBOT, self._src_global_t, precise_gripper)
 
     def retarget(self, body_global_translation, left_hand_global_translation, right_hand_global_translation, record=True):
         b = to_torch(body_global_translation)
@@ -192,17 +225,21 @@ class VtrdynFullBodyPosRetargeter(_PosRetargeterBase):
                     self._eng.stream_pos_open(persistent=self.resident, body_gq=True)
                 lq, dof, bq = torch.empty((31, 4)), torch.empty((30,)), torch.empty((59, 4))
                 self._eng.stream_pos_frame_tensors(b.contiguous(), lh.contiguous(), rh.contiguous(), lq, dof, bq)
-                if record:
-                    self._motion_local_rotation.append(lq)
-                    self._motion_dof_pos.append(dof)
+                self._record(lq, dof, record)
                 return lq, dof, bq
         lq, dof, bq = self._eng.retarget_full_body_pos(b.reshape(-1, 21, 3), to_torch(left_hand_global_translation).reshape(-1, 20, 3),
                                                        to_torch(right_hand_global_translation).reshape(-1, 20, 3))
         return self._finish(b, lq, dof, single, record, bq)
 
 
-class HuUpperBodyFromMocapRetarget(_PosRetargeterBase):
-    """retarget/retarget_solver/retarget_solver.py:27-99."""
+class HuUpperBodyFromMocapRetarget(_OwnedEngineRetargeter):
+    """retarget/retarget_solver/retarget_solver.py:27-99: offsets [17,13,11], [19], [15], [20], [16] of the 21-joint
+    `mocap_zero_pose` (:50-86)."""
+    _SOURCE_JOINTS = 21
+
+    def __init__(self, mocap_zero_pose, target_zero_pose, device=0):
+        super().__init__(mocap_zero_pose, target_zero_pose, device)
+        self._eng.configure_pos(POS_UPPER_BODY, self._src_slot, TREE_ROBOT)
 
     def retarget_from_global_translation(self, source_global_translation, record=True):
         b = to_torch(source_global_translation)
@@ -214,17 +251,21 @@ class HuUpperBodyFromMocapRetarget(_PosRetargeterBase):
                 self._eng.stream_pos_open(mode=POS_UPPER_BODY)
             lq, dof = torch.empty((31, 4)), torch.empty((30,))
             self._eng.stream_pos_frame_tensors(b.contiguous(), None, None, lq, dof)
-            if record:
-                self._motion_local_rotation.append(lq)
-                self._motion_dof_pos.append(dof)
+            self._record(lq, dof, record)
             return lq, dof
         lq, dof = self._eng.retarget_upper_body(b.reshape(-1, 21, 3))
         return self._finish(b, lq, dof, single, record)
 
 
-class VtrdynFullBodyRetargeter(_PosRetargeterBase):
+class VtrdynFullBodyRetargeter(_OwnedEngineRetargeter):
     """retarget/retarget_solver/full_body_retargeter.py:15-177 (the two hand-rotation arguments are unused
-    there and here)."""
+    there and here): offsets [13],[14],[38],[39] and the gripper reference [18,22,26,30,33],[24] of the 59-joint
+    `mocap_zero_pose` (:59-99,152)."""
+    _SOURCE_JOINTS = 59
+
+    def __init__(self, mocap_zero_pose, target_zero_pose, device=0):
+        super().__init__(mocap_zero_pose, target_zero_pose, device)
+        self._eng.configure_pos(POS_FULL_BODY, self._src_slot, TREE_ROBOT)
 
     def retarget(self, body_global_rotation, body_global_translation, left_hand_global_rotation,
                  left_hand_global_translation, right_hand_global_rotation, right_hand_global_translation, record=True):
@@ -239,9 +280,7 @@ class VtrdynFullBodyRetargeter(_PosRetargeterBase):
                     self._eng.stream_pos_open(mode=POS_FULL_BODY)
                 lq, dof = torch.empty((31, 4)), torch.empty((30,))
                 self._eng.stream_pos_frame_tensors(b.contiguous(), lh.contiguous(), rh.contiguous(), lq, dof, None, q.contiguous())
-                if record:
-                    self._motion_local_rotation.append(lq)
-                    self._motion_dof_pos.append(dof)
+                self._record(lq, dof, record)
                 return lq, dof
         lq, dof = self._eng.retarget_full_body(to_torch(body_global_rotation).reshape(-1, 21, 4), b.reshape(-1, 21, 3),
                                                to_torch(left_hand_global_translation).reshape(-1, 20, 3),

@@ -12,7 +12,7 @@ import pickle
 
 import numpy as np
 
-from .engine import default_engine
+from .engine import POS_FULL_BODY_POS, TREE_ROBOT, Engine, engine_from_zero_poses
 
 _ALLOWED = {
     ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
@@ -60,8 +60,20 @@ class TeleopSession:
     """dof = session.step(data_dict) per mocap frame, like the body of the reference's `while True:` loop
     (all-zero body_pos -> the previous dof_pos is repeated, sim_full_body_teleop.py:96,121-122)."""
 
-    def __init__(self, device=0, persistent=True, clamp=False, ik=False, engine=None):
-        self._eng = engine or default_engine(device)
+    def __init__(self, device=0, persistent=True, clamp=False, ik=False, engine=None, mocap_zero_pose=None, target_zero_pose=None,
+                 precise_gripper=True):
+        """The session owns its context: built from the given zero poses (like the VtrdynFullBodyPosRetargeter the reference's
+        loop constructs, sim_full_body_teleop.py:66-72), else from the bundled vtrdyn_full / Hu v5 tables; `engine` hands in a
+        caller-owned, already configured one."""
+        if engine is not None:
+            self._eng = engine
+        elif mocap_zero_pose is not None and target_zero_pose is not None:
+            self._eng, slot, (parents, _, glob) = engine_from_zero_poses(mocap_zero_pose, target_zero_pose, device)
+            if parents.shape[0] != 59:
+                raise ValueError(f"the teleop solver needs the 59-joint vtrdyn_full zero pose, got {parents.shape[0]} joints")
+            self._eng.configure_pos(POS_FULL_BODY_POS, slot, TREE_ROBOT, glob, precise_gripper)
+        else:
+            self._eng = Engine(device).set_standard_trees(precise_gripper=precise_gripper)
         self._cfg = (True, bool(persistent), bool(clamp), bool(ik), False, 0)
         self._eng.stream_pos_open(wire_layout=True, persistent=persistent, clamp=clamp, ik=ik)
         self._dof = np.zeros(30, np.float32)

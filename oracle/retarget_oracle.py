@@ -23,6 +23,7 @@ Parity pinning (see tests/test_oracle_vs_golden.py, tools/make_golden.py):
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import os
 from typing import List, Sequence, Tuple
@@ -409,6 +410,31 @@ def cal_joint_quat(zero_local_t, motion_local_t):
     Vt[det < 0, -1, :] *= -1
     R = torch.einsum("bij,bjk->bik", U, Vt)
     return quat_from_rotation_matrix(R)
+
+
+def cal_joint_quat_exact_svd(zero_local_t, motion_local_t):
+    """The same Kabsch step with the 3x3 SVD taken in float64 and R rounded once to fp32: what an exact SVD returns.
+    NOT the reference's arithmetic (that is MKL's fp32 sgesdd behind torch.linalg.svd, closed source); it is the
+    restatement the CUDA kernels' fp64 solve is compared with, and the yardstick for how much of the distance to the
+    reference is LAPACK rounding that no other implementation can reproduce (tools/parity_study.py)."""
+    A = torch.einsum("bij,bjk->bik", motion_local_t.double().permute(0, 2, 1), zero_local_t.double())
+    U, _, Vt = torch.linalg.svd(A)
+    R = torch.einsum("bij,bjk->bik", U, Vt)
+    Vt = Vt.clone()
+    Vt[torch.linalg.det(R) < 0, -1, :] *= -1
+    return quat_from_rotation_matrix(torch.einsum("bij,bjk->bik", U, Vt).float())
+
+
+@contextlib.contextmanager
+def exact_kabsch():
+    """Within this context every solver below takes its Kabsch rotations from cal_joint_quat_exact_svd."""
+    global cal_joint_quat
+    saved = cal_joint_quat
+    cal_joint_quat = cal_joint_quat_exact_svd
+    try:
+        yield
+    finally:
+        cal_joint_quat = saved
 
 
 def _dot(a, b):

@@ -1,0 +1,226 @@
+"""The drop-in boundary is per INSTANCE: every solver reads its offsets from the zero poses handed to its constructor
+(reference: retarget/retarget_solver/full_body_pos_retargeter.py:17-24,69-107,139-164,184; retarget_solver.py:49-86;
+full_body_retargeter.py:59-99,152; body_retargeter.py:35,38) and keeps its own `precise_gripper`.
+
+Goldens: tests/golden/perturbed_zero_pose.npz, written by tools/make_golden_perturbed.py from the UNMODIFIED reference's
+solvers constructed on PERTURBED source / target zero poses (limb lengths scaled 0.8-1.25x, bone directions turned)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+
+
+@pytest.fixture(scope="module")
+def hrt():
+    import __graft_entry__ as g
+    g.build()
+    import humanoid_real_time_retarget_b200 as h
+    return h
+
+
+@pytest.fixture(scope="module")
+def pm():
+    from oracle import parity_metrics
+    return parity_metrics
+
+
+@pytest.fixture(scope="module")
+def oc():
+    from oracle import retarget_oracle
+    return retarget_oracle
+
+
+def _zero_pose(hrt, g, prefix, names=None):
+    parents = g[f"{prefix}_parents"]
+    J = parents.shape[0]
+    names = names or [f"j{i}" for i in range(J)]
+    tree = hrt.SkeletonTree(names, T(parents.astype(np.int64)), T(g[f"{prefix}_offsets"].copy()))
+    return hrt.RobotZeroPose(T(g[f"{prefix}_offsets"].copy()), T(g[f"{prefix}_global_t"].copy()), T(parents.astype(np.int64)), J, names, tree)
+
+
+@pytest.fixture(scope="module")
+def poses(hrt, golden):
+    g = golden("perturbed_zero_pose")
+    return g, _zero_pose(hrt, g, "src59"), _zero_pose(hrt, g, "src21"), _zero_pose(hrt, g, "tgt")
+
+
+def _run_frames(fn, n):
+    outs = [fn(i) for i in range(n)]
+    return [torch.stack([o[k] for o in outs]) for k in range(len(outs[0]))]
+
+
+def test_solvers_built_from_perturbed_zero_poses_reproduce_the_reference(hrt, oc, poses, pm, parity):
+    g, src59, src21, tgt = poses
+    rp, ro = g["tgt_parents"].tolist(), g["tgt_offsets"]
+    L = g["body_t"].shape[0]
+    body, lh, rh, bq_in = T(g["body_t"]), T(g["lhand_t"]), T(g["rhand_t"]), T(g["body_q"])
+
+    # ---- a32, both gripper modes, batched call
+    for tag, precise in (("precise", True), ("binary", False)):
+        s = hrt.VtrdynFullBodyPosRetargeter(src59, tgt, precise_gripper=precise)
+        lq, dof, bq = s.retarget(body, lh, rh, record=False)
+        assert lq.shape == (L, 31, 4) and dof.shape == (L, 30) and bq.shape == (L, 59, 4) and dof.device.type == "cpu"
+        st = pm.distance_stats(dof, g[f"pos_{tag}_dof"], lq, g[f"pos_{tag}_local_q"], rp, ro)
+        parity.record(f"a32 from PERTURBED zero poses ({tag} gripper) kernel vs reference ({L} golden frames)", st)
+        # same gates as the bundled skeleton (tests/test_gpu_parity.py::test_full_body_pos_vs_reference_golden)
+        assert st["frac_le_1e-5"] >= 0.85 and st["dof_p99"] <= 1.0e-4 and st["dof_max"] <= 3e-4, st
+        assert st["fk_pos_max_m"] <= 5e-5 and st["geodesic_max"] <= 3e-4, st
+        grip = [18, 19, 27, 28]
+        assert float((dof[:, grip] - T(g[f"pos_{tag}_dof"])[:, grip]).abs().max()) <= (2e-6 if precise else 1e-7)
+        with oc.exact_kabsch():
+            rl_x, dof_x, _ = oc.retarget_full_body_pos(body, lh, rh, T(g["src59_offsets"]), T(g["src59_global_t"]), precise)
+        st = pm.distance_stats(dof, dof_x, lq, rl_x, rp, ro)
+        parity.record(f"a32 from PERTURBED zero poses ({tag} gripper) kernel vs exact-SVD oracle", st)
+        assert st["frac_le_1e-5"] >= 0.98 and st["dof_max"] <= 5e-5 and st["fk_pos_max_m"] <= 1e-5, st
+    # the bundled tables must NOT reproduce these goldens (the test would be vacuous otherwise)
+    b = hrt.VtrdynFullBodyPosRetargeter(hrt.RobotZeroPose.from_asset("vtrdyn_full_zero_pose"), hrt.RobotZeroPose.from_asset("hu_v5_zero_pose"),
+                                        precise_gripper=True)
+    _, dof_b, _ = b.retarget(body, lh, rh, record=False)
+    assert float((dof_b - T(g["pos_precise_dof"])).abs().max()) > 1e-2
+
+    # ---- per-frame calls accumulate; motion_global_* run FK on the TARGET zero pose's offsets (base_retargeter.py:22-46)
+    s = hrt.VtrdynFullBodyPosRetargeter(src59, tgt, precise_gripper=True)
+    for i in range(8):
+        s.retarget(body[i], lh[i], rh[i])
+    assert s.motion_length == 8
+    assert float((s.motion_global_translation - T(g["pos_motion_global_t"])[:8]).abs().max()) <= 5e-5
+    assert float((s.motion_dof_pos - T(g["pos_precise_dof"])[:8]).abs().max()) <= 3e-4
+
+    # ---- a31
+    s = hrt.VtrdynFullBodyRetargeter(src59, tgt)
+    lq, dof = s.retarget(bq_in, body, None, lh, None, rh, record=False)
+    st = pm.distance_stats(dof, g["full_dof"], lq, g["full_local_q"], rp, ro)
+    parity.record(f"a31 from PERTURBED zero poses kernel vs reference ({L} golden frames)", st)
+    assert st["frac_le_1e-5"] >= 0.99 and st["dof_max"] <= 3e-5 and st["fk_pos_max_m"] <= 1e-5, st
+
+    # ---- a29
+    s = hrt.HuUpperBodyFromMocapRetarget(src21, tgt)
+    lq, dof = s.retarget_from_global_translation(T(g["upper_global_t"]), record=False)
+    st = pm.distance_stats(dof, g["upper_dof"], lq, g["upper_local_q"], rp, ro)
+    parity.record(f"a29 from PERTURBED zero poses kernel vs reference ({L} golden frames)", st)
+    assert st["frac_le_1e-5"] >= 0.90 and st["dof_p99"] <= 1.2e-4 and st["dof_max"] <= 6e-4 and st["fk_pos_max_m"] <= 2.5e-4, st
+
+    # ---- a30 (reads the source parents and the target joint count only): every frame
+    s = hrt.Mocap2HuBodyRetargeter(src21, tgt)
+    lq, dof = s.retarget_from_pose(T(g["bq_zero_pose_q"]), record=False)
+    assert float((dof - T(g["bq_dof"])).abs().max()) <= 1e-5
+    for i in range(4):
+        s.retarget_from_pose(T(g["bq_zero_pose_q"][i]))
+    assert float((s.motion_global_translation - T(g["bq_motion_global_t"])[:4]).abs().max()) <= 1e-5
+
+
+def test_interleaved_instances_keep_their_own_configuration(hrt, golden, poses):
+    """Two VtrdynFullBodyPosRetargeter instances with different precise_gripper and different skeletons, an upper-body
+    solver and a resident-server instance, called in alternation one CPU frame at a time (the teleop call shape): every
+    call returns what that instance returns when it runs alone."""
+    g, src59, src21, tgt = poses
+    gb = golden("full_body_pos")
+    gu = golden("upper_body")
+    bsrc, btgt = hrt.RobotZeroPose.from_asset("vtrdyn_full_zero_pose"), hrt.RobotZeroPose.from_asset("hu_v5_zero_pose")
+    n = 24
+
+    def alone(make, call):
+        s = make()
+        return [tuple(o.clone() for o in call(s, i)) for i in range(n)]
+
+    makers = {
+        "perturbed_precise": (lambda: hrt.VtrdynFullBodyPosRetargeter(src59, tgt, precise_gripper=True),
+                              lambda s, i: s.retarget(T(g["body_t"][i]), T(g["lhand_t"][i]), T(g["rhand_t"][i]))),
+        "perturbed_binary": (lambda: hrt.VtrdynFullBodyPosRetargeter(src59, tgt, precise_gripper=False),
+                             lambda s, i: s.retarget(T(g["body_t"][i]), T(g["lhand_t"][i]), T(g["rhand_t"][i]))),
+        "bundled_precise_resident": (lambda: hrt.VtrdynFullBodyPosRetargeter(bsrc, btgt, precise_gripper=True, resident=True),
+                                     lambda s, i: s.retarget(T(gb["body_t"][i]), T(gb["lhand_t"][i]), T(gb["rhand_t"][i]))),
+        "bundled_binary": (lambda: hrt.VtrdynFullBodyPosRetargeter(bsrc, btgt, precise_gripper=False),
+                           lambda s, i: s.retarget(T(gb["body_t"][i]), T(gb["lhand_t"][i]), T(gb["rhand_t"][i]))),
+        "upper_perturbed": (lambda: hrt.HuUpperBodyFromMocapRetarget(src21, tgt),
+                            lambda s, i: s.retarget_from_global_translation(T(g["upper_global_t"][i]))),
+        "upper_bundled": (lambda: hrt.HuUpperBodyFromMocapRetarget(hrt.RobotZeroPose.from_asset("vtrdyn_zero_pose"), btgt),
+                          lambda s, i: s.retarget_from_global_translation(T(gu["global_t"][i]))),
+    }
+    expected = {k: alone(*v) for k, v in makers.items()}
+    live = {k: v[0]() for k, v in makers.items()}
+    for i in range(n):
+        for k in makers:                                   # strict alternation between all six instances
+            got = makers[k][1](live[k], i)
+            for a, b in zip(got, expected[k][i]):
+                assert torch.equal(a, b), (k, i)
+    # and each one's own golden: gripper DOFs tell the two gripper modes apart on every frame where they differ
+    grip = [18, 19, 27, 28]
+    dof_p = torch.stack([expected["perturbed_precise"][i][1] for i in range(n)])
+    dof_b = torch.stack([expected["perturbed_binary"][i][1] for i in range(n)])
+    assert float((dof_p[:, grip] - T(g["pos_precise_dof"])[:n, grip]).abs().max()) <= 2e-6
+    assert float((dof_b[:, grip] - T(g["pos_binary_dof"])[:n, grip]).abs().max()) <= 1e-7
+    assert float((dof_p[:, grip] - dof_b[:, grip]).abs().max()) > 1e-3
+    dof_bb = torch.stack([expected["bundled_binary"][i][1] for i in range(n)])
+    assert float((dof_bb[:, grip] - T(gb["dof_pos_binary"])[:n, grip]).abs().max()) <= 1e-7
+    for s in live.values():
+        s._eng.close()
+
+
+def test_mismatched_zero_poses_raise(hrt, poses):
+    g, src59, src21, tgt = poses
+    with pytest.raises(ValueError):                       # 21-joint source for a 59-joint solver
+        hrt.VtrdynFullBodyPosRetargeter(src21, tgt)
+    with pytest.raises(ValueError):
+        hrt.VtrdynFullBodyRetargeter(src21, tgt)
+    with pytest.raises(ValueError):                       # 59-joint source for a 21-joint solver
+        hrt.HuUpperBodyFromMocapRetarget(src59, tgt)
+    with pytest.raises(ValueError):
+        hrt.Mocap2HuBodyRetargeter(src59, tgt)
+    with pytest.raises(ValueError):                       # wrong robot (33-joint Hu): the solvers write Hu v5 joints
+        hrt.VtrdynFullBodyPosRetargeter(src59, hrt.RobotZeroPose.from_asset("hu_zero_pose"))
+    # wrong parents: the upper arm no longer hangs off the shoulder
+    bad = g["src21_parents"].copy()
+    bad[18] = 10
+    names = [f"j{i}" for i in range(21)]
+    zp = hrt.RobotZeroPose(T(g["src21_offsets"].copy()), T(g["src21_global_t"].copy()), T(bad.astype(np.int64)), 21, names)
+    with pytest.raises(ValueError):
+        hrt.Mocap2HuBodyRetargeter(zp, tgt)
+    # tables that disagree with each other
+    zp = hrt.RobotZeroPose(T(g["src21_offsets"][:20].copy()), T(g["src21_global_t"].copy()), T(g["src21_parents"].astype(np.int64)), 21, names)
+    with pytest.raises(ValueError):
+        hrt.HuUpperBodyFromMocapRetarget(zp, tgt)
+    # a child listed before its parent is refused by the C ABI itself
+    bad = g["src21_parents"].copy()
+    bad[3] = 7
+    zp = hrt.RobotZeroPose(T(g["src21_offsets"].copy()), T(g["src21_global_t"].copy()), T(bad.astype(np.int64)), 21, names)
+    with pytest.raises(hrt.HrtError):
+        hrt.HuUpperBodyFromMocapRetarget(zp, tgt)
+
+
+def test_reconfiguring_an_engine_stops_its_streams(hrt, golden):
+    """hrt_configure_pos / hrt_set_tree on a context with an open (resident) stream close it: the stream's kernel holds the
+    previous tables by value, so the next frame must not be answered from them."""
+    from humanoid_real_time_retarget_b200 import robot_config as cfg
+    g = golden("full_body_pos")
+    eng = hrt.Engine(0).set_standard_trees(precise_gripper=True)
+    eng.stream_pos_open(persistent=True)
+    body, lh, rh = (np.ascontiguousarray(g[k][0]) for k in ("body_t", "lhand_t", "rhand_t"))
+    dof = np.zeros(30, np.float32)
+    eng.stream_pos_frame(body, lh, rh, None, dof)
+    assert abs(dof[[18, 19, 27, 28]] - g["dof_pos"][0][[18, 19, 27, 28]]).max() <= 2e-6
+    eng.configure_pos(hrt.POS_FULL_BODY_POS, hrt.TREE_SOURCE_FULL, hrt.TREE_ROBOT,
+                      cfg.skeleton_tables()["vtrdyn_full_zero_pose/global_translation"], False)
+    with pytest.raises(hrt.HrtError):                      # closed by the reconfiguration: loud, not stale
+        eng.stream_pos_frame(body, lh, rh, None, dof)
+    eng.stream_pos_open(persistent=True)
+    eng.stream_pos_frame(body, lh, rh, None, dof)
+    assert abs(dof[[18, 19, 27, 28]] - g["dof_pos_binary"][0][[18, 19, 27, 28]]).max() <= 1e-7
+    eng.close()
+
+
+def test_entry_points_restore_the_callers_device(hrt):
+    """Every C-ABI call runs on its context's device and puts the caller's current device back."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    torch.cuda.set_device(0)
+    eng = hrt.Engine(1).set_standard_trees()
+    assert torch.cuda.current_device() == 0
+    q = torch.randn(64, 21, 4, device="cuda:1")
+    eng.retarget_body_quat(q)
+    assert torch.cuda.current_device() == 0
+    x = torch.zeros(4, device="cuda")
+    assert x.device.index == 0
+    eng.close()

@@ -109,7 +109,7 @@ def test_rotation3d_transcendental(hrt, golden):
     assert r.quat_mul(qa[:0], T(g2["qb"])[:0]).shape == (0, 4)
 
 
-def test_transform3d(hrt, golden):
+def test_transform3d(hrt, golden, parity):
     t, g = hrt.transform3d, golden("rotation_ops2")
     v, w, nn, qa, qb = T(g["v"]), T(g["w"]), T(g["nn"]), T(g["qa"]), T(g["qb"])
     assert exact(t.quat_between_two_vecs(v, w), g["quat_between_two_vecs"])
@@ -141,14 +141,33 @@ def test_transform3d(hrt, golden):
     dots = (q * T(g["cal_joint_quat_n4"])).sum(-1).abs().clamp(max=1.0)
     assert float(np.quantile((2 * torch.acos(dots)).numpy(), 0.99)) <= 1e-3 and q.shape == (384, 4)
     gp = golden("primitives")
-    assert md(t.cal_joint_quat(T(gp["Z3"]), T(gp["M3"])), gp["kabsch3"]) <= 1e-3
-    assert float(np.median(np.abs(t.cal_joint_quat(T(gp["Z5"]), T(gp["M5"])).numpy() - gp["kabsch5"]))) <= 2e-7
+    # a11: the reference's rotation comes out of MKL's fp32 sgesdd; an exact (float64) SVD of the same matrix sits p50 1.2e-7 /
+    # p99 2.6e-6 / max 1.2e-5 (3 points) and 1.6e-7 / 4.9e-6 / 1.1e-5 (5 points) away (profiles/parity_study_cpu_r02.json).
+    # The kernel is held to that floor against the reference and to 1 ulp-class against the exact-SVD restatement.
+    from oracle import retarget_oracle as oc
+    for key, Z, M in (("kabsch3", "Z3", "M3"), ("kabsch5", "Z5", "M5")):
+        q = t.cal_joint_quat(T(gp[Z]), T(gp[M]))
+        e_ref = np.abs(q.numpy() - gp[key]).max(-1)
+        e_x = np.abs(q.numpy() - oc.cal_joint_quat_exact_svd(T(gp[Z]), T(gp[M])).numpy()).max(-1)
+        parity.record(f"a11 cal_joint_quat {key} kernel vs reference (256 golden fits, quaternion components)",
+                      {"p50": float(np.median(e_ref)), "p99": float(np.quantile(e_ref, .99)), "max": float(e_ref.max()),
+                       "vs_exact_svd_p99": float(np.quantile(e_x, .99)), "vs_exact_svd_max": float(e_x.max())})
+        assert np.median(e_ref) <= 3e-7 and np.quantile(e_ref, .99) <= 1e-5 and e_ref.max() <= 3e-5, key
+        assert e_x.max() <= 5e-7, key
     # cal_shoulderPR / cal_elbowP_and_shoulderY (module-level functions of retarget_solver.py) against the reference's outputs
     from humanoid_real_time_retarget_b200 import cal_elbowP_and_shoulderY, cal_shoulderPR
     pit, rol = cal_shoulderPR(T(gp["v1"]), T(gp["v0_upper"]), T(gp["parent_q"]))
     yaw, elp = cal_elbowP_and_shoulderY(T(gp["v1"]), T(gp["v0_lower"]), T(gp["parent_q"]))
-    for got, key in ((pit, "sh_pitch"), (rol, "sh_roll"), (yaw, "sh_yaw"), (elp, "el_pitch")):
-        assert float(np.quantile(np.abs(got.numpy() - gp[key]).max(-1), 0.95)) <= 2e-6 and md(got, gp[key]) <= 2e-3, key
+    from oracle import parity_metrics as pmx
+    for name, keys, got in (("a14 cal_shoulderPR", ("sh_pitch", "sh_roll"), (pit, rol)),
+                            ("a15 cal_elbowP_and_shoulderY", ("sh_yaw", "el_pitch"), (yaw, elp))):
+        comp = np.maximum(*[np.abs(q.numpy() - gp[k]).max(-1) for q, k in zip(got, keys)])
+        geo = torch.maximum(*[pmx.geodesic(q, T(gp[k])) for q, k in zip(got, keys)]).numpy()
+        parity.record(f"{name} kernel vs reference (256 golden calls)",
+                      {"component_p50": float(np.median(comp)), "component_p99": float(np.quantile(comp, .99)), "component_max": float(comp.max()),
+                       "frac_geodesic_le_1e-5": float((geo <= 1e-5).mean()), "geodesic_p99": float(np.quantile(geo, .99)), "geodesic_max": float(geo.max())})
+        # no SVD in these two: inputs are given, so the distance is libm only (acos near +-1 amplifies one ulp by 1/sin)
+        assert np.quantile(comp, .99) <= 5e-6 and np.quantile(geo, .99) <= 1e-5 and geo.max() <= 2e-3, name
     p1, r1 = cal_shoulderPR(T(gp["v1"][7]), T(gp["v0_upper"]), T(gp["parent_q"][7:8]))       # the reference's call shape
     assert p1.shape == (4,) and torch.equal(p1, pit[7]) and torch.equal(r1, rol[7])
     # names the reference module re-exports for `from transform3d import *` users
@@ -217,7 +236,7 @@ def test_retarget_to_and_asset_pickles(hrt, golden, skeletons):
     assert RobotZeroPose is hrt.RobotZeroPose
 
 
-def test_main_path(hrt, golden):
+def test_main_path(hrt, golden, parity):
     g = golden("main_path")
     eng = hrt.default_engine(0)
     gt = T(g["global_t"])
@@ -238,10 +257,16 @@ def test_main_path(hrt, golden):
     assert md(mocap_motion.global_translation, g["rebuilt_global_translation"]) <= 2e-5
     assert r.rebuild_error <= 1e-4
     assert md(mocap_motion.global_velocity, g["rebuilt_velocity"]) <= 1e-3
-    err = (retargeted.local_rotation - T(g["robot_local_rotation"])).abs().amax(dim=(1, 2))
-    print(f"main path robot_local_rotation: median {float(err.median()):.2e} p90 {float(np.quantile(err.numpy(), 0.9)):.2e} max {float(err.max()):.2e}")
-    assert float(np.quantile(err.numpy(), 0.9)) <= 2e-4 and float(err.max()) <= 5e-3
-    assert md(retargeted.global_translation, g["robot_global_translation"]) <= 2e-3
+    from oracle import parity_metrics as pmx
+    geo = pmx.geodesic(retargeted.local_rotation, T(g["robot_local_rotation"])).amax(dim=-1).numpy()
+    perr = (retargeted.global_translation.double() - T(g["robot_global_translation"]).double()).norm(dim=-1).amax(dim=-1).numpy()
+    st = {"frames": int(geo.shape[0]), "frac_geodesic_le_1e-5": float((geo <= 1e-5).mean()), "geodesic_p50": float(np.median(geo)),
+          "geodesic_p99": float(np.quantile(geo, .99)), "geodesic_max": float(geo.max()),
+          "link_pos_p99_m": float(np.quantile(perr, .99)), "link_pos_max_m": float(perr.max())}
+    parity.record("a33 RetargetHuV5fromMocap (retarget/main.py path) kernel vs reference (golden clip)", st)
+    # two Kabsch fits (joints 0 and 10, MKL fp32 SVD in the reference) feed every arm angle: same floor class as a29
+    assert st["geodesic_p99"] <= 2e-4 and st["geodesic_max"] <= 5e-3
+    assert st["link_pos_p99_m"] <= 1e-4 and st["link_pos_max_m"] <= 2e-3
     assert retargeted.tensor.shape == g["robot_tensor"].shape
 
 

@@ -40,6 +40,30 @@ def oc():
     return retarget_oracle
 
 
+@pytest.fixture(scope="module")
+def pm():
+    from oracle import parity_metrics
+    return parity_metrics
+
+
+# Measured floors (profiles/parity_study_cpu_r02.json): the oracle with an EXACT (float64) SVD in the Kabsch step and every
+# other op bit-identical to the reference already sits this far from the reference's goldens, because the reference's
+# rotation comes out of MKL's fp32 sgesdd: a32 0.89 of frames within 1e-5 rad, p99 5.1e-5, max 9.1e-5, FK max 1.8e-5 m;
+# a29 0.95 / 5.9e-5 / 1.8e-4 / 8.5e-5 m.  Gates against the REFERENCE are those floors plus a margin; gates against the
+# oracle with the same exact SVD (the kernel's own arithmetic class) are the north-star bars on every frame.
+def check_dist(st, frac=None, p99=None, dmax=None, fk_max=None, geo_max=None):
+    if frac is not None:
+        assert st["frac_le_1e-5"] >= frac, st
+    if p99 is not None:
+        assert st["dof_p99"] <= p99, st
+    if dmax is not None:
+        assert st["dof_max"] <= dmax, st
+    if fk_max is not None:
+        assert st["fk_pos_max_m"] <= fk_max, st
+    if geo_max is not None:
+        assert st["geodesic_max"] <= geo_max, st
+
+
 def maxdiff(a, b):
     a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
     b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
@@ -460,7 +484,7 @@ def test_full_size_properties(hrt, eng, eng_hu, oc, skeletons):
     assert float(np.quantile(err.numpy(), 0.98)) <= ANGLE_TOL and float(err.max()) <= 1e-3
 
 
-def test_full_size_properties_position_path(hrt, eng, oc, skeletons):
+def test_full_size_properties_position_path(hrt, eng, oc, skeletons, pm, parity):
     """Config 3p size: 2^20 frames through the position solver (16-warp CTAs).  Size-independent properties: frames are
     independent (any sub-range run on its own gives the same bits), the gripper DOFs take only their defined values, the
     limit-aware refinement keeps every arm hinge inside its limits, and a strided sample agrees with the oracle."""
@@ -502,22 +526,15 @@ def test_full_size_properties_position_path(hrt, eng, oc, skeletons):
     idx = torch.arange(0, B, 509)
     off = T(skeletons["vtrdyn_full_zero_pose/offsets"])
     zgt = T(skeletons["vtrdyn_full_zero_pose/global_translation"])
-    _, dof_o, _ = oc.retarget_full_body_pos(body[idx].cpu(), lh[idx].cpu(), rh[idx].cpu(), off, zgt, True)
-    err = (dof[idx].cpu() - dof_o).abs().max(dim=-1).values
-    f2 = torch.isfinite(err)
-    _pos_report("full_body_pos 2^20 (strided sample) vs oracle", err[f2])
-    assert float(np.quantile(err[f2].numpy(), 0.80)) <= ANGLE_TOL
+    with oc.exact_kabsch():
+        _, dof_o, _ = oc.retarget_full_body_pos(body[idx].cpu(), lh[idx].cpu(), rh[idx].cpu(), off, zgt, True)
+    st = pm.distance_stats(dof[idx], dof_o, robot_parents=skeletons["hu_v5_zero_pose/parents"].tolist(),
+                           robot_offsets=skeletons["hu_v5_zero_pose/offsets"])
+    parity.record("a32 full_body_pos 2^20 frames (strided sample of 2061) kernel vs exact-SVD oracle", st)
+    check_dist(st, frac=0.97, p99=3e-5, dmax=2e-3, fk_max=2e-4)
 
 
 # ------------------------------------------------------------------------------- position-input paths
-def _pos_report(name, err, self_delta=None):
-    e = err.numpy() if torch.is_tensor(err) else err
-    msg = f"{name}: within 1e-5: {float((e <= ANGLE_TOL).mean()):.4f}; median {np.median(e):.2e} p99 {np.quantile(e, 0.99):.2e} max {e.max():.2e}"
-    if self_delta is not None:
-        msg += f"; reference self-delta (1-ulp jitter): within 1e-5 {float((self_delta <= ANGLE_TOL).mean()):.4f} max {self_delta.max():.2e}"
-    print(msg)
-
-
 def test_primitives_kabsch_vs_reference_golden(hrt, eng, golden):
     """cal_joint_quat through the full_body_pos kernel is covered below; here the known-answer arm of
     retarget/rotation_test.py:96-152 through the upper-body solver: zero pose in -> zero angles."""
@@ -527,21 +544,38 @@ def test_primitives_kabsch_vs_reference_golden(hrt, eng, golden):
     assert float(dof.abs().max()) <= 1e-3
 
 
-def test_full_body_pos_vs_reference_golden(hrt, eng, golden):
+def test_full_body_pos_vs_reference_golden(hrt, eng, oc, golden, skeletons, pm, parity):
     g = golden("full_body_pos")
-    lq, dof, bq = eng.retarget_full_body_pos(T(g["body_t"]), T(g["lhand_t"]), T(g["rhand_t"]))
-    err = (dof.cpu() - T(g["dof_pos"])).abs().max(dim=-1).values
-    _pos_report("full_body_pos vs reference (256 golden frames)", err, g["self_delta"])
-    # the reference itself moves by more than 1e-5 rad on ~10 % of frames under 1-ulp input
-    # jitter (acos(clamp(dot)), 2*acos(w)); acceptance = conditioning-aware.
-    cond = T(g["self_delta"]) < 2e-6
-    assert float(cond.float().mean()) > 0.1
-    assert float(np.quantile(err.numpy(), 0.80)) <= ANGLE_TOL
-    assert float(err.max()) <= 5e-3
-    # the rotations themselves are well conditioned: geodesic error of every published quaternion
-    assert maxdiff(bq, g["body_global_q"]) <= 1e-4
-    dq = (lq.cpu() * T(g["robot_local_q"])).sum(-1).abs().clamp(max=1.0)
-    assert float((2 * torch.acos(dq)).max()) <= 2e-3
+    body, lh, rh = T(g["body_t"]), T(g["lhand_t"]), T(g["rhand_t"])
+    lq, dof, bq = eng.retarget_full_body_pos(body, lh, rh)
+    rp, ro = skeletons["hu_v5_zero_pose/parents"].tolist(), skeletons["hu_v5_zero_pose/offsets"]
+    sd = g["self_delta"]
+    # (1) against the UNMODIFIED reference's outputs: bounded by the MKL-SVD floor (see check_dist above)
+    st = pm.distance_stats(dof, g["dof_pos"], lq, g["robot_local_q"], rp, ro)
+    parity.record("a32 VtrdynFullBodyPosRetargeter kernel vs reference (256 golden frames)", st,
+                  reference_self_delta_frac_le_1e5=float((sd <= ANGLE_TOL).mean()), reference_self_delta_p99=float(np.quantile(sd, .99)),
+                  reference_self_delta_max=float(sd.max()),
+                  conditioned_subset_coverage=float((sd < 2e-6).mean()))
+    check_dist(st, frac=0.85, p99=1.0e-4, dmax=3e-4, fk_max=5e-5, geo_max=3e-4)
+    # (2) against the oracle with the exact SVD (the kernel's arithmetic class): north-star bars on every frame
+    with oc.exact_kabsch():
+        rl_x, dof_x, bq_x = oc.retarget_full_body_pos(body, lh, rh, T(skeletons["vtrdyn_full_zero_pose/offsets"]),
+                                                      T(skeletons["vtrdyn_full_zero_pose/global_translation"]), True)
+    st = pm.distance_stats(dof, dof_x, lq, rl_x, rp, ro)
+    parity.record("a32 VtrdynFullBodyPosRetargeter kernel vs exact-SVD oracle (256 golden frames)", st)
+    check_dist(st, frac=0.98, p99=2e-5, dmax=5e-5, fk_max=POS_TOL, geo_max=5e-5)
+    # the conditioned subset (reference moves < 2e-6 under 1-ulp jitter): coverage asserted, every frame of it to 1e-5
+    cond = sd < 2e-6
+    assert float(cond.mean()) >= 0.30, float(cond.mean())
+    e_c = (dof.cpu() - T(g["dof_pos"])).abs().max(dim=-1).values.numpy()[cond]
+    parity.record("a32 conditioned subset (reference self-delta < 2e-6) kernel vs reference",
+                  {"frames": int(cond.sum()), "coverage": float(cond.mean()), "frac_le_1e-5": float((e_c <= ANGLE_TOL).mean()),
+                   "dof_max": float(e_c.max())})
+    assert float((e_c <= ANGLE_TOL).mean()) >= 0.97
+    # the published torso / wrist quaternions: Kabsch outputs, same floor (kabsch_fp64_vs_reference_quat: max 1.2e-5)
+    st_q = {"bq_max_abs": maxdiff(bq, g["body_global_q"]), "bq_vs_exact_svd_max_abs": maxdiff(bq, bq_x)}
+    parity.record("a32 body_global_rotation (torso + wrist Kabsch quaternions)", st_q)
+    assert st_q["bq_max_abs"] <= 5e-5 and st_q["bq_vs_exact_svd_max_abs"] <= 2e-6
     # binary gripper variant
     e2 = hrt.Engine(0).set_standard_trees()
     from humanoid_real_time_retarget_b200 import robot_config as cfg
@@ -559,9 +593,9 @@ def test_full_body_pos_vs_reference_golden(hrt, eng, golden):
         assert torch.equal(dof_i, dof[i].cpu())
 
 
-def test_full_body_pos_vs_oracle_large(hrt, eng, oc, skeletons):
-    """20,000 frames of the SURVEY 8(d) config-3p clip against the oracle (which reproduces the per-frame
-    reference to 1.2e-7 on every golden frame)."""
+def test_full_body_pos_vs_oracle_large(hrt, eng, oc, skeletons, pm, parity):
+    """20,000 frames of the SURVEY 8(d) config-3p clip: kernel vs the oracle as the reference computes it (MKL fp32 SVD;
+    the oracle reproduces the per-frame reference to 1.2e-7 on every golden frame) and vs the oracle with the exact SVD."""
     B = 20_000
     g = torch.Generator().manual_seed(0)
     em = 0.4 * torch.randn(B, 59, 3, generator=g)
@@ -574,47 +608,36 @@ def test_full_body_pos_vs_oracle_large(hrt, eng, oc, skeletons):
     body, lh, rh = gt[:, full2body].contiguous(), gt[:, 14:34].contiguous(), gt[:, 39:59].contiguous()
     off = T(skeletons["vtrdyn_full_zero_pose/offsets"])
     zgt = T(skeletons["vtrdyn_full_zero_pose/global_translation"])
+    rp, ro = skeletons["hu_v5_zero_pose/parents"].tolist(), skeletons["hu_v5_zero_pose/offsets"]
     rl_o, dof_o, bq_o = oc.retarget_full_body_pos(body, lh, rh, off, zgt, True)
-    # The reference's own sensitivity, per DOF: the largest move of the oracle's angle under 1-ulp input
-    # jitter over four independent probes (acos(clamp(dot)), 2*acos(w), sqrt in
-    # quat_from_rotation_matrix all amplify a 6e-8 rounding difference).
-    delta = torch.zeros_like(dof_o)
-    for p in range(4):
-        gj = torch.Generator().manual_seed(1 + p)
-        jit = lambda x: torch.nextafter(x, x + torch.sign(torch.randn(x.shape, generator=gj)))
-        _, dof_j, _ = oc.retarget_full_body_pos(jit(body), jit(lh), jit(rh), off, zgt, True)
-        delta = torch.maximum(delta, (dof_j - dof_o).abs())
-    self_delta = delta.max(dim=-1).values
+    with oc.exact_kabsch():
+        rl_x, dof_x, bq_x = oc.retarget_full_body_pos(body, lh, rh, off, zgt, True)
+    # the reference's own sensitivity: the oracle against itself under 1-ulp input jitter (one probe, like the goldens)
+    gj = torch.Generator().manual_seed(1)
+    jit = lambda x: torch.nextafter(x, x + torch.sign(torch.randn(x.shape, generator=gj)))
+    _, dof_j, _ = oc.retarget_full_body_pos(jit(body), jit(lh), jit(rh), off, zgt, True)
+    st_self = pm.distance_stats(dof_j, dof_o, robot_parents=rp, robot_offsets=ro)
+    parity.record("a32 oracle (MKL SVD) vs itself under 1-ulp input jitter (20k frames)", st_self)
+    st_floor = pm.distance_stats(dof_x, dof_o, rl_x, rl_o, rp, ro)
+    parity.record("a32 exact-SVD oracle vs oracle as the reference computes it (20k frames) = MKL sgesdd floor", st_floor)
     lq_k, dof_k, bq_k = eng.retarget_full_body_pos(body, lh, rh)
-    err_d = (dof_k.cpu() - dof_o).abs()
-    err = err_d.max(dim=-1).values
-    _pos_report("full_body_pos vs oracle (20k frames)", err, self_delta.numpy())
-    ok = torch.isfinite(err)
-    assert float(ok.float().mean()) > 0.999
-    assert float(np.quantile(err[ok].numpy(), 0.80)) <= ANGLE_TOL
-    # Per-DOF tolerance = the 1e-5 bar, or four times what the reference itself moves by under 1-ulp
-    # jitter, or the step of the reference's angle read-back 2*acos(w) at that angle (one ulp of w near 1
-    # is 4*6e-8/theta; below 7e-4 rad the reference snaps to 0): the kernel must stay inside the
-    # reference's own noise on >= 99.8 % of frames, and within sqrt(eps)-class amplification on all.
-    stair = 5e-7 / torch.maximum(torch.minimum(dof_o.abs(), dof_k.cpu().abs()), torch.tensor(7e-4))
-    tol = torch.maximum(torch.maximum(torch.full_like(delta, ANGLE_TOL), 4.0 * delta), stair)
-    inside = (err_d <= tol).all(dim=-1) | ~ok
-    cond = (self_delta < 2e-6) & ok
-    print(f"inside the reference's own noise: {float(inside.float().mean()):.5f} of frames; conditioned (4 probes) coverage "
-          f"{float(cond.float().mean()):.3f}, kernel within 1e-5 on it: {float((err[cond] <= ANGLE_TOL).float().mean()):.4f}")
-    assert float(inside.float().mean()) >= 0.998
-    assert float((err[cond] <= ANGLE_TOL).float().mean()) >= 0.99
-    assert float(err[ok].max()) <= 2e-3
-    # FK of the angles is well conditioned even where the raw angles are not
-    _, gt_k = eng.fk_angles(hrt.TREE_ROBOT, dof_k, clip=False)
-    _, gt_o = eng.fk_angles(hrt.TREE_ROBOT, dof_o, clip=False)
-    arm = list(range(12, 19)) + list(range(21, 28))
-    perr = (gt_k[:, arm] - gt_o[:, arm]).norm(dim=-1).amax(dim=-1).cpu()
-    print(f"FK link-position error of kernel angles vs oracle angles: p99 {float(np.quantile(perr[ok].numpy(), 0.99)):.2e} max {float(perr[ok].max()):.2e}")
-    assert float(np.quantile(perr[ok].numpy(), 0.99)) <= 5e-5
+    st_ref = pm.distance_stats(dof_k, dof_o, lq_k, rl_o, rp, ro)
+    parity.record("a32 kernel vs oracle as the reference computes it (20k frames)", st_ref)
+    st_x = pm.distance_stats(dof_k, dof_x, lq_k, rl_x, rp, ro)
+    parity.record("a32 kernel vs exact-SVD oracle (20k frames)", st_x)
+    assert st_ref["finite_frames"] >= 0.999 * B
+    # against the reference's arithmetic the kernel may not be further away than the exact-SVD restatement is (+ margin)
+    assert st_ref["frac_le_1e-5"] >= st_floor["frac_le_1e-5"] - 0.02, (st_ref, st_floor)
+    assert st_ref["dof_p99"] <= 1.5 * st_floor["dof_p99"] + 1e-5, (st_ref, st_floor)
+    assert st_ref["fk_pos_p99_m"] <= 1.5 * st_floor["fk_pos_p99_m"] + 2e-6, (st_ref, st_floor)
+    # against its own arithmetic class: the north-star bars, p99 on raw angles (2*acos(w) read-back stairs remain) and
+    # FK link positions / geodesic on all frames except the degenerate tail (fits with sigma_2 ~ 0: < 0.1 % of random poses)
+    check_dist(st_x, frac=0.97, p99=3e-5)
+    assert st_x["fk_pos_p99_m"] <= POS_TOL, st_x
+    assert st_x["geodesic_p99"] <= 3e-5, st_x
 
 
-def test_pos_path_cta_shapes_agree(hrt, eng, oc, skeletons):
+def test_pos_path_cta_shapes_agree(hrt, eng, oc, skeletons, pm, parity):
     """The position kernels are instantiated for 8 / 12 / 16 warps per CTA and the host picks by what fits in shared memory
     and by clip length (short clips: 8).  Same device code, so the same angles, whichever shape runs and whichever outputs
     are requested (local rotations and body quaternions are written straight to HBM, only dof_pos is staged)."""
@@ -647,10 +670,13 @@ def test_pos_path_cta_shapes_agree(hrt, eng, oc, skeletons):
     assert (dof_s - dof16[:1000])[ok[:1000]].abs().max().item() <= 1e-6
     # upper-body path, long clip (16 warps) against its oracle on a sample
     _, dof_u = eng.retarget_upper_body(body)
-    rl_o, dof_o = oc.retarget_upper_body(body[:4096].cpu(), T(skeletons["vtrdyn_zero_pose/offsets"]))
-    err = (dof_u[:4096].cpu() - dof_o).abs().max(dim=-1).values
-    fin = torch.isfinite(err)
-    assert float(np.quantile(err[fin].numpy(), 0.80)) <= ANGLE_TOL and float(fin.float().mean()) > 0.999
+    with oc.exact_kabsch():
+        rl_o, dof_o = oc.retarget_upper_body(body[:4096].cpu(), T(skeletons["vtrdyn_zero_pose/offsets"]))
+    st = pm.distance_stats(dof_u[:4096], dof_o, robot_parents=skeletons["hu_v5_zero_pose/parents"].tolist(),
+                           robot_offsets=skeletons["hu_v5_zero_pose/offsets"])
+    parity.record("a29 upper_body long clip (16-warp CTAs, 4096-frame sample) kernel vs exact-SVD oracle", st)
+    assert st["finite_frames"] >= 0.999 * 4096
+    check_dist(st, frac=0.97, p99=3e-5)
 
 
 def test_full_body_pos_limits_and_refinement_vs_oracle(hrt, eng, oc, skeletons, golden):
@@ -694,20 +720,27 @@ def test_full_body_pos_limits_and_refinement_vs_oracle(hrt, eng, oc, skeletons, 
     assert maxdiff(lq2[:, 12:19].reshape(-1, 4), q) <= 2e-6
 
 
-def test_upper_body_and_full_body_vs_reference_golden(hrt, eng, golden):
+def test_upper_body_and_full_body_vs_reference_golden(hrt, eng, oc, golden, skeletons, pm, parity):
+    rp, ro = skeletons["hu_v5_zero_pose/parents"].tolist(), skeletons["hu_v5_zero_pose/offsets"]
     g = golden("upper_body")
     lq, dof = eng.retarget_upper_body(T(g["global_t"]))
-    err = (dof.cpu() - T(g["dof_pos"])).abs().max(dim=-1).values
-    _pos_report("upper_body vs reference", err)
-    assert float(np.quantile(err.numpy(), 0.80)) <= ANGLE_TOL and float(err.max()) <= 5e-3
+    st = pm.distance_stats(dof, g["dof_pos"], lq, g["robot_local_q"], rp, ro)
+    parity.record("a29 HuUpperBodyFromMocapRetarget kernel vs reference (256 golden frames)", st)
+    check_dist(st, frac=0.90, p99=1.2e-4, dmax=6e-4, fk_max=2.5e-4, geo_max=1.5e-3)      # MKL-SVD floor: .95 / 5.9e-5 / 1.8e-4 / 8.5e-5 / 4.9e-4
+    with oc.exact_kabsch():
+        rl_x, dof_x = oc.retarget_upper_body(T(g["global_t"]), T(skeletons["vtrdyn_zero_pose/offsets"]))
+    st = pm.distance_stats(dof, dof_x, lq, rl_x, rp, ro)
+    parity.record("a29 HuUpperBodyFromMocapRetarget kernel vs exact-SVD oracle (256 golden frames)", st)
+    check_dist(st, frac=0.98, p99=2e-5, dmax=5e-5, fk_max=POS_TOL, geo_max=5e-5)
     used = [11, 12, 13, 14, 20, 21, 22, 23]
     rest = [i for i in range(30) if i not in used]
     assert float(dof[:, rest].abs().max()) == 0.0          # 8 of 30 DOFs are ever non-zero
+    # a31 has no Kabsch step (measured parent / wrist quaternions): every frame to the north-star bars against the reference
     g = golden("full_body")
     lq, dof = eng.retarget_full_body(T(g["body_q"]), T(g["body_t"]), T(g["lhand_t"]), T(g["rhand_t"]))
-    err = (dof.cpu() - T(g["dof_pos"])).abs().max(dim=-1).values
-    _pos_report("full_body vs reference", err)
-    assert float(np.quantile(err.numpy(), 0.80)) <= ANGLE_TOL and float(err.max()) <= 5e-3
+    st = pm.distance_stats(dof, g["dof_pos"], lq, g["robot_local_q"], rp, ro)
+    parity.record("a31 VtrdynFullBodyRetargeter kernel vs reference (256 golden frames, no Kabsch on this path)", st)
+    check_dist(st, frac=0.99, p99=ANGLE_TOL, dmax=3e-5, fk_max=POS_TOL, geo_max=3e-5)
     assert maxdiff(dof[:, [18, 19, 27, 28]], g["dof_pos"][:, [18, 19, 27, 28]]) <= 1e-7
     src = hrt.RobotZeroPose.from_asset("vtrdyn_zero_pose")
     tgt = hrt.RobotZeroPose.from_asset("hu_v5_zero_pose")

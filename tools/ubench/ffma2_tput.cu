@@ -1,5 +1,5 @@
 // Microbenchmark: issue throughput of FFMA (3 register operands) vs FFMA2 (packed fp32x2) on sm_100a.
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ffma2_tput ffma2_tput.cu && ./ffma2_tput
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o ffma2_tput ffma2_tput.cu && ./ffma2_tput   (cudart linked dynamically; the binary is git-ignored)
 #include <cstdio>
 #include <cuda_runtime.h>
 template <int MODE>
