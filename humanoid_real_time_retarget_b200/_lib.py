@@ -21,6 +21,8 @@ _SIGNATURES = {
     "hrt_fk_local_quats": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, _P, C.c_uint, _P]),
     "hrt_fk_angles": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, C.c_int, _P, _P, C.c_uint, _P]),
     "hrt_fk_jacobian": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P]),
+    "hrt_fk_vjp": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "hrt_ik_refine": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_uint, _P, _P, _P]),
     "hrt_local_from_global": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P]),
     "hrt_zero_pose_transform": (C.c_int, [_P, C.c_int, C.c_int64, _P, C.c_int, _P, _P]),
     "hrt_configure_body_quat": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),

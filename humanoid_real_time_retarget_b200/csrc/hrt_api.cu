@@ -18,6 +18,7 @@
 #include "hrt_pos.cuh"
 #include "hrt_ops.cuh"
 #include "hrt_motion.cuh"
+#include "hrt_fk_vjp.cuh"
 
 using namespace hrt;
 
@@ -588,6 +589,54 @@ int hrt_fk_jacobian(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, co
         if ((rc = grid_for(ctx, jacobian_kernel<HRT_MAX_CHAIN>, JAC_WARPS_PER_CTA * 32, smem, ctas, &grid, &jc16))) return rc;
         jacobian_kernel<HRT_MAX_CHAIN><<<grid, JAC_WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(t->tp, jp, a);
     }
+    HRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hrt_fk_vjp(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, const float* d_root_t, const float* d_root_q, int clip,
+               const float* d_g_gq, const float* d_g_gt, float* d_g_angles, float* d_g_root_t, float* d_g_root_q, void* stream) {
+    HRT_ENTER(ctx);
+    Tree* t;
+    if ((rc = get_tree(ctx, tree, &t))) return rc;
+    if (!t->has_dof) return fail(HRT_E_NOT_CONFIGURED, "tree %d has no dof_axis table", tree);
+    if (B == 0) return 0;
+    if (B < 0 || !d_angles || !d_g_angles) return fail(HRT_E_INVALID_ARG, "bad B / null pointer");
+    if (!aligned16(d_root_q) || !aligned16(d_g_gq) || !aligned16(d_g_root_q))
+        return fail(HRT_E_ALIGNMENT, "root_q, g_gq and g_root_q must be 16-byte aligned");
+    FkVjpArgs a{};
+    a.B = B; a.angles = d_angles; a.root_t = d_root_t; a.root_q = d_root_q; a.clip = clip;
+    a.g_gq = d_g_gq; a.g_gt = d_g_gt; a.g_angles = d_g_angles; a.g_root_t = d_g_root_t; a.g_root_q = d_g_root_q;
+    const size_t smem = vjp_smem_bytes(t->tp.J - 1);
+    const long long groups = (B + 31) / 32;
+    int grid = 1;
+    static LaunchCache cache;
+    if ((rc = grid_for(ctx, fk_vjp_kernel, VJP_WARPS * 32, smem, (groups + VJP_WARPS - 1) / VJP_WARPS, &grid, &cache))) return rc;
+    fk_vjp_kernel<<<grid, VJP_WARPS * 32, smem, (cudaStream_t)stream>>>(t->tp, a);
+    HRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hrt_ik_refine(hrt_ctx* ctx, int64_t B, const float* d_theta0, const float* d_pe_t, const float* d_pw_t, const float* d_qw_t,
+                  int iters, float damping, float rot_weight, unsigned flags, float* d_theta, float* d_residual, void* stream) {
+    HRT_ENTER(ctx);
+    if (!ctx->bq_set) return fail(HRT_E_NOT_CONFIGURED, "hrt_configure_body_quat has not been called (it installs the robot's arm tables)");
+    if (iters < 0 || iters > 1000) return fail(HRT_E_INVALID_ARG, "iters out of range");
+    if (B == 0) return 0;
+    if (B < 0 || !d_theta0 || !d_pe_t || !d_pw_t || !d_qw_t || !d_theta) return fail(HRT_E_INVALID_ARG, "bad B / null pointer");
+    if (!aligned16(d_qw_t)) return fail(HRT_E_ALIGNMENT, "qw_t must be 16-byte aligned");
+    IkArmTables tb;
+    for (int side = 0; side < 2; ++side) {
+        const ArmParams& ap = ctx->bq.arm[side];
+        memcpy(tb.off[side], ap.off, sizeof(ap.off));
+        memcpy(tb.lower[side], ap.lower, sizeof(ap.lower));
+        memcpy(tb.upper[side], ap.upper, sizeof(ap.upper));
+        for (int k = 0; k < 3; ++k) tb.p_sh[side][k] = ctx->bq.shoulder_p[side][k];
+    }
+    IkRefineArgs a{};
+    a.B = B; a.theta0 = d_theta0; a.pe_t = d_pe_t; a.pw_t = d_pw_t; a.qw_t = d_qw_t; a.theta = d_theta; a.residual = d_residual;
+    a.iters = iters; a.damping = damping; a.rot_weight = rot_weight; a.active_set = (flags & HRT_BQ_ACTIVE_SET) ? 1 : 0;
+    const int grid = (int)std::max(1LL, std::min((2 * (long long)B + 127) / 128, (long long)ctx->sm_count * 8));
+    ik_refine_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(tb, a);
     HRT_CUDA(cudaGetLastError());
     return 0;
 }

@@ -154,6 +154,34 @@ class Engine:
                                             _np_ptr(links), K, _ptr(jac), self._stream()))
         return jac
 
+    def fk_vjp(self, tree, angles, g_gq=None, g_gt=None, root_t=None, root_q=None, clip=True, want_root=True):
+        """Backward of fk_angles: upstream gradients of (global quats, link positions) -> (g_angles, g_root_t, g_root_q)."""
+        J = self._trees[tree]
+        angles = _f32c(angles, self.device)
+        B = angles.numel() // (J - 1)
+        g_gq = None if g_gq is None else _f32c(g_gq, self.device)
+        g_gt = None if g_gt is None else _f32c(g_gt, self.device)
+        root_t = None if root_t is None else _f32c(root_t, self.device)
+        root_q = None if root_q is None else _f32c(root_q, self.device)
+        ga = torch.empty((B, J - 1), device=self.device, dtype=torch.float32)
+        grt = torch.empty((B, 3), device=self.device, dtype=torch.float32) if want_root else None
+        grq = torch.empty((B, 4), device=self.device, dtype=torch.float32) if want_root else None
+        _lib.check(self.lib.hrt_fk_vjp(self._h, tree, B, _ptr(angles), _ptr(root_t), _ptr(root_q), int(bool(clip)), _ptr(g_gq), _ptr(g_gt),
+                                       _ptr(ga), _ptr(grt), _ptr(grq), self._stream()))
+        return ga, grt, grq
+
+    def ik_refine(self, theta0, pe_t, pw_t, qw_t, iters=10, damping=0.1, rot_weight=0.2, active_set=False, want_residual=False):
+        """Stand-alone DLS refinement of both arms: theta0 (B,2,7), pe_t / pw_t (B,2,3), qw_t (B,2,4) -> theta (B,2,7)
+        [, residual (B,2,iters+1)].  Needs configure_body_quat (robot arm tables)."""
+        theta0, pe_t, pw_t, qw_t = (_f32c(x, self.device) for x in (theta0, pe_t, pw_t, qw_t))
+        B = theta0.numel() // 14
+        assert pe_t.numel() == B * 6 and pw_t.numel() == B * 6 and qw_t.numel() == B * 8
+        th = torch.empty((B, 2, 7), device=self.device, dtype=torch.float32)
+        res = torch.empty((B, 2, iters + 1), device=self.device, dtype=torch.float32) if want_residual else None
+        _lib.check(self.lib.hrt_ik_refine(self._h, B, _ptr(theta0), _ptr(pe_t), _ptr(pw_t), _ptr(qw_t), int(iters), float(damping),
+                                          float(rot_weight), BQ_ACTIVE_SET if active_set else 0, _ptr(th), _ptr(res), self._stream()))
+        return (th, res) if want_residual else th
+
     def local_from_global(self, tree, global_q):
         J = self._trees[tree]
         global_q = _f32c(global_q, self.device)

@@ -153,6 +153,32 @@ class BaseForwardModel:
                                       zero_pose_local_translation=self.sk_local_translation)
 
 
+class _HuFKFunction(torch.autograd.Function):
+    """forward = hrt_fk_angles, backward = hrt_fk_vjp (the Jacobian is contracted on the device, never materialised).
+    The clamp is straight-through like the reference's `(clamp(x) - x).detach() + x` (hu_forward_model.py:27-33): the
+    backward is evaluated at the clipped angles and hands the gradient to the raw angles unchanged."""
+
+    @staticmethod
+    def forward(ctx, angles, root_t, root_q, eng, clip, exact):
+        L = angles.shape[0]
+        gq, gt = eng.fk_angles(TREE_ROBOT, angles.reshape(L, -1), root_t, root_q.reshape(L, 4), clip=clip, exact=exact)
+        ctx.save_for_backward(angles, root_t, root_q)
+        ctx.eng, ctx.clip = eng, clip
+        return gq.to(angles.device), gt.to(angles.device)
+
+    @staticmethod
+    def backward(ctx, g_gq, g_gt):
+        angles, root_t, root_q = ctx.saved_tensors
+        L = angles.shape[0]
+        want_root = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        ga, grt, grq = ctx.eng.fk_vjp(TREE_ROBOT, angles.reshape(L, -1), g_gq, g_gt, root_t, root_q.reshape(L, 4), clip=ctx.clip,
+                                      want_root=want_root)
+        ga = ga.reshape(angles.shape).to(angles.device) if ctx.needs_input_grad[0] else None
+        grt = grt.reshape(root_t.shape).to(root_t.device) if ctx.needs_input_grad[1] else None
+        grq = grq.reshape(root_q.shape).to(root_q.device) if ctx.needs_input_grad[2] else None
+        return ga, grt, grq, None, None, None
+
+
 class HuForwardModel(BaseForwardModel):
     """Angles -> FK with the straight-through joint-limit clamp's forward value.  The reference wires
     this class to the 33-joint Hu tables (hu_forward_model.py:9); a 31-joint tree selects Hu v5."""
@@ -174,6 +200,12 @@ class HuForwardModel(BaseForwardModel):
                            exact=False):
         L = motion_joint_angles.shape[0]
         src_dev = motion_joint_angles.device
+        if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad
+                                           for t in (motion_joint_angles, motion_root_translation, motion_root_rotation)):
+            # optimisation-based callers: autograd flows through FK (hu_forward_model.py:27-33, SURVEY section 4 invariant 4)
+            rt = motion_root_translation.to(torch.float32).expand(L, 3)
+            return _HuFKFunction.apply(motion_joint_angles.to(torch.float32), rt, motion_root_rotation.to(torch.float32),
+                                       self._eng, bool(clip_angles), bool(exact))
         gq, gt = self._eng.fk_angles(TREE_ROBOT, motion_joint_angles.reshape(L, -1), motion_root_translation,
                                      motion_root_rotation.reshape(L, 4), clip=clip_angles, exact=exact)
         return gq.to(src_dev), gt.to(src_dev)

@@ -90,6 +90,26 @@ int hrt_fk_angles(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, cons
 int hrt_fk_jacobian(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, const float* d_root_t,
                     const float* d_root_q, int clip, const int32_t* links, int K, float* d_jac, void* stream);
 
+/* Backward of hrt_fk_angles: the vector-Jacobian product that lets autograd flow through
+ * HuForwardModel.forward_kinematics, which is what the reference's straight-through clamp
+ * `(clamp(x) - x).detach() + x` (robot_kinematics_model/hu_forward_model.py:27-33) exists for.
+ * d_g_gq (B,J,4)|NULL, d_g_gt (B,J,3)|NULL: upstream gradients of the two outputs ->
+ * d_g_angles (B,J-1), d_g_root_t (B,3)|NULL, d_g_root_q (B,4)|NULL.  Evaluated at the clipped angles; the clamp
+ * itself passes the gradient through unchanged.  The (B,K,6,D) Jacobian is never formed. */
+int hrt_fk_vjp(hrt_ctx* ctx, int tree, int64_t B, const float* d_angles, const float* d_root_t, const float* d_root_q,
+               int clip, const float* d_g_gq, const float* d_g_gt, float* d_g_angles, float* d_g_root_t,
+               float* d_g_root_q, void* stream);
+
+/* Stand-alone damped-least-squares refinement of both arms of the configured robot (no reference counterpart,
+ * SURVEY.md F2 / section 8(b); spec: DESIGN.md section 5).  The same device code as the stage fused into
+ * hrt_retarget_body_quat / hrt_retarget_full_body_pos_ex.  Needs hrt_configure_body_quat (arm tables).
+ * d_theta0 (B,2,7) warm start (clamped on entry), targets in the robot root frame: d_pe_t / d_pw_t (B,2,3)
+ * elbow-pitch / wrist-yaw link positions, d_qw_t (B,2,4) wrist-yaw link orientation -> d_theta (B,2,7);
+ * d_residual (B,2,iters+1)|NULL receives ||e|| before every step and after the last.  flags: HRT_BQ_ACTIVE_SET. */
+int hrt_ik_refine(hrt_ctx* ctx, int64_t B, const float* d_theta0, const float* d_pe_t, const float* d_pw_t,
+                  const float* d_qw_t, int iters, float damping, float rot_weight, unsigned flags, float* d_theta,
+                  float* d_residual, void* stream);
+
 /* cal_local_rotation (robot_kinematics_model/kinematics.py:41-63); equals SkeletonState.local_rotation
  * (skeleton3d.py:460-484) when tree.quat is identity. */
 int hrt_local_from_global(hrt_ctx* ctx, int tree, int64_t B, const float* d_gq, float* d_lq, void* stream);

@@ -255,11 +255,76 @@ def hu_forward_kinematics(angles, root_t, root_q, parents, offsets, dof_axis, lo
         lo = torch.tensor(lower, dtype=torch.float32).reshape(1, -1, 1)
         hi = torch.tensor(upper, dtype=torch.float32).reshape(1, -1, 1)
         clamped = torch.clamp(angles.clone(), min=lo, max=hi)
-        angles = (clamped - angles) + angles
+        # (clamp(x) - x).detach() + x  (hu_forward_model.py:27-33): the forward value is the clamped angle, the gradient
+        # passes straight through
+        angles = (clamped - angles).detach() + angles
     axis = torch.eye(3)[dof_axis].repeat(L, 1, 1)
     lq = quat_from_angle_axis(angles.reshape(-1), axis.reshape(-1, 3)).reshape(L, D, 4)
     lq = torch.cat([root_q, lq], dim=1)
     return cal_forward_kinematics(lq, root_t, parents, offsets)
+
+
+def fk_vjp_analytic(angles, root_t, root_q, g_gq, g_gt, parents, offsets, dof_axis, lower, upper, clip_angles: bool):
+    """Vector-Jacobian product of hu_forward_kinematics written out by hand (the spec of the CUDA `fk_vjp_kernel`; checked
+    against torch.autograd of hu_forward_kinematics in tests/test_oracle_ik.py).  Upstream gradients g_gq (L,J,4), g_gt (L,J,3)
+    -> (g_angles (L,D), g_root_t (L,3), g_root_q (L,4)).  float64 throughout.
+
+    With a_i = R_parent(i) e_i the world axis of hinge i, p_i its pivot, f_k = g_gt[k] and
+    tau_k = 1/2 (w g_u + u x g_u - g_w u) for q_k = (u, w), g_gq[k] = (g_u, g_w)   (d q_k = 1/2 [dphi, 0] q_k):
+        d L / d theta_i = a_i . sum_{k in subtree(i)} [ tau_k + (p_k - p_i) x f_k ]
+    (the straight-through clamp contributes no factor; the normalisation in quat_mul_norm and the sign flip of quat_pos
+    map tangent vectors to themselves).  The root quaternion enters un-normalised (kinematics.py:27-35): link 0's rotation
+    IS root_q (direct term), every other link turns with root_q's direction (tangential term) and the children of the
+    root sit at root_t + |root_q|^2 R offset (radial term)."""
+    dd = torch.float64
+    L, D = angles.shape[0], len(dof_axis)
+    J = D + 1
+    th = angles.reshape(L, D).to(dd)
+    if clip_angles:
+        th = torch.minimum(torch.maximum(th, torch.tensor(lower, dtype=dd)), torch.tensor(upper, dtype=dd))
+    q0 = root_q.reshape(L, 4).to(dd)
+    t0 = root_t.reshape(L, 3).to(dd)
+    off = torch.as_tensor(offsets, dtype=dd)
+    g_gq, g_gt = g_gq.to(dd), g_gt.to(dd)
+    s2 = (q0 * q0).sum(-1, keepdim=True)
+    n0 = q0 / s2.sqrt()
+    eye = torch.eye(3, dtype=dd)
+    q, p, a = [n0], [t0], [None]
+    for j in range(1, J):
+        pj = parents[j]
+        e = eye[dof_axis[j - 1]].expand(L, 3)
+        a.append(quat_rotate(q[pj], e))
+        step = quat_rotate(q[pj], off[j].expand(L, 3))
+        p.append(p[pj] + (step * s2 if pj == 0 else step))
+        half = 0.5 * th[:, j - 1]
+        lq = torch.cat([e * half.sin().unsqueeze(-1), half.cos().unsqueeze(-1)], dim=-1)
+        qq = quat_mul(q[pj], lq)
+        qq = qq / qq.norm(dim=-1, keepdim=True)
+        # tau is ODD in q_k: it must be taken at the PUBLISHED representative (quat_pos: w >= 0), the one g_gq refers to
+        q.append(torch.where(qq[:, 3:] < 0, -qq, qq))
+
+    def tau(k, qk):
+        u, w = qk[:, :3], qk[:, 3:]
+        gu, gw = g_gq[:, k, :3], g_gq[:, k, 3:]
+        return 0.5 * (w * gu + torch.cross(u, gu, dim=-1) - gw * u)
+
+    S = [torch.zeros(L, 3, dtype=dd)] + [tau(k, q[k]) + torch.cross(p[k], g_gt[:, k], dim=-1) for k in range(1, J)]
+    F = [torch.zeros(L, 3, dtype=dd)] + [g_gt[:, k].clone() for k in range(1, J)]
+    g_ang = torch.zeros(L, D, dtype=dd)
+    g_s = torch.zeros(L, dtype=dd)
+    for j in range(J - 1, 0, -1):
+        g_ang[:, j - 1] = (a[j] * (S[j] - torch.cross(p[j], F[j], dim=-1))).sum(-1)
+        pj = parents[j]
+        if pj == 0:
+            g_s = g_s + 2.0 * ((p[j] - t0) * F[j]).sum(-1)
+        S[pj] = S[pj] + S[j]
+        F[pj] = F[pj] + F[j]
+    g_phi = S[0] - torch.cross(t0, F[0], dim=-1)
+    g_root_t = F[0] + g_gt[:, 0]
+    u, w = q0[:, :3], q0[:, 3:]
+    tang = torch.cat([w * g_phi + torch.cross(g_phi, u, dim=-1), -(g_phi * u).sum(-1, keepdim=True)], dim=-1)
+    g_root_q = g_gq[:, 0] + (2.0 / s2) * tang + (g_s.unsqueeze(-1) / s2) * q0
+    return g_ang, g_root_t, g_root_q
 
 
 # ----------------------------------------------------------------------------------------------
@@ -665,20 +730,25 @@ def geometric_jacobian(angles, root_t, root_q, parents, offsets, dof_axis, lower
 ARM_AXIS = [1, 0, 2, 1, 0, 1, 2]          # Hu_DOF_AXIS[11:18] == Hu_DOF_AXIS[20:27]
 
 
-def ik_refine_arm(theta0, p_sh, offs, lower, upper, pe_t, pw_t, qw_t, iters, damping, rot_weight, active_set=False):
+def ik_refine_arm(theta0, p_sh, offs, lower, upper, pe_t, pw_t, qw_t, iters, damping, rot_weight, active_set=False,
+                  residual_history=None):
     """DESIGN.md section 5.  theta0 (B,7) warm start (already clamped); offs (9,3) offsets of the 7 arm
     hinges + 2 gripper links; targets in the robot root frame.  Each step:
       FK of the 7-hinge chain; e = [pe* - p_elbow; pw* - p_wrist; w_o * rotvec(qw* qw^-1)];
       dtheta = (J^T J + lambda^2 I)^-1 J^T e;  theta <- clamp(theta + dtheta, lower, upper).
     Exactly `iters` steps, no early exit.  active_set: a hinge sitting on a limit while its gradient component
-    (J^T e)_i pushes further out is frozen for that step (row / column removed from the system)."""
+    (J^T e)_i pushes further out is frozen for that step (row / column removed from the system).
+    The arithmetic runs in theta0's dtype: float32 is the spec the kernels implement, float64 the ground truth both are
+    measured against.  residual_history (a list) receives ||e|| before every step."""
     B = theta0.shape[0]
+    dt = theta0.dtype                      # float32 = the spec the kernels implement; float64 = ground truth for it
     th = theta0.clone()
-    eye = torch.eye(3)
-    lo = torch.tensor(lower, dtype=torch.float32)
-    hi = torch.tensor(upper, dtype=torch.float32)
+    eye = torch.eye(3, dtype=dt)
+    lo = torch.tensor(lower, dtype=torch.float32).to(dt)        # the limits are fp32 constants in both
+    hi = torch.tensor(upper, dtype=torch.float32).to(dt)
+    p_sh, offs, pe_t, pw_t, qw_t = (x.to(dt) for x in (p_sh, offs, pe_t, pw_t, qw_t))
     for _ in range(iters):
-        G = quat_identity((B,))
+        G = quat_identity((B,)).to(dt)
         p = p_sh.expand(B, 3)
         ax, pc = [], []
         for c in range(7):
@@ -691,7 +761,9 @@ def ik_refine_arm(theta0, p_sh, offs, lower, upper, pe_t, pw_t, qw_t, iters, dam
         n = qe[:, :3].norm(dim=-1)
         sc = torch.where(n > 1e-8, 2 * torch.atan2(n, qe[:, 3]) / n.clamp(min=1e-30), torch.full_like(n, 2.0))
         e = torch.cat([pe_t - pc[3], pw_t - pc[6], rot_weight * sc.unsqueeze(-1) * qe[:, :3]], dim=-1)   # (B,9)
-        Jm = torch.zeros(B, 9, 7)
+        if residual_history is not None:
+            residual_history.append((e * e).sum(-1).sqrt())
+        Jm = torch.zeros(B, 9, 7, dtype=dt)
         for c in range(7):
             if c < 3:
                 Jm[:, 0:3, c] = torch.cross(ax[c], pc[3] - pc[c], dim=-1)
@@ -701,10 +773,10 @@ def ik_refine_arm(theta0, p_sh, offs, lower, upper, pe_t, pw_t, qw_t, iters, dam
         g = (Jm.transpose(1, 2) @ e.unsqueeze(-1))
         if active_set:
             blocked = ((th >= hi) & (g.squeeze(-1) > 0)) | ((th <= lo) & (g.squeeze(-1) < 0))
-            m = (~blocked).float()
+            m = (~blocked).to(dt)
             Jm = Jm * m.unsqueeze(1)
             g = g * m.unsqueeze(-1)
-        A = Jm.transpose(1, 2) @ Jm + (damping * damping) * torch.eye(7)
+        A = Jm.transpose(1, 2) @ Jm + (damping * damping) * torch.eye(7, dtype=dt)
         L = torch.linalg.cholesky(A)
         d = torch.cholesky_solve(g, L).squeeze(-1)
         th = torch.minimum(torch.maximum(th + d, lo), hi)
@@ -714,8 +786,9 @@ def ik_refine_arm(theta0, p_sh, offs, lower, upper, pe_t, pw_t, qw_t, iters, dam
 def arm_chain(th, p_sh, offs):
     """FK of the 7-hinge arm chain at angles th (B,7): hinge positions pc[0..6] and the final orientation."""
     B = th.shape[0]
-    G = quat_identity((B,))
-    p = p_sh.expand(B, 3)
+    G = quat_identity((B,)).to(th.dtype)
+    p = p_sh.to(th.dtype).expand(B, 3)
+    offs = offs.to(th.dtype)
     pc = []
     for c in range(7):
         pc.append(p)
@@ -750,10 +823,13 @@ def refine_pos_dof(dof, sk, clamp=True, ik_iters=10, damping=0.1, rot_weight=0.2
     return out
 
 
-def body_quat_pipeline(raw_gq, sk, clamp=True, ik_iters=10, damping=0.1, rot_weight=0.2, pre_transformed=False, active_set=False):
+def body_quat_pipeline(raw_gq, sk, clamp=True, ik_iters=10, damping=0.1, rot_weight=0.2, pre_transformed=False, active_set=False,
+                       ik_dtype=torch.float32, residual_history=None):
     """The fused config-3q pipeline: a24 -> a21 -> a30 (+a16, a17) -> [limits -> IK] -> FK.
     Returns robot_local_q (B,31,4), dof (B,30), link_pos (B,31,3).  With clamp=False, ik_iters=0 the
-    first two are exactly the reference's retarget_from_pose outputs."""
+    first two are exactly the reference's retarget_from_pose outputs.  ik_dtype=torch.float64 runs the refinement (targets,
+    FK of the chain, Jacobian, Cholesky) in float64 from the SAME fp32 closed-form warm start: the ground truth the fp32
+    spec and the kernels are both measured against; dof then comes back as float64."""
     T = torch.from_numpy
     src_par = sk["vtrdyn_zero_pose/parents"].tolist()
     rob_par = sk["hu_v5_zero_pose/parents"].tolist()
@@ -765,27 +841,30 @@ def body_quat_pipeline(raw_gq, sk, clamp=True, ik_iters=10, damping=0.1, rot_wei
     if clamp or do_ik:
         lo = torch.tensor(HU_V5_DOF_LOWER)
         hi = torch.tensor(HU_V5_DOF_UPPER)
-        dof = dof.clone()
+        dof = dof.clone().to(ik_dtype) if do_ik else dof.clone()
         # zero-pose positions of the robot (identity rotations): p_j = off_j + p_parent
         pos = torch.zeros(31, 3)
         for j in range(1, 31):
             pos[j] = rob_off[j] + pos[rob_par[j]]
         for side, (first, sj) in enumerate([(12, [10, 17, 18, 19, 20]), (21, [10, 13, 14, 15, 16])]):
             d0 = first - 1
-            th = torch.minimum(torch.maximum(dof[:, d0:d0 + 7], lo[d0:d0 + 7]), hi[d0:d0 + 7])
+            th = torch.minimum(torch.maximum(dof[:, d0:d0 + 7], lo[d0:d0 + 7].to(dof.dtype)), hi[d0:d0 + 7].to(dof.dtype))
             if do_ik:
-                Tc = quat_conjugate(zq[:, sj[0]])
-                Ru = quat_normalize(quat_mul(Tc, zq[:, sj[2]]))
-                Rf = quat_normalize(quat_mul(Tc, zq[:, sj[3]]))
-                Rh = quat_normalize(quat_mul(Tc, zq[:, sj[4]]))
-                p_sh = pos[first]
-                pe_t = p_sh + quat_rotate(Ru, (pos[first + 3] - pos[first]).expand(B, 3))
-                pw_t = pe_t + quat_rotate(Rf, (pos[first + 6] - pos[first + 3]).expand(B, 3))
+                zz = zq.to(ik_dtype)
+                Tc = quat_conjugate(zz[:, sj[0]])
+                Ru = quat_normalize(quat_mul(Tc, zz[:, sj[2]]))
+                Rf = quat_normalize(quat_mul(Tc, zz[:, sj[3]]))
+                Rh = quat_normalize(quat_mul(Tc, zz[:, sj[4]]))
+                pp = pos.to(ik_dtype)
+                p_sh = pp[first]
+                pe_t = p_sh + quat_rotate(Ru, (pp[first + 3] - pp[first]).expand(B, 3))
+                pw_t = pe_t + quat_rotate(Rf, (pp[first + 6] - pp[first + 3]).expand(B, 3))
                 th = ik_refine_arm(th, p_sh, rob_off[first:first + 9], HU_V5_DOF_LOWER[d0:d0 + 7],
-                                   HU_V5_DOF_UPPER[d0:d0 + 7], pe_t, pw_t, Rh, ik_iters, damping, rot_weight, active_set)
+                                   HU_V5_DOF_UPPER[d0:d0 + 7], pe_t, pw_t, Rh, ik_iters, damping, rot_weight, active_set,
+                                   residual_history=residual_history)
             dof[:, d0:d0 + 7] = th
             for c in range(7):
-                rl[:, first + c] = _axis_quat(th[:, c], ARM_AXIS[c])
+                rl[:, first + c] = _axis_quat(th[:, c].float(), ARM_AXIS[c])
     _, link_pos = cal_forward_kinematics(rl, torch.zeros(B, 3), rob_par, rob_off)
     return rl, dof, link_pos
 

@@ -56,3 +56,54 @@ def test_zero_pose_is_a_fixed_point(skeletons):
     rl, dof, lp = oc.body_quat_pipeline(raw, sk, clamp=True, ik_iters=10, pre_transformed=True)
     assert float(dof.abs().max()) < 1e-6
     assert np.allclose(lp[0].numpy(), sk["hu_v5_zero_pose/global_translation"], atol=1e-6)
+
+
+def test_fk_vjp_spec_matches_autograd(skeletons):
+    """oracle.fk_vjp_analytic (the spec of the CUDA fk_vjp_kernel) against torch.autograd through hu_forward_kinematics,
+    whose clamp is the reference's straight-through `(clamp(x) - x).detach() + x` (hu_forward_model.py:27-33); float64,
+    unit and non-unit root quaternions, clip on and off, Hu (33 joints) and Hu v5 (31)."""
+    sk = skeletons
+    torch.manual_seed(0)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        for name, ax, lo, hi in (("hu_zero_pose", oc.HU_DOF_AXIS, oc.HU_DOF_LOWER, oc.HU_DOF_UPPER),
+                                 ("hu_v5_zero_pose", oc.HU_V5_DOF_AXIS, oc.HU_V5_DOF_LOWER, oc.HU_V5_DOF_UPPER)):
+            parents = sk[name + "/parents"].tolist()
+            off = T(sk[name + "/offsets"]).double()
+            D, L = len(ax), 12
+            for clip in (True, False):
+                for scale in (1.0, 1.3):
+                    ang = (torch.randn(L, D, 1) * 0.8).requires_grad_(True)
+                    rt = torch.randn(L, 3).requires_grad_(True)
+                    rq = torch.randn(L, 1, 4)
+                    rq = (rq / rq.norm(dim=-1, keepdim=True) * scale).requires_grad_(True)
+                    gq, gt = oc.hu_forward_kinematics(ang, rt, rq, parents, off, ax, lo, hi, clip)
+                    g_gq, g_gt = torch.randn_like(gq), torch.randn_like(gt)
+                    ((gq * g_gq).sum() + (gt * g_gt).sum()).backward()
+                    ga, grt, grq = oc.fk_vjp_analytic(ang.detach(), rt.detach(), rq.detach(), g_gq, g_gt, parents, off, ax, lo, hi, clip)
+                    tol = 1e-6 if clip else 1e-12          # with clip the limit tables are fp32 constants on one side only
+                    assert float((ga - ang.grad.reshape(L, D)).abs().max()) <= tol * max(1.0, float(ang.grad.abs().max()))
+                    assert float((grt - rt.grad).abs().max()) <= 1e-12
+                    assert float((grq - rq.grad.reshape(L, 4)).abs().max()) <= tol * max(1.0, float(rq.grad.abs().max()))
+    finally:
+        torch.set_default_dtype(prev)
+
+
+def test_fp32_ik_spec_tracks_its_float64_run(skeletons):
+    """The fp32 refinement (the spec the kernels implement) against the same loop in float64: the distance of the two is the
+    yardstick the GPU tests hold the kernel to (|kernel - fp64| must not exceed |fp32 oracle - fp64|)."""
+    sk = skeletons
+    raw = oc.synth_clip_3q(512, seed=9, sk=sk)
+    _, dof32, _ = oc.body_quat_pipeline(raw, sk, clamp=True, ik_iters=10)
+    _, dof64, _ = oc.body_quat_pipeline(raw, sk, clamp=True, ik_iters=10, ik_dtype=torch.float64)
+    err = (dof32.double() - dof64).abs().max(dim=-1).values.numpy()
+    assert np.quantile(err, 0.5) <= 2e-6 and np.quantile(err, 0.99) <= 2e-4
+    hist = []
+    oc.body_quat_pipeline(raw, sk, clamp=True, ik_iters=10, ik_dtype=torch.float64, active_set=True, residual_history=hist)
+    for arm in (0, 1):
+        res = torch.stack(hist[arm * 10:arm * 10 + 10], dim=1)            # ||e|| before each of this arm's 10 steps
+        # the active-set iteration is a descent method: from one step to the next the objective does not rise
+        down = ((res[:, 1:] - res[:, :-1]) <= 1e-9).double()
+        print(f"arm {arm}: non-increasing steps {float(down.mean()):.4f}, frames monotone over all 10 steps {float(down.all(dim=1).double().mean()):.4f}")
+        assert float(down.mean()) >= 0.97
