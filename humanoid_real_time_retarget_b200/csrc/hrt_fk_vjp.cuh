@@ -7,7 +7,7 @@
 // the gradient of hinge i is   a_i . sum_{k in subtree(i)} [ tau_k + (p_k - p_i) x f_k ],
 // i.e. one reverse sweep over the tree accumulating a wrench (S, F) = (sum tau_k + p_k x f_k, sum f_k) per subtree.
 // The spec, term by term (root quaternion enters un-normalised: direct, tangential and radial parts), is
-// oracle/retarget_oracle.py:fk_vjp_analytic, which tests/test_oracle_ik.py checks against torch.autograd.
+// `fk_vjp_analytic` of the test-side CPU restatement, which tests/test_oracle_ik.py checks against torch.autograd.
 //
 // One thread per configuration.  Forward walk in registers: the parent of joint j is joint j-1 or one of <= 4 parked
 // branch points (TreeParams slots, allocated by liveness on the host).  Per joint the walk leaves pivot, axis and the
@@ -179,7 +179,7 @@ fk_vjp_kernel(const __grid_constant__ TreeParams tp, const FkVjpArgs a) {
 // ---------------------------------------------------------------------------------------------
 // Stand-alone damped-least-squares refinement of both arms (the stage that is fused into body_quat_kernel /
 // pos_retarget_kernel, callable on its own: SURVEY.md section 8(b) `hrt_ik_refine`; spec in DESIGN.md section 5,
-// oracle/retarget_oracle.py:ik_refine_arm).  One thread per (frame, arm).
+// `ik_refine_arm` of the test-side CPU restatement).  One thread per (frame, arm).
 // ---------------------------------------------------------------------------------------------
 struct IkRefineArgs {
     long long B;

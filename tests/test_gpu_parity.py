@@ -584,7 +584,8 @@ def test_full_body_pos_vs_reference_golden(hrt, eng, oc, golden, skeletons, pm, 
     # the published torso / wrist quaternions: Kabsch outputs, same floor (kabsch_fp64_vs_reference_quat: max 1.2e-5)
     st_q = {"bq_max_abs": maxdiff(bq, g["body_global_q"]), "bq_vs_exact_svd_max_abs": maxdiff(bq, bq_x)}
     parity.record("a32 body_global_rotation (torso + wrist Kabsch quaternions)", st_q)
-    assert st_q["bq_max_abs"] <= 5e-5 and st_q["bq_vs_exact_svd_max_abs"] <= 2e-6
+    # vs the reference the near-planar 5-point wrist fits carry MKL's fp32 SVD noise (measured 7.4e-5); vs the exact SVD: 1 ulp
+    assert st_q["bq_max_abs"] <= 2e-4 and st_q["bq_vs_exact_svd_max_abs"] <= 5e-7
     # binary gripper variant
     e2 = hrt.Engine(0).set_standard_trees()
     from humanoid_real_time_retarget_b200 import robot_config as cfg
