@@ -7,7 +7,7 @@
 // the gradient of hinge i is   a_i . sum_{k in subtree(i)} [ tau_k + (p_k - p_i) x f_k ],
 // i.e. one reverse sweep over the tree accumulating a wrench (S, F) = (sum tau_k + p_k x f_k, sum f_k) per subtree.
 // The spec, term by term (root quaternion enters un-normalised: direct, tangential and radial parts), is
-// `fk_vjp_analytic` of the test-side CPU restatement, which tests/test_oracle_ik.py checks against torch.autograd.
+// `fk_vjp_analytic` of the test-side CPU restatement, which the CPU test suite checks against torch.autograd.
 //
 // One thread per configuration.  Forward walk in registers: the parent of joint j is joint j-1 or one of <= 4 parked
 // branch points (TreeParams slots, allocated by liveness on the host).  Per joint the walk leaves pivot, axis and the
