@@ -1,18 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- retargeted frames/s of the fused quaternion-path pipeline (BASELINE.json configs[2]:
-quat mapping + angle decomposition + 10-iter IK + FK on a synthetic 2^20-frame vtrdyn clip).
+"""bench.py -- retargeted frames/s of the fused quaternion-path pipeline (quat mapping + angle decomposition + 10-iter IK
++ FK on a synthetic vtrdyn clip).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames F]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames F] [--total-frames T]
 
-One "step" = one pass of the hot path over one synthetic clip of F frames (per GPU).
+One "step" = one pass of the hot path over one synthetic clip.
+  N = 1 : BASELINE.json configs[2], a 2^20-frame clip on one GPU.
+  N > 1 : BASELINE.json configs[4] as written: a 2^24-frame clip sharded over the N GPUs (strong scaling), dof_pos
+          REASSEMBLED ON EVERY RANK inside the timed region (the kernels store their dof spans straight into every
+          rank's buffer over NVLink: sharding.PeerReassembly); the no-gather and the NCCL all-gather figures ride along
+          as side keys.
   value  : whole-job frames/s, inputs resident in HBM, CUDA-event timed on the launching stream.
   e2e    : same metric through the reference-facing host-buffer C-ABI call (pinned host in ->
            pinned host out, H2D + D2H inside the timed region).
   roofline: algorithmic bytes (336 B in + 120 B dof + 372 B link positions = 828 B/frame,
            SURVEY.md 8(d)) / the fused kernel's CUDA-event launch time, vs the measured HBM peak.
   cpu_baseline: the CPU oracle (batched torch restatement of the reference) on a bounded sample.
---impl reference times the CPU implementation alone (the reference is pure Python/torch; the
-oracle port is the travelling form of it -- see DESIGN.md section 6).
+--impl reference times the CPU implementation alone: the UNMODIFIED reference when its tree is present (HRT_REFERENCE or
+/root/reference: dev container), else the oracle port, the travelling form of it (the GPU box has no reference tree) --
+see DESIGN.md section 6.
 """
 import argparse
 import json
@@ -41,14 +47,20 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel, from the committed
-    `ncu --set full` summary of this same command (profiles/traffic.json), or None."""
+def _ncu_capture():
+    """The committed `ncu --set full` capture of this same command (profiles/traffic.json, written by tools/ncu_hot.py).
+    These are PROFILER numbers of a past run, labelled as such in the line; nothing here is measured live."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return float(json.load(open(p))["body_quat_kernel"]["dram_bytes_per_launch"])
+        return json.load(open(p))["body_quat_kernel"]
     except Exception:
-        return None
+        return {}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel from that capture, or None."""
+    v = _ncu_capture().get("dram_bytes_per_launch")
+    return float(v) if v else None
 
 
 def issue_roofline(kern_ms, clocks, n_sms):
@@ -61,16 +73,14 @@ def issue_roofline(kern_ms, clocks, n_sms):
     peak = 4.0 * n_sms * mhz * 1e6
     achieved = n / (kern_ms * 1e-3)
     return {"bound": "issue", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "G warp-instructions/s",
-            "frac": achieved / peak, "warp_instructions_per_launch": n}
+            "frac": achieved / peak, "warp_instructions_per_launch": n,
+            "warp_instructions_source": "ncu capture (not live): " + str(_ncu_capture().get("source", "profiles/traffic.json"))}
 
 
 def ncu_warp_instructions():
     """smsp__inst_executed.sum per launch of the fused kernel from the same committed capture, or None."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
-    try:
-        return float(json.load(open(p))["body_quat_kernel"]["warp_instructions_per_launch"])
-    except Exception:
-        return None
+    v = _ncu_capture().get("warp_instructions_per_launch")
+    return float(v) if v else None
 
 
 class ClockSampler:
@@ -135,6 +145,39 @@ def cpu_oracle_rate(frames, threads):
     return frames / dt, dt
 
 
+def reference_tree():
+    """Path of the UNMODIFIED reference when it is present on this machine (dev container), else None (GPU box)."""
+    p = os.environ.get("HRT_REFERENCE", "/root/reference")
+    return p if os.path.isdir(os.path.join(p, "retarget", "retarget_solver")) else None
+
+
+def verbatim_reference_rate(frames, threads):
+    """BASELINE.md row C1q with the reference's own code: vtrdyn_zero_pose_transform batched once, then
+    Mocap2HuBodyRetargeter.retarget_from_pose per frame (its per-frame Python loop; the reference has no IK stage and
+    no batched form).  Returns (frames/s, seconds)."""
+    import warnings
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ref_shim
+    from make_golden import clip_3q
+    torch.set_num_threads(threads)
+    ref = ref_shim.load()
+    warnings.simplefilter("ignore")
+    src21 = ref.rkm.RobotZeroPose.from_skeleton_state(ref_shim.load_asset(ref, "asset/zero_pose/vtrdyn_zero_pose.pkl"))
+    tgt = ref.rkm.RobotZeroPose.from_skeleton_state(ref_shim.load_asset(ref, "asset/hu_pose/hu_v5_zero_pose.pkl"))
+    raw = clip_3q(ref, frames + 50)
+    solver = ref.solvers.Mocap2HuBodyRetargeter(src21, tgt)
+    zq = ref.parse_mocap.vtrdyn_zero_pose_transform(raw)
+    for i in range(50):
+        solver.retarget_from_pose(zq[i])
+    t0 = time.perf_counter()
+    zq = ref.parse_mocap.vtrdyn_zero_pose_transform(raw)
+    for i in range(50, frames + 50):
+        solver.retarget_from_pose(zq[i])
+    dt = time.perf_counter() - t0
+    return frames / dt, dt
+
+
 def run_reference(args):
     """The reference arm: the CPU implementation of the path on this box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -142,26 +185,34 @@ def run_reference(args):
         return
     import torch
     cores = os.cpu_count() or 1
-    sample = args.ref_frames
-    rates = []
-    for _ in range(args.warmup):
+    verbatim = reference_tree() is not None and not args.force_port
+    sample = min(args.ref_frames, 2000) if verbatim else args.ref_frames
+    rate_fn = verbatim_reference_rate if verbatim else cpu_oracle_rate
+    for _ in range(0 if verbatim else args.warmup):
         cpu_oracle_rate(min(sample, 2048), cores)
     t_all = 0.0
-    for _ in range(args.steps):
-        r, dt = cpu_oracle_rate(sample, cores)
-        rates.append(r)
+    steps = min(args.steps, 3) if verbatim else args.steps
+    for _ in range(steps):
+        r, dt = rate_fn(sample, cores)
         t_all += dt
-    value = sample * args.steps / t_all
+    value = sample * steps / t_all
+    if verbatim:
+        kind = "reference"
+        what = (f"{sample} frames/step of the configs[2] clip through the UNMODIFIED reference ({reference_tree()}): "
+                "vtrdyn_zero_pose_transform batched + Mocap2HuBodyRetargeter.retarget_from_pose per frame (closed form only: the "
+                f"reference has no IK / FK stage), torch threads={cores}")
+    else:
+        kind = "port"
+        what = (f"{sample} frames/step of the 2^20-frame clip, batched torch-CPU oracle incl. {IK_ITERS}-iter IK + FK, "
+                f"torch threads={torch.get_num_threads()} (no reference tree on this machine)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (+f64 Euler split)",
         "data": "synthetic",
         "config": {"workload": "configs[2]: full quaternion-path pipeline, vtrdyn (21 joints) -> Hu v5 (31 joints), "
                                f"{IK_ITERS}-iter IK + FK", "frames_per_step": sample, "ik_iters": IK_ITERS},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} frames/step of the 2^20-frame clip, batched torch-CPU oracle, "
-                                   f"torch threads={torch.get_num_threads()}"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": what},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -301,6 +352,23 @@ def side_measurements(eng, hrt, oc, sk, dev):
     return out
 
 
+def synth_clip_on_device(hrt, oc, sk, dev, n, seed, chunk=1 << 20):
+    """SURVEY 8(d) config-3q / config-5 recipe built on the device: local exp-maps 0.5*N(0,1) on the vtrdyn T-pose tree ->
+    quaternions -> FK -> raw global quats (n,21,4).  Seeded per shard; chunked so that any rank can regenerate any chunk."""
+    import torch
+    parents = sk["vtrdyn_t_pose/parents"].tolist()
+    off = torch.from_numpy(sk["vtrdyn_t_pose/offsets"])
+    out = torch.empty((n, 21, 4), device=dev, dtype=torch.float32)
+    for c, f0 in enumerate(range(0, n, chunk)):
+        m = min(chunk, n - f0)
+        g = torch.Generator(device=dev).manual_seed(seed * 4096 + c)
+        em = 0.5 * torch.randn(m, 21, 3, device=dev, generator=g)
+        lq = hrt.rotation3d.exp_map_to_quat(em)
+        gq, _ = hrt.cal_forward_kinematics(lq, torch.zeros(m, 3, device=dev), parents, off, exact=True)
+        out[f0:f0 + m] = gq
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -314,40 +382,63 @@ def run_ours(args):
     import __graft_entry__ as g
     g.build()
     import humanoid_real_time_retarget_b200 as hrt
-    from oracle import retarget_oracle as oc            # input synthesis + the cpu_baseline leg only
+    from humanoid_real_time_retarget_b200.sharding import PeerReassembly, gpu_local_host_memory, shard_range
+    from oracle import retarget_oracle as oc            # skeleton tables for input synthesis + the cpu_baseline leg only
 
     dev = torch.device("cuda", local_rank)
-    eng = hrt.default_engine(local_rank)
-    B = args.frames
+    eng = hrt.Engine(local_rank).set_standard_trees()
     flags = hrt.BQ_CLAMP | hrt.BQ_IK
     sk = oc.load_skeletons()
-    # synthetic clip (SURVEY 8(d) config 3q recipe), per-rank seed; built on the host in chunks
-    from humanoid_real_time_retarget_b200.sharding import gpu_local_host_memory
-    with gpu_local_host_memory(dev) as numa:               # pinned staging buffers on this GPU's NUMA node
-        raw_h = torch.empty((B, 21, 4), dtype=torch.float32).pin_memory()
-        h_dof = torch.empty((B, 30)).pin_memory()
-        h_lp = torch.empty((B, 31, 3)).pin_memory()
-    chunk = 1 << 18
-    for i, f0 in enumerate(range(0, B, chunk)):
-        n = min(chunk, B - f0)
-        raw_h[f0:f0 + n] = oc.synth_clip_3q(n, seed=1000 * rank + i, sk=sk)
-    raw_d = raw_h.to(dev)
-    lq_d = None                                            # the headline path publishes dof + link positions
-    dof_d = torch.empty((B, 30), device=dev)
+    multi = world > 1
+    if multi:
+        n_total = args.total_frames                       # configs[4]: 2^24 frames over the box, strong scaling
+        lo, hi = shard_range(n_total, rank, world)
+        B = hi - lo
+    else:
+        n_total = B = args.frames                         # configs[2]: 2^20 frames on one GPU
+        lo = 0
+    raw_d = synth_clip_on_device(hrt, oc, sk, dev, B, seed=1000 + rank)
+    # e2e runs on a bounded host-resident sample per rank (PCIe-bound; the pinned staging buffers live on this GPU's NUMA node)
+    Be = min(B, args.frames)
+    with gpu_local_host_memory(dev) as numa:
+        raw_h = torch.empty((Be, 21, 4), dtype=torch.float32).pin_memory()
+        h_dof = torch.empty((Be, 30)).pin_memory()
+        h_lp = torch.empty((Be, 31, 3)).pin_memory()
+    raw_h.copy_(raw_d[:Be])
     lp_d = torch.empty((B, 31, 3), device=dev)
+    dof_d = torch.empty((B, 30), device=dev)
+    pr = PeerReassembly(eng, n_total) if multi else None
 
-    def step_dev():
-        eng.retarget_body_quat(raw_d, flags=flags, ik_iters=IK_ITERS, damping=DAMPING, rot_weight=ROT_WEIGHT,
-                               out=(lq_d, dof_d, lp_d))
+    def step_plain():                                      # one launch of body_quat_kernel, outputs stay on this GPU
+        eng.retarget_body_quat(raw_d, flags=flags, ik_iters=IK_ITERS, damping=DAMPING, rot_weight=ROT_WEIGHT, out=(None, dof_d, lp_d))
 
-    def step_e2e():
+    def step_gather():                                     # the same launch storing dof_pos into EVERY rank's clip-wide buffer + flag exchange
+        pr.step(raw_d, flags, IK_ITERS, DAMPING, ROT_WEIGHT, link_pos=lp_d)
+
+    step_dev = step_gather if multi else step_plain
+
+    def step_e2e(dof_only=False):
         eng.retarget_body_quat_host(raw_h, flags=flags, ik_iters=IK_ITERS, damping=DAMPING, rot_weight=ROT_WEIGHT,
-                                    out_dof=h_dof, out_link_pos=h_lp)
+                                    out_dof=h_dof, out_link_pos=None if dof_only else h_lp)
 
     def barrier():
-        if world > 1:
+        if multi:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    def timed(step, steps):
+        """K steps between barriers: (total ms by CUDA events around the region, mean per-step ms by per-step events)."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        start.record()
+        for a, b in ev:
+            a.record()
+            step()
+            b.record()
+        end.record()
+        barrier()
+        return start.elapsed_time(end), sum(a.elapsed_time(b) for a, b in ev) / steps
 
     # ---- device-resident timing (value, roofline) -------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -357,20 +448,14 @@ def run_ours(args):
         step_dev()
     barrier()
     if rank == 0:                       # nvidia-smi needs ~0.3 s to deliver its first row: stay under load meanwhile
-        sampler.wait_samples(2, lambda: (step_dev(), torch.cuda.synchronize(dev)))
+        sampler.wait_samples(2, lambda: (step_plain(), torch.cuda.synchronize(dev)))
     first_sample = sampler.mark()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    start.record()
-    for a, b in ev:
-        a.record()
-        step_dev()          # one launch of body_quat_kernel; the 336 MB input exceeds L2 (126 MB)
-        b.record()
-    end.record()
-    barrier()
-    total_ms = start.elapsed_time(end)
-    kern_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    total_ms, kern_ms = timed(step_dev, args.steps)
+    plain_total_ms = plain_kern_ms = None
+    if multi:                            # side figure: the same shards with nothing communicated
+        for _ in range(2):
+            step_plain()
+        plain_total_ms, plain_kern_ms = timed(step_plain, args.steps)
     # ---- end-to-end timing through the host-buffer C-ABI call ----------------------------------
     for _ in range(2):
         step_e2e()
@@ -380,102 +465,126 @@ def run_ours(args):
         step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_dof_s = None
+    if not multi:
+        step_e2e(True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e(True)
+        barrier()
+        e2e_dof_s = time.perf_counter() - t0
     # keep the same load up until a few rows have been sampled inside the measurement window
     if rank == 0:
-        sampler.wait_samples(first_sample + 4, lambda: (step_dev(), torch.cuda.synchronize(dev)))
+        sampler.wait_samples(first_sample + 4, lambda: (step_plain(), torch.cuda.synchronize(dev)))
     clocks = sampler.stop(first_sample) if rank == 0 else None
 
-    t = torch.tensor([total_ms, kern_ms, e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
+    vals = [total_ms, kern_ms, e2e_s, plain_total_ms or 0.0, plain_kern_ms or 0.0]
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
+    if multi:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms, e2e_s = t.tolist()
+    total_ms, kern_ms, e2e_s, plain_total_ms, plain_kern_ms = t.tolist()
 
-    # ---- optional: reassemble dof_pos on every rank (the only collective the path ever needs) ---
-    gather_ms = None
+    # ---- N > 1: check the reassembled clip, and time the NCCL all-gather it replaces ---------------------------------
     gather_info = None
-    if world > 1:
-        from humanoid_real_time_retarget_b200.sharding import retarget_clip_overlapped
-        out = torch.empty((world * B, 30), device=dev)
-        dist.all_gather_into_tensor(out, dof_d)
-        barrier()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        dist.all_gather_into_tensor(out, dof_d)
-        e.record()
-        barrier()
-        # (a) compute then one all-gather, back to back; (b) block-cyclic shards, gather of block c overlapped with
-        # the compute of block c+1 on a second stream (lands directly in frame order)
-        n_blocks = 4
-        blk = B // n_blocks
-        raw_blocks = raw_d.reshape(n_blocks, blk, 21, 4)
-        comm = torch.cuda.Stream(dev)
-        res = torch.empty((n_blocks * world * blk, 30), device=dev)
-        times = []
-        for mode in ("sequential", "overlapped"):
-            for it in range(2 + 5):
-                barrier()
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                if mode == "sequential":
-                    step_dev()
-                    dist.all_gather_into_tensor(out, dof_d)
-                else:
-                    retarget_clip_overlapped(eng, raw_blocks, world * B, flags, IK_ITERS, DAMPING, ROT_WEIGHT, n_blocks=n_blocks,
-                                             comm_stream=comm, out=res)
-                a1.record()
-                barrier()
-                if it >= 2:
-                    times.append((mode, a0.elapsed_time(a1)))
-        seq = sum(t for m, t in times if m == "sequential") / 5
-        ovl = sum(t for m, t in times if m == "overlapped") / 5
-        gt = torch.tensor([s.elapsed_time(e), seq, ovl], dtype=torch.float64, device=dev)
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        gather_ms, seq, ovl = gt.tolist()
-        gather_info = {"allgather_dof_ms": gather_ms, "compute_then_gather_ms": seq, "overlapped_block_cyclic_ms": ovl,
-                       "blocks": n_blocks, "frames_per_s_with_gather_overlapped": world * B / (ovl * 1e-3),
-                       "note": "dof_pos (120 B/frame) reassembled on every rank over NCCL/NVLink; block-cyclic shards make "
-                               "each block's all-gather land in final frame order"}
+    if multi:
+        step_gather()
+        step_plain()
+        torch.cuda.synchronize(dev)
+        ok_own = bool(torch.equal(pr.dof[lo:hi], dof_d))
+        # a neighbour's first chunk, regenerated here from its seed and retargeted locally, must be what that rank stored
+        nb = (rank + 1) % world
+        nlo, nhi = shard_range(n_total, nb, world)
+        m = min(1 << 20, nhi - nlo)
+        raw_nb = synth_clip_on_device(hrt, oc, sk, dev, m, seed=1000 + nb)          # = that rank's first chunk (same size, same seed)
+        _, dof_nb, _ = eng.retarget_body_quat(raw_nb[:m], flags=flags, ik_iters=IK_ITERS, damping=DAMPING, rot_weight=ROT_WEIGHT,
+                                              want_local_q=False, want_link_pos=False)
+        ok_nb = bool(torch.equal(pr.dof[nlo:nlo + m], dof_nb))
+        del raw_nb, dof_nb
+        full = torch.empty((n_total, 30), device=dev)
+        equal_shards = (n_total % world == 0) and (n_total // world == B)
+
+        def step_nccl():
+            step_plain()
+            if equal_shards:
+                dist.all_gather_into_tensor(full, dof_d)
+        for _ in range(2):
+            step_nccl()
+        nccl_total_ms, _ = timed(step_nccl, max(3, args.steps // 2))
+        nccl_ms = nccl_total_ms / max(3, args.steps // 2)
+        gt = torch.tensor([nccl_ms, float(ok_own), float(ok_nb)], dtype=torch.float64, device=dev)
+        dist.all_reduce(gt[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(gt[1:], op=dist.ReduceOp.MIN)
+        nccl_ms, ok_own, ok_nb = gt.tolist()
+        sent = pr.nvlink_bytes_sent_per_step
+        gather_info = {
+            "transport": "TMA bulk stores to CUDA-IPC peer buffers over NVLink, issued by the compute kernel (no NCCL on the data path)",
+            "payload": "dof_pos (120 B/frame) of the whole clip on every rank",
+            "nvlink_bytes_sent_per_rank_per_step": sent, "nvlink_bytes_received_per_rank_per_step": (n_total - B) * 120,
+            "nvlink_send_GBps_per_rank": sent / (kern_ms * 1e-3) / 1e9,
+            "fused_step_ms": total_ms / args.steps,
+            "no_gather_step_ms": plain_total_ms / args.steps,
+            "no_gather_frames_per_s": n_total * args.steps / (plain_total_ms * 1e-3),
+            "nccl_compute_then_all_gather_step_ms": nccl_ms if equal_shards else None,
+            "nccl_frames_per_s": (n_total / (nccl_ms * 1e-3)) if equal_shards else None,
+            "reassembled_own_shard_bit_equal": bool(ok_own), "reassembled_neighbour_chunk_bit_equal": bool(ok_nb),
+        }
+        del full
+        assert ok_own and ok_nb, "reassembled dof_pos differs from the locally computed one"
 
     extras = {}
-    if rank == 0 and world == 1 and not args.no_extras:
+    if rank == 0 and not multi and not args.no_extras:
         extras = side_measurements(eng, hrt, oc, sk, dev)
     if rank == 0:
         peak, peak_src = hbm_peak()
-        value = world * B * args.steps / (total_ms * 1e-3)
+        value = n_total * args.steps / (total_ms * 1e-3)
         achieved = ALG_BYTES_PER_FRAME * B / (kern_ms * 1e-3) / 1e9
         cores = os.cpu_count() or 1
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if not multi and not args.no_cpu_baseline:
             r, dt = cpu_oracle_rate(args.cpu_frames, cores)
             cpu = {"value": r, "unit": "frames/s", "cores": cores, "kind": "port",
                    "sample": f"first {args.cpu_frames} frames of the clip, batched torch-CPU oracle ({dt:.1f} s); the "
-                             "reference's own per-frame Python loop runs at ~2e2 frames/s (BASELINE.md)"}
+                             "reference's own per-frame Python loop runs at ~2e2 frames/s (BASELINE.md, "
+                             "profiles/r01_reference_cpu_devbox.json; `bench.py --impl reference` runs it where its tree exists)"}
+        if multi:
+            workload = (f"configs[4]: {n_total}-frame synthetic vtrdyn clip sharded over {world} GPUs (strong scaling), full quaternion-path "
+                        f"pipeline -> Hu v5, {IK_ITERS}-iter IK + FK, dof_pos reassembled on every rank INSIDE the timed region")
+        else:
+            workload = ("configs[2]: full quaternion-path pipeline, vtrdyn (21 joints) -> Hu v5 (31 joints), "
+                        f"{IK_ITERS}-iter IK + FK")
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (+f64 Euler split)", "data": "synthetic",
-            "config": {"workload": "configs[2]: full quaternion-path pipeline, vtrdyn (21 joints) -> Hu v5 (31 joints), "
-                                   f"{IK_ITERS}-iter IK + FK", "frames_per_gpu_per_step": B, "ik_iters": IK_ITERS,
-                       "l2": "input clip 336 MB/GPU > 126 MB L2, streamed once per step", "parallelism": f"frames x{world}",
-                       "host_staging": numa.info},
-            "e2e": {"value": world * B * args.steps / e2e_s, "unit": "frames/s",
-                    "h2d_bytes_per_step": B * 21 * 16, "d2h_bytes_per_step": B * (30 * 4 + 31 * 12)},
-            "gpu_launches": args.steps,
+            "scaling": "strong" if multi else "weak", "vs_baseline": None, "dtype": "f32 (+f64 Euler split)", "data": "synthetic",
+            "config": {"workload": workload, "frames_total_per_step": n_total, "frames_per_gpu_per_step": B, "ik_iters": IK_ITERS,
+                       "l2": f"input shard {B * 336 >> 20} MB/GPU > 126 MB L2, streamed once per step", "parallelism": f"frames x{world}",
+                       "e2e_frames_per_gpu_per_step": Be, "host_staging": numa.info},
+            "e2e": {"value": world * Be * args.steps / e2e_s, "unit": "frames/s",
+                    "h2d_bytes_per_step": Be * 21 * 16, "d2h_bytes_per_step": Be * (30 * 4 + 31 * 12)},
+            "gpu_launches": args.steps * (2 if multi else 1),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "body_quat_kernel",
-                         "kernel_ms": kern_ms, "algorithmic_bytes_per_frame": ALG_BYTES_PER_FRAME,
+                         "traffic": ncu_traffic(), "traffic_source": "ncu capture of a past run of this command, per 2^20-frame launch (not live): "
+                         + str(_ncu_capture().get("source", "profiles/traffic.json")),
+                         "peak_source": peak_src, "kernel": "body_quat_kernel",
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_frame": ALG_BYTES_PER_FRAME, "frames_per_launch": B,
                          "note": "with 10 IK iterations the kernel is issue-bound by construction (~0.4 Mflop/frame); "
                                  "see profiles/ for issue-slot utilisation",
-                         "issue": issue_roofline(kern_ms, clocks, torch.cuda.get_device_properties(dev).multi_processor_count)},
+                         "issue": issue_roofline(kern_ms * (1 << 20) / B, clocks, torch.cuda.get_device_properties(dev).multi_processor_count)},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
+        if e2e_dof_s is not None:
+            line["e2e_dof_only"] = {"value": Be * args.steps / e2e_dof_s, "unit": "frames/s", "h2d_bytes_per_step": Be * 21 * 16,
+                                    "d2h_bytes_per_step": Be * 30 * 4, "note": "same call with out_link_pos=None: 120 B/frame back instead of 492"}
         line.update(extras)
         if gather_info is not None:
             line["gather"] = gather_info
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if multi:
+        pr.close()
         dist.destroy_process_group()
+    eng.close()
 
 
 def main():
@@ -484,7 +593,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=1 << 20, help="frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=1 << 20, help="N = 1: frames per step (configs[2]); also the e2e sample per rank")
+    ap.add_argument("--total-frames", type=int, default=1 << 24, help="N > 1: frames of the whole clip per step (configs[4])")
+    ap.add_argument("--force-port", action="store_true", help="--impl reference: time the oracle port even where the reference tree exists")
     ap.add_argument("--cpu-frames", type=int, default=1 << 16, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-frames", type=int, default=1 << 15, help="frames per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")

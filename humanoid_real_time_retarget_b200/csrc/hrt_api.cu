@@ -358,6 +358,9 @@ int fill_body_quat_args(hrt_ctx* ctx, int64_t B, const float* src, unsigned flag
     a->out_local_q = lq;
     a->out_dof = dof;
     a->out_link_pos = lp;
+    a->n_peer = 0;
+    a->peer_frame0 = 0;
+    for (int r = 0; r < HRT_MAX_PEERS; ++r) a->peer_dof[r] = nullptr;
     return 0;
 }
 
@@ -771,6 +774,84 @@ int hrt_retarget_body_quat(hrt_ctx* ctx, int64_t B, const float* d_src_gq, unsig
     if (!aligned16(d_src_gq) || !aligned16(d_robot_local_q) || !aligned16(d_dof) || !aligned16(d_link_pos))
         return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
     return launch_body_quat(ctx, a, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU reassembly over NVLink, one process per GPU (BASELINE configs[4]): plain cudaMalloc buffers shared by
+// CUDA IPC, filled by the compute kernel's own TMA bulk stores; a flag exchange closes the step.
+// ---------------------------------------------------------------------------------------------
+int hrt_peer_alloc(hrt_ctx* ctx, size_t bytes, void** d_ptr, unsigned char* handle64) {
+    HRT_ENTER(ctx);
+    if (!d_ptr || !handle64 || bytes == 0) return fail(HRT_E_INVALID_ARG, "null pointer / zero size");
+    static_assert(sizeof(cudaIpcMemHandle_t) == HRT_IPC_HANDLE_BYTES, "IPC handle size");
+    void* p = nullptr;
+    HRT_CUDA(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail((int)e, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, sizeof(h));
+    *d_ptr = p;
+    return 0;
+}
+
+int hrt_peer_free(hrt_ctx* ctx, void* d_ptr) {
+    HRT_ENTER(ctx);
+    if (d_ptr) HRT_CUDA(cudaFree(d_ptr));
+    return 0;
+}
+
+int hrt_peer_open(hrt_ctx* ctx, const unsigned char* handle64, void** d_ptr) {
+    HRT_ENTER(ctx);
+    if (!d_ptr || !handle64) return fail(HRT_E_INVALID_ARG, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    HRT_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int hrt_peer_close(hrt_ctx* ctx, void* d_ptr) {
+    HRT_ENTER(ctx);
+    if (d_ptr) HRT_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
+int hrt_retarget_body_quat_gather(hrt_ctx* ctx, int64_t B, const float* d_src_gq, unsigned flags, int ik_iters, float damping,
+                                  float rot_weight, float* d_link_pos, int n_peer, float* const* d_peer_dof, int64_t frame0,
+                                  void* stream) {
+    HRT_ENTER(ctx);
+    BodyQuatArgs a;
+    if ((rc = fill_body_quat_args(ctx, B, d_src_gq, flags, ik_iters, damping, rot_weight, nullptr, nullptr, d_link_pos, &a))) return rc;
+    if (n_peer < 1 || n_peer > HRT_MAX_PEERS || !d_peer_dof) return fail(HRT_E_INVALID_ARG, "n_peer must be 1..%d", HRT_MAX_PEERS);
+    if (frame0 < 0 || (frame0 * (ctx->bq.J_rob - 1) * 4) % 16 != 0)
+        return fail(HRT_E_ALIGNMENT, "frame0 must keep the dof rows 16-byte aligned (a multiple of 4 frames for 30 DOFs)");
+    if (B == 0) return 0;
+    if (!d_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
+    if (!aligned16(d_src_gq) || !aligned16(d_link_pos)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
+    a.flags &= ~BQ_PACKED_IK;
+    a.n_peer = n_peer;
+    a.peer_frame0 = frame0;
+    for (int r = 0; r < n_peer; ++r) {
+        if (!d_peer_dof[r] || !aligned16(d_peer_dof[r])) return fail(HRT_E_ALIGNMENT, "peer buffer %d null or not 16-byte aligned", r);
+        a.peer_dof[r] = d_peer_dof[r];
+    }
+    return launch_body_quat(ctx, a, (cudaStream_t)stream);
+}
+
+int hrt_peer_barrier(hrt_ctx* ctx, int n_peer, int my_rank, unsigned* const* d_peer_flags, unsigned epoch, void* stream) {
+    HRT_ENTER(ctx);
+    if (n_peer < 1 || n_peer > HRT_MAX_PEERS || my_rank < 0 || my_rank >= n_peer || !d_peer_flags)
+        return fail(HRT_E_INVALID_ARG, "bad peer set");
+    PeerFlags pf;
+    for (int r = 0; r < HRT_MAX_PEERS; ++r) pf.flags[r] = r < n_peer ? d_peer_flags[r] : nullptr;
+    for (int r = 0; r < n_peer; ++r)
+        if (!pf.flags[r]) return fail(HRT_E_INVALID_ARG, "peer flag array %d is null", r);
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, n_peer, my_rank, epoch, 20ull * 1000 * 1000 * 1000);
+    HRT_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int hrt_retarget_body_quat_host(hrt_ctx* ctx, int64_t B, const float* h_src_gq, unsigned flags, int ik_iters,

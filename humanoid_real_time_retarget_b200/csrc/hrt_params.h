@@ -8,6 +8,9 @@
 #define HRT_MAX_SLOTS 4
 #define HRT_MAX_CHAIN 16
 #define HRT_MAX_LINKS 4
+#ifndef HRT_MAX_PEERS
+#define HRT_MAX_PEERS 8
+#endif
 
 #ifdef __CUDACC__
 #define HRT_HD __host__ __device__

@@ -100,6 +100,12 @@ struct BodyQuatArgs {
     float* __restrict__ out_local_q;      // (B, 31, 4) or nullptr
     float* __restrict__ out_dof;          // (B, 30)    or nullptr
     float* __restrict__ out_link_pos;     // (B, 31, 3) or nullptr
+    // reassembly fused into the store (multi-GPU, configs[4]): when n_peer > 0 every warp also sends its dof span to the
+    // clip-wide dof buffer of EVERY rank (peer-mapped device memory, this rank's own buffer included), at frame
+    // peer_frame0 + f of that buffer -- the all-gather is n_peer bulk stores per 16 frames, no second kernel
+    int n_peer;
+    long long peer_frame0;
+    float* peer_dof[HRT_MAX_PEERS];
 };
 
 // the arm's hinge axes (Hu_DOF_AXIS[11..17] == Hu_DOF_AXIS[20..26]); checked on the host
@@ -314,7 +320,8 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
         }
         cp_async_commit();
         // while the copy is in flight: pre-fill the output images with their constant parts
-        if (a.out_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
+        const bool want_dof = a.out_dof != nullptr || a.n_peer > 0;
+        if (want_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
         cp_async_wait<0>();
         __syncwarp();
         const float* row = tile + fr * JS * 4;
@@ -409,7 +416,7 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
         }
 
         // ---- 7. outputs: each lane drops its arm into the warp's staged images ---------------------
-        if (a.out_dof && fl < nfr) {
+        if (want_dof && fl < nfr) {
             float* r = dof_t + fl * D + (ap.rob_first - 1);
 #pragma unroll
             for (int c = 0; c < 7; ++c) r[c] = th[c];
@@ -447,6 +454,9 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
             if (lane == 0) {
                 if (a.out_dof) bulk_store_s2g(a.out_dof + f0 * D, dof_t, (unsigned)(BQ_FRAMES_PER_WARP * D * 4));
                 if (a.out_link_pos) bulk_store_s2g(a.out_link_pos + f0 * W, lp_t, (unsigned)(BQ_FRAMES_PER_WARP * W * 4));
+                // the same staged image goes to every rank's reassembly buffer over NVLink (TMA bulk stores to peer memory)
+                for (int r = 0; r < a.n_peer; ++r)
+                    bulk_store_s2g(a.peer_dof[r] + (a.peer_frame0 + f0) * D, dof_t, (unsigned)(BQ_FRAMES_PER_WARP * D * 4));
                 bulk_commit();
             }
             pending_store = true;
@@ -454,6 +464,7 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
             __syncwarp();
             if (a.out_dof) warp_store_span(a.out_dof + f0 * D, dof_t, nfr * D, lane);
             if (a.out_link_pos) warp_store_span(a.out_link_pos + f0 * W, lp_t, nfr * W, lane);
+            for (int r = 0; r < a.n_peer; ++r) warp_store_span(a.peer_dof[r] + (a.peer_frame0 + f0) * D, dof_t, nfr * D, lane);
             __syncwarp();
         }
     }
@@ -509,6 +520,29 @@ bq_stream_server_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQua
     if (threadIdx.x == 0) {
         __threadfence_system();
         bq_st_sys(ctrl + 17, 1u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Step barrier of the fused reassembly: lane r tells rank r "my stores into your buffer are done" (they were issued by
+// the compute kernel that precedes this one on the stream) and waits for rank r's word in this rank's own flag array.
+// flags[r] = rank r's array of HRT_MAX_PEERS words (peer-mapped); word [me] of it is written by rank `me` only.
+// Epochs only grow; a wait that exceeds timeout_ns traps (a lost peer must not hang the box).
+// ---------------------------------------------------------------------------------------------
+struct PeerFlags { unsigned* flags[HRT_MAX_PEERS]; };
+
+__global__ void __launch_bounds__(32)
+peer_barrier_kernel(const PeerFlags pf, int n_peer, int me, unsigned epoch, unsigned long long timeout_ns) {
+    const int r = threadIdx.x;
+    if (r >= n_peer) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(pf.flags[r] + me), "r"(epoch) : "memory");
+    const unsigned long long t0 = bq_timer_ns();
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(pf.flags[me] + r) : "memory");
+        if ((int)(v - epoch) >= 0) break;
+        if (bq_timer_ns() - t0 > timeout_ns) __trap();
     }
 }
 

@@ -215,6 +215,39 @@ class Engine:
                                                    _ptr(lq), _ptr(dof), _ptr(lp), self._stream()))
         return lq, dof, lp
 
+    # ------------------------------------------------------------------ multi-GPU reassembly over NVLink (configs[4])
+    def peer_alloc(self, nbytes):
+        """Device allocation exportable to the other ranks: (device pointer, 64-byte CUDA IPC handle)."""
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        _lib.check(self.lib.hrt_peer_alloc(self._h, int(nbytes), C.byref(p), h))
+        return p.value, h.raw
+
+    def peer_open(self, handle):
+        p = C.c_void_p()
+        _lib.check(self.lib.hrt_peer_open(self._h, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def peer_close(self, ptr):
+        _lib.check(self.lib.hrt_peer_close(self._h, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr):
+        _lib.check(self.lib.hrt_peer_free(self._h, C.c_void_p(ptr)))
+
+    def retarget_body_quat_gather(self, src_gq, peer_dof_ptrs, frame0, flags=0, ik_iters=10, damping=0.1, rot_weight=0.2, link_pos=None):
+        """The fused quaternion path on this rank's frames, its dof rows stored into EVERY rank's clip-wide buffer
+        (peer_dof_ptrs: device pointers, own buffer included) at frame `frame0` onwards."""
+        JS, JR = self._bq
+        src_gq = _f32c(src_gq, self.device)
+        B = src_gq.numel() // (JS * 4)
+        arr = (C.c_void_p * len(peer_dof_ptrs))(*peer_dof_ptrs)
+        _lib.check(self.lib.hrt_retarget_body_quat_gather(self._h, B, _ptr(src_gq), flags, ik_iters, damping, rot_weight, _ptr(link_pos),
+                                                          len(peer_dof_ptrs), arr, int(frame0), self._stream()))
+
+    def peer_barrier(self, peer_flag_ptrs, my_rank, epoch):
+        arr = (C.c_void_p * len(peer_flag_ptrs))(*peer_flag_ptrs)
+        _lib.check(self.lib.hrt_peer_barrier(self._h, len(peer_flag_ptrs), int(my_rank), arr, int(epoch) & 0xFFFFFFFF, self._stream()))
+
     def _pos_outputs(self, B, want_local_q, want_dof, want_body_gq=False):
         lq = torch.empty((B, 31, 4), device=self.device, dtype=torch.float32) if want_local_q else None
         dof = torch.empty((B, 30), device=self.device, dtype=torch.float32) if want_dof else None

@@ -47,6 +47,73 @@ def retarget_clip_sharded(engine, raw_global_q_full, flags, ik_iters=10, damping
 
 
 # ---------------------------------------------------------------------------------------------------
+# Reassembly fused into the kernel's store (BASELINE configs[4]).  Every rank owns a clip-wide dof buffer; the buffers
+# are exchanged once as CUDA IPC handles; from then on a step is ONE compute kernel per rank whose warps send each
+# 16-frame dof span to all ranks as TMA bulk stores over NVLink, plus a one-warp flag exchange.  No NCCL call, no second
+# pass over the data, and the transfer is spread over the whole kernel instead of queued behind it.
+# ---------------------------------------------------------------------------------------------------
+class _DevView:
+    """A cudaMalloc'd span as a torch tensor (CUDA array interface); keeps nothing alive: the owner frees it."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+class PeerReassembly:
+    """dof_pos of an n_frames clip, sharded by shard_range over the ranks of `group`, reassembled on every rank.
+    step(engine-resident input shard) -> the clip-wide (n_frames, D) tensor of THIS rank (valid once the current stream has
+    passed the step's barrier kernel).  close() must be called on every rank (it is a collective)."""
+
+    def __init__(self, engine, n_frames, dof=30, group=None):
+        self.eng, self.group, self.n, self.D = engine, group, int(n_frames), int(dof)
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("peer reassembly serves the GPUs of one box (<= 8 ranks)")
+        self.lo, self.hi = shard_range(self.n, self.rank, self.world)
+        if self.lo % 4:
+            raise ValueError("shard boundaries must keep dof rows 16-byte aligned")
+        self._buf, h_buf = engine.peer_alloc(max(self.n, 1) * self.D * 4)
+        self._flags, h_flags = engine.peer_alloc(64)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (h_buf, h_flags), group=group)
+        self.buf_ptrs, self.flag_ptrs = [], []
+        for r, (hb, hf) in enumerate(handles):
+            self.buf_ptrs.append(self._buf if r == self.rank else engine.peer_open(hb))
+            self.flag_ptrs.append(self._flags if r == self.rank else engine.peer_open(hf))
+        self.epoch = 0
+        self.dof = torch.as_tensor(_DevView(self._buf, (self.n, self.D)), device=engine.device)
+        dist.barrier(group=group)                          # every rank has mapped every buffer before the first store
+
+    def step(self, raw_local, flags, ik_iters=10, damping=0.1, rot_weight=0.2, link_pos=None):
+        assert raw_local.shape[0] == self.hi - self.lo
+        self.eng.retarget_body_quat_gather(raw_local, self.buf_ptrs, self.lo, flags=flags, ik_iters=ik_iters, damping=damping,
+                                           rot_weight=rot_weight, link_pos=link_pos)
+        self.epoch += 1
+        self.eng.peer_barrier(self.flag_ptrs, self.rank, self.epoch)
+        return self.dof
+
+    @property
+    def nvlink_bytes_sent_per_step(self):
+        return (self.world - 1) * (self.hi - self.lo) * self.D * 4
+
+    def close(self):
+        if self._buf is None:
+            return
+        torch.cuda.synchronize(self.eng.device)
+        dist.barrier(group=self.group)                     # nobody is still storing into a buffer about to be unmapped
+        for r in range(self.world):
+            if r != self.rank:
+                self.eng.peer_close(self.buf_ptrs[r])
+                self.eng.peer_close(self.flag_ptrs[r])
+        dist.barrier(group=self.group)
+        self.dof = None
+        self.eng.peer_free(self._buf)
+        self.eng.peer_free(self._flags)
+        self._buf = self._flags = None
+
+
+# ---------------------------------------------------------------------------------------------------
 # Block-cyclic sharding: the all-gather of block c lands in final frame order, so it can run on a second
 # stream while block c+1 is still being computed (SURVEY.md section 8(e): "chunked and overlapped").
 # ---------------------------------------------------------------------------------------------------
@@ -111,20 +178,36 @@ VELOCITY_HALO = 9
 def exchange_halo(local, halo, group=None):
     """Neighbour exchange of `halo` leading / trailing frames between consecutive ranks (point-to-point over
     NCCL / NVLink, gloo in the CPU tests).  Returns (padded, lead): `padded` = [prev rank's tail | local | next
-    rank's head], `lead` = number of frames put in front of the local ones."""
+    rank's head], `lead` = number of frames put in front of the local ones.
+    The shard lengths are agreed on first (one tiny all-gather), so that every rank takes the same decision before any
+    point-to-point operation is posted: ranks without frames (ragged tails of short clips) are skipped -- a rank's
+    neighbour is the nearest rank that HAS frames -- and a non-empty shard shorter than the halo raises on EVERY rank
+    instead of leaving its neighbours blocked in a posted send."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    if local.shape[0] < halo:
-        raise ValueError(f"shard of {local.shape[0]} frames is shorter than the {halo}-frame halo")
-    prev_buf = torch.empty((halo,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) if rank > 0 else None
-    next_buf = torch.empty((halo,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) if rank < world - 1 else None
+    mine = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    lens_t = torch.empty(world, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(lens_t, mine, group=group)
+    lens = lens_t.tolist()
+    active = [r for r in range(world) if lens[r] > 0]
+    short = [r for r in active if lens[r] < halo]
+    if short and len(active) > 1:
+        raise ValueError(f"shards of ranks {short} hold fewer than the {halo}-frame halo ({[lens[r] for r in short]} frames): "
+                         "use fewer ranks for this clip")
+    if rank not in active or len(active) == 1:
+        return local, 0
+    k = active.index(rank)
+    prev_rank = active[k - 1] if k > 0 else None
+    next_rank = active[k + 1] if k + 1 < len(active) else None
+    prev_buf = torch.empty((halo,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) if prev_rank is not None else None
+    next_buf = torch.empty((halo,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) if next_rank is not None else None
     ops = []
-    if rank > 0:
-        ops.append(dist.P2POp(dist.isend, local[:halo].contiguous(), rank - 1, group))
-        ops.append(dist.P2POp(dist.irecv, prev_buf, rank - 1, group))
-    if rank < world - 1:
-        ops.append(dist.P2POp(dist.isend, local[-halo:].contiguous(), rank + 1, group))
-        ops.append(dist.P2POp(dist.irecv, next_buf, rank + 1, group))
+    if prev_rank is not None:
+        ops.append(dist.P2POp(dist.isend, local[:halo].contiguous(), prev_rank, group))
+        ops.append(dist.P2POp(dist.irecv, prev_buf, prev_rank, group))
+    if next_rank is not None:
+        ops.append(dist.P2POp(dist.isend, local[-halo:].contiguous(), next_rank, group))
+        ops.append(dist.P2POp(dist.irecv, next_buf, next_rank, group))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()

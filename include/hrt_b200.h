@@ -144,6 +144,26 @@ int hrt_retarget_body_quat_host(hrt_ctx* ctx, int64_t B, const float* h_src_gq, 
                                 float damping, float rot_weight, float* h_robot_local_q, float* h_dof,
                                 float* h_link_pos);
 
+/* Multi-GPU reassembly fused into the kernel's store (BASELINE.json configs[4]: a clip sharded over the GPUs of one box,
+ * dof_pos reassembled on every rank; SURVEY.md section 8(e) -- the reference has no multi-device code).  One process per
+ * GPU.  Every rank owns a clip-wide dof buffer and a flag array, both plain device allocations exported with CUDA IPC:
+ *   hrt_peer_alloc   allocate + zero `bytes` of device memory, return its 64-byte IPC handle
+ *   hrt_peer_open    map another rank's allocation (enables peer access over NVLink) / hrt_peer_close
+ *   hrt_retarget_body_quat_gather   hrt_retarget_body_quat whose dof rows go, as TMA bulk stores, to frame
+ *                    frame0 + f of EVERY rank's buffer d_peer_dof[0..n_peer) (own buffer included); d_link_pos stays local
+ *   hrt_peer_barrier after it on the same stream: publishes "my stores are done" to every rank's flag array and waits for
+ *                    theirs (d_peer_flags[r] = rank r's array of HRT_MAX_PEERS words; epoch must grow by one per step) */
+#define HRT_IPC_HANDLE_BYTES 64
+#define HRT_MAX_PEERS 8
+int hrt_peer_alloc(hrt_ctx* ctx, size_t bytes, void** d_ptr, unsigned char* handle64);
+int hrt_peer_free(hrt_ctx* ctx, void* d_ptr);
+int hrt_peer_open(hrt_ctx* ctx, const unsigned char* handle64, void** d_ptr);
+int hrt_peer_close(hrt_ctx* ctx, void* d_ptr);
+int hrt_retarget_body_quat_gather(hrt_ctx* ctx, int64_t B, const float* d_src_gq, unsigned flags, int ik_iters,
+                                  float damping, float rot_weight, float* d_link_pos, int n_peer,
+                                  float* const* d_peer_dof, int64_t frame0, void* stream);
+int hrt_peer_barrier(hrt_ctx* ctx, int n_peer, int my_rank, unsigned* const* d_peer_flags, unsigned epoch, void* stream);
+
 /* Position-input solvers.  mode 0: VtrdynFullBodyPosRetargeter (retarget/retarget_solver/
  * full_body_pos_retargeter.py:25-217), mode 1: HuUpperBodyFromMocapRetarget (retarget_solver.py:40-99),
  * mode 2: VtrdynFullBodyRetargeter (full_body_retargeter.py:19-177).  The joint indices those classes

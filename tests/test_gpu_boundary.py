@@ -225,3 +225,36 @@ def test_entry_points_restore_the_callers_device(hrt):
     x = torch.zeros(4, device="cuda")
     assert x.device.index == 0
     eng.close()
+
+
+def test_fused_reassembly_single_rank(hrt, oc, skeletons):
+    """sharding.PeerReassembly with a world of one (the N > 1 path runs in bench.py / tools/peer_gather_check.py under
+    torchrun): the kernel stores its dof spans into the IPC-exportable buffer, the flag exchange closes the step, and the
+    result is bit-equal to the plain call -- for whole warps' worth of frames and for a ragged tail."""
+    import os
+    import socket
+    import torch.distributed as dist
+    from humanoid_real_time_retarget_b200.sharding import PeerReassembly
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        eng = hrt.Engine(0).set_standard_trees()
+        flags = hrt.BQ_CLAMP | hrt.BQ_IK
+        for n in (40_000, 16 * 1000 + 5, 7):
+            raw = oc.synth_clip_3q(n, seed=3, sk=skeletons).cuda()
+            pr = PeerReassembly(eng, n)
+            lp = torch.empty(n, 31, 3, device="cuda")
+            for _ in range(3):                                    # epochs advance, the buffer is rewritten in place
+                full = pr.step(raw, flags, link_pos=lp)
+            torch.cuda.synchronize()
+            _, dof, lp0 = eng.retarget_body_quat(raw, flags=flags)
+            assert full.shape == (n, 30) and torch.equal(full, dof) and torch.equal(lp, lp0)
+            assert pr.nvlink_bytes_sent_per_step == 0
+            pr.close()
+        eng.close()
+    finally:
+        dist.destroy_process_group()
