@@ -361,6 +361,7 @@ int fill_body_quat_args(hrt_ctx* ctx, int64_t B, const float* src, unsigned flag
     a->n_peer = 0;
     a->peer_frame0 = 0;
     for (int r = 0; r < HRT_MAX_PEERS; ++r) a->peer_dof[r] = nullptr;
+    a->mc_dof = nullptr;
     return 0;
 }
 
@@ -838,6 +839,23 @@ int hrt_retarget_body_quat_gather(hrt_ctx* ctx, int64_t B, const float* d_src_gq
         if (!d_peer_dof[r] || !aligned16(d_peer_dof[r])) return fail(HRT_E_ALIGNMENT, "peer buffer %d null or not 16-byte aligned", r);
         a.peer_dof[r] = d_peer_dof[r];
     }
+    return launch_body_quat(ctx, a, (cudaStream_t)stream);
+}
+
+int hrt_retarget_body_quat_multicast(hrt_ctx* ctx, int64_t B, const float* d_src_gq, unsigned flags, int ik_iters, float damping,
+                                     float rot_weight, float* d_link_pos, float* d_mc_dof, int64_t frame0, void* stream) {
+    HRT_ENTER(ctx);
+    BodyQuatArgs a;
+    if ((rc = fill_body_quat_args(ctx, B, d_src_gq, flags, ik_iters, damping, rot_weight, nullptr, nullptr, d_link_pos, &a))) return rc;
+    if (!d_mc_dof || !aligned16(d_mc_dof)) return fail(HRT_E_ALIGNMENT, "multicast address null or not 16-byte aligned");
+    if (frame0 < 0 || (frame0 * (ctx->bq.J_rob - 1) * 4) % 16 != 0)
+        return fail(HRT_E_ALIGNMENT, "frame0 must keep the dof rows 16-byte aligned (a multiple of 4 frames for 30 DOFs)");
+    if (B == 0) return 0;
+    if (!d_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
+    if (!aligned16(d_src_gq) || !aligned16(d_link_pos)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
+    a.flags &= ~BQ_PACKED_IK;
+    a.peer_frame0 = frame0;
+    a.mc_dof = d_mc_dof;
     return launch_body_quat(ctx, a, (cudaStream_t)stream);
 }
 

@@ -106,10 +106,27 @@ struct BodyQuatArgs {
     int n_peer;
     long long peer_frame0;
     float* peer_dof[HRT_MAX_PEERS];
+    // the same with ONE store per span: mc_dof is the NVSwitch multicast address of the ranks' clip-wide buffers
+    // (multimem.st: the switch replicates the store into every rank's copy, this rank's included)
+    float* mc_dof;
 };
 
 // the arm's hinge axes (Hu_DOF_AXIS[11..17] == Hu_DOF_AXIS[20..26]); checked on the host
 #define HRT_ARM_AXIS(c) ((c) == 0 ? 1 : (c) == 1 ? 0 : (c) == 2 ? 2 : (c) == 3 ? 1 : (c) == 4 ? 0 : (c) == 5 ? 1 : 2)
+
+// one warp publishes a staged span through an NVSwitch multicast address: 16 bytes per lane per instruction, the
+// switch writes every bound device's copy (PTX multimem.st; plain st on a multimem address is undefined)
+HRT_DEV void warp_multimem_store_span(float* mc_dst, const float* tile, int n_words, int lane) {
+    const int n4 = n_words >> 2;
+    const float4* t4 = reinterpret_cast<const float4*>(tile);
+    for (int i = lane; i < n4; i += 32) {
+        const float4 v = t4[i];
+        asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(mc_dst + 4 * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+    }
+    for (int i = 4 * n4 + lane; i < n_words; i += 32)
+        asm volatile("multimem.st.weak.global.f32 [%0], %1;\n" ::"l"(mc_dst + i), "f"(tile[i]) : "memory");
+}
 
 HRT_DEV void warp_store_span(float* __restrict__ dst, const float* tile, int n_words, int lane) {
     // dst is 16-byte aligned (frame-group base); vector body + scalar tail
@@ -320,7 +337,7 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
         }
         cp_async_commit();
         // while the copy is in flight: pre-fill the output images with their constant parts
-        const bool want_dof = a.out_dof != nullptr || a.n_peer > 0;
+        const bool want_dof = a.out_dof != nullptr || a.n_peer > 0 || a.mc_dof != nullptr;
         if (want_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
         cp_async_wait<0>();
         __syncwarp();
@@ -459,12 +476,14 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
                     bulk_store_s2g(a.peer_dof[r] + (a.peer_frame0 + f0) * D, dof_t, (unsigned)(BQ_FRAMES_PER_WARP * D * 4));
                 bulk_commit();
             }
+            if (a.mc_dof) warp_multimem_store_span(a.mc_dof + (a.peer_frame0 + f0) * D, dof_t, BQ_FRAMES_PER_WARP * D, lane);
             pending_store = true;
         } else if (nfr > 0) {
             __syncwarp();
             if (a.out_dof) warp_store_span(a.out_dof + f0 * D, dof_t, nfr * D, lane);
             if (a.out_link_pos) warp_store_span(a.out_link_pos + f0 * W, lp_t, nfr * W, lane);
             for (int r = 0; r < a.n_peer; ++r) warp_store_span(a.peer_dof[r] + (a.peer_frame0 + f0) * D, dof_t, nfr * D, lane);
+            if (a.mc_dof) warp_multimem_store_span(a.mc_dof + (a.peer_frame0 + f0) * D, dof_t, nfr * D, lane);
             __syncwarp();
         }
     }

@@ -244,6 +244,15 @@ class Engine:
         _lib.check(self.lib.hrt_retarget_body_quat_gather(self._h, B, _ptr(src_gq), flags, ik_iters, damping, rot_weight, _ptr(link_pos),
                                                           len(peer_dof_ptrs), arr, int(frame0), self._stream()))
 
+    def retarget_body_quat_multicast(self, src_gq, mc_dof_ptr, frame0, flags=0, ik_iters=10, damping=0.1, rot_weight=0.2, link_pos=None):
+        """The fused quaternion path on this rank's frames, its dof rows published ONCE through the NVSwitch multicast
+        address `mc_dof_ptr` of the ranks' clip-wide buffers (multimem.st; the switch writes every rank's copy)."""
+        JS, JR = self._bq
+        src_gq = _f32c(src_gq, self.device)
+        B = src_gq.numel() // (JS * 4)
+        _lib.check(self.lib.hrt_retarget_body_quat_multicast(self._h, B, _ptr(src_gq), flags, ik_iters, damping, rot_weight, _ptr(link_pos),
+                                                             C.c_void_p(int(mc_dof_ptr)), int(frame0), self._stream()))
+
     def peer_barrier(self, peer_flag_ptrs, my_rank, epoch):
         arr = (C.c_void_p * len(peer_flag_ptrs))(*peer_flag_ptrs)
         _lib.check(self.lib.hrt_peer_barrier(self._h, len(peer_flag_ptrs), int(my_rank), arr, int(epoch) & 0xFFFFFFFF, self._stream()))

@@ -62,55 +62,113 @@ class _DevView:
 class PeerReassembly:
     """dof_pos of an n_frames clip, sharded by shard_range over the ranks of `group`, reassembled on every rank.
     step(engine-resident input shard) -> the clip-wide (n_frames, D) tensor of THIS rank (valid once the current stream has
-    passed the step's barrier kernel).  close() must be called on every rank (it is a collective)."""
+    passed the step's barrier kernel).  close() must be called on every rank (it is a collective).
 
-    def __init__(self, engine, n_frames, dof=30, group=None):
+    transport="multicast": the clip-wide buffers are one torch symmetric-memory allocation (torch.distributed plumbing:
+    cuMemCreate + handle exchange + an NVSwitch multicast object over all ranks' copies); every warp publishes its dof span
+    once with multimem.st and the switch replicates it -- a rank sends 1/N of the bytes of the unicast form.
+    transport="unicast": plain cudaMalloc buffers exchanged as CUDA IPC handles; every warp sends its span to each rank
+    with one TMA bulk store per rank.  transport="auto" takes multicast when the box offers it (NVLS), else unicast."""
+
+    def __init__(self, engine, n_frames, dof=30, group=None, transport="auto"):
         self.eng, self.group, self.n, self.D = engine, group, int(n_frames), int(dof)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         if self.world > 8:
             raise ValueError("peer reassembly serves the GPUs of one box (<= 8 ranks)")
+        if transport not in ("auto", "multicast", "unicast"):
+            raise ValueError(f"unknown transport {transport!r}")
         self.lo, self.hi = shard_range(self.n, self.rank, self.world)
         if self.lo % 4:
             raise ValueError("shard boundaries must keep dof rows 16-byte aligned")
-        self._buf, h_buf = engine.peer_alloc(max(self.n, 1) * self.D * 4)
+        self._buf = self._symm = None
+        self.mc_ptr = 0
+        self.transport_error = None
+        if transport in ("auto", "multicast") and self.world > 1 and torch.device(engine.device).type == "cuda":
+            self._try_multicast(require=(transport == "multicast"))
         self._flags, h_flags = engine.peer_alloc(64)
+        if self.mc_ptr:
+            self.transport = "multicast"
+            h_buf = None
+        else:
+            self.transport = "unicast"
+            self._buf, h_buf = engine.peer_alloc(max(self.n, 1) * self.D * 4)
         handles = [None] * self.world
         dist.all_gather_object(handles, (h_buf, h_flags), group=group)
         self.buf_ptrs, self.flag_ptrs = [], []
         for r, (hb, hf) in enumerate(handles):
-            self.buf_ptrs.append(self._buf if r == self.rank else engine.peer_open(hb))
+            if not self.mc_ptr:
+                self.buf_ptrs.append(self._buf if r == self.rank else engine.peer_open(hb))
             self.flag_ptrs.append(self._flags if r == self.rank else engine.peer_open(hf))
         self.epoch = 0
-        self.dof = torch.as_tensor(_DevView(self._buf, (self.n, self.D)), device=engine.device)
+        if not self.mc_ptr:
+            self.dof = torch.as_tensor(_DevView(self._buf, (self.n, self.D)), device=engine.device)
         dist.barrier(group=group)                          # every rank has mapped every buffer before the first store
+
+    def _try_multicast(self, require):
+        """One symmetric allocation of the clip-wide buffer with a multicast mapping; the decision is taken collectively
+        (a rank that cannot map it makes every rank fall back)."""
+        ok, err = 1, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            dev = torch.device(self.eng.device)
+            t = symm_mem.empty(max(self.n, 1) * self.D, dtype=torch.float32, device=dev)
+            hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            mc = int(hdl.multicast_ptr or 0)
+            if mc == 0:
+                ok, err = 0, "no multicast address (NVLS not available on this box)"
+        except Exception as e:                             # no symmetric memory on this build / box
+            ok, err, t, hdl, mc = 0, f"{type(e).__name__}: {e}"[:200], None, None, 0
+        agree = torch.tensor([ok], dtype=torch.int32, device=self.eng.device)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=self.group)
+        if int(agree.item()) == 1:
+            t.zero_()
+            torch.cuda.synchronize(self.eng.device)
+            self._symm, self._hdl, self.mc_ptr = t, hdl, mc
+            self.dof = t.view(max(self.n, 1), self.D)[: self.n]
+        else:
+            self.transport_error = err or "another rank could not map the multicast object"
+            if require:
+                raise RuntimeError("multicast reassembly unavailable: " + self.transport_error)
 
     def step(self, raw_local, flags, ik_iters=10, damping=0.1, rot_weight=0.2, link_pos=None):
         assert raw_local.shape[0] == self.hi - self.lo
-        self.eng.retarget_body_quat_gather(raw_local, self.buf_ptrs, self.lo, flags=flags, ik_iters=ik_iters, damping=damping,
-                                           rot_weight=rot_weight, link_pos=link_pos)
+        if self.mc_ptr:
+            self.eng.retarget_body_quat_multicast(raw_local, self.mc_ptr, self.lo, flags=flags, ik_iters=ik_iters, damping=damping,
+                                                  rot_weight=rot_weight, link_pos=link_pos)
+        else:
+            self.eng.retarget_body_quat_gather(raw_local, self.buf_ptrs, self.lo, flags=flags, ik_iters=ik_iters, damping=damping,
+                                               rot_weight=rot_weight, link_pos=link_pos)
         self.epoch += 1
         self.eng.peer_barrier(self.flag_ptrs, self.rank, self.epoch)
         return self.dof
 
     @property
     def nvlink_bytes_sent_per_step(self):
-        return (self.world - 1) * (self.hi - self.lo) * self.D * 4
+        """Bytes this rank puts on its NVLink egress per step (multicast: its shard once; unicast: once per peer)."""
+        shard = (self.hi - self.lo) * self.D * 4
+        if self.world == 1:
+            return 0
+        return shard if self.mc_ptr else (self.world - 1) * shard
 
     def close(self):
-        if self._buf is None:
+        if self._flags is None:
             return
         torch.cuda.synchronize(self.eng.device)
         dist.barrier(group=self.group)                     # nobody is still storing into a buffer about to be unmapped
         for r in range(self.world):
             if r != self.rank:
-                self.eng.peer_close(self.buf_ptrs[r])
+                if not self.mc_ptr:
+                    self.eng.peer_close(self.buf_ptrs[r])
                 self.eng.peer_close(self.flag_ptrs[r])
         dist.barrier(group=self.group)
         self.dof = None
-        self.eng.peer_free(self._buf)
+        if self._buf is not None:
+            self.eng.peer_free(self._buf)
         self.eng.peer_free(self._flags)
         self._buf = self._flags = None
+        self._symm = self._hdl = None                      # the symmetric allocation is released with its tensor
+        self.mc_ptr = 0
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -163,6 +163,14 @@ int hrt_retarget_body_quat_gather(hrt_ctx* ctx, int64_t B, const float* d_src_gq
                                   float damping, float rot_weight, float* d_link_pos, int n_peer,
                                   float* const* d_peer_dof, int64_t frame0, void* stream);
 int hrt_peer_barrier(hrt_ctx* ctx, int n_peer, int my_rank, unsigned* const* d_peer_flags, unsigned epoch, void* stream);
+/* The same reassembly through NVSwitch multicast (NVLS): d_mc_dof is the multicast address of the ranks' clip-wide dof
+ * buffers (a CUDA multicast object with every rank's buffer bound at offset 0 and mapped; e.g. the `multicast_ptr` of a
+ * torch symmetric-memory rendezvous).  Every warp publishes its dof span ONCE with multimem.st and the switch writes all
+ * N copies (this rank's included): 1/N of the egress bytes of hrt_retarget_body_quat_gather, no NCCL.  Close the step
+ * with hrt_peer_barrier as above. */
+int hrt_retarget_body_quat_multicast(hrt_ctx* ctx, int64_t B, const float* d_src_gq, unsigned flags, int ik_iters,
+                                     float damping, float rot_weight, float* d_link_pos, float* d_mc_dof,
+                                     int64_t frame0, void* stream);
 
 /* Position-input solvers.  mode 0: VtrdynFullBodyPosRetargeter (retarget/retarget_solver/
  * full_body_pos_retargeter.py:25-217), mode 1: HuUpperBodyFromMocapRetarget (retarget_solver.py:40-99),

@@ -27,18 +27,21 @@ def main():
     eng = hrt.Engine(local).set_standard_trees()
     flags = hrt.BQ_CLAMP | hrt.BQ_IK
     ok = True
-    for n in (1 << 18, 100_003, 16 * world * 3 + 5):
-        raw = oc.synth_clip_3q(n, seed=5, sk=sk).cuda()
-        lo, hi = shard_range(n, rank, world)
-        pr = PeerReassembly(eng, n)
-        for _ in range(3):
-            full = pr.step(raw[lo:hi], flags)
-        torch.cuda.synchronize()
-        _, want, _ = eng.retarget_body_quat(raw, flags=flags, want_local_q=False, want_link_pos=False)
-        same = bool(torch.equal(full, want))
-        print(f"rank {rank}/{world} n={n}: shard [{lo},{hi}) reassembled clip bit-equal to the local result: {same}", flush=True)
-        ok &= same
-        pr.close()
+    for transport in ("auto", "unicast"):
+        for n in (1 << 18, 100_003, 16 * world * 3 + 5):
+            raw = oc.synth_clip_3q(n, seed=5, sk=sk).cuda()
+            lo, hi = shard_range(n, rank, world)
+            pr = PeerReassembly(eng, n, transport=transport)
+            for _ in range(3):
+                full = pr.step(raw[lo:hi], flags)
+            torch.cuda.synchronize()
+            dist.barrier()
+            _, want, _ = eng.retarget_body_quat(raw, flags=flags, want_local_q=False, want_link_pos=False)
+            same = bool(torch.equal(full, want))
+            print(f"rank {rank}/{world} n={n} transport={pr.transport} ({pr.transport_error}): shard [{lo},{hi}) reassembled clip "
+                  f"bit-equal to the local result: {same}", flush=True)
+            ok &= same
+            pr.close()
     t = torch.tensor([float(ok)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
