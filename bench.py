@@ -517,28 +517,36 @@ def run_ours(args):
         dist.all_reduce(gt[1:], op=dist.ReduceOp.MIN)
         nccl_ms, ok_own, ok_nb = gt.tolist()
         sent = pr.nvlink_bytes_sent_per_step
-        # side figure: the other transport of the fused reassembly (unicast TMA bulk stores to every peer) on the same shards
-        uni_ms = None
-        if pr.transport == "multicast":
-            pr_u = PeerReassembly(eng, n_total, transport="unicast")
-            step_u = lambda: pr_u.step(raw_d, flags, IK_ITERS, DAMPING, ROT_WEIGHT, link_pos=lp_d)  # noqa: E731
+        # side figures: the other transports of the fused reassembly on the same shards
+        side_ms = {}
+        for other in ("multicast", "unicast"):
+            if other == pr.transport or (other == "multicast" and pr.transport == "unicast"):
+                continue
+            pr_o = PeerReassembly(eng, n_total, transport=other)
+            step_o = lambda: pr_o.step(raw_d, flags, IK_ITERS, DAMPING, ROT_WEIGHT, link_pos=lp_d)  # noqa: E731
             for _ in range(2):
-                step_u()
-            u_total, _ = timed(step_u, max(3, args.steps // 2))
-            ut = torch.tensor([u_total / max(3, args.steps // 2)], dtype=torch.float64, device=dev)
-            dist.all_reduce(ut, op=dist.ReduceOp.MAX)
-            uni_ms = float(ut.item())
-            pr_u.close()
+                step_o()
+            k_o = max(3, args.steps // 2)
+            o_total, _ = timed(step_o, k_o)
+            ot = torch.tensor([o_total / k_o], dtype=torch.float64, device=dev)
+            dist.all_reduce(ot, op=dist.ReduceOp.MAX)
+            side_ms[other] = float(ot.item())
+            pr_o.close()
+            del pr_o
         transports = {
-            "multicast": "multimem.st to the NVSwitch multicast address of the ranks' symmetric buffers, issued by the compute kernel: "
-                         "each dof span leaves the GPU once and the switch writes all N copies (no NCCL on the data path)",
-            "unicast": "TMA bulk stores to CUDA-IPC peer buffers over NVLink, issued by the compute kernel, one per rank and span "
-                       "(no NCCL on the data path)"}
+            "packed": "reassembly inside the compute kernel: the 14 arm hinge angles of a frame (56 B; every other DOF of this solver is "
+                      "structurally 0) go out once through the NVSwitch multicast address of the ranks' symmetric staging buffers "
+                      "(multimem.st), a flag per CTA round follows (fence.sys + multimem.st.release), and the same warps unpack the "
+                      "peers' landed rounds into the local (n, 30) dof_pos between their own rounds (no NCCL on the data path)",
+            "multicast": "multimem.st of full 120-byte dof rows to the NVSwitch multicast address of the ranks' symmetric buffers, issued "
+                         "by the compute kernel (no NCCL on the data path)",
+            "unicast": "TMA bulk stores of full 120-byte dof rows to CUDA-IPC peer buffers over NVLink, issued by the compute kernel, one "
+                       "per rank and span (no NCCL on the data path)"}
         gather_info = {
             "transport": transports[pr.transport], "transport_kind": pr.transport, "multicast_unavailable": pr.transport_error,
-            "unicast_fused_step_ms": uni_ms,
+            "full_row_multicast_step_ms": side_ms.get("multicast"), "full_row_unicast_step_ms": side_ms.get("unicast"),
             "payload": "dof_pos (120 B/frame) of the whole clip on every rank",
-            "nvlink_bytes_sent_per_rank_per_step": sent, "nvlink_bytes_received_per_rank_per_step": (n_total - B) * 120,
+            "nvlink_bytes_sent_per_rank_per_step": sent, "nvlink_bytes_received_per_rank_per_step": pr.nvlink_bytes_received_per_step,
             "nvlink_send_GBps_per_rank": sent / (kern_ms * 1e-3) / 1e9,
             "fused_step_ms": total_ms / args.steps,
             "no_gather_step_ms": plain_total_ms / args.steps,
@@ -613,7 +621,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1 << 20, help="N = 1: frames per step (configs[2]); also the e2e sample per rank")
     ap.add_argument("--total-frames", type=int, default=1 << 24, help="N > 1: frames of the whole clip per step (configs[4])")
-    ap.add_argument("--transport", default="auto", choices=["auto", "multicast", "unicast"], help="N > 1: how the fused reassembly travels")
+    ap.add_argument("--transport", default="auto", choices=["auto", "packed", "multicast", "unicast"], help="N > 1: how the fused reassembly travels")
     ap.add_argument("--force-port", action="store_true", help="--impl reference: time the oracle port even where the reference tree exists")
     ap.add_argument("--cpu-frames", type=int, default=1 << 16, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-frames", type=int, default=1 << 15, help="frames per step of the reference arm")

@@ -35,6 +35,10 @@ _SIGNATURES = {
     "hrt_retarget_body_quat_gather": (C.c_int, [_P, C.c_int64, _P, C.c_uint, C.c_int, C.c_float, C.c_float, _P, C.c_int,
                                                 C.POINTER(_P), C.c_int64, _P]),
     "hrt_peer_barrier": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.c_uint, _P]),
+    "hrt_reassembly_layout": (C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                        C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
+    "hrt_retarget_body_quat_reassemble": (C.c_int, [_P, C.c_int64, _P, C.c_uint, C.c_int, C.c_float, C.c_float, _P, _P, C.c_int64, C.c_int,
+                                                    C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _P, _P, C.c_uint, _P]),
     "hrt_retarget_body_quat_multicast": (C.c_int, [_P, C.c_int64, _P, C.c_uint, C.c_int, C.c_float, C.c_float, _P, _P, C.c_int64, _P]),
     "hrt_configure_pos": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
     "hrt_retarget_full_body_pos": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),

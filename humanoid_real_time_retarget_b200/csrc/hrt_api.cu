@@ -362,6 +362,7 @@ int fill_body_quat_args(hrt_ctx* ctx, int64_t B, const float* src, unsigned flag
     a->peer_frame0 = 0;
     for (int r = 0; r < HRT_MAX_PEERS; ++r) a->peer_dof[r] = nullptr;
     a->mc_dof = nullptr;
+    memset(&a->g, 0, sizeof(a->g));
     return 0;
 }
 
@@ -827,9 +828,9 @@ int hrt_retarget_body_quat_gather(hrt_ctx* ctx, int64_t B, const float* d_src_gq
     BodyQuatArgs a;
     if ((rc = fill_body_quat_args(ctx, B, d_src_gq, flags, ik_iters, damping, rot_weight, nullptr, nullptr, d_link_pos, &a))) return rc;
     if (n_peer < 1 || n_peer > HRT_MAX_PEERS || !d_peer_dof) return fail(HRT_E_INVALID_ARG, "n_peer must be 1..%d", HRT_MAX_PEERS);
+    if (B == 0) return 0;
     if (frame0 < 0 || (frame0 * (ctx->bq.J_rob - 1) * 4) % 16 != 0)
         return fail(HRT_E_ALIGNMENT, "frame0 must keep the dof rows 16-byte aligned (a multiple of 4 frames for 30 DOFs)");
-    if (B == 0) return 0;
     if (!d_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
     if (!aligned16(d_src_gq) || !aligned16(d_link_pos)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
     a.flags &= ~BQ_PACKED_IK;
@@ -848,15 +849,98 @@ int hrt_retarget_body_quat_multicast(hrt_ctx* ctx, int64_t B, const float* d_src
     BodyQuatArgs a;
     if ((rc = fill_body_quat_args(ctx, B, d_src_gq, flags, ik_iters, damping, rot_weight, nullptr, nullptr, d_link_pos, &a))) return rc;
     if (!d_mc_dof || !aligned16(d_mc_dof)) return fail(HRT_E_ALIGNMENT, "multicast address null or not 16-byte aligned");
+    if (B == 0) return 0;
     if (frame0 < 0 || (frame0 * (ctx->bq.J_rob - 1) * 4) % 16 != 0)
         return fail(HRT_E_ALIGNMENT, "frame0 must keep the dof rows 16-byte aligned (a multiple of 4 frames for 30 DOFs)");
-    if (B == 0) return 0;
     if (!d_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
     if (!aligned16(d_src_gq) || !aligned16(d_link_pos)) return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
     a.flags &= ~BQ_PACKED_IK;
     a.peer_frame0 = frame0;
     a.mc_dof = d_mc_dof;
     return launch_body_quat(ctx, a, (cudaStream_t)stream);
+}
+
+int hrt_reassembly_layout(hrt_ctx* ctx, int64_t n_total, int n_rank, const int64_t* shard_frames, size_t* staging_bytes,
+                          size_t* flag_offset, size_t* total_bytes, int* max_rounds) {
+    HRT_ENTER(ctx);
+    if (n_total < 0 || n_rank < 1 || n_rank > HRT_MAX_PEERS || !shard_frames) return fail(HRT_E_INVALID_ARG, "bad shard description");
+    const long long T = (long long)ctx->sm_count * BQ_WARPS_WIDE;
+    long long rounds = 1;
+    for (int r = 0; r < n_rank; ++r) {
+        const long long g = (shard_frames[r] + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
+        rounds = std::max(rounds, (g + T - 1) / T);
+    }
+    if (rounds > BQ_GATHER_MAX_ROUNDS) return fail(HRT_E_INVALID_ARG, "shards of more than %lld frames per rank are not supported by the in-kernel reassembly",
+                                                   (long long)BQ_GATHER_MAX_ROUNDS * T * BQ_FRAMES_PER_WARP);
+    size_t stage = (size_t)std::max<int64_t>(n_total, 1) * BQ_PK * sizeof(float);
+    stage = (stage + 255) / 256 * 256;
+    const size_t flags = (size_t)n_rank * (size_t)rounds * (size_t)ctx->sm_count * sizeof(unsigned);
+    if (staging_bytes) *staging_bytes = stage;
+    if (flag_offset) *flag_offset = stage;
+    if (total_bytes) *total_bytes = stage + (flags + 255) / 256 * 256;
+    if (max_rounds) *max_rounds = (int)rounds;
+    return 0;
+}
+
+int hrt_retarget_body_quat_reassemble(hrt_ctx* ctx, int64_t B, const float* d_src_gq, unsigned flags, int ik_iters, float damping,
+                                      float rot_weight, float* d_link_pos, float* d_full_dof, int64_t n_total, int n_rank, int my_rank,
+                                      const int64_t* shard_lo, const int64_t* shard_frames, void* d_symm, void* d_symm_mc,
+                                      unsigned epoch, void* stream) {
+    HRT_ENTER(ctx);
+    if (n_rank < 1 || n_rank > HRT_MAX_PEERS || my_rank < 0 || my_rank >= n_rank || !shard_lo || !shard_frames)
+        return fail(HRT_E_INVALID_ARG, "bad rank / shard description");
+    if (!d_full_dof || !d_symm || !d_symm_mc) return fail(HRT_E_INVALID_ARG, "null reassembly buffer");
+    if (B != shard_frames[my_rank]) return fail(HRT_E_INVALID_ARG, "B must be this rank's shard length");
+    if (ctx->bq.arm[0].rob_first + 7 > ctx->bq.arm[1].rob_first && ctx->bq.arm[1].rob_first + 7 > ctx->bq.arm[0].rob_first)
+        return fail(HRT_E_INVALID_ARG, "the two arms' hinge ranges overlap");
+    if ((ctx->bq.J_rob - 1) % 2) return fail(HRT_E_INVALID_ARG, "an odd DOF count is not supported by the in-kernel reassembly");
+    BodyQuatArgs a;
+    // B == 0 is a legal shard here: the rank still unpacks what its peers send
+    if ((rc = fill_body_quat_args(ctx, std::max<int64_t>(B, 0), d_src_gq, flags, ik_iters, damping, rot_weight, nullptr,
+                                  d_full_dof + shard_lo[my_rank] * (ctx->bq.J_rob - 1), d_link_pos, &a))) return rc;
+    if (B > 0 && !d_src_gq) return fail(HRT_E_INVALID_ARG, "null input");
+    if (!aligned16(d_src_gq) || !aligned16(d_link_pos) || !aligned16(d_full_dof) || !aligned16(d_symm) || !aligned16(d_symm_mc))
+        return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
+    a.flags &= ~BQ_PACKED_IK;
+    size_t flag_off = 0;
+    int max_rounds = 0;
+    if ((rc = hrt_reassembly_layout(ctx, n_total, n_rank, shard_frames, nullptr, &flag_off, nullptr, &max_rounds))) return rc;
+    int64_t covered = 0;
+    for (int r = 0; r < n_rank; ++r) {
+        if ((shard_frames[r] > 0 && shard_lo[r] % BQ_FRAMES_PER_WARP) || shard_lo[r] != covered || shard_frames[r] < 0)
+            return fail(HRT_E_INVALID_ARG, "shards must tile the clip in rank order and start at multiples of %d frames", BQ_FRAMES_PER_WARP);
+        covered += shard_frames[r];
+        a.g.lo[r] = shard_lo[r];
+        a.g.n[r] = shard_frames[r];
+    }
+    if (covered != n_total) return fail(HRT_E_INVALID_ARG, "shards do not add up to the clip");
+    a.g.mc_pk = (float*)d_symm_mc;
+    a.g.pk = (const float*)d_symm;
+    a.g.mc_flags = (unsigned*)((char*)d_symm_mc + flag_off);
+    a.g.flags = (const unsigned*)((const char*)d_symm + flag_off);
+    a.g.full = d_full_dof;
+    a.g.n_rank = n_rank;
+    a.g.me = my_rank;
+    a.g.max_rounds = max_rounds;
+    a.g.epoch = epoch;
+    a.g.timeout_ns = 20ull * 1000 * 1000 * 1000;
+    {
+        static const unsigned dbg = [] { const char* e = getenv("HRT_GATHER_DEBUG"); return e ? (unsigned)atoi(e) : 0u; }();
+        a.g.debug = dbg;
+    }
+    // every rank launches the same geometry (one CTA per SM, 16 warps): a flag is indexed by (rank, round, CTA)
+    const size_t smem = ((size_t)BQ_CONST_WORDS + (size_t)BQ_WARPS_WIDE * bq_tile_words(ctx->bq.J_src, ctx->bq.J_rob, false) +
+                         (size_t)bq_gather_words(BQ_WARPS_WIDE)) * sizeof(float);
+    auto kern = body_quat_kernel<BQ_WARPS_WIDE, true, true>;
+    static size_t attr_done[16] = {0};
+    const int d = ctx->device & 15;
+    if (attr_done[d] < smem) {
+        HRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[d] = smem;
+    }
+    kern<<<ctx->sm_count, BQ_WARPS_WIDE * 32, smem, (cudaStream_t)stream>>>(ctx->bq, a);
+    HRT_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int hrt_peer_barrier(hrt_ctx* ctx, int n_peer, int my_rank, unsigned* const* d_peer_flags, unsigned epoch, void* stream) {

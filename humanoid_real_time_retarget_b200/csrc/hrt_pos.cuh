@@ -87,13 +87,17 @@ struct PosArgs {
 // ---------------------------------------------------------------------------------------------
 HRT_DEV vec3 scale3_x(const vec3 v, float s) { return make_vec3(mul_rn(v.x, s), mul_rn(v.y, s), mul_rn(v.z, s)); }
 HRT_DEV vec3 sub3_x(const vec3 a, const vec3 b) { return make_vec3(sub_rn(a.x, b.x), sub_rn(a.y, b.y), sub_rn(a.z, b.z)); }
-HRT_DEV vec3 div3_x(const vec3 v, float s) { return make_vec3(div_rn(v.x, s), div_rn(v.y, s), div_rn(v.z, s)); }
+// three numerators, one denominator: one refined reciprocal, then the exactly rounded quotient of each (hrt_math.cuh)
+HRT_DEV vec3 div3_x(const vec3 v, float s) {
+    const float y = rcp_refined(s);
+    return make_vec3(div_by_rn(v.x, s, y), div_by_rn(v.y, s, y), div_by_rn(v.z, s, y));
+}
 HRT_DEV float sign_f(float x) { return (float)((x > 0.f) - (x < 0.f)); }
 
 // transform3d.py:62-75   v - (dot(v,n) / ||n||^2) * n
 HRT_DEV vec3 proj_in_plane_x(const vec3 v, const vec3 n) {
     const float nn = norm3_x(n);
-    const float d = div_rn(dot3_x(v, n), mul_rn(nn, nn));
+    const float d = divn_rn(dot3_x(v, n), mul_rn(nn, nn));
     return sub3_x(v, scale3_x(n, d));
 }
 
@@ -124,10 +128,11 @@ HRT_DEV void bone_angles_x(const vec3 v, float* theta, float* phi) {
 // rotation3d.py:147-193 in the reference's order, including the four sequential masked fix-ups
 HRT_DEV float4 quat_from_rotation_matrix_x(const float m[3][3]) {
     const float d0 = m[0][0], d1 = m[1][1], d2 = m[2][2];
-    float w = sqrt_rn(fmaxf(div_rn(add_rn(add_rn(add_rn(d0, d1), d2), 1.f), 4.f), 0.f));
-    float x = sqrt_rn(fmaxf(div_rn(add_rn(sub_rn(sub_rn(d0, d1), d2), 1.f), 4.f), 0.f));
-    float y = sqrt_rn(fmaxf(div_rn(add_rn(sub_rn(add_rn(-d0, d1), d2), 1.f), 4.f), 0.f));
-    float z = sqrt_rn(fmaxf(div_rn(add_rn(add_rn(sub_rn(-d0, d1), d2), 1.f), 4.f), 0.f));
+    // x / 4 is x * 0.25 bit for bit (a power of two)
+    float w = sqrtn_rn(fmaxf(mul_rn(add_rn(add_rn(add_rn(d0, d1), d2), 1.f), 0.25f), 0.f));
+    float x = sqrtn_rn(fmaxf(mul_rn(add_rn(sub_rn(sub_rn(d0, d1), d2), 1.f), 0.25f), 0.f));
+    float y = sqrtn_rn(fmaxf(mul_rn(add_rn(sub_rn(add_rn(-d0, d1), d2), 1.f), 0.25f), 0.f));
+    float z = sqrtn_rn(fmaxf(mul_rn(add_rn(add_rn(sub_rn(-d0, d1), d2), 1.f), 0.25f), 0.f));
     if ((w >= x) && (w >= y) && (w >= z)) {
         x = mul_rn(x, sign_f(sub_rn(m[2][1], m[1][2])));
         y = mul_rn(y, sign_f(sub_rn(m[0][2], m[2][0])));
@@ -154,18 +159,25 @@ HRT_DEV float4 quat_from_rotation_matrix_x(const float m[3][3]) {
 // ---------------------------------------------------------------------------------------------
 // Kabsch (transform3d.py:32-50): A = M^T Z (3x3), R = U diag(1,1,det) V^T.  fp64.
 // ---------------------------------------------------------------------------------------------
-// One Jacobi rotation annihilating a_pq, branch-free so that independent problems interleave:
-// tau = (a_qq - a_pp)/2, r = sqrt(tau^2 + a_pq^2), t = a_pq / (tau + copysign(r, tau)), c = rsqrt(1 + t^2), s = t c
+// One Jacobi rotation annihilating a_pq (the inner rotation, |theta| <= pi/4), branch-free and without a division or a
+// square root, so that independent problems interleave and nothing leaves the fp64 FMA pipe but two MUFU seeds:
+//   tau = (a_qq - a_pp)/2,  r = hypot(tau, a_pq),  cos 2theta = |tau| / r,  sin 2theta = sign(tau) a_pq / r,
+//   c = sqrt(h), h = (1 + cos 2theta)/2 in [1/2, 1],  s = sin 2theta / (2c),  t a_pq = sign(tau) (r - |tau|)
+// (the last identity replaces t = s/c: the diagonal moves by exactly the amount that keeps the trace).
 HRT_DEV void jacobi_rot(double& app, double& aqq, double& apq, double& arp, double& arq,
                         double& v0p, double& v0q, double& v1p, double& v1q, double& v2p, double& v2q) {
     const double tau = 0.5 * (aqq - app);
-    const double r = sqrt(fma(tau, tau, apq * apq));
-    const double den = tau + copysign(r, tau);
-    const double t = (fabs(apq) > 1e-300) ? apq / den : 0.0;
-    const double c = rsqrt(fma(t, t, 1.0));
-    const double s = t * c;
-    const double app_n = fma(-t, apq, app), aqq_n = fma(t, apq, aqq);
-    app = app_n; aqq = aqq_n; apq = 0.0;
+    const double at = fabs(tau);
+    const double x = fma(tau, tau, apq * apq);
+    const bool live = x > 1e-290;                       // a_pq = 0 and a_pp = a_qq: nothing to rotate
+    const double ri = drsqrt_n(live ? x : 1.0);
+    const double r = x * ri;
+    const double h = live ? fma(at * ri, 0.5, 0.5) : 1.0;
+    const double ci = drsqrt_n(h);
+    const double c = h * ci;
+    const double s = (apq * ri) * (ci * copysign(0.5, tau));
+    const double d = copysign(r - at, tau);
+    app -= d; aqq += d; apq = 0.0;
     const double rp = c * arp - s * arq, rq = s * arp + c * arq;
     arp = rp; arq = rq;
     double a, b;
@@ -230,11 +242,11 @@ HRT_DEV void kabsch_multi(const double (*A)[3][3], float4* out) {
             ua[i] = A[n][i][0] * va[0] + A[n][i][1] * va[1] + A[n][i][2] * va[2];
             ub[i] = A[n][i][0] * vb[0] + A[n][i][1] * vb[1] + A[n][i][2] * vb[2];
         }
-        const double na = rsqrt(ua[0] * ua[0] + ua[1] * ua[1] + ua[2] * ua[2]);
+        const double na = drsqrt_n(ua[0] * ua[0] + ua[1] * ua[1] + ua[2] * ua[2]);
         ua[0] *= na; ua[1] *= na; ua[2] *= na;
         const double d = ua[0] * ub[0] + ua[1] * ub[1] + ua[2] * ub[2];
         ub[0] -= d * ua[0]; ub[1] -= d * ua[1]; ub[2] -= d * ua[2];
-        const double nb = rsqrt(ub[0] * ub[0] + ub[1] * ub[1] + ub[2] * ub[2]);
+        const double nb = drsqrt_n(ub[0] * ub[0] + ub[1] * ub[1] + ub[2] * ub[2]);
         ub[0] *= nb; ub[1] *= nb; ub[2] *= nb;
         const double uc[3] = {ua[1] * ub[2] - ua[2] * ub[1], ua[2] * ub[0] - ua[0] * ub[2], ua[0] * ub[1] - ua[1] * ub[0]};
         const double vc[3] = {va[1] * vb[2] - va[2] * vb[1], va[2] * vb[0] - va[0] * vb[2], va[0] * vb[1] - va[1] * vb[0]};
@@ -512,9 +524,9 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
                 const float dxn = sub_rn(xn, x0);
                 sum = (n == 0) ? dxn : add_rn(sum, dxn);
             }
-            const float ratio = div_rn(div_rn(sum, 5.f), pp.orig_x);
+            const float ratio = divn_rn(divn_rn(sum, 5.f), pp.orig_x);
             if (MODE == POS_FULL_BODY_POS && pp.precise_gripper) {
-                const float s = div_rn(fminf(fmaxf(sub_rn(ratio, 0.5f), 0.f), 0.5f), 0.5f);
+                const float s = mul_rn(fminf(fmaxf(sub_rn(ratio, 0.5f), 0.f), 0.5f), 2.f);      // x / 0.5 == x * 2 exactly
                 th[7] = mul_rn(s, 0.044f);
                 th[8] = mul_rn(s, -0.044f);
             } else {

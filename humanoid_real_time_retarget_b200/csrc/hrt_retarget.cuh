@@ -109,7 +109,40 @@ struct BodyQuatArgs {
     // the same with ONE store per span: mc_dof is the NVSwitch multicast address of the ranks' clip-wide buffers
     // (multimem.st: the switch replicates the store into every rank's copy, this rank's included)
     float* mc_dof;
+    // reassembly INSIDE the kernel with a packed wire format (GATHER instantiation): only the 14 arm
+    // hinge angles of a frame travel (the other DOFs of this solver are structurally 0); every warp publishes its packed
+    // span through the multicast address of the ranks' staging buffers, the last warp of a CTA round raises that round's
+    // flag on every rank, and the same warps unpack the peers' earlier rounds into this rank's clip-wide dof buffer while
+    // they wait for nothing: the transfer and the unpacking hide under the issue-bound solve.
+    struct Gather {
+        float* mc_pk;                     // multicast address of the staging buffers: (n_total, 14) packed rows
+        const float* pk;                  // this rank's copy of it
+        unsigned* mc_flags;               // multicast address of the flag arrays [rank][max_rounds][n_ctas]
+        const unsigned* flags;            // this rank's copy
+        float* full;                      // this rank's clip-wide dof buffer (n_total, D); own rows are written directly
+        long long lo[HRT_MAX_PEERS];      // first clip frame of every rank's shard (multiples of 16)
+        long long n[HRT_MAX_PEERS];       // frames of every rank's shard
+        int n_rank, me, max_rounds;
+        unsigned epoch;                   // grows by one per step
+        unsigned long long timeout_ns;    // a lost peer traps instead of hanging the box
+        unsigned debug;                   // diagnostics (env HRT_GATHER_DEBUG): 1 no data stores, 2 no unpack stores, 4 no unpack loads, 8 no flag release, 16 no counters / flags / drain
+    } g;
 };
+constexpr int BQ_PK = 14;                                                  // packed floats per frame: 2 arms x 7 hinges
+constexpr int BQ_PK_WORDS = BQ_FRAMES_PER_WARP * BQ_PK;                    // 224 per 16-frame group
+constexpr int BQ_PK_SLOT = BQ_PK_WORDS + 4;                                // + one 16-byte block of zeros (word BQ_PK_WORDS)
+constexpr int BQ_GATHER_DED_SLOTS = HRT_MAX_PEERS - 3;                     // dedicated slots per warp; two more live in the dof image
+// one flag per CTA and block of this many rounds: the release (MEMBAR.SYS) that orders a block's stores before its flag
+// stalls the warp that issues it for ~13 us (measured), and that warp is the last of its round, i.e. on the critical path
+constexpr int BQ_GATHER_FLAG_ROUNDS = 8;
+constexpr int BQ_GATHER_MAX_ROUNDS = 2048;
+constexpr int BQ_GATHER_MAX_BLOCKS = BQ_GATHER_MAX_ROUNDS / BQ_GATHER_FLAG_ROUNDS;
+constexpr int BQ_GATHER_TBL = 256;                                         // float2 number of a dof image -> its two source words
+// shared-memory block behind the tiles: [warps x dedicated slots] [expansion table] [block counters] [warps x 4 state words]
+HRT_HD inline int bq_gather_tbl_word(int warps) { return warps * BQ_GATHER_DED_SLOTS * BQ_PK_SLOT; }
+HRT_HD inline int bq_gather_cnt_word(int warps) { return bq_gather_tbl_word(warps) + BQ_GATHER_TBL; }
+HRT_HD inline int bq_gather_state_word(int warps) { return bq_gather_cnt_word(warps) + BQ_GATHER_MAX_BLOCKS; }
+HRT_HD inline int bq_gather_words(int warps) { return bq_gather_state_word(warps) + warps * 4; }
 
 // the arm's hinge axes (Hu_DOF_AXIS[11..17] == Hu_DOF_AXIS[20..26]); checked on the host
 #define HRT_ARM_AXIS(c) ((c) == 0 ? 1 : (c) == 1 ? 0 : (c) == 2 ? 2 : (c) == 3 ? 1 : (c) == 4 ? 0 : (c) == 5 ? 1 : 2)
@@ -284,7 +317,170 @@ HRT_DEV void bq_align(int warp) {
 }
 
 // all frame groups of `a` that fall to CTA `cta` of `n_ctas`
-template <int BQ_WARPS_PER_CTA, bool SYSMEM, bool WITH_IK = true>
+HRT_DEV unsigned long long bq_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+    return t;
+}
+// flag poll: a strong system-scope load WITHOUT the acquire's L1 invalidation (ld.acquire.sys = LDG.STRONG.SYS + CCTL.IVALL,
+// and every warp polls every round).  The data the flag guards is then read at L2 (ld.global.cg), where peer writes
+// land, by loads that are issued after the flag value has been consumed by a branch.
+HRT_DEV unsigned ld_relaxed_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// In-kernel reassembly (GATHER instantiation of body_quat_kernel).  Per 16-frame round a warp
+//   * at the top: if a round of the peers has landed that it has not unpacked yet, cp.async's its group of that round
+//     of EVERY peer (packed staging rows, 896 B each) into shared-memory slots -- same async group as its own input
+//     rows, so one wait covers both and no register is held -- then expands each slot into full dof rows of the
+//     clip-wide buffer (table-driven: 2 LDS + 1 STG.64 per float2);
+//   * at the end: writes its 14 hinge angles per frame to every rank through the multicast address, and once per flag
+//     block the last warp of the CTA raises the block's flag on every rank (release at system scope).
+// State (cursor, ready, peer_rounds) lives in shared memory: the solve in between uses every register.
+// ---------------------------------------------------------------------------------------------
+HRT_DEV void gather_setup(const BodyQuatArgs::Gather& g, float* gbase, int warps, int n_ctas, int D, int col_a, int col_b) {
+    unsigned* tbl = reinterpret_cast<unsigned*>(gbase + bq_gather_tbl_word(warps));
+    unsigned* blk_cnt = reinterpret_cast<unsigned*>(gbase + bq_gather_cnt_word(warps));
+    int* state = reinterpret_cast<int*>(gbase + bq_gather_state_word(warps));
+    for (int i = threadIdx.x; i < BQ_GATHER_MAX_BLOCKS; i += blockDim.x) blk_cnt[i] = 0u;
+    // float2 number i of a 16-frame dof image (D/2 per row): the slot words its two floats come from
+    // (BQ_PK_WORDS = the block of zeros, for the DOFs that do not travel)
+    const int half = D >> 1;
+    for (int i = threadIdx.x; i < BQ_GATHER_TBL; i += blockDim.x) {
+        const int row = i / half, c2 = (i - row * half) * 2;
+        unsigned w[2];
+        for (int e = 0; e < 2; ++e) {
+            const int c = c2 + e;
+            const int da = c - col_a, db = c - col_b;
+            const int slot = ((unsigned)da < 7u) ? da : ((unsigned)db < 7u) ? 7 + db : -1;
+            w[e] = (slot >= 0 && row < BQ_FRAMES_PER_WARP) ? (unsigned)(row * BQ_PK + slot) : (unsigned)BQ_PK_WORDS;
+        }
+        tbl[i] = w[0] | (w[1] << 16);
+    }
+    if (threadIdx.x < warps) {
+        const long long T = (long long)n_ctas * warps;
+        int peer_rounds = 0;
+        for (int p = 0; p < g.n_rank; ++p) {
+            if (p == g.me) continue;
+            const long long gp = (g.n[p] + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
+            peer_rounds = max(peer_rounds, (int)((gp + T - 1) / T));
+        }
+        state[threadIdx.x * 4 + 0] = 0;                 // cursor: next peer round this warp unpacks
+        state[threadIdx.x * 4 + 1] = 0;                 // ready: peer rounds known to have landed
+        state[threadIdx.x * 4 + 2] = peer_rounds;
+    }
+    __syncthreads();
+}
+
+// slot q of a warp: the first two share the (idle at that point) dof image, the others are dedicated
+HRT_DEV float* gather_slot(float* dof_t, float* ded, int q) { return q < 2 ? dof_t + q * BQ_PK_SLOT : ded + (q - 2) * BQ_PK_SLOT; }
+
+// Top of a round, before the input rows' cp.async group is committed.  Returns the peer round whose groups were put in
+// flight (to be expanded after the wait), or -1.  `my_round`: rounds this warp has finished -- the peers run at the same
+// pace, so the flag block after `ready` is polled only once it is due; `drain`: poll unconditionally.
+HRT_DEV int gather_fetch(const BodyQuatArgs::Gather& g, float* gbase, float* dof_t, int warps, int n_ctas, int cta, int warp, int lane,
+                         int my_round, bool drain) {
+    volatile int* state = reinterpret_cast<volatile int*>(gbase + bq_gather_state_word(warps)) + warp * 4;
+    const int cursor = state[0], peer_rounds = state[2];
+    int ready = state[1];
+    const long long T = (long long)n_ctas * warps;
+    if (cursor >= ready && cursor < peer_rounds && (drain || my_round >= ready + BQ_GATHER_FLAG_ROUNDS)) {
+        // have all peers raised this CTA's flag of the block that holds round `cursor`?  (lane p looks at rank p)
+        bool ok = true;
+        if (lane < g.n_rank && lane != g.me) {
+            const long long gp = (g.n[lane] + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
+            if (cursor < (int)((gp + T - 1) / T)) {
+                const unsigned v = ld_relaxed_sys_u32(g.flags + ((size_t)lane * g.max_rounds + cursor / BQ_GATHER_FLAG_ROUNDS) * n_ctas + cta);
+                ok = (int)(v - g.epoch) >= 0;
+            }
+        }
+        if (__all_sync(0xffffffffu, ok)) {
+            ready = min(ready + BQ_GATHER_FLAG_ROUNDS, peer_rounds);
+            if (lane == 0) state[1] = ready;
+        }
+    }
+    if (cursor >= ready) return -1;
+    float* ded = gbase + warp * BQ_GATHER_DED_SLOTS * BQ_PK_SLOT;
+    const long long fp = ((long long)cursor * T + (long long)cta * warps + warp) * BQ_FRAMES_PER_WARP;
+    for (int q = 0; q < g.n_rank - 1; ++q) {
+        const int p = q + (q >= g.me ? 1 : 0);
+        const long long np = g.n[p];
+        if (fp >= np) continue;
+        const int cnt = (int)min((long long)BQ_FRAMES_PER_WARP, np - fp);
+        const int n4 = (cnt * BQ_PK + 3) >> 2;              // a ragged tail reads up to 8 bytes past its rows: inside the buffer
+        const float* src = g.pk + (g.lo[p] + fp) * BQ_PK;
+        float* slot = gather_slot(dof_t, ded, q);
+        if (!(g.debug & 4u))
+            for (int i = lane; i < n4; i += 32) cp_async16(slot + i * 4, src + i * 4);
+        if (lane < 4) slot[BQ_PK_WORDS + lane] = 0.f;
+    }
+    return cursor;
+}
+
+// after the wait: expand the slots of peer round `j` into full dof rows
+HRT_DEV void gather_expand(const BodyQuatArgs::Gather& g, float* gbase, float* dof_t, int warps, int n_ctas, int cta, int warp, int lane,
+                           int D, int j) {
+    float* ded = gbase + warp * BQ_GATHER_DED_SLOTS * BQ_PK_SLOT;
+    const unsigned* tbl = reinterpret_cast<const unsigned*>(gbase + bq_gather_tbl_word(warps));
+    const long long T = (long long)n_ctas * warps;
+    const long long fp = ((long long)j * T + (long long)cta * warps + warp) * BQ_FRAMES_PER_WARP;
+    unsigned w[BQ_GATHER_TBL / 32];
+#pragma unroll
+    for (int t = 0; t < BQ_GATHER_TBL / 32; ++t) w[t] = tbl[lane + 32 * t];
+    const int half = D >> 1;
+    for (int q = 0; q < g.n_rank - 1; ++q) {
+        const int p = q + (q >= g.me ? 1 : 0);
+        const long long np = g.n[p];
+        if (fp >= np) continue;
+        const int n2 = (int)min((long long)BQ_FRAMES_PER_WARP, np - fp) * half;
+        const float* slot = gather_slot(dof_t, ded, q);
+        float2* dst = reinterpret_cast<float2*>(g.full + (g.lo[p] + fp) * D) + lane;
+        if (!(g.debug & 2u)) {
+#pragma unroll
+            for (int t = 0; t < BQ_GATHER_TBL / 32; ++t)
+                if (lane + 32 * t < n2) __stcs(dst + 32 * t, make_float2(slot[w[t] & 0xffffu], slot[w[t] >> 16]));
+        }
+    }
+    if (lane == 0) {
+        volatile int* state = reinterpret_cast<volatile int*>(gbase + bq_gather_state_word(warps)) + warp * 4;
+        state[0] = j + 1;
+    }
+    __syncwarp();
+}
+
+// End of a round: the warp's packed hinge angles (lane = (frame, arm): 7 angles) go to every rank through the multicast
+// address; once per flag block the warp is counted in and the CTA's last warp raises the block's flag on every rank.
+HRT_DEV void gather_publish(const BodyQuatArgs::Gather& g, float* gbase, int warps, int n_ctas, int cta, int warp, int lane,
+                            const float th[7], int nfr, long long f0, int rnd, int rounds) {
+    const int fl = lane >> 1, side = lane & 1;
+    float* pk_t = gbase + warp * BQ_GATHER_DED_SLOTS * BQ_PK_SLOT;          // dedicated slot 0 is idle between the top-of-round unpacks
+    if (fl < nfr) {
+        float* r = pk_t + fl * BQ_PK + side * 7;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) r[c] = th[c];
+    }
+    __syncwarp();
+    if (nfr > 0 && !(g.debug & 1u)) warp_multimem_store_span(g.mc_pk + (g.lo[g.me] + f0) * BQ_PK, pk_t, nfr * BQ_PK, lane);
+    __syncwarp();
+    // Every warp has finished all rounds of the block when it is counted in (program order), and the release orders
+    // everything the CTA has stored so far (observed through the counter) before the flag.
+    if (lane == 0 && ((rnd + 1) % BQ_GATHER_FLAG_ROUNDS == 0 || rnd + 1 == rounds) && !(g.debug & 16u)) {
+        unsigned* blk_cnt = reinterpret_cast<unsigned*>(gbase + bq_gather_cnt_word(warps));
+        const int blk = rnd / BQ_GATHER_FLAG_ROUNDS;
+        __threadfence_block();
+        const unsigned old = atomicAdd(&blk_cnt[blk], 1u);
+        if (old == (unsigned)warps - 1u) {
+            unsigned* f = g.mc_flags + ((size_t)g.me * g.max_rounds + blk) * n_ctas + cta;
+            if (g.debug & 8u) asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;\n" ::"l"(f), "r"(g.epoch) : "memory");
+            else asm volatile("multimem.st.release.sys.global.u32 [%0], %1;\n" ::"l"(f), "r"(g.epoch) : "memory");
+        }
+    }
+}
+
+template <int BQ_WARPS_PER_CTA, bool SYSMEM, bool WITH_IK = true, bool GATHER = false>
 HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* smem, int n_ctas, int cta) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -303,6 +499,11 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
     const bool do_clamp = (a.flags & (BQ_CLAMP | BQ_IK)) != 0;
     const bool do_ik = (a.flags & BQ_IK) != 0;
     const vec3 p_sh = make_vec3(bp.shoulder_p[side][0], bp.shoulder_p[side][1], bp.shoulder_p[side][2]);
+
+    // in-kernel reassembly (GATHER instantiation): out-of-line helpers with their state in shared memory, so that the
+    // solve keeps its register allocation
+    float* gbase = smem + BQ_CONST_WORDS + BQ_WARPS_PER_CTA * bq_tile_words(bp.J_src, bp.J_rob, with_lq);
+    if (GATHER) gather_setup(a.g, gbase, BQ_WARPS_PER_CTA, n_ctas, bp.J_rob - 1, bp.arm[0].rob_first - 1, bp.arm[1].rob_first - 1);
 
     // every warp of the CTA runs the same number of rounds (the named barriers below need that);
     // a warp without a group in the last round shadows the last group and publishes nothing
@@ -335,12 +536,20 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
         } else {
             warp_span_g2s(tile, a.src_gq + f0 * JS * 4, nld * JS * 4, lane);
         }
+        // in-kernel reassembly: a landed round of every peer is fetched together with this round's input rows
+        int g_round = -1;
+        if (GATHER) g_round = gather_fetch(a.g, gbase, dof_t, BQ_WARPS_PER_CTA, n_ctas, cta, warp, lane, (int)rnd, false);
         cp_async_commit();
         // while the copy is in flight: pre-fill the output images with their constant parts
         const bool want_dof = a.out_dof != nullptr || a.n_peer > 0 || a.mc_dof != nullptr;
-        if (want_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
+        if (!GATHER && want_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
         cp_async_wait<0>();
         __syncwarp();
+        if (GATHER) {
+            if (g_round >= 0) gather_expand(a.g, gbase, dof_t, BQ_WARPS_PER_CTA, n_ctas, cta, warp, lane, D, g_round);
+            if (want_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;     // the dof image doubled as two slots
+            __syncwarp();
+        }
         const float* row = tile + fr * JS * 4;
         float4 zT = *reinterpret_cast<const float4*>(row + ap.src_torso * 4);
         float4 zS = *reinterpret_cast<const float4*>(row + ap.src_shoulder * 4);
@@ -486,17 +695,35 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
             if (a.mc_dof) warp_multimem_store_span(a.mc_dof + (a.peer_frame0 + f0) * D, dof_t, nfr * D, lane);
             __syncwarp();
         }
+        if (GATHER) {
+            // ---- 9. publish the group's packed hinge angles to every rank and count the round ----------------------------
+            gather_publish(a.g, gbase, BQ_WARPS_PER_CTA, n_ctas, cta, warp, lane, th, nfr, f0, (int)rnd, (int)rounds);
+        }
     }
     if (pending_store && lane == 0) bulk_wait_read_all();
+    if (GATHER) {
+        // drain: the peers' remaining rounds (at least their last flag block)
+        const unsigned long long t0 = bq_timer_ns();
+        for (bool done = (a.g.debug & 16u) != 0; !done;) {
+            const int j = gather_fetch(a.g, gbase, dof_t, BQ_WARPS_PER_CTA, n_ctas, cta, warp, lane, 0x7fffffff, true);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncwarp();
+            if (j >= 0) gather_expand(a.g, gbase, dof_t, BQ_WARPS_PER_CTA, n_ctas, cta, warp, lane, bp.J_rob - 1, j);
+            volatile int* state = reinterpret_cast<volatile int*>(gbase + bq_gather_state_word(BQ_WARPS_PER_CTA)) + warp * 4;
+            done = state[0] >= state[2];
+            if (!done && bq_timer_ns() - t0 > a.g.timeout_ns) __trap();     // a lost peer must not hang the box
+        }
+    }
 }
 
 
-template <int BQ_WARPS_PER_CTA, bool WITH_IK = true>
+template <int BQ_WARPS_PER_CTA, bool WITH_IK = true, bool GATHER = false>
 __global__ void __launch_bounds__(BQ_WARPS_PER_CTA * 32, 1)
 body_quat_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a) {
     extern __shared__ __align__(16) float smem[];
     bq_setup(bp, smem);
-    bq_process<BQ_WARPS_PER_CTA, false, WITH_IK>(bp, a, smem, (int)gridDim.x, (int)blockIdx.x);
+    bq_process<BQ_WARPS_PER_CTA, false, WITH_IK, GATHER>(bp, a, smem, (int)gridDim.x, (int)blockIdx.x);
 }
 
 // Resident single-frame server of the quaternion path (same protocol as pos_stream_server_kernel in hrt_pos.cuh:
@@ -507,11 +734,6 @@ HRT_DEV unsigned bq_ld_sys(const unsigned* p) {
     return v;
 }
 HRT_DEV void bq_st_sys(unsigned* p, unsigned v) { asm volatile("st.volatile.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
-HRT_DEV unsigned long long bq_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
-    return t;
-}
 
 __global__ void __launch_bounds__(32, 1)
 bq_stream_server_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a, unsigned* ctrl, unsigned served,

@@ -253,6 +253,28 @@ class Engine:
         _lib.check(self.lib.hrt_retarget_body_quat_multicast(self._h, B, _ptr(src_gq), flags, ik_iters, damping, rot_weight, _ptr(link_pos),
                                                              C.c_void_p(int(mc_dof_ptr)), int(frame0), self._stream()))
 
+    def reassembly_layout(self, n_total, shard_frames):
+        """Bytes of the symmetric allocation the in-kernel reassembly needs per rank: (staging, flag offset, total, max rounds)."""
+        arr = (C.c_int64 * len(shard_frames))(*[int(x) for x in shard_frames])
+        st, fo, tot, mr = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_int()
+        _lib.check(self.lib.hrt_reassembly_layout(self._h, int(n_total), len(shard_frames), arr, C.byref(st), C.byref(fo), C.byref(tot), C.byref(mr)))
+        return st.value, fo.value, tot.value, mr.value
+
+    def retarget_body_quat_reassemble(self, src_gq, full_dof, n_total, my_rank, shard_lo, shard_frames, symm_ptr, symm_mc_ptr, epoch,
+                                      flags=0, ik_iters=10, damping=0.1, rot_weight=0.2, link_pos=None):
+        """The fused quaternion path on this rank's shard with the reassembly of dof_pos INSIDE the kernel: packed hinge angles
+        go out through the multicast address `symm_mc_ptr`, the peers' packed rows that have landed in `symm_ptr` are unpacked
+        into `full_dof` (n_total, D) between this rank's own rounds."""
+        JS, JR = self._bq
+        B = int(shard_frames[my_rank])
+        src = _f32c(src_gq, self.device) if B else None
+        lo = (C.c_int64 * len(shard_lo))(*[int(x) for x in shard_lo])
+        nn = (C.c_int64 * len(shard_frames))(*[int(x) for x in shard_frames])
+        _lib.check(self.lib.hrt_retarget_body_quat_reassemble(self._h, B, _ptr(src), flags, ik_iters, damping, rot_weight, _ptr(link_pos),
+                                                              _ptr(full_dof), int(n_total), len(shard_frames), int(my_rank), lo, nn,
+                                                              C.c_void_p(int(symm_ptr)), C.c_void_p(int(symm_mc_ptr)),
+                                                              int(epoch) & 0xFFFFFFFF, self._stream()))
+
     def peer_barrier(self, peer_flag_ptrs, my_rank, epoch):
         arr = (C.c_void_p * len(peer_flag_ptrs))(*peer_flag_ptrs)
         _lib.check(self.lib.hrt_peer_barrier(self._h, len(peer_flag_ptrs), int(my_rank), arr, int(epoch) & 0xFFFFFFFF, self._stream()))

@@ -64,11 +64,14 @@ class PeerReassembly:
     step(engine-resident input shard) -> the clip-wide (n_frames, D) tensor of THIS rank (valid once the current stream has
     passed the step's barrier kernel).  close() must be called on every rank (it is a collective).
 
-    transport="multicast": the clip-wide buffers are one torch symmetric-memory allocation (torch.distributed plumbing:
-    cuMemCreate + handle exchange + an NVSwitch multicast object over all ranks' copies); every warp publishes its dof span
-    once with multimem.st and the switch replicates it -- a rank sends 1/N of the bytes of the unicast form.
+    transport="packed": the form the 8-GPU figure runs.  One torch symmetric-memory allocation per rank (torch.distributed
+    plumbing: cuMemCreate + handle exchange + an NVSwitch multicast object over all ranks' copies) holds packed staging rows
+    (the 14 arm hinge angles of a frame, 56 B instead of 120: every other DOF of this solver is structurally 0) and flags;
+    the compute kernel publishes each 16-frame span once with multimem.st, raises a flag per CTA round, and unpacks the
+    peers' rounds that have landed into this rank's clip-wide buffer between its own rounds (hrt_retarget_body_quat_reassemble).
+    transport="multicast": full 120-byte dof rows through the multicast address, no unpacking (ingress-bound at 8 GPUs).
     transport="unicast": plain cudaMalloc buffers exchanged as CUDA IPC handles; every warp sends its span to each rank
-    with one TMA bulk store per rank.  transport="auto" takes multicast when the box offers it (NVLS), else unicast."""
+    with one TMA bulk store per rank.  transport="auto" = packed when the box offers multicast (NVLS), else unicast."""
 
     def __init__(self, engine, n_frames, dof=30, group=None, transport="auto"):
         self.eng, self.group, self.n, self.D = engine, group, int(n_frames), int(dof)
@@ -76,19 +79,22 @@ class PeerReassembly:
         self.rank = dist.get_rank(group)
         if self.world > 8:
             raise ValueError("peer reassembly serves the GPUs of one box (<= 8 ranks)")
-        if transport not in ("auto", "multicast", "unicast"):
+        if transport not in ("auto", "packed", "multicast", "unicast"):
             raise ValueError(f"unknown transport {transport!r}")
         self.lo, self.hi = shard_range(self.n, self.rank, self.world)
-        if self.lo % 4:
+        if self.hi > self.lo and self.lo % 4:
             raise ValueError("shard boundaries must keep dof rows 16-byte aligned")
         self._buf = self._symm = None
         self.mc_ptr = 0
         self.transport_error = None
-        if transport in ("auto", "multicast") and self.world > 1 and torch.device(engine.device).type == "cuda":
-            self._try_multicast(require=(transport == "multicast"))
+        self.packed = False
+        self.shard_lo = [shard_range(self.n, r, self.world)[0] for r in range(self.world)]
+        self.shard_n = [shard_range(self.n, r, self.world)[1] - shard_range(self.n, r, self.world)[0] for r in range(self.world)]
+        if transport in ("auto", "packed", "multicast") and self.world > 1 and torch.device(engine.device).type == "cuda":
+            self._try_multicast(require=(transport in ("multicast", "packed")), packed=(transport in ("auto", "packed")))
         self._flags, h_flags = engine.peer_alloc(64)
         if self.mc_ptr:
-            self.transport = "multicast"
+            self.transport = "packed" if self.packed else "multicast"
             h_buf = None
         else:
             self.transport = "unicast"
@@ -105,14 +111,18 @@ class PeerReassembly:
             self.dof = torch.as_tensor(_DevView(self._buf, (self.n, self.D)), device=engine.device)
         dist.barrier(group=group)                          # every rank has mapped every buffer before the first store
 
-    def _try_multicast(self, require):
-        """One symmetric allocation of the clip-wide buffer with a multicast mapping; the decision is taken collectively
-        (a rank that cannot map it makes every rank fall back)."""
+    def _try_multicast(self, require, packed):
+        """One symmetric allocation (the clip-wide dof buffer, or the packed staging rows + flags) with a multicast mapping;
+        the decision is taken collectively (a rank that cannot map it makes every rank fall back)."""
         ok, err = 1, None
         try:
             import torch.distributed._symmetric_memory as symm_mem
             dev = torch.device(self.eng.device)
-            t = symm_mem.empty(max(self.n, 1) * self.D, dtype=torch.float32, device=dev)
+            if packed:
+                _, _, total, _ = self.eng.reassembly_layout(self.n, self.shard_n)
+                t = symm_mem.empty(total // 4, dtype=torch.float32, device=dev)
+            else:
+                t = symm_mem.empty(max(self.n, 1) * self.D, dtype=torch.float32, device=dev)
             hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
             mc = int(hdl.multicast_ptr or 0)
             if mc == 0:
@@ -125,7 +135,13 @@ class PeerReassembly:
             t.zero_()
             torch.cuda.synchronize(self.eng.device)
             self._symm, self._hdl, self.mc_ptr = t, hdl, mc
-            self.dof = t.view(max(self.n, 1), self.D)[: self.n]
+            self.packed = packed
+            if packed:
+                self._full = torch.zeros((max(self.n, 1), self.D), dtype=torch.float32, device=self.eng.device)
+                self.dof = self._full[: self.n]
+                dist.barrier(group=self.group)              # every rank's staging rows and flags are zero before the first store
+            else:
+                self.dof = t.view(max(self.n, 1), self.D)[: self.n]
         else:
             self.transport_error = err or "another rank could not map the multicast object"
             if require:
@@ -133,6 +149,13 @@ class PeerReassembly:
 
     def step(self, raw_local, flags, ik_iters=10, damping=0.1, rot_weight=0.2, link_pos=None):
         assert raw_local.shape[0] == self.hi - self.lo
+        if self.packed:
+            self.epoch += 1
+            self.eng.retarget_body_quat_reassemble(raw_local, self._full, self.n, self.rank, self.shard_lo, self.shard_n,
+                                                   self._symm.data_ptr(), self.mc_ptr, self.epoch, flags=flags, ik_iters=ik_iters,
+                                                   damping=damping, rot_weight=rot_weight, link_pos=link_pos)
+            self.eng.peer_barrier(self.flag_ptrs, self.rank, self.epoch)
+            return self.dof
         if self.mc_ptr:
             self.eng.retarget_body_quat_multicast(raw_local, self.mc_ptr, self.lo, flags=flags, ik_iters=ik_iters, damping=damping,
                                                   rot_weight=rot_weight, link_pos=link_pos)
@@ -149,7 +172,20 @@ class PeerReassembly:
         shard = (self.hi - self.lo) * self.D * 4
         if self.world == 1:
             return 0
+        if self.packed:
+            return (self.hi - self.lo) * 14 * 4
         return shard if self.mc_ptr else (self.world - 1) * shard
+
+    @property
+    def nvlink_bytes_received_per_step(self):
+        """Bytes arriving over this rank's NVLink ingress per step (a multicast store also comes back to its sender)."""
+        if self.world == 1:
+            return 0
+        if self.packed:
+            return self.n * 14 * 4
+        if self.mc_ptr:
+            return self.n * self.D * 4
+        return (self.n - (self.hi - self.lo)) * self.D * 4
 
     def close(self):
         if self._flags is None:
@@ -167,7 +203,7 @@ class PeerReassembly:
             self.eng.peer_free(self._buf)
         self.eng.peer_free(self._flags)
         self._buf = self._flags = None
-        self._symm = self._hdl = None                      # the symmetric allocation is released with its tensor
+        self._symm = self._hdl = self._full = None         # the symmetric allocation is released with its tensor
         self.mc_ptr = 0
 
 

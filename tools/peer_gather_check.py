@@ -27,8 +27,8 @@ def main():
     eng = hrt.Engine(local).set_standard_trees()
     flags = hrt.BQ_CLAMP | hrt.BQ_IK
     ok = True
-    for transport in ("auto", "unicast"):
-        for n in (1 << 18, 100_003, 16 * world * 3 + 5):
+    for transport in ("auto", "multicast", "unicast"):
+        for n in (1 << 18, 100_003, 16 * world * 3 + 5, 7):
             raw = oc.synth_clip_3q(n, seed=5, sk=sk).cuda()
             lo, hi = shard_range(n, rank, world)
             pr = PeerReassembly(eng, n, transport=transport)
