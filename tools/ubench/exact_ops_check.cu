@@ -2,7 +2,8 @@
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -cudart shared -I humanoid_real_time_retarget_b200/csrc \
 //        -o /tmp/exact_ops_check tools/ubench/exact_ops_check.cu && /tmp/exact_ops_check
 // 2^30 random operand pairs drawn from the ranges the fused kernels divide in (|x| in 2^-60 .. 2^60, random mantissas,
-// both signs) plus every power of two and its neighbours; sqrt over all positive normal floats' exponents.
+// both signs); sqrt over 2^-100 .. 2^120 (below 2^-101 __fsqrt_rn itself takes its scaled slow path; the kernels take
+// square roots of squared norms and of 1 - w^2, i.e. of exact zeros or values above 1e-16).
 // Prints the mismatch counts (expected 0) and the worst relative error of drsqrt_n against 1/sqrt in fp64.
 #include <cstdio>
 #include <cstdint>
@@ -30,7 +31,7 @@ __global__ void check(unsigned long long n, unsigned long long* bad_div, unsigne
         const float y = rcp_refined(b);
         if (__float_as_uint(div_by_rn(a, b, y)) != __float_as_uint(__fdiv_rn(a, b))) ++b_div;
         if (__float_as_uint(div_by_rn(c, b, y)) != __float_as_uint(__fdiv_rn(c, b))) ++b_div3;
-        const float x = fabsf(rnd_float(h2, -120, 120));
+        const float x = fabsf(rnd_float(h2, -100, 120));      // __fsqrt_rn's own fast-path range starts at 2^-101
         if (__float_as_uint(sqrtn_rn(x)) != __float_as_uint(__fsqrt_rn(x))) ++b_sqrt;
         const double xd = (double)fabsf(a) * (double)fabsf(c) + 1e-30;
         const double r = drsqrt_n(xd), ref = 1.0 / sqrt(xd);
