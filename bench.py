@@ -534,10 +534,12 @@ def run_ours(args):
             pr_o.close()
             del pr_o
         transports = {
-            "packed": "reassembly inside the compute kernel: the 14 arm hinge angles of a frame (56 B; every other DOF of this solver is "
-                      "structurally 0) go out once through the NVSwitch multicast address of the ranks' symmetric staging buffers "
-                      "(multimem.st), a flag per CTA round follows (fence.sys + multimem.st.release), and the same warps unpack the "
-                      "peers' landed rounds into the local (n, 30) dof_pos between their own rounds (no NCCL on the data path)",
+            "packed": "reassembly inside the compute kernel, warp-specialised: the 14 arm hinge angles of a frame (every other DOF of "
+                      "this solver is structurally 0) + a 16-byte check block per 16 frames go out once through the NVSwitch multicast "
+                      "address of the ranks' symmetric staging buffers (multimem.st, no flags, no fences: a group validates itself); "
+                      "four unpack warps per CTA (one per scheduler, 32 registers each after setmaxnreg; the 16 compute warps keep 112) "
+                      "fetch the peers' groups one round behind, check them and expand them into the local (n, 30) dof_pos under the "
+                      "issue-bound solve (no NCCL on the data path)",
             "multicast": "multimem.st of full 120-byte dof rows to the NVSwitch multicast address of the ranks' symmetric buffers, issued "
                          "by the compute kernel (no NCCL on the data path)",
             "unicast": "TMA bulk stores of full 120-byte dof rows to CUDA-IPC peer buffers over NVLink, issued by the compute kernel, one "

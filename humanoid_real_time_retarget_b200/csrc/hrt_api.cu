@@ -870,14 +870,14 @@ int hrt_reassembly_layout(hrt_ctx* ctx, int64_t n_total, int n_rank, const int64
         const long long g = (shard_frames[r] + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
         rounds = std::max(rounds, (g + T - 1) / T);
     }
-    if (rounds > BQ_GATHER_MAX_ROUNDS) return fail(HRT_E_INVALID_ARG, "shards of more than %lld frames per rank are not supported by the in-kernel reassembly",
-                                                   (long long)BQ_GATHER_MAX_ROUNDS * T * BQ_FRAMES_PER_WARP);
-    size_t stage = (size_t)std::max<int64_t>(n_total, 1) * BQ_PK * sizeof(float);
+    if (rounds > 0x3fffffff) return fail(HRT_E_INVALID_ARG, "shard too long for the in-kernel reassembly");
+    // one self-validating group (16 frames x 14 hinge angles + a check block) per 16 clip frames; no flags
+    const size_t groups = (size_t)((std::max<int64_t>(n_total, 1) + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP);
+    size_t stage = groups * BQ_PK_GROUP * sizeof(float);
     stage = (stage + 255) / 256 * 256;
-    const size_t flags = (size_t)n_rank * (size_t)rounds * (size_t)ctx->sm_count * sizeof(unsigned);
     if (staging_bytes) *staging_bytes = stage;
     if (flag_offset) *flag_offset = stage;
-    if (total_bytes) *total_bytes = stage + (flags + 255) / 256 * 256;
+    if (total_bytes) *total_bytes = stage;
     if (max_rounds) *max_rounds = (int)rounds;
     return 0;
 }
@@ -902,9 +902,8 @@ int hrt_retarget_body_quat_reassemble(hrt_ctx* ctx, int64_t B, const float* d_sr
     if (!aligned16(d_src_gq) || !aligned16(d_link_pos) || !aligned16(d_full_dof) || !aligned16(d_symm) || !aligned16(d_symm_mc))
         return fail(HRT_E_ALIGNMENT, "buffers must be 16-byte aligned");
     a.flags &= ~BQ_PACKED_IK;
-    size_t flag_off = 0;
-    int max_rounds = 0;
-    if ((rc = hrt_reassembly_layout(ctx, n_total, n_rank, shard_frames, nullptr, &flag_off, nullptr, &max_rounds))) return rc;
+    if ((rc = hrt_reassembly_layout(ctx, n_total, n_rank, shard_frames, nullptr, nullptr, nullptr, nullptr))) return rc;
+    if (epoch == 0u) return fail(HRT_E_INVALID_ARG, "epoch 0 is the zero-filled staging buffers' own: start at 1");
     int64_t covered = 0;
     for (int r = 0; r < n_rank; ++r) {
         if ((shard_frames[r] > 0 && shard_lo[r] % BQ_FRAMES_PER_WARP) || shard_lo[r] != covered || shard_frames[r] < 0)
@@ -916,29 +915,33 @@ int hrt_retarget_body_quat_reassemble(hrt_ctx* ctx, int64_t B, const float* d_sr
     if (covered != n_total) return fail(HRT_E_INVALID_ARG, "shards do not add up to the clip");
     a.g.mc_pk = (float*)d_symm_mc;
     a.g.pk = (const float*)d_symm;
-    a.g.mc_flags = (unsigned*)((char*)d_symm_mc + flag_off);
-    a.g.flags = (const unsigned*)((const char*)d_symm + flag_off);
     a.g.full = d_full_dof;
     a.g.n_rank = n_rank;
     a.g.me = my_rank;
-    a.g.max_rounds = max_rounds;
+    // equal shard strides (what sharding.shard_range produces) let the kernel derive every peer address from a group index
+    a.g.shard_groups = 0;
+    if (n_rank > 1 && shard_lo[1] > 0 && shard_lo[1] % BQ_FRAMES_PER_WARP == 0 && n_total / BQ_FRAMES_PER_WARP < (1LL << 30)) {
+        bool affine = true;
+        for (int r = 0; r < n_rank; ++r) affine = affine && shard_lo[r] == (int64_t)r * shard_lo[1];
+        if (affine) a.g.shard_groups = (int)(shard_lo[1] / BQ_FRAMES_PER_WARP);
+    }
     a.g.epoch = epoch;
     a.g.timeout_ns = 20ull * 1000 * 1000 * 1000;
     {
         static const unsigned dbg = [] { const char* e = getenv("HRT_GATHER_DEBUG"); return e ? (unsigned)atoi(e) : 0u; }();
         a.g.debug = dbg;
     }
-    // every rank launches the same geometry (one CTA per SM, 16 warps): a flag is indexed by (rank, round, CTA)
+    // every rank launches the same geometry (one CTA per SM, 16 warps): a group's round and warp follow from its index
     const size_t smem = ((size_t)BQ_CONST_WORDS + (size_t)BQ_WARPS_WIDE * bq_tile_words(ctx->bq.J_src, ctx->bq.J_rob, false) +
                          (size_t)bq_gather_words(BQ_WARPS_WIDE)) * sizeof(float);
-    auto kern = body_quat_kernel<BQ_WARPS_WIDE, true, true>;
+    auto kern = body_quat_gather_kernel<BQ_WARPS_WIDE>;
     static size_t attr_done[16] = {0};
     const int d = ctx->device & 15;
     if (attr_done[d] < smem) {
         HRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[d] = smem;
     }
-    kern<<<ctx->sm_count, BQ_WARPS_WIDE * 32, smem, (cudaStream_t)stream>>>(ctx->bq, a);
+    kern<<<ctx->sm_count, (BQ_WARPS_WIDE + BQ_GATHER_UNPACK_WARPS) * 32, smem, (cudaStream_t)stream>>>(ctx->bq, a);
     HRT_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1100,6 +1103,16 @@ int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const 
             for (int c = 0; c < 7; ++c) { pp.ik[side].lower[c] = rt.lim[f + c][0]; pp.ik[side].upper[c] = rt.lim[f + c][1]; }
             for (int k = 0; k < 3; ++k) pp.ik[side].p_sh[k] = pos[f * 3 + k];
         }
+    }
+    {
+        // zero-pose bone angles: computed on the device once (the frames' own code path), kept in the parameter block
+        float* d_za = nullptr;
+        HRT_CUDA(cudaMalloc(&d_za, 8 * sizeof(float)));
+        pos_zero_angles_kernel<<<1, 32>>>(pp.arm[0], pp.arm[1], d_za);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpy(&pp.zero_ang[0][0], d_za, 8 * sizeof(float), cudaMemcpyDeviceToHost);
+        cudaFree(d_za);
+        if (e != cudaSuccess) return fail((int)e, "zero-pose bone angles: %s", cudaGetErrorString(e));
     }
     ctx->pos_set[mode] = true;
     if (mode == POS_FULL_BODY_POS) {

@@ -98,6 +98,11 @@ HRT_DEV void bulk_store_s2g(float* gmem_dst, const float* smem_src, unsigned byt
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_src);
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(s), "r"(bytes) : "memory");
 }
+// hint: pull a contiguous span (16-byte aligned; whole 16-byte blocks of it) into L2 ahead of the cp.async that will read it
+HRT_DEV void l2_prefetch_span(const float* gmem_src, int n_words) {
+    const unsigned bytes = ((unsigned)n_words * 4u) & ~15u;
+    if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 HRT_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 HRT_DEV void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 HRT_DEV void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }

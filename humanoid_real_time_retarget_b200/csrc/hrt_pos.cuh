@@ -62,6 +62,9 @@ struct PosParams {
     int precise_gripper;
     PosArm arm[2];
     ArmIkParams ik[2];
+    // bone angles of the zero pose, [side][theta0_sh, phi0_sh, theta0_el, phi0_el]: evaluated ONCE per configuration by
+    // pos_zero_angles_kernel with the very device code the frames run through (same libm, same rounding order)
+    float zero_ang[2][4];
 };
 // CTA-shared constants in shared memory: [2 x PosArm][8 zero-pose angles][2 x ArmIkParams]
 HRT_HD inline int pos_zero_ang_word() { return 2 * (int)sizeof(PosArm) / 4; }
@@ -338,22 +341,25 @@ HRT_DEV void pos_align(int warp) {
 
 // CTA-shared constants: both PosArm tables + the zero-pose bone angles (once per CTA)
 HRT_DEV void pos_setup(const PosParams& pp, float* smem) {
-    PosArm* arms_s = reinterpret_cast<PosArm*>(smem);
     float* zero_ang = smem + pos_zero_ang_word();         // [side][4] = theta0_sh, phi0_sh, theta0_el, phi0_el
     const float* src = reinterpret_cast<const float*>(&pp.arm[0]);
     for (int i = threadIdx.x; i < 2 * (int)sizeof(PosArm) / 4; i += blockDim.x) smem[i] = src[i];
     const float* iks = reinterpret_cast<const float*>(&pp.ik[0]);
     for (int i = threadIdx.x; i < 2 * (int)sizeof(ArmIkParams) / 4; i += blockDim.x) smem[pos_ik_word() + i] = iks[i];
+    if (threadIdx.x < 8) zero_ang[threadIdx.x] = pp.zero_ang[threadIdx.x >> 2][threadIdx.x & 3];
     __syncthreads();
+}
+
+// one thread per arm; launched by hrt_configure_pos, the result goes into PosParams::zero_ang
+__global__ void pos_zero_angles_kernel(const PosArm a0, const PosArm a1, float* out) {
     if (threadIdx.x < 2) {
-        const PosArm& ar = arms_s[threadIdx.x];
+        const PosArm& ar = threadIdx.x == 0 ? a0 : a1;
         float t, p;
         bone_angles_x<1>(make_vec3(ar.v0_upper[0], ar.v0_upper[1], ar.v0_upper[2]), &t, &p);
-        zero_ang[threadIdx.x * 4 + 0] = t; zero_ang[threadIdx.x * 4 + 1] = p;
+        out[threadIdx.x * 4 + 0] = t; out[threadIdx.x * 4 + 1] = p;
         bone_angles_x<2>(make_vec3(ar.v0_lower[0], ar.v0_lower[1], ar.v0_lower[2]), &t, &p);
-        zero_ang[threadIdx.x * 4 + 2] = t; zero_ang[threadIdx.x * 4 + 3] = p;
+        out[threadIdx.x * 4 + 2] = t; out[threadIdx.x * 4 + 3] = p;
     }
-    __syncthreads();
 }
 
 // all frame groups of `a` that fall to CTA `cta` of `n_ctas`
@@ -424,6 +430,18 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
         }
         if (QUATS) pos_stage_span<SYSMEM>(bodyq_s, a.body_q + f0 * pp.n_bodyq * 4, nld * pp.n_bodyq * 4, lane);
         cp_async_commit();
+        // the next round's rows start their way from HBM to L2 now: the staging tile has no room for a second buffer, but
+        // the copy above then meets L2 latency instead of DRAM latency one round later
+        if (!SYSMEM && lane == 0 && grp_raw + total_warps < n_groups) {
+            const long long fn = (grp_raw + total_warps) * BQ_FRAMES_PER_WARP;
+            const int nn = (int)min((long long)BQ_FRAMES_PER_WARP, a.B - fn);
+            l2_prefetch_span(a.body_t + fn * NB * 3, nn * NB * 3);
+            if (HANDS) {
+                l2_prefetch_span(a.lhand_t + fn * NH * 3, nn * NH * 3);
+                l2_prefetch_span(a.rhand_t + fn * NH * 3, nn * NH * 3);
+            }
+            if (QUATS) l2_prefetch_span(a.body_q + fn * pp.n_bodyq * 4, nn * pp.n_bodyq * 4);
+        }
         if (a.out_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
         cp_async_wait<0>();
         __syncwarp();

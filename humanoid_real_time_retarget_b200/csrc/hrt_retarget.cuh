@@ -110,39 +110,63 @@ struct BodyQuatArgs {
     // (multimem.st: the switch replicates the store into every rank's copy, this rank's included)
     float* mc_dof;
     // reassembly INSIDE the kernel with a packed wire format (GATHER instantiation): only the 14 arm
-    // hinge angles of a frame travel (the other DOFs of this solver are structurally 0); every warp publishes its packed
-    // span through the multicast address of the ranks' staging buffers, the last warp of a CTA round raises that round's
-    // flag on every rank, and the same warps unpack the peers' earlier rounds into this rank's clip-wide dof buffer while
-    // they wait for nothing: the transfer and the unpacking hide under the issue-bound solve.
+    // hinge angles of a frame travel (the other DOFs of this solver are structurally 0); every warp publishes its 16-frame
+    // group (224 words + a 4-word check block) through the multicast address of the ranks' staging buffers, and the same
+    // warps fetch the peers' groups of an earlier round, accept them when the check block matches this step's epoch and
+    // the words that arrived, and expand them into this rank's clip-wide dof buffer: no flags, no fences, no counters --
+    // the transfer and the unpacking hide under the issue-bound solve.
     struct Gather {
-        float* mc_pk;                     // multicast address of the staging buffers: (n_total, 14) packed rows
+        float* mc_pk;                     // multicast address of the staging buffers: ceil(n_total / 16) groups of BQ_PK_GROUP words
         const float* pk;                  // this rank's copy of it
-        unsigned* mc_flags;               // multicast address of the flag arrays [rank][max_rounds][n_ctas]
-        const unsigned* flags;            // this rank's copy
         float* full;                      // this rank's clip-wide dof buffer (n_total, D); own rows are written directly
         long long lo[HRT_MAX_PEERS];      // first clip frame of every rank's shard (multiples of 16)
         long long n[HRT_MAX_PEERS];       // frames of every rank's shard
-        int n_rank, me, max_rounds;
-        unsigned epoch;                   // grows by one per step
+        int n_rank, me;
+        int shard_groups;                 // 16-frame groups between consecutive ranks' shard starts when lo[p] = p * stride, else 0
+        unsigned epoch;                   // grows by one per step, never 0
         unsigned long long timeout_ns;    // a lost peer traps instead of hanging the box
-        unsigned debug;                   // diagnostics (env HRT_GATHER_DEBUG): 1 no data stores, 2 no unpack stores, 4 no unpack loads, 8 no flag release, 16 no counters / flags / drain
+        // diagnostics (env HRT_GATHER_DEBUG): 1 no data stores, 2 no unpack stores, 4 no unpack loads, 16 no drain,
+        // 32 every fetched group counts as valid (single-GPU cost probes with fake peers)
+        unsigned debug;
     } g;
 };
 constexpr int BQ_PK = 14;                                                  // packed floats per frame: 2 arms x 7 hinges
-constexpr int BQ_PK_WORDS = BQ_FRAMES_PER_WARP * BQ_PK;                    // 224 per 16-frame group
-constexpr int BQ_PK_SLOT = BQ_PK_WORDS + 4;                                // + one 16-byte block of zeros (word BQ_PK_WORDS)
-constexpr int BQ_GATHER_DED_SLOTS = HRT_MAX_PEERS - 3;                     // dedicated slots per warp; two more live in the dof image
-// one flag per CTA and block of this many rounds: the release (MEMBAR.SYS) that orders a block's stores before its flag
-// stalls the warp that issues it for ~13 us (measured), and that warp is the last of its round, i.e. on the critical path
-constexpr int BQ_GATHER_FLAG_ROUNDS = 8;
-constexpr int BQ_GATHER_MAX_ROUNDS = 2048;
-constexpr int BQ_GATHER_MAX_BLOCKS = BQ_GATHER_MAX_ROUNDS / BQ_GATHER_FLAG_ROUNDS;
-constexpr int BQ_GATHER_TBL = 256;                                         // float2 number of a dof image -> its two source words
-// shared-memory block behind the tiles: [warps x dedicated slots] [expansion table] [block counters] [warps x 4 state words]
-HRT_HD inline int bq_gather_tbl_word(int warps) { return warps * BQ_GATHER_DED_SLOTS * BQ_PK_SLOT; }
-HRT_HD inline int bq_gather_cnt_word(int warps) { return bq_gather_tbl_word(warps) + BQ_GATHER_TBL; }
-HRT_HD inline int bq_gather_state_word(int warps) { return bq_gather_cnt_word(warps) + BQ_GATHER_MAX_BLOCKS; }
-HRT_HD inline int bq_gather_words(int warps) { return bq_gather_state_word(warps) + warps * 4; }
+constexpr int BQ_PK_WORDS = BQ_FRAMES_PER_WARP * BQ_PK;                    // 224 data words per 16-frame group
+constexpr int BQ_PK_GROUP = BQ_PK_WORDS + 4;                               // + the check block: on the wire and in the staging buffers
+constexpr int BQ_PK_SLOT = BQ_PK_GROUP;
+// The reassembly kernel is warp-specialised: 16 compute warps (the plain pipeline + one multicast publish per round) and
+// 4 unpack warps, one per scheduler, that fetch / check / expand the peers' groups.  The solve is issue-bound and uses
+// the whole register file at 128 registers per thread, so the registers are re-split after the prologue (setmaxnreg):
+// the CTA is launched with 640 x 96 = 61,440 registers (the most 20 warps can get) and that pool becomes 16 x 32 x 112 for
+// the compute warps + 4 x 32 x 32 for the unpack warps (an .inc beyond the CTA's own pool would wait forever).  The unpack warps' instructions
+// (latency-bound shared-memory / global traffic) then fill issue slots the solve leaves idle instead of sitting in
+// every compute warp's instruction stream, where they cost 13-22 % (measured, profiles/r02_notes.md).
+constexpr int BQ_GATHER_UNPACK_WARPS = 4;
+constexpr int BQ_GATHER_COMPUTE_REGS = 112;
+constexpr int BQ_GATHER_UNPACK_REGS = 32;
+// a peer's group of round j is fetched once this rank's own warp has finished round j + LAG: the ranks run at the same
+// pace, so the group has had LAG rounds (~40 us each) to cross the switch; a group that fails its check is fetched again
+constexpr int BQ_GATHER_LAG = 1;
+// an unpack warp's ring: one slot per peer + the 16-row image the slots are expanded through
+constexpr int BQ_GATHER_RING_WORDS = ((HRT_MAX_PEERS - 1) * BQ_PK_SLOT + BQ_FRAMES_PER_WARP * 32 + 3) / 4 * 4;
+// per-warp reassembly state in shared memory (ints): [0] cursor = next peer round to unpack, [1] rounds this warp has
+// groups of any peer for, [2] leading rounds in which it has a FULL group of EVERY peer at an address that follows from
+// the group index alone (the fast path: equal shards, 30 DOFs), [3] -; then per peer slot q (the general path: ragged
+// ends, any shard layout): {source address lo, hi, destination address lo, hi (both of the warp's group of round 0),
+// rounds this warp has a group of that peer for, frames of its last group}
+constexpr int BQ_GATHER_STATE_HDR = 4;
+constexpr int BQ_GATHER_STATE_WORDS = BQ_GATHER_STATE_HDR + 6 * (HRT_MAX_PEERS - 1) + 2;
+constexpr int BQ_GATHER_FAST_D = 30;                                       // DOF count the unrolled path is written for
+// shared-memory block behind the tiles: [compute warps x publish staging] [unpack warps x ring] [compute warps x state]
+// [compute warps x rounds finished]
+HRT_HD inline int bq_gather_ring_word(int warps) { return warps * BQ_PK_SLOT; }
+HRT_HD inline int bq_gather_state_word(int warps) { return bq_gather_ring_word(warps) + BQ_GATHER_UNPACK_WARPS * BQ_GATHER_RING_WORDS; }
+HRT_HD inline int bq_gather_progress_word(int warps) { return bq_gather_state_word(warps) + warps * BQ_GATHER_STATE_WORDS; }
+HRT_HD inline int bq_gather_words(int warps) { return (bq_gather_progress_word(warps) + warps + 3) / 4 * 4; }
+// check block of a group: {xor of the 224 words ^ salt, their sum + salt, epoch, 0}: a group is accepted when all three
+// match what was fetched.  Stale groups carry the previous epoch; a group caught half-way through its arrival
+// fails the sums (or holds, bit for bit, the same words as the new one).
+HRT_HD inline unsigned bq_gather_salt(unsigned epoch) { return epoch * 0x9E3779B9u + 0x7F4A7C15u; }
 
 // the arm's hinge axes (Hu_DOF_AXIS[11..17] == Hu_DOF_AXIS[20..26]); checked on the host
 #define HRT_ARM_AXIS(c) ((c) == 0 ? 1 : (c) == 1 ? 0 : (c) == 2 ? 2 : (c) == 3 ? 1 : (c) == 4 ? 0 : (c) == 5 ? 1 : 2)
@@ -322,162 +346,243 @@ HRT_DEV unsigned long long bq_timer_ns() {
     asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
     return t;
 }
-// flag poll: a strong system-scope load WITHOUT the acquire's L1 invalidation (ld.acquire.sys = LDG.STRONG.SYS + CCTL.IVALL,
-// and every warp polls every round).  The data the flag guards is then read at L2 (ld.global.cg), where peer writes
-// land, by loads that are issued after the flag value has been consumed by a branch.
-HRT_DEV unsigned ld_relaxed_sys_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // ---------------------------------------------------------------------------------------------
-// In-kernel reassembly (GATHER instantiation of body_quat_kernel).  Per 16-frame round a warp
-//   * at the top: if a round of the peers has landed that it has not unpacked yet, cp.async's its group of that round
-//     of EVERY peer (packed staging rows, 896 B each) into shared-memory slots -- same async group as its own input
-//     rows, so one wait covers both and no register is held -- then expands each slot into full dof rows of the
-//     clip-wide buffer (table-driven: 2 LDS + 1 STG.64 per float2);
-//   * at the end: writes its 14 hinge angles per frame to every rank through the multicast address, and once per flag
-//     block the last warp of the CTA raises the block's flag on every rank (release at system scope).
-// State (cursor, ready, peer_rounds) lives in shared memory: the solve in between uses every register.
+// In-kernel reassembly (body_quat_gather_kernel).
+//   * a compute warp, at the end of a round: writes its 14 hinge angles per frame and the group's check block to every
+//     rank through the multicast address (plain multimem.st: nothing orders them, the check block is what makes a group
+//     self-validating) and bumps its round counter in shared memory;
+//   * an unpack warp (one per scheduler, serving that scheduler's four compute warps): once a compute warp has finished
+//     round j + LAG it cp.async's that warp's group of round j of EVERY peer (staging groups, 912 B each) into its ring,
+//     checks every slot against its check block and, when all of them are this step's, turns each into a full 16-row
+//     dof image (lane = (frame, arm) drops its 7 hinge angles into an image whose other words stay zero) and copies the
+//     image out with 128-bit stores; a round that does not check out yet is fetched again after a short sleep.
 // ---------------------------------------------------------------------------------------------
-HRT_DEV void gather_setup(const BodyQuatArgs::Gather& g, float* gbase, int warps, int n_ctas, int D, int col_a, int col_b) {
-    unsigned* tbl = reinterpret_cast<unsigned*>(gbase + bq_gather_tbl_word(warps));
-    unsigned* blk_cnt = reinterpret_cast<unsigned*>(gbase + bq_gather_cnt_word(warps));
+HRT_DEV void gather_setup(const BodyQuatArgs::Gather& g, float* gbase, int warps, int n_ctas, int cta, int D) {
     int* state = reinterpret_cast<int*>(gbase + bq_gather_state_word(warps));
-    for (int i = threadIdx.x; i < BQ_GATHER_MAX_BLOCKS; i += blockDim.x) blk_cnt[i] = 0u;
-    // float2 number i of a 16-frame dof image (D/2 per row): the slot words its two floats come from
-    // (BQ_PK_WORDS = the block of zeros, for the DOFs that do not travel)
-    const int half = D >> 1;
-    for (int i = threadIdx.x; i < BQ_GATHER_TBL; i += blockDim.x) {
-        const int row = i / half, c2 = (i - row * half) * 2;
-        unsigned w[2];
-        for (int e = 0; e < 2; ++e) {
-            const int c = c2 + e;
-            const int da = c - col_a, db = c - col_b;
-            const int slot = ((unsigned)da < 7u) ? da : ((unsigned)db < 7u) ? 7 + db : -1;
-            w[e] = (slot >= 0 && row < BQ_FRAMES_PER_WARP) ? (unsigned)(row * BQ_PK + slot) : (unsigned)BQ_PK_WORDS;
-        }
-        tbl[i] = w[0] | (w[1] << 16);
-    }
     if (threadIdx.x < warps) {
-        const long long T = (long long)n_ctas * warps;
+        reinterpret_cast<int*>(gbase + bq_gather_progress_word(warps))[threadIdx.x] = 0;
+        int* st = state + threadIdx.x * BQ_GATHER_STATE_WORDS;
+        const long long T = (long long)n_ctas * warps, w0 = (long long)cta * warps + threadIdx.x;
         int peer_rounds = 0;
-        for (int p = 0; p < g.n_rank; ++p) {
-            if (p == g.me) continue;
+        for (int q = 0; q < g.n_rank - 1; ++q) {
+            const int p = q + (q >= g.me ? 1 : 0);
             const long long gp = (g.n[p] + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
-            peer_rounds = max(peer_rounds, (int)((gp + T - 1) / T));
+            const int rq = gp > w0 ? (int)((gp - w0 + T - 1) / T) : 0;
+            peer_rounds = max(peer_rounds, rq);
+            const unsigned long long src = reinterpret_cast<unsigned long long>(g.pk + (g.lo[p] / BQ_FRAMES_PER_WARP + w0) * BQ_PK_GROUP);
+            const unsigned long long dst = reinterpret_cast<unsigned long long>(g.full + (g.lo[p] + w0 * BQ_FRAMES_PER_WARP) * D);
+            const long long last_f = ((long long)(rq - 1) * T + w0) * BQ_FRAMES_PER_WARP;
+            st[BQ_GATHER_STATE_HDR + 6 * q + 0] = (int)(unsigned)src; st[BQ_GATHER_STATE_HDR + 6 * q + 1] = (int)(unsigned)(src >> 32);
+            st[BQ_GATHER_STATE_HDR + 6 * q + 2] = (int)(unsigned)dst; st[BQ_GATHER_STATE_HDR + 6 * q + 3] = (int)(unsigned)(dst >> 32);
+            st[BQ_GATHER_STATE_HDR + 6 * q + 4] = rq;
+            st[BQ_GATHER_STATE_HDR + 6 * q + 5] = rq > 0 ? (int)min((long long)BQ_FRAMES_PER_WARP, g.n[p] - last_f) : 0;
         }
-        state[threadIdx.x * 4 + 0] = 0;                 // cursor: next peer round this warp unpacks
-        state[threadIdx.x * 4 + 1] = 0;                 // ready: peer rounds known to have landed
-        state[threadIdx.x * 4 + 2] = peer_rounds;
+        // fast path: as long as every peer has a whole group for this warp, at a group index that is affine in the rank
+        int rq_full = 0;
+        if (g.shard_groups > 0 && D == BQ_GATHER_FAST_D && g.n_rank > 1) {
+            rq_full = 0x7fffffff;
+            for (int p = 0; p < g.n_rank; ++p) {
+                if (p == g.me) continue;
+                const long long gf = g.n[p] / BQ_FRAMES_PER_WARP;                     // whole groups of that shard
+                rq_full = min(rq_full, gf > w0 ? (int)((gf - w0 + T - 1) / T) : 0);
+                if (g.lo[p] != (long long)p * g.shard_groups * BQ_FRAMES_PER_WARP) rq_full = 0;
+            }
+        }
+        st[0] = 0;
+        st[1] = peer_rounds;
+        st[2] = rq_full;
+        st[3] = 0;
     }
     __syncthreads();
 }
 
-// slot q of a warp: the first two share the (idle at that point) dof image, the others are dedicated
-HRT_DEV float* gather_slot(float* dof_t, float* ded, int q) { return q < 2 ? dof_t + q * BQ_PK_SLOT : ded + (q - 2) * BQ_PK_SLOT; }
-
-// Top of a round, before the input rows' cp.async group is committed.  Returns the peer round whose groups were put in
-// flight (to be expanded after the wait), or -1.  `my_round`: rounds this warp has finished -- the peers run at the same
-// pace, so the flag block after `ready` is polled only once it is due; `drain`: poll unconditionally.
-HRT_DEV int gather_fetch(const BodyQuatArgs::Gather& g, float* gbase, float* dof_t, int warps, int n_ctas, int cta, int warp, int lane,
-                         int my_round, bool drain) {
-    volatile int* state = reinterpret_cast<volatile int*>(gbase + bq_gather_state_word(warps)) + warp * 4;
-    const int cursor = state[0], peer_rounds = state[2];
-    int ready = state[1];
-    const long long T = (long long)n_ctas * warps;
-    if (cursor >= ready && cursor < peer_rounds && (drain || my_round >= ready + BQ_GATHER_FLAG_ROUNDS)) {
-        // have all peers raised this CTA's flag of the block that holds round `cursor`?  (lane p looks at rank p)
-        bool ok = true;
-        if (lane < g.n_rank && lane != g.me) {
-            const long long gp = (g.n[lane] + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
-            if (cursor < (int)((gp + T - 1) / T)) {
-                const unsigned v = ld_relaxed_sys_u32(g.flags + ((size_t)lane * g.max_rounds + cursor / BQ_GATHER_FLAG_ROUNDS) * n_ctas + cta);
-                ok = (int)(v - g.epoch) >= 0;
-            }
-        }
-        if (__all_sync(0xffffffffu, ok)) {
-            ready = min(ready + BQ_GATHER_FLAG_ROUNDS, peer_rounds);
-            if (lane == 0) state[1] = ready;
-        }
+// ---- fast path (state[2]): unrolled over the peer slots, addresses from the group index, no per-peer state ----------
+// The three passes over the peers' slots are rolled loops on purpose: the unpack warps run on 32 registers and share
+// their scheduler's instruction fetch with four issue-bound compute warps, so their code is kept short (a few dozen
+// instructions per peer) and their addresses advance by additions.
+// g_rel = peer round * (compute warps of the grid) + the compute warp's number
+HRT_DEV void gather_fetch_fast(const BodyQuatArgs::Gather& g, float* ring, unsigned g_rel, int lane) {
+    const unsigned long long stride = (unsigned long long)(unsigned)g.shard_groups * (unsigned long long)(BQ_PK_GROUP * 4);
+    const char* src = reinterpret_cast<const char*>(g.pk) + (unsigned long long)g_rel * (unsigned long long)(BQ_PK_GROUP * 4) + lane * 16;
+    float* slot = ring + lane * 4;
+    const int np = g.n_rank - 1;
+#pragma unroll 1
+    for (int q = 0; q < np; ++q) {
+        if (q == g.me) src += stride;                       // this rank's own shard is skipped
+        cp_async16(slot, src);
+        if (lane < BQ_PK_GROUP / 4 - 32) cp_async16(slot + 128, src + 512);
+        src += stride;
+        slot += BQ_PK_SLOT;
     }
-    if (cursor >= ready) return -1;
-    float* ded = gbase + warp * BQ_GATHER_DED_SLOTS * BQ_PK_SLOT;
-    const long long fp = ((long long)cursor * T + (long long)cta * warps + warp) * BQ_FRAMES_PER_WARP;
-    for (int q = 0; q < g.n_rank - 1; ++q) {
-        const int p = q + (q >= g.me ? 1 : 0);
-        const long long np = g.n[p];
-        if (fp >= np) continue;
-        const int cnt = (int)min((long long)BQ_FRAMES_PER_WARP, np - fp);
-        const int n4 = (cnt * BQ_PK + 3) >> 2;              // a ragged tail reads up to 8 bytes past its rows: inside the buffer
-        const float* src = g.pk + (g.lo[p] + fp) * BQ_PK;
-        float* slot = gather_slot(dof_t, ded, q);
-        if (!(g.debug & 4u))
-            for (int i = lane; i < n4; i += 32) cp_async16(slot + i * 4, src + i * 4);
-        if (lane < 4) slot[BQ_PK_WORDS + lane] = 0.f;
-    }
-    return cursor;
 }
 
-// after the wait: expand the slots of peer round `j` into full dof rows
-HRT_DEV void gather_expand(const BodyQuatArgs::Gather& g, float* gbase, float* dof_t, int warps, int n_ctas, int cta, int warp, int lane,
-                           int D, int j) {
-    float* ded = gbase + warp * BQ_GATHER_DED_SLOTS * BQ_PK_SLOT;
-    const unsigned* tbl = reinterpret_cast<const unsigned*>(gbase + bq_gather_tbl_word(warps));
-    const long long T = (long long)n_ctas * warps;
-    const long long fp = ((long long)j * T + (long long)cta * warps + warp) * BQ_FRAMES_PER_WARP;
-    unsigned w[BQ_GATHER_TBL / 32];
+HRT_DEV bool gather_validate_fast(const BodyQuatArgs::Gather& g, const float* ring, int lane) {
+    const int np = g.n_rank - 1;
+    const unsigned salt = bq_gather_salt(g.epoch);
+    unsigned bad = 0u;
+    const unsigned* slot = reinterpret_cast<const unsigned*>(ring);
+#pragma unroll 1
+    for (int q = 0; q < np; ++q) {
+        const unsigned* mine = slot + lane * 7;
+        unsigned x = mine[0] ^ mine[1] ^ mine[2], y = mine[0] + mine[1] + mine[2];
+        x ^= mine[3] ^ mine[4]; y += mine[3] + mine[4];
+        x ^= mine[5] ^ mine[6]; y += mine[5] + mine[6];
+        x = __reduce_xor_sync(0xffffffffu, x);
+        y = __reduce_add_sync(0xffffffffu, y);
+        const uint4 chk = *reinterpret_cast<const uint4*>(slot + BQ_PK_WORDS);
+        bad |= (chk.x ^ x ^ salt) | (chk.y - y - salt) | (chk.z ^ g.epoch);
+        slot += BQ_PK_SLOT;
+    }
+    return bad == 0u || (g.debug & 32u) != 0;
+}
+
+// every slot of an accepted fast round -> 16 full dof rows each: lane = (frame, arm) drops its 7 hinge angles into the
+// image (`col`: first hinge column of the lane's arm), the image leaves with 128-bit stores
+HRT_DEV void gather_store_fast(const BodyQuatArgs::Gather& g, const float* ring, float* img, unsigned g_rel, int lane, int col) {
+    if (g.debug & 2u) return;
+    constexpr int N4 = BQ_FRAMES_PER_WARP * BQ_GATHER_FAST_D / 4;           // 120 sixteen-byte blocks per image
+    const unsigned long long stride = (unsigned long long)(unsigned)g.shard_groups * (unsigned long long)(N4 * 16);
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<char*>(g.full) + (unsigned long long)g_rel * (unsigned long long)(N4 * 16)) + lane;
+    const float* mine = ring + lane * 7;
+    float* row = img + (lane >> 1) * BQ_GATHER_FAST_D + col;
+    const float4* img4 = reinterpret_cast<const float4*>(img) + lane;
+    const int np = g.n_rank - 1;
+#pragma unroll 1
+    for (int q = 0; q < np; ++q) {
+        if (q == g.me) dst = reinterpret_cast<float4*>(reinterpret_cast<char*>(dst) + stride);
+        __syncwarp();                                       // the image's previous copy-out (or its zero fill) is done
 #pragma unroll
-    for (int t = 0; t < BQ_GATHER_TBL / 32; ++t) w[t] = tbl[lane + 32 * t];
-    const int half = D >> 1;
-    for (int q = 0; q < g.n_rank - 1; ++q) {
-        const int p = q + (q >= g.me ? 1 : 0);
-        const long long np = g.n[p];
-        if (fp >= np) continue;
-        const int n2 = (int)min((long long)BQ_FRAMES_PER_WARP, np - fp) * half;
-        const float* slot = gather_slot(dof_t, ded, q);
-        float2* dst = reinterpret_cast<float2*>(g.full + (g.lo[p] + fp) * D) + lane;
-        if (!(g.debug & 2u)) {
+        for (int c = 0; c < 7; ++c) row[c] = mine[c];
+        __syncwarp();
 #pragma unroll
-            for (int t = 0; t < BQ_GATHER_TBL / 32; ++t)
-                if (lane + 32 * t < n2) __stcs(dst + 32 * t, make_float2(slot[w[t] & 0xffffu], slot[w[t] >> 16]));
+        for (int t = 0; t < (N4 + 31) / 32; ++t)
+            if (t < N4 / 32 || lane < N4 % 32) __stcs(dst + 32 * t, img4[32 * t]);
+        dst = reinterpret_cast<float4*>(reinterpret_cast<char*>(dst) + stride);
+        mine += BQ_PK_SLOT;
+    }
+}
+
+// the image the slots are expanded through: 16 x D words whose non-hinge words stay zero
+HRT_DEV void gather_image_clear(float* img, int D, int lane) {
+    float4* img4 = reinterpret_cast<float4*>(img);
+    for (int i = lane; i < BQ_FRAMES_PER_WARP * D / 4; i += 32) img4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ---- general path (ragged last groups, unequal shards, other DOF counts): per-peer state, one peer at a time -------
+// Run by the COMPUTE warps after their last round (they have the registers, and it is a handful of groups per clip):
+// peer slot q's group of peer round `j` that belongs to this warp is fetched into `slot`, checked, expanded through
+// `img` (cleared by the caller) and stored; repeated until the group checks out.
+HRT_DEV void gather_tail_one(const BodyQuatArgs::Gather& g, const int* st, float* slot, float* img, int warps, int n_ctas, int lane,
+                             int D, int col, int j, int q) {
+    const int rq = st[BQ_GATHER_STATE_HDR + 6 * q + 4];
+    if (j >= rq) return;
+    const unsigned long long soff = (unsigned long long)j * (unsigned long long)((unsigned)(n_ctas * warps) * (unsigned)(BQ_PK_GROUP * 4)) + (unsigned)lane * 16u;
+    const char* src = reinterpret_cast<const char*>(((unsigned long long)(unsigned)st[BQ_GATHER_STATE_HDR + 6 * q + 1] << 32 | (unsigned)st[BQ_GATHER_STATE_HDR + 6 * q]) + soff);
+    const unsigned salt = bq_gather_salt(g.epoch);
+    const unsigned* us = reinterpret_cast<const unsigned*>(slot);
+    const unsigned long long t0 = bq_timer_ns();
+    for (;;) {
+        if (!(g.debug & 4u)) {
+            cp_async16(slot + lane * 4, src);
+            if (lane < BQ_PK_GROUP / 4 - 32) cp_async16(slot + lane * 4 + 128, src + 512);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        const unsigned* mine = us + lane * 7;
+        unsigned x = mine[0] ^ mine[1] ^ mine[2], y = mine[0] + mine[1] + mine[2];
+        x ^= mine[3] ^ mine[4]; y += mine[3] + mine[4];
+        x ^= mine[5] ^ mine[6]; y += mine[5] + mine[6];
+        x = __reduce_xor_sync(0xffffffffu, x);
+        y = __reduce_add_sync(0xffffffffu, y);
+        if ((us[BQ_PK_WORDS] == (x ^ salt) && us[BQ_PK_WORDS + 1] == y + salt && us[BQ_PK_WORDS + 2] == g.epoch) || (g.debug & 32u)) break;
+        if (bq_timer_ns() - t0 > g.timeout_ns) __trap();        // a lost peer must not hang the box
+        __nanosleep(2000);
+        __syncwarp();
+    }
+    if (g.debug & 2u) return;
+    float* row = img + (lane >> 1) * D + col;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) row[c] = slot[lane * 7 + c];
+    __syncwarp();
+    const unsigned long long doff = (unsigned long long)j * (unsigned long long)((unsigned)(n_ctas * warps) * (unsigned)(BQ_FRAMES_PER_WARP * 4) * (unsigned)D);
+    float* dst = reinterpret_cast<float*>(((unsigned long long)(unsigned)st[BQ_GATHER_STATE_HDR + 6 * q + 3] << 32 | (unsigned)st[BQ_GATHER_STATE_HDR + 6 * q + 2]) + doff);
+    const int cnt = (j == rq - 1) ? st[BQ_GATHER_STATE_HDR + 6 * q + 5] : BQ_FRAMES_PER_WARP;
+    for (int i = lane; i < cnt * D; i += 32) __stcs(dst + i, img[i]);          // a ragged group stores its own rows only
+    __syncwarp();
+}
+
+// one (peer round, compute warp) item of an unpack warp: fetch, check (again until it checks out), expand
+HRT_DEV void gather_item_fast(const BodyQuatArgs::Gather& g, float* ring, float* img, unsigned g_rel, int lane, int col) {
+    unsigned long long t0 = 0ull;
+    for (;;) {
+        if (!(g.debug & 4u)) gather_fetch_fast(g, ring, g_rel, lane);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        if (gather_validate_fast(g, ring, lane)) break;
+        const unsigned long long now = bq_timer_ns();
+        if (t0 == 0ull) t0 = now;
+        if (now - t0 > g.timeout_ns) __trap();                  // a lost peer must not hang the box
+        __nanosleep(2000);
+    }
+    gather_store_fast(g, ring, img, g_rel, lane, col);
+    __syncwarp();                                               // the slots may be overwritten
+}
+
+// One unpack warp (uw = 0 .. 3): the peers' groups of the fast rounds of the compute warps of its own scheduler.
+template <int WARPS>
+HRT_DEV void gather_unpack_warp(const BodyQuatArgs::Gather& g, float* gbase, int uw, int lane, int n_ctas, int cta, int col) {
+    float* ring = gbase + bq_gather_ring_word(WARPS) + uw * BQ_GATHER_RING_WORDS;
+    float* img = ring + (HRT_MAX_PEERS - 1) * BQ_PK_SLOT;
+    const int* state = reinterpret_cast<const int*>(gbase + bq_gather_state_word(WARPS)) + uw * BQ_GATHER_STATE_WORDS;
+    const volatile int* progress = reinterpret_cast<const volatile int*>(gbase + bq_gather_progress_word(WARPS)) + uw;
+    const unsigned T = (unsigned)(n_ctas * WARPS);
+    gather_image_clear(img, BQ_GATHER_FAST_D, lane);           // the zero words stay: only hinge words are ever rewritten
+    __syncwarp();
+    int max_rounds = 0;
+#pragma unroll
+    for (int k = 0; k < WARPS / BQ_GATHER_UNPACK_WARPS; ++k) max_rounds = max(max_rounds, state[BQ_GATHER_UNPACK_WARPS * k * BQ_GATHER_STATE_WORDS + 2]);
+    if (g.debug & 16u) max_rounds = 0;
+#pragma unroll 1
+    for (int j = 0; j < max_rounds; ++j) {
+        // pacing: the peers run at this rank's pace, and the four compute warps of a scheduler move in lockstep: one poll
+        // per round on the first of them (a finished compute warp reports INT_MAX); correctness rests on the check blocks
+        while (*progress < j + 1 + BQ_GATHER_LAG) __nanosleep(5000);
+#pragma unroll 1
+        for (int k = 0; k < WARPS / BQ_GATHER_UNPACK_WARPS; ++k) {
+            const int rq_full = state[BQ_GATHER_UNPACK_WARPS * k * BQ_GATHER_STATE_WORDS + 2];
+            if (j >= rq_full) continue;
+            const unsigned g_rel = (unsigned)j * T + (unsigned)(cta * WARPS + uw + BQ_GATHER_UNPACK_WARPS * k);
+            gather_item_fast(g, ring, img, g_rel, lane, col);
         }
     }
+}
+
+// End of a round: the warp's packed hinge angles (lane = (frame, arm): words 7 lane .. 7 lane + 6) and the group's check
+// block go to every rank through the multicast address.
+HRT_DEV void gather_publish(const BodyQuatArgs::Gather& g, float* gbase, int warp, int lane, const float th[7], int nfr, long long f0) {
+    if (nfr <= 0) return;
+    float* pk_t = gbase + warp * BQ_PK_SLOT;                                 // the compute warp's own publish staging
+    unsigned x = 0u, y = 0u;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        const float v = (lane >> 1) < nfr ? th[c] : 0.f;                    // a ragged group travels whole, zero padded
+        pk_t[lane * 7 + c] = v;
+        x ^= __float_as_uint(v);
+        y += __float_as_uint(v);
+    }
+    x = __reduce_xor_sync(0xffffffffu, x);
+    y = __reduce_add_sync(0xffffffffu, y);
     if (lane == 0) {
-        volatile int* state = reinterpret_cast<volatile int*>(gbase + bq_gather_state_word(warps)) + warp * 4;
-        state[0] = j + 1;
+        const unsigned salt = bq_gather_salt(g.epoch);
+        unsigned* chk = reinterpret_cast<unsigned*>(pk_t + BQ_PK_WORDS);
+        chk[0] = x ^ salt; chk[1] = y + salt; chk[2] = g.epoch; chk[3] = 0u;
     }
     __syncwarp();
-}
-
-// End of a round: the warp's packed hinge angles (lane = (frame, arm): 7 angles) go to every rank through the multicast
-// address; once per flag block the warp is counted in and the CTA's last warp raises the block's flag on every rank.
-HRT_DEV void gather_publish(const BodyQuatArgs::Gather& g, float* gbase, int warps, int n_ctas, int cta, int warp, int lane,
-                            const float th[7], int nfr, long long f0, int rnd, int rounds) {
-    const int fl = lane >> 1, side = lane & 1;
-    float* pk_t = gbase + warp * BQ_GATHER_DED_SLOTS * BQ_PK_SLOT;          // dedicated slot 0 is idle between the top-of-round unpacks
-    if (fl < nfr) {
-        float* r = pk_t + fl * BQ_PK + side * 7;
-#pragma unroll
-        for (int c = 0; c < 7; ++c) r[c] = th[c];
-    }
+    if (!(g.debug & 1u))
+        warp_multimem_store_span(g.mc_pk + ((g.lo[g.me] + f0) / BQ_FRAMES_PER_WARP) * BQ_PK_GROUP, pk_t, BQ_PK_GROUP, lane);
     __syncwarp();
-    if (nfr > 0 && !(g.debug & 1u)) warp_multimem_store_span(g.mc_pk + (g.lo[g.me] + f0) * BQ_PK, pk_t, nfr * BQ_PK, lane);
-    __syncwarp();
-    // Every warp has finished all rounds of the block when it is counted in (program order), and the release orders
-    // everything the CTA has stored so far (observed through the counter) before the flag.
-    if (lane == 0 && ((rnd + 1) % BQ_GATHER_FLAG_ROUNDS == 0 || rnd + 1 == rounds) && !(g.debug & 16u)) {
-        unsigned* blk_cnt = reinterpret_cast<unsigned*>(gbase + bq_gather_cnt_word(warps));
-        const int blk = rnd / BQ_GATHER_FLAG_ROUNDS;
-        __threadfence_block();
-        const unsigned old = atomicAdd(&blk_cnt[blk], 1u);
-        if (old == (unsigned)warps - 1u) {
-            unsigned* f = g.mc_flags + ((size_t)g.me * g.max_rounds + blk) * n_ctas + cta;
-            if (g.debug & 8u) asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;\n" ::"l"(f), "r"(g.epoch) : "memory");
-            else asm volatile("multimem.st.release.sys.global.u32 [%0], %1;\n" ::"l"(f), "r"(g.epoch) : "memory");
-        }
-    }
 }
 
 template <int BQ_WARPS_PER_CTA, bool SYSMEM, bool WITH_IK = true, bool GATHER = false>
@@ -500,10 +605,8 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
     const bool do_ik = (a.flags & BQ_IK) != 0;
     const vec3 p_sh = make_vec3(bp.shoulder_p[side][0], bp.shoulder_p[side][1], bp.shoulder_p[side][2]);
 
-    // in-kernel reassembly (GATHER instantiation): out-of-line helpers with their state in shared memory, so that the
-    // solve keeps its register allocation
+    // in-kernel reassembly (body_quat_gather_kernel): the compute warps only publish; gbase = the block behind the tiles
     float* gbase = smem + BQ_CONST_WORDS + BQ_WARPS_PER_CTA * bq_tile_words(bp.J_src, bp.J_rob, with_lq);
-    if (GATHER) gather_setup(a.g, gbase, BQ_WARPS_PER_CTA, n_ctas, bp.J_rob - 1, bp.arm[0].rob_first - 1, bp.arm[1].rob_first - 1);
 
     // every warp of the CTA runs the same number of rounds (the named barriers below need that);
     // a warp without a group in the last round shadows the last group and publishes nothing
@@ -536,20 +639,17 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
         } else {
             warp_span_g2s(tile, a.src_gq + f0 * JS * 4, nld * JS * 4, lane);
         }
-        // in-kernel reassembly: a landed round of every peer is fetched together with this round's input rows
-        int g_round = -1;
-        if (GATHER) g_round = gather_fetch(a.g, gbase, dof_t, BQ_WARPS_PER_CTA, n_ctas, cta, warp, lane, (int)rnd, false);
         cp_async_commit();
+        // the next round's rows start their way from HBM to L2 now (no room for a second staging buffer)
+        if (!SYSMEM && lane == 0 && grp_raw + total_warps < n_groups) {
+            const long long fn = (grp_raw + total_warps) * BQ_FRAMES_PER_WARP;
+            l2_prefetch_span(a.src_gq + fn * JS * 4, (int)min((long long)BQ_FRAMES_PER_WARP, a.B - fn) * JS * 4);
+        }
         // while the copy is in flight: pre-fill the output images with their constant parts
         const bool want_dof = a.out_dof != nullptr || a.n_peer > 0 || a.mc_dof != nullptr;
-        if (!GATHER && want_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
+        if (want_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
         cp_async_wait<0>();
         __syncwarp();
-        if (GATHER) {
-            if (g_round >= 0) gather_expand(a.g, gbase, dof_t, BQ_WARPS_PER_CTA, n_ctas, cta, warp, lane, D, g_round);
-            if (want_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;     // the dof image doubled as two slots
-            __syncwarp();
-        }
         const float* row = tile + fr * JS * 4;
         float4 zT = *reinterpret_cast<const float4*>(row + ap.src_torso * 4);
         float4 zS = *reinterpret_cast<const float4*>(row + ap.src_shoulder * 4);
@@ -697,22 +797,24 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
         }
         if (GATHER) {
             // ---- 9. publish the group's packed hinge angles to every rank and count the round ----------------------------
-            gather_publish(a.g, gbase, BQ_WARPS_PER_CTA, n_ctas, cta, warp, lane, th, nfr, f0, (int)rnd, (int)rounds);
+            gather_publish(a.g, gbase, warp, lane, th, nfr, f0);
+            // the CTA's unpack warps pace themselves on the rounds this warp has finished
+            if (lane == 0) reinterpret_cast<volatile int*>(gbase + bq_gather_progress_word(BQ_WARPS_PER_CTA))[warp] = (int)rnd + 1;
         }
     }
     if (pending_store && lane == 0) bulk_wait_read_all();
     if (GATHER) {
-        // drain: the peers' remaining rounds (at least their last flag block)
-        const unsigned long long t0 = bq_timer_ns();
-        for (bool done = (a.g.debug & 16u) != 0; !done;) {
-            const int j = gather_fetch(a.g, gbase, dof_t, BQ_WARPS_PER_CTA, n_ctas, cta, warp, lane, 0x7fffffff, true);
-            cp_async_commit();
-            cp_async_wait<0>();
+        if (lane == 0) reinterpret_cast<volatile int*>(gbase + bq_gather_progress_word(BQ_WARPS_PER_CTA))[warp] = 0x7fffffff;
+        __syncwarp();                                                  // the last bulk stores have read the staging tiles
+        // the peer rounds the unpack warps leave to this warp (general path): its publish staging is the slot, its dof
+        // tile the image
+        const int* st = reinterpret_cast<const int*>(gbase + bq_gather_state_word(BQ_WARPS_PER_CTA)) + warp * BQ_GATHER_STATE_WORDS;
+        if (st[2] < st[1] && !(a.g.debug & 16u)) {
+            gather_image_clear(dof_t, D, lane);
             __syncwarp();
-            if (j >= 0) gather_expand(a.g, gbase, dof_t, BQ_WARPS_PER_CTA, n_ctas, cta, warp, lane, bp.J_rob - 1, j);
-            volatile int* state = reinterpret_cast<volatile int*>(gbase + bq_gather_state_word(BQ_WARPS_PER_CTA)) + warp * 4;
-            done = state[0] >= state[2];
-            if (!done && bq_timer_ns() - t0 > a.g.timeout_ns) __trap();     // a lost peer must not hang the box
+            for (int j = st[2]; j < st[1]; ++j)
+                for (int q = 0; q < a.g.n_rank - 1; ++q)
+                    gather_tail_one(a.g, st, gbase + warp * BQ_PK_SLOT, dof_t, BQ_WARPS_PER_CTA, n_ctas, lane, D, ap.rob_first - 1, j, q);
         }
     }
 }
@@ -724,6 +826,26 @@ body_quat_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a
     extern __shared__ __align__(16) float smem[];
     bq_setup(bp, smem);
     bq_process<BQ_WARPS_PER_CTA, false, WITH_IK, GATHER>(bp, a, smem, (int)gridDim.x, (int)blockIdx.x);
+}
+
+// The reassembly form of the same pipeline: WARPS compute warps + 4 unpack warps, registers re-split
+// after the prologue.
+template <int WARPS>
+__global__ void __launch_bounds__((WARPS + BQ_GATHER_UNPACK_WARPS) * 32, 1)
+body_quat_gather_kernel(const __grid_constant__ BodyQuatParams bp, const BodyQuatArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    bq_setup(bp, smem);
+    float* gbase = smem + BQ_CONST_WORDS + WARPS * bq_tile_words(bp.J_src, bp.J_rob, false);
+    gather_setup(a.g, gbase, WARPS, (int)gridDim.x, (int)blockIdx.x, bp.J_rob - 1);
+    const int warp = threadIdx.x >> 5;
+    if (warp >= WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(BQ_GATHER_UNPACK_REGS));
+        const int lane = threadIdx.x & 31;
+        gather_unpack_warp<WARPS>(a.g, gbase, warp - WARPS, lane, (int)gridDim.x, (int)blockIdx.x, bp.arm[lane & 1].rob_first - 1);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(BQ_GATHER_COMPUTE_REGS));
+        bq_process<WARPS, false, true, true>(bp, a, smem, (int)gridDim.x, (int)blockIdx.x);
+    }
 }
 
 // Resident single-frame server of the quaternion path (same protocol as pos_stream_server_kernel in hrt_pos.cuh:

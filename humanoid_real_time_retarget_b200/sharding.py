@@ -173,7 +173,7 @@ class PeerReassembly:
         if self.world == 1:
             return 0
         if self.packed:
-            return (self.hi - self.lo) * 14 * 4
+            return -(-(self.hi - self.lo) // 16) * 912
         return shard if self.mc_ptr else (self.world - 1) * shard
 
     @property
@@ -182,7 +182,7 @@ class PeerReassembly:
         if self.world == 1:
             return 0
         if self.packed:
-            return self.n * 14 * 4
+            return -(-self.n // 16) * 912
         if self.mc_ptr:
             return self.n * self.D * 4
         return (self.n - (self.hi - self.lo)) * self.D * 4

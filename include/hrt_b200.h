@@ -169,15 +169,19 @@ int hrt_peer_barrier(hrt_ctx* ctx, int n_peer, int my_rank, unsigned* const* d_p
  * N copies (this rank's included): 1/N of the egress bytes of hrt_retarget_body_quat_gather, no NCCL.  Close the step
  * with hrt_peer_barrier as above. */
 /* Reassembly INSIDE the compute kernel, packed wire format (the form bench.py's configs[4] line runs).  Only the 14 arm
- * hinge angles of a frame travel (56 B instead of 120: the other DOFs of this solver are structurally 0).  d_symm is this
- * rank's copy, d_symm_mc the multicast address, of ONE symmetric allocation of hrt_reassembly_layout()'s total_bytes per
- * rank, zero-filled once: [packed staging rows of the whole clip | flags].  Every warp publishes its packed span with
- * multimem.st, the last warp of a CTA round raises flag (rank, round, CTA) on every rank (fence.sys + multimem.st.release),
- * and the same warps unpack the peers' rounds that have landed into d_full_dof (n_total x D, this rank's clip-wide
- * result; own rows are written directly) between their own rounds, so transfer and unpacking hide under the solve.
- * Shards tile the clip in rank order, start at multiples of 16 frames; all ranks run the same GPU model (the flag index
- * uses the launch geometry).  epoch grows by one per step; separate consecutive steps with hrt_peer_barrier (a slow rank
- * may still be unpacking the staging rows the next step overwrites).  A peer that never arrives traps after 20 s. */
+ * hinge angles of a frame travel (the other DOFs of this solver are structurally 0).  d_symm is this rank's copy,
+ * d_symm_mc the multicast address, of ONE symmetric allocation of hrt_reassembly_layout()'s total_bytes per rank,
+ * zero-filled once: one 912-byte group per 16 clip frames = 16 x 14 hinge angles + a 16-byte check block {xor and
+ * position-weighted sum of the 224 words, salted with the step's epoch; the epoch}.  Every warp publishes its group with
+ * multimem.st (no flag, no fence: a group validates itself), and the same warps fetch the peers' groups of two rounds
+ * earlier, accept those whose check block matches the words that arrived and this step's epoch, and expand them into
+ * d_full_dof (n_total x D, this rank's clip-wide result; own rows are written directly) between their own rounds, so
+ * transfer and unpacking hide under the solve; a group that does not check out yet is fetched again later.
+ * Shards tile the clip in rank order and start at multiples of 16 frames; all ranks run the same GPU model (a group's
+ * round and warp follow from the launch geometry).  epoch starts at 1 and grows by one per step; separate consecutive
+ * steps with hrt_peer_barrier (a slow rank may still be unpacking the staging groups the next step overwrites).  A peer
+ * that never arrives traps after 20 s.  flag_offset == total_bytes == staging_bytes (kept for ABI stability); max_rounds
+ * = rounds of 16-frame groups per warp of the longest shard. */
 int hrt_reassembly_layout(hrt_ctx* ctx, int64_t n_total, int n_rank, const int64_t* shard_frames, size_t* staging_bytes,
                           size_t* flag_offset, size_t* total_bytes, int* max_rounds);
 int hrt_retarget_body_quat_reassemble(hrt_ctx* ctx, int64_t B, const float* d_src_gq, unsigned flags, int ik_iters,

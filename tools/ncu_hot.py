@@ -1,5 +1,7 @@
-"""Summarise an ncu report's source page: per CUDA source line, executed warp instructions and
-stall samples.   python tools/ncu_hot.py gpurun_out/prof.ncu-rep [top_n]"""
+"""Summarise an ncu report's source page per CUDA source line: executed warp instructions, stall samples and the top
+stall reasons (the report must have been captured with --import-source on and the kernel compiled with -lineinfo).
+    python tools/ncu_hot.py gpurun_out/prof.ncu-rep [top_n] [file-substring:first-last ...]
+Extra arguments sum a line range of one file, e.g.  hrt_retarget.cuh:330:470  (instructions / samples of that range)."""
 import csv
 import subprocess
 import sys
@@ -7,40 +9,52 @@ from collections import defaultdict
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+ranges = [a.split(":") for a in sys.argv[3:]]
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-# find header row
-hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
-hdr = rows[hi]
-col = {h: i for i, h in enumerate(hdr)}
-print("columns:", [h for h in hdr[:8]])
-agg = defaultdict(lambda: [0, 0, 0, defaultdict(int)])
-cur = None
-tot_inst = tot_samp = 0
-stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-for r in rows[hi + 1:]:
-    if len(r) < len(hdr):
+cur_file, hdr, col = "?", None, {}
+lines = {}                       # (file, line) -> [source text, inst, samples, {stall: n}]
+for r in rows:
+    if len(r) == 2 and r[0] == "File Path":
+        cur_file = r[1].rsplit("/", 1)[-1]
         continue
-    src = r[col["Source"]]
-    addr = r[col.get("Address", 0)] if "Address" in col else ""
+    if r and r[0] == "Line No":
+        hdr = r
+        col = {}
+        for i, h in enumerate(hdr):
+            col.setdefault(h, i)
+        continue
+    if hdr is None or len(r) < len(hdr) or not r[0].strip().isdigit():
+        continue                 # SASS rows have an empty line number: the CUDA row above carries their sum
     try:
         inst = int(float(r[col["Instructions Executed"]] or 0))
         samp = int(float(r[col["# Samples"]] or 0))
     except ValueError:
         continue
-    key = src.strip()[:110]
-    # in cuda,sass view, cuda lines carry aggregated numbers; sass lines follow. keep cuda-line rows only
-    agg[key][0] += inst
-    agg[key][1] += samp
-    for s in stall_cols:
-        try:
-            agg[key][3][s] += int(float(r[col[s]] or 0))
-        except ValueError:
-            pass
-    tot_inst += inst
-    tot_samp += samp
-print("total inst", tot_inst, "samples", tot_samp)
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
-    st = sorted(v[3].items(), key=lambda kv: -kv[1])[:3]
-    print(f"{v[0]:>12d} inst {v[1]:>7d} samp  {k}   {[(a.replace('stall_',''), b) for a, b in st if b]}")
+    key = (cur_file, int(r[0]))
+    e = lines.setdefault(key, [r[1].strip()[:100], 0, 0, defaultdict(int)])
+    e[1] += inst
+    e[2] += samp
+    for h, i in col.items():
+        if h.startswith("stall_"):
+            try:
+                e[3][h[6:]] += int(float(r[i] or 0))
+            except ValueError:
+                pass
+tot_i = sum(e[1] for e in lines.values())
+tot_s = sum(e[2] for e in lines.values())
+print(f"total warp instructions {tot_i}, samples {tot_s}")
+byfile = defaultdict(lambda: [0, 0])
+for (f, _), e in lines.items():
+    byfile[f][0] += e[1]
+    byfile[f][1] += e[2]
+for f, (i, s) in sorted(byfile.items(), key=lambda kv: -kv[1][1]):
+    print(f"  {f:28s} {i:>13d} inst ({100 * i / max(tot_i, 1):5.1f} %) {s:>8d} samples ({100 * s / max(tot_s, 1):5.1f} %)")
+for f, a, b in ranges:
+    i = sum(e[1] for (ff, l), e in lines.items() if f in ff and int(a) <= l <= int(b))
+    s = sum(e[2] for (ff, l), e in lines.items() if f in ff and int(a) <= l <= int(b))
+    print(f"range {f}:{a}-{b}: {i} inst ({100 * i / max(tot_i, 1):.2f} %), {s} samples ({100 * s / max(tot_s, 1):.2f} %)")
+for (f, l), e in sorted(lines.items(), key=lambda kv: -kv[1][2])[:top]:
+    st = sorted(e[3].items(), key=lambda kv: -kv[1])[:3]
+    print(f"{e[1]:>12d} inst {e[2]:>7d} samp  {f}:{l}  {e[0]}   {[(a, b) for a, b in st if b]}")
