@@ -189,10 +189,16 @@ HRT_DEV void jacobi_rot(double& app, double& aqq, double& apq, double& arp, doub
     a = c * v2p - s * v2q; b = s * v2p + c * v2q; v2p = a; v2q = b;
 }
 
+// Sweeps stop when the squared off-diagonal mass is below this fraction of the squared trace: off / trace <= 1e-11 leaves
+// the rotation 1e-11 from the converged one, four orders below the fp32 rounding of its elements (it used to be 1e-36,
+// i.e. 1e-18: one more sweep for 78 % of the wrist fits and, a warp running as long as its slowest lane, for every warp)
+#ifndef HRT_KABSCH_OFF_TOL
+#define HRT_KABSCH_OFF_TOL 1e-22
+#endif
 // NK independent Kabsch problems solved together (their fp64 dependency chains interleave: the torso
 // and the wrist fit of one arm cost little more than one).  A = M^T Z in fp64 (exact products of fp32
 // inputs) -> rotation quaternions.  Cyclic Jacobi on A^T A converges quadratically: sweeps stop when the
-// off-diagonal mass is below 1e-18 of the trace for every problem (2-3 sweeps; 8 at most).
+// off-diagonal mass is below 1e-11 of the trace for every problem (2 sweeps on the hand fits; 8 at most).
 template <int NK>
 HRT_DEV void kabsch_multi(const double (*A)[3][3], float4* out) {
     double s00[NK], s01[NK], s02[NK], s11[NK], s12[NK], s22[NK];
@@ -214,7 +220,7 @@ HRT_DEV void kabsch_multi(const double (*A)[3][3], float4* out) {
         for (int n = 0; n < NK; ++n) {
             const double off = fma(s01[n], s01[n], fma(s02[n], s02[n], s12[n] * s12[n]));
             const double tr = s00[n] + s11[n] + s22[n];
-            done = done && !(off > 1e-36 * tr * tr);
+            done = done && !(off > HRT_KABSCH_OFF_TOL * tr * tr);
         }
         if (done) break;
 #pragma unroll
@@ -334,9 +340,27 @@ HRT_DEV void pos_stage_span(float* dst, const float* src, int n_words, int lane)
     }
 }
 // the resident server runs ONE warp: no cross-warp instruction-fetch alignment there
+// HRT_POS_ALIGN_GROUP: warps of a scheduler that re-align together at phase boundaries (the unrolled bodies exceed the
+// instruction caches, so warps that share a scheduler should fetch the same lines).  4 = all of a 16-warp CTA's warps of
+// that scheduler, one instruction stream; 2 (default) = two pairs per scheduler that start HRT_POS_PAIR_SKEW_NS apart, so
+// that one pair's fp64 Jacobi phase (fp64-pipe-bound: all four warps in it at once saturate the pipe while the fp32
+// pipes idle) runs under the other pair's fp32 phases.  Measured on config 3p / 2^20 frames (profiles/r02_notes.md):
+// 4: 0.1201 / 0.3888 ms, pairs without skew: no change, pairs 5 us apart: 0.1146 / 0.3830 ms, no alignment: +2 %.
+#ifndef HRT_POS_ALIGN_GROUP
+#define HRT_POS_ALIGN_GROUP 2
+#endif
+#ifndef HRT_POS_PAIR_SKEW_NS
+#define HRT_POS_PAIR_SKEW_NS 5000
+#endif
 template <bool SYSMEM, int WARPS>
 HRT_DEV void pos_align(int warp) {
-    if (!SYSMEM) smsp_align<WARPS>(warp);
+    if (SYSMEM) return;
+    if (WARPS == 16 && HRT_POS_ALIGN_GROUP == 2) {
+        // warps w and w + 8 share a scheduler (w & 3) and a pair ((w >> 2) & 1)
+        asm volatile("bar.sync %0, 64;\n" ::"r"(1 + (warp & 7)) : "memory");
+    } else if (HRT_POS_ALIGN_GROUP != 0) {
+        smsp_align<WARPS>(warp);
+    }
 }
 
 // CTA-shared constants: both PosArm tables + the zero-pose bone angles (once per CTA)
@@ -392,6 +416,9 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
     const long long n_groups = (a.B + BQ_FRAMES_PER_WARP - 1) / BQ_FRAMES_PER_WARP;
     const long long total_warps = (long long)n_ctas * WARPS;
     const long long rounds = (n_groups + total_warps - 1) / total_warps;
+    // the second pair of every scheduler starts a third of a round late (clips of a few rounds would only pay for it)
+    if (!SYSMEM && WARPS == 16 && HRT_POS_ALIGN_GROUP == 2 && HRT_POS_PAIR_SKEW_NS > 0 && rounds >= 4 && ((warp >> 2) & 1))
+        __nanosleep(HRT_POS_PAIR_SKEW_NS);
     for (long long rnd = 0; rnd < rounds; ++rnd) {
         const long long grp_raw = rnd * total_warps + (long long)cta * WARPS + warp;
         const bool live = grp_raw < n_groups;
