@@ -1663,7 +1663,16 @@ namespace {
 template <int OP>
 int launch_rot_op(hrt_ctx* ctx, const RotOpArgs& a, cudaStream_t st) {
     const long long tiles = (a.n + 31) / 32;
-    const int grid = (int)std::max(1LL, std::min((tiles + ROT_WARPS - 1) / ROT_WARPS, (long long)ctx->sm_count * 8));
+    // one wave of exactly the CTAs that are resident together (grid-stride loop inside): a fixed 8 per SM left a second,
+    // one-third-full wave behind for every instantiation above 32 registers
+    static int occ[16] = {0};
+    const int d = ctx->device & 15;
+    if (!occ[d]) {
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, rot_op_kernel<OP>, ROT_WARPS * 32, 0) != cudaSuccess || o < 1) o = 4;
+        occ[d] = o;
+    }
+    const int grid = (int)std::max(1LL, std::min((tiles + ROT_WARPS - 1) / ROT_WARPS, (long long)ctx->sm_count * occ[d]));
     rot_op_kernel<OP><<<grid, ROT_WARPS * 32, 0, st>>>(a);
     return 0;
 }
