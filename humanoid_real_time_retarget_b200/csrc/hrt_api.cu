@@ -930,6 +930,9 @@ int hrt_retarget_body_quat_reassemble(hrt_ctx* ctx, int64_t B, const float* d_sr
     {
         static const unsigned dbg = [] { const char* e = getenv("HRT_GATHER_DEBUG"); return e ? (unsigned)atoi(e) : 0u; }();
         a.g.debug = dbg;
+        // no multicast mapping (d_symm_mc == d_symm, which a real multicast address never is): nothing is published; the
+        // rank only unpacks what is already in its staging buffer (single-process replay of a rank, used by the tests)
+        if (d_symm_mc == d_symm) a.g.debug |= 1u;
     }
     // every rank launches the same geometry (one CTA per SM, 16 warps): a group's round and warp follow from its index
     const size_t smem = ((size_t)BQ_CONST_WORDS + (size_t)BQ_WARPS_WIDE * bq_tile_words(ctx->bq.J_src, ctx->bq.J_rob, false) +

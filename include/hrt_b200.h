@@ -181,7 +181,8 @@ int hrt_peer_barrier(hrt_ctx* ctx, int n_peer, int my_rank, unsigned* const* d_p
  * round and warp follow from the launch geometry).  epoch starts at 1 and grows by one per step; separate consecutive
  * steps with hrt_peer_barrier (a slow rank may still be unpacking the staging groups the next step overwrites).  A peer
  * that never arrives traps after 20 s.  flag_offset == total_bytes == staging_bytes (kept for ABI stability); max_rounds
- * = rounds of 16-frame groups per warp of the longest shard. */
+ * = rounds of 16-frame groups per warp of the longest shard.  d_symm_mc == d_symm means "no multicast mapping": the
+ * rank publishes nothing and only unpacks the groups already present in d_symm (replay of one rank in one process). */
 int hrt_reassembly_layout(hrt_ctx* ctx, int64_t n_total, int n_rank, const int64_t* shard_frames, size_t* staging_bytes,
                           size_t* flag_offset, size_t* total_bytes, int* max_rounds);
 int hrt_retarget_body_quat_reassemble(hrt_ctx* ctx, int64_t B, const float* d_src_gq, unsigned flags, int ik_iters,
