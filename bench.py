@@ -285,30 +285,27 @@ def side_measurements(eng, hrt, oc, sk, dev):
     gq = torch.empty((65536, 33, 4), device=dev)
     gtt = torch.empty((65536, 33, 3), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    times = []
-    for i in range(13):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        eng_hu.fk_angles(hrt.TREE_ROBOT, ang, clip=True, out=(gq, gtt))
-        b.record()
+    def kernel_ms(launch, flush_l2, reps=13, skip=3):
+        """Device time of ONE launch: an event pair around each of `reps` launches queued back to back (with the L2 flush in
+        between where asked), one synchronize at the end: the host-side cost of issuing the call (ctypes marshalling, ~5-10 us)
+        overlaps the previous kernel / the flush instead of sitting between the two events."""
+        evs = []
         torch.cuda.synchronize(dev)
-        if i >= 3:
-            times.append(a.elapsed_time(b))
-    ms = float(np.median(times))
+        for _ in range(reps):
+            if flush_l2:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            launch()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize(dev)
+        return float(np.median([a.elapsed_time(b) for a, b in evs[skip:]]))
+
+    ms = kernel_ms(lambda: eng_hu.fk_angles(hrt.TREE_ROBOT, ang, clip=True, out=(gq, gtt)), True)
     peak, _ = hbm_peak()
     jac = torch.empty((65536, 2, 6, 32), device=dev)
-    jt = []
-    for i in range(13):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        eng_hu.fk_jacobian(hrt.TREE_ROBOT, ang, [20, 29], clip=True, out=jac)
-        b.record()
-        torch.cuda.synchronize(dev)
-        if i >= 3:
-            jt.append(a.elapsed_time(b))
-    jms = float(np.median(jt))
+    jms = kernel_ms(lambda: eng_hu.fk_jacobian(hrt.TREE_ROBOT, ang, [20, 29], clip=True, out=jac), True)
     # the same FK on the host cores: the oracle's restatement of HuForwardModel.forward_kinematics (natively batched)
     ang_h = ang.cpu()
     torch.set_num_threads(os.cpu_count() or 1)
@@ -322,8 +319,9 @@ def side_measurements(eng, hrt, oc, sk, dev):
                        "hbm_frac": 65536 * 1080 / (ms * 1e-3) / 1e9 / peak,
                        "jacobian_2_links_ms": jms, "jacobian_hbm_frac": 65536 * 1664 / (jms * 1e-3) / 1e9 / peak,
                        "cpu_port_configs_per_s": 65536 / cpu_s,
-                       "note": "70.8 MB = 11 us at peak: launch-bound at this size; see profiles/ for 2^20-2^22 configurations"}
-    del jac, gq, gtt, flush
+                       "note": "device time per launch (event pair per launch, launches queued back to back); 70.8 MB = 11 us at peak, 13.6 us at the "
+                               "kernel's steady-state rate: 6-8 us per launch are ramp-up and drain of a single wave (profiles/r02_notes.md)"}
+    del jac, gq, gtt
     # the position-input (teleop) solver batched over a 2^18-frame clip, device-resident
     n3 = 1 << 18
     g3 = torch.Generator().manual_seed(3)
@@ -336,16 +334,7 @@ def side_measurements(eng, hrt, oc, sk, dev):
     d3 = torch.empty(n3, 30, device=dev)
     res = {}
     for name, fl in (("closed_form", 0), ("limits_and_10_refinement_steps", hrt.POS_CLAMP | hrt.POS_IK)):
-        tt = []
-        for i in range(8):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            eng.retarget_full_body_pos(b3, l3, r3, out=(None, d3, None), flags=fl)
-            b.record()
-            torch.cuda.synchronize(dev)
-            if i >= 3:
-                tt.append(a.elapsed_time(b))
-        m3 = float(np.median(tt))
+        m3 = kernel_ms(lambda: eng.retarget_full_body_pos(b3, l3, r3, out=(None, d3, None), flags=fl), False, reps=10)
         res[name] = {"ms": m3, "frames_per_s": n3 / (m3 * 1e-3), "hbm_frac": n3 * 852 / (m3 * 1e-3) / 1e9 / peak}
     out["pos_path_2p18"] = {"workload": "config 3p: VtrdynFullBodyPosRetargeter batched, 732 B in + 120 B dof per frame, 2^18 frames (192 MB in)",
                             **res}

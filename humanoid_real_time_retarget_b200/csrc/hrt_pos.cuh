@@ -117,12 +117,29 @@ HRT_DEV float radians_between_x(vec3 v1, vec3 v2, vec3 n) {
 
 // theta / phi of a bone for the shoulder pitch-roll solve (plane normal y) or the
 // shoulder-yaw / elbow-pitch solve (plane normal z); v already in the parent frame
+#ifndef HRT_POS_ONEHOT_SHORTCUT
+#define HRT_POS_ONEHOT_SHORTCUT 1
+#endif
 template <int PLANE>   // 1: xz-plane (normal y), 2: xy-plane (normal z)
 HRT_DEV void bone_angles_x(const vec3 v, float* theta, float* phi) {
-    const vec3 ex = make_vec3(1.f, 0.f, 0.f);
     const vec3 nrm = (PLANE == 1) ? make_vec3(0.f, 1.f, 0.f) : make_vec3(0.f, 0.f, 1.f);
+#if HRT_POS_ONEHOT_SHORTCUT
+    // proj_in_plane_x(v, e_k) and radians_between_x(e_x, vp, e_k) with the one-hot operands folded by hand (the compiler
+    // cannot: x * 0 is not 0 for NaN / inf, and the reciprocal is inline PTX).  Every dropped operation is exact --
+    // a / 1, a * 1, a * 0 = +-0, a + (+-0) -- so the values are the reference's own up to the sign of a zero, which
+    // acos, the sign test and the products downstream do not see; a NaN in v reaches every component of v (it comes out
+    // of a quaternion rotation), so NaN in -> NaN out still holds.
+    const vec3 vp = (PLANE == 1) ? make_vec3(v.x, 0.f, v.z) : make_vec3(v.x, v.y, 0.f);
+    {
+        const vec3 v2 = div3_x(vp, norm3_x(vp));
+        const float ang = acosf(fminf(fmaxf(v2.x, -1.f), 1.f));
+        *theta = mul_rn(ang, sign_f((PLANE == 1) ? -v2.z : v2.y));
+    }
+#else
+    const vec3 ex = make_vec3(1.f, 0.f, 0.f);
     const vec3 vp = proj_in_plane_x(v, nrm);
     *theta = radians_between_x(ex, vp, nrm);
+#endif
     // shoulderPR: n = cross(v_proj, y);  elbow: n = cross(z, v_proj)
     const vec3 n2 = (PLANE == 1) ? cross3_x(vp, nrm) : cross3_x(nrm, vp);
     *phi = radians_between_x(vp, v, n2);
