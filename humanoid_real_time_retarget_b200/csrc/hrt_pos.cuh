@@ -95,7 +95,7 @@ HRT_DEV vec3 div3_x(const vec3 v, float s) {
     const float y = rcp_refined(s);
     return make_vec3(div_by_rn(v.x, s, y), div_by_rn(v.y, s, y), div_by_rn(v.z, s, y));
 }
-HRT_DEV float sign_f(float x) { return (float)((x > 0.f) - (x < 0.f)); }
+HRT_DEV float sign_f(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }     // torch.sign: 0 for 0 (and for NaN here)
 
 // transform3d.py:62-75   v - (dot(v,n) / ||n||^2) * n
 HRT_DEV vec3 proj_in_plane_x(const vec3 v, const vec3 n) {
@@ -352,6 +352,10 @@ HRT_DEV void pos_stage_span(float* dst, const float* src, int n_words, int lane)
         } else {
             for (int i = lane; i < n_words; i += 32) dst[i] = __ldcv(src + i);
         }
+    } else if (n_words == BQ_FRAMES_PER_WARP * 63) {      // a full group of 21-point body rows
+        warp_span_g2s_n4<BQ_FRAMES_PER_WARP * 63 / 4>(dst, src, lane);
+    } else if (n_words == BQ_FRAMES_PER_WARP * 60) {      // ... of 20-point hand rows
+        warp_span_g2s_n4<BQ_FRAMES_PER_WARP * 60 / 4>(dst, src, lane);
     } else {
         warp_span_g2s(dst, src, n_words, lane);
     }
@@ -486,7 +490,13 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
             }
             if (QUATS) l2_prefetch_span(a.body_q + fn * pp.n_bodyq * 4, nn * pp.n_bodyq * 4);
         }
-        if (a.out_dof) for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
+        if (a.out_dof) {
+            if (nfr == BQ_FRAMES_PER_WARP) {                     // 16 rows are whole 16-byte blocks for any D
+                for (int i = lane; i < BQ_FRAMES_PER_WARP * D / 4; i += 32) reinterpret_cast<float4*>(dof_t)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int i = lane; i < nfr * D; i += 32) dof_t[i] = 0.f;
+            }
+        }
         cp_async_wait<0>();
         __syncwarp();
 

@@ -592,7 +592,6 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
     const int fl = lane >> 1;
     const int side = lane & 1;
     const ArmParams& ap = reinterpret_cast<const ArmParams*>(smem)[side];
-    const float* rest_s = smem + 2 * sizeof(ArmParams) / 4;
     const bool with_lq = a.out_local_q != nullptr;
     float* tile = smem + BQ_CONST_WORDS + warp * bq_tile_words(bp.J_src, bp.J_rob, with_lq);
     float* lp_t = tile;                                   // input rows, later the link-position image
