@@ -212,7 +212,7 @@ HRT_DEV void chol_solve7(float* A, float* b) {
             float s = A[i * (i + 1) / 2 + j];
 #pragma unroll
             for (int k = 0; k < j; ++k) s -= A[i * (i + 1) / 2 + k] * A[j * (j + 1) / 2 + k];
-            if (i == j) inv[i] = rsqrtf(s);
+            if (i == j) inv[i] = rsqrt_fast(s);         // pivots are >= lambda^2 > 0: the bare MUFU.RSQ, no subnormal rescue
             else A[i * (i + 1) / 2 + j] = s * inv[j];
         }
     }
@@ -262,7 +262,8 @@ HRT_DEV void ik_step_f(float th[7], const vec3 p_sh, const float (*off)[3], cons
     e[3] = pw_t.x - pc[6].x; e[4] = pw_t.y - pc[6].y; e[5] = pw_t.z - pc[6].z;
     {
         const float4 qe = quat_normalize_f(quat_mul_f(Rh, quat_conj(G)));
-        const float n = sqrtf(qe.x * qe.x + qe.y * qe.y + qe.z * qe.z);
+        const float n2 = qe.x * qe.x + qe.y * qe.y + qe.z * qe.z;
+        const float n = n2 > 1e-30f ? n2 * rsqrt_fast(n2) : 0.f;       // |vector part| (sqrtf's range checks are dead weight here)
         const float sc = wo * rotvec_scale_f(n, qe.w);
         e[6] = qe.x * sc; e[7] = qe.y * sc; e[8] = qe.z * sc;
     }
