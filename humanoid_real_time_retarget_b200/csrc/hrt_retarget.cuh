@@ -434,6 +434,9 @@ HRT_DEV bool gather_validate_fast(const BodyQuatArgs::Gather& g, const float* ri
         bad |= (chk.x ^ x ^ salt) | (chk.y - y - salt) | (chk.z ^ g.epoch);
         slot += BQ_PK_SLOT;
     }
+    // one verdict for the warp (every lane read the check blocks on its own), and every lane is done reading the slots
+    // before any lane refetches them
+    bad = __reduce_or_sync(0xffffffffu, bad);
     return bad == 0u || (g.debug & 32u) != 0;
 }
 
@@ -496,7 +499,8 @@ HRT_DEV void gather_tail_one(const BodyQuatArgs::Gather& g, const int* st, float
         x ^= mine[5] ^ mine[6]; y += mine[5] + mine[6];
         x = __reduce_xor_sync(0xffffffffu, x);
         y = __reduce_add_sync(0xffffffffu, y);
-        if ((us[BQ_PK_WORDS] == (x ^ salt) && us[BQ_PK_WORDS + 1] == y + salt && us[BQ_PK_WORDS + 2] == g.epoch) || (g.debug & 32u)) break;
+        const bool good = us[BQ_PK_WORDS] == (x ^ salt) && us[BQ_PK_WORDS + 1] == y + salt && us[BQ_PK_WORDS + 2] == g.epoch;
+        if (__all_sync(0xffffffffu, good) || (g.debug & 32u)) break;                     // one verdict for the warp
         if (bq_timer_ns() - t0 > g.timeout_ns) __trap();        // a lost peer must not hang the box
         __nanosleep(2000);
         __syncwarp();
