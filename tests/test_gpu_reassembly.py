@@ -79,3 +79,41 @@ def test_reassembled_clip_equals_single_gpu_result(hrt, oc, n_frames, world):
                                           symm.data_ptr(), symm.data_ptr(), epoch, flags=flags)
         torch.cuda.synchronize()
         assert torch.equal(full[:n_frames], want), (n_frames, world, me)
+
+
+def test_stale_and_half_arrived_groups_are_refused_until_the_steps_own_land(hrt, oc):
+    """The staging buffer starts with the PREVIOUS step's groups of another clip (right check sums, old epoch); this
+    step's groups arrive by DMA on a second stream ~1.5 ms after the kernel has started, piecewise, while the unpack
+    warps (fast path) and the compute warps' tail (ragged last group) keep fetching: nothing stale or half-arrived may
+    reach the result."""
+    from humanoid_real_time_retarget_b200.sharding import shard_range
+    sk = oc.load_skeletons()
+    eng = hrt.Engine(0).set_standard_trees()
+    flags = hrt.BQ_CLAMP | hrt.BQ_IK
+    n_frames, world, me, epoch = 148 * 16 * 16 * 2 + 16 * 9 + 3, 2, 0, 5
+    clips = []
+    for seed in (21, 22):
+        raw = oc.synth_clip_3q(1 << 14, seed=seed, sk=sk).cuda().repeat(-(-n_frames // (1 << 14)), 1, 1)[:n_frames].contiguous()
+        _, dof, _ = eng.retarget_body_quat(raw, flags=flags, want_local_q=False, want_link_pos=False)
+        clips.append((raw, dof))
+    (raw, want), (_, other) = clips
+    shard_lo = [shard_range(n_frames, r, world)[0] for r in range(world)]
+    shard_n = [shard_range(n_frames, r, world)[1] - shard_lo[r] for r in range(world)]
+    _, _, total_bytes, _ = eng.reassembly_layout(n_frames, shard_n)
+    old, new = np.zeros(total_bytes // 4, np.uint32), np.zeros(total_bytes // 4, np.uint32)
+    _pack_groups(other.cpu().numpy(), shard_lo[1], shard_n[1], epoch - 1, old)
+    _pack_groups(want.cpu().numpy(), shard_lo[1], shard_n[1], epoch, new)
+    symm = torch.from_numpy(old.view(np.float32)).cuda()
+    new_h = torch.from_numpy(new.view(np.float32)).pin_memory()
+    full = torch.zeros(n_frames, 30, device="cuda")
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        torch.cuda._sleep(3_000_000)                       # ~1.5 ms: the kernel below is well under way by then
+        n_piece = symm.numel() // 7 // 4 * 4
+        for k in reversed(range(0, symm.numel(), n_piece)):      # the copy engine moves it in pieces, last groups first
+            symm[k:k + n_piece].copy_(new_h[k:k + n_piece], non_blocking=True)
+    eng.retarget_body_quat_reassemble(raw[:shard_n[0]], full, n_frames, me, shard_lo, shard_n, symm.data_ptr(), symm.data_ptr(), epoch,
+                                      flags=flags)
+    torch.cuda.synchronize()
+    assert torch.equal(full, want)
