@@ -366,12 +366,12 @@ HRT_DEV void pos_stage_span(float* dst, const float* src, int n_words, int lane)
 // that scheduler, one instruction stream; 2 (default) = two pairs per scheduler that start HRT_POS_PAIR_SKEW_NS apart, so
 // that one pair's fp64 Jacobi phase (fp64-pipe-bound: all four warps in it at once saturate the pipe while the fp32
 // pipes idle) runs under the other pair's fp32 phases.  Measured on config 3p / 2^20 frames (profiles/r02_notes.md):
-// 4: 0.1201 / 0.3888 ms, pairs without skew: no change, pairs 5 us apart: 0.1146 / 0.3830 ms, no alignment: +2 %.
+// 4: 0.1201 / 0.3888 ms, pairs without skew: no change, pairs 5 us apart: 0.1146 / 0.3830 ms (3-8 us apart are within 3 % of each other; 6.5 us is the default), no alignment: +2 %.
 #ifndef HRT_POS_ALIGN_GROUP
 #define HRT_POS_ALIGN_GROUP 2
 #endif
 #ifndef HRT_POS_PAIR_SKEW_NS
-#define HRT_POS_PAIR_SKEW_NS 5000
+#define HRT_POS_PAIR_SKEW_NS 6500
 #endif
 template <bool SYSMEM, int WARPS>
 HRT_DEV void pos_align(int warp) {
