@@ -147,6 +147,9 @@ constexpr int BQ_GATHER_UNPACK_REGS = 32;
 // a peer's group of round j is fetched once this rank's own warp has finished round j + LAG: the ranks run at the same
 // pace, so the group has had LAG rounds (~40 us each) to cross the switch; a group that fails its check is fetched again
 constexpr int BQ_GATHER_LAG = 1;
+#ifndef HRT_GATHER_POLL_NS
+#define HRT_GATHER_POLL_NS 5000
+#endif
 // an unpack warp's ring: one slot per peer + the 16-row image the slots are expanded through
 constexpr int BQ_GATHER_RING_WORDS = ((HRT_MAX_PEERS - 1) * BQ_PK_SLOT + BQ_FRAMES_PER_WARP * 32 + 3) / 4 * 4;
 // per-warp reassembly state in shared memory (ints): [0] cursor = next peer round to unpack, [1] rounds this warp has
@@ -553,7 +556,7 @@ HRT_DEV void gather_unpack_warp(const BodyQuatArgs::Gather& g, float* gbase, int
     for (int j = 0; j < max_rounds; ++j) {
         // pacing: the peers run at this rank's pace, and the four compute warps of a scheduler move in lockstep: one poll
         // per round on the first of them (a finished compute warp reports INT_MAX); correctness rests on the check blocks
-        while (*progress < j + 1 + BQ_GATHER_LAG) __nanosleep(5000);
+        while (*progress < j + 1 + BQ_GATHER_LAG) __nanosleep(HRT_GATHER_POLL_NS);
 #pragma unroll 1
         for (int k = 0; k < WARPS / BQ_GATHER_UNPACK_WARPS; ++k) {
             const int rq_full = state[BQ_GATHER_UNPACK_WARPS * k * BQ_GATHER_STATE_WORDS + 2];
