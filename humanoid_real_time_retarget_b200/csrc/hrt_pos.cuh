@@ -69,7 +69,9 @@ struct PosParams {
 // CTA-shared constants in shared memory: [2 x PosArm][8 zero-pose angles][2 x ArmIkParams]
 HRT_HD inline int pos_zero_ang_word() { return 2 * (int)sizeof(PosArm) / 4; }
 HRT_HD inline int pos_ik_word() { return (pos_zero_ang_word() + 8 + 3) / 4 * 4; }
-HRT_HD inline int pos_const_words() { return (pos_ik_word() + 2 * (int)sizeof(ArmIkParams) / 4 + 3) / 4 * 4; }
+// zero-pose offsets of the Kabsch fits as doubles ([3][3] torso, then [side][5][3] wrist): converted once per CTA, not per frame
+HRT_HD inline int pos_zd_word() { return (pos_ik_word() + 2 * (int)sizeof(ArmIkParams) / 4 + 3) / 4 * 4; }
+HRT_HD inline int pos_const_words() { return pos_zd_word() + 2 * (9 + 2 * 15) + 2; }
 
 struct PosArgs {
     long long B;
@@ -308,6 +310,23 @@ HRT_DEV void kabsch_accumulate(const vec3* M, const vec3* Z, double A[3][3]) {
     }
 }
 
+// the same with the zero-pose offsets already widened (the widening is exact: same sums)
+template <int N>
+HRT_DEV void kabsch_accumulate_zd(const vec3* M, const double* Zd, double A[3][3]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) A[i][k] = 0.0;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        const double m[3] = {(double)M[n].x, (double)M[n].y, (double)M[n].z};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) A[i][k] = fma(m[i], Zd[n * 3 + k], A[i][k]);
+    }
+}
+
 // M: measured offsets (n x 3), Z: zero-pose offsets (n x 3), both fp32.  Returns the quaternion.
 template <int N>
 HRT_DEV float4 kabsch_quat(const vec3* M, const vec3* Z) {
@@ -392,6 +411,11 @@ HRT_DEV void pos_setup(const PosParams& pp, float* smem) {
     const float* iks = reinterpret_cast<const float*>(&pp.ik[0]);
     for (int i = threadIdx.x; i < 2 * (int)sizeof(ArmIkParams) / 4; i += blockDim.x) smem[pos_ik_word() + i] = iks[i];
     if (threadIdx.x < 8) zero_ang[threadIdx.x] = pp.zero_ang[threadIdx.x >> 2][threadIdx.x & 3];
+    double* zd = reinterpret_cast<double*>(smem + pos_zd_word());
+    for (int i = threadIdx.x; i < 9 + 30; i += blockDim.x) {             // (the resident server runs this with one warp)
+        const int w = i - 9, sd = w / 15, r = w % 15;
+        zd[i] = i < 9 ? (double)pp.ztorso[i / 3][i % 3] : (double)pp.arm[sd].zwrist[r / 3][r % 3];
+    }
     __syncthreads();
 }
 
@@ -421,6 +445,7 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
     const ArmIkParams& ik = reinterpret_cast<const ArmIkParams*>(smem + pos_ik_word())[side];
     const PosArm& ap = arms_s[side];
     const int const_words = pos_const_words();
+    const double* zd_s = reinterpret_cast<const double*>(smem + pos_zd_word());
     const bool with_lq = a.out_local_q != nullptr;
     const bool with_bq = (MODE == POS_FULL_BODY_POS) && a.out_body_gq != nullptr;
     float* tile = smem + const_words + warp * pos_tile_words(pp, with_lq, with_bq);
@@ -518,24 +543,18 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
             // the torso fit and (full_body_pos) this arm's wrist fit are independent: solved together
             double A[2][3][3];
             {
-                vec3 M[3], Z[3];
+                vec3 M[3];
                 const vec3 org = bpt(pp.torso_org);
 #pragma unroll
-                for (int n = 0; n < 3; ++n) {
-                    M[n] = sub3_x(bpt(pp.torso_pts[n]), org);
-                    Z[n] = make_vec3(pp.ztorso[n][0], pp.ztorso[n][1], pp.ztorso[n][2]);
-                }
-                kabsch_accumulate<3>(M, Z, A[0]);
+                for (int n = 0; n < 3; ++n) M[n] = sub3_x(bpt(pp.torso_pts[n]), org);
+                kabsch_accumulate_zd<3>(M, zd_s, A[0]);
             }
             if (MODE == POS_FULL_BODY_POS) {
-                vec3 M[5], Z[5];
+                vec3 M[5];
                 const vec3 org = ld3(hand + pp.hand_org * 3);
 #pragma unroll
-                for (int n = 0; n < 5; ++n) {
-                    M[n] = sub3_x(ld3(hand + pp.hand_kabsch[n] * 3), org);
-                    Z[n] = make_vec3(ap.zwrist[n][0], ap.zwrist[n][1], ap.zwrist[n][2]);
-                }
-                kabsch_accumulate<5>(M, Z, A[1]);
+                for (int n = 0; n < 5; ++n) M[n] = sub3_x(ld3(hand + pp.hand_kabsch[n] * 3), org);
+                kabsch_accumulate_zd<5>(M, zd_s + 9 + side * 15, A[1]);
                 float4 q[2];
                 kabsch_multi<2>(A, q);
                 torso = q[0];
