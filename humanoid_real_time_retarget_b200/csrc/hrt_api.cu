@@ -128,6 +128,7 @@ struct DeviceGuard {
     int rc = dev_guard_.enter(ctx); \
     if (rc) return rc
 
+constexpr float kArmLimitMax = 3.1447f;              // 2 x the range sincos_half_lim is fitted on (a hair above pi)
 constexpr unsigned long long kServerIdleNs = 20ull * 1000 * 1000;     // a resident kernel leaves after 20 ms without a frame
 
 // Post one request to a resident server kernel and spin on its answer.  ctrl words (mapped pinned memory):
@@ -743,6 +744,9 @@ int hrt_configure_body_quat(hrt_ctx* ctx, int src_tree, int rob_tree, const int3
             if (c > 0 && rt.parent[f + c] != f + c - 1) return fail(HRT_E_UNSUPPORTED_TREE, "arm joints must form a chain");
             ap.lower[c] = rt.lim[f + c][0];
             ap.upper[c] = rt.lim[f + c][1];
+            // the arm chain's half-angle sine / cosine (sincos_half_lim) is written for hinge angles within [-pi, pi]
+            if (!(ap.lower[c] >= -kArmLimitMax && ap.upper[c] <= kArmLimitMax))
+                return fail(HRT_E_UNSUPPORTED_TREE, "arm hinge %d: limits [%g, %g] reach beyond +-pi", f + c, ap.lower[c], ap.upper[c]);
         }
         if (rt.parent[f + 7] != f + 6 || rt.parent[f + 8] != f + 6)
             return fail(HRT_E_UNSUPPORTED_TREE, "expected two gripper links under the wrist-yaw link");
@@ -1103,7 +1107,12 @@ int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const 
             const int f = rob_first[side];
             for (int c = 0; c < 9; ++c)
                 for (int k = 0; k < 3; ++k) pp.ik[side].off[c][k] = rt.jr[f + c].off[k];
-            for (int c = 0; c < 7; ++c) { pp.ik[side].lower[c] = rt.lim[f + c][0]; pp.ik[side].upper[c] = rt.lim[f + c][1]; }
+            for (int c = 0; c < 7; ++c) {
+                pp.ik[side].lower[c] = rt.lim[f + c][0];
+                pp.ik[side].upper[c] = rt.lim[f + c][1];
+                if (!(pp.ik[side].lower[c] >= -kArmLimitMax && pp.ik[side].upper[c] <= kArmLimitMax))
+                    return fail(HRT_E_UNSUPPORTED_TREE, "arm hinge %d: limits [%g, %g] reach beyond +-pi", f + c, pp.ik[side].lower[c], pp.ik[side].upper[c]);
+            }
             for (int k = 0; k < 3; ++k) pp.ik[side].p_sh[k] = pos[f * 3 + k];
         }
     }

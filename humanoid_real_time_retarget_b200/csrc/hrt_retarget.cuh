@@ -199,7 +199,7 @@ HRT_DEV void warp_store_span(float* __restrict__ dst, const float* tile, int n_w
 template <int C>
 HRT_DEV float4 arm_local_quat(float th) {
     float s, c;
-    sincos_half_nf(0.5f * th, &s, &c);
+    sincos_half_lim(0.5f * th, &s, &c);
     constexpr int k = HRT_ARM_AXIS(C);
     return make_float4(k == 0 ? s : 0.f, k == 1 ? s : 0.f, k == 2 ? s : 0.f, c);
 }
@@ -244,7 +244,7 @@ HRT_DEV void arm_chain_f(const float th[7], const vec3 p_sh, const float (*off)[
         ax[c] = (HRT_ARM_AXIS(c) == 0) ? quat_axis_f<0>(G) : (HRT_ARM_AXIS(c) == 1) ? quat_axis_f<1>(G) : quat_axis_f<2>(G);
         pc[c] = p;
         float s, cs;
-        sincos_half_nf(0.5f * th[c], &s, &cs);
+        sincos_half_lim(0.5f * th[c], &s, &cs);
         // products of unit quaternions: renormalising once, where G is used, is enough
         G = quat_mul_axis_f(G, HRT_ARM_AXIS(c), s, cs);
         if (c < 6) p = add3(p, quat_rotate_f(G, make_vec3(off[c + 1][0], off[c + 1][1], off[c + 1][2])));
