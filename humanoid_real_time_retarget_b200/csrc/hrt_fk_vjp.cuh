@@ -231,9 +231,10 @@ ik_refine_kernel(const __grid_constant__ IkArmTables tb, const IkRefineArgs a) {
         const float4 Rh = __ldg(reinterpret_cast<const float4*>(a.qw_t) + i);
         nan_probe += ((pe_t.x + pe_t.y) + (pe_t.z + pw_t.x)) + ((pw_t.y + pw_t.z) + ((Rh.x + Rh.y) + (Rh.z + Rh.w)));
         const float lam2 = a.damping * a.damping;
+        const mat3c H = quat_to_mat3c(Rh);
         for (int it = 0; it < a.iters; ++it) {
             if (a.residual) a.residual[i * (a.iters + 1) + it] = ik_residual_norm_f(th, p_sh, tb.off[side], pe_t, pw_t, Rh, a.rot_weight);
-            ik_step_f(th, p_sh, tb.off[side], tb.lower[side], tb.upper[side], pe_t, pw_t, Rh, lam2, a.rot_weight, a.active_set != 0);
+            ik_step_f(th, p_sh, tb.off[side], tb.lower[side], tb.upper[side], pe_t, pw_t, H, lam2, a.rot_weight, a.active_set != 0);
         }
         if (a.residual) a.residual[i * (a.iters + 1) + a.iters] = ik_residual_norm_f(th, p_sh, tb.off[side], pe_t, pw_t, Rh, a.rot_weight);
 #pragma unroll

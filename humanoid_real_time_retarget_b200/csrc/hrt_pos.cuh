@@ -640,11 +640,11 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
                 float4 G;
                 arm_chain_f(th, p_sh, ik.off, ax, pc, G);
                 const vec3 pe_t = pc[3], pw_t = pc[6];
-                const float4 Rh = quat_normalize_f(G);
+                const mat3c H = quat_to_mat3c(quat_normalize_f(G));
                 const float lam2 = a.damping * a.damping;
                 for (int it = 0; it < a.ik_iters; ++it) {
                     pos_align<SYSMEM, WARPS>(warp);
-                    ik_step_f(thc, p_sh, ik.off, ik.lower, ik.upper, pe_t, pw_t, Rh, lam2, a.rot_weight, true);
+                    ik_step_f(thc, p_sh, ik.off, ik.lower, ik.upper, pe_t, pw_t, H, lam2, a.rot_weight, true);
                 }
             }
 #pragma unroll

@@ -251,43 +251,110 @@ HRT_DEV void arm_chain_f(const float th[7], const vec3 p_sh, const float (*off)[
     }
 }
 
-// one damped-least-squares step: e = [pe* - p_elbow; pw* - p_wrist; w_o rotvec(qw* qw^-1)],
+// One damped-least-squares step: e = [pe* - p_elbow; pw* - p_wrist; w_o rotvec(R* R^T)],
 // dtheta = (J^T J + lambda^2 I)^-1 J^T e (7x7 Cholesky in registers), theta <- clamp(theta + dtheta).
 // active_set: a hinge that sits on a limit while the gradient J^T e pushes it further out is frozen for this
 // step (its row / column leave the system), which makes the clamped iteration a descent method.
+//
+// The chain is carried as a rotation MATRIX (three columns).  As a quaternion a hinge costs ~55 instructions (hinge
+// axis = a column of R(G): 9, G * q_hinge: 8, rotating the next offset: 21, half-angle pair: 14, position add: 3); with
+// the columns at hand the axis is free, a hinge turns two columns into each other (12), the offset is nine FMAs
+// straight into the position, and the full-angle pair comes from the half-angle one by the double-angle formulas (4):
+// ~39.  The orientation residual is read off E = H R^T (H = target orientation as a matrix, loop invariant):
+// sin(phi) n = 1/2 sum_k r_k x h_k, cos(phi) = (tr E - 1) / 2, rotvec = phi n.  J^T J + lambda^2 I and J^T e are single
+// FMA chains over the rows column i has (orientation rows carry the weight: axw = wo * ax).
+// 930 -> 842 instructions per step; 10-step call on 2^20 frames 0.934 -> 0.846 ms; against the float64 run of the same
+// spec the result is as close as the quaternion chain's was (profiles/parity_r02.json, profiles/r02_notes.md).
+struct mat3c { vec3 c[3]; };                         // columns
+
+HRT_DEV mat3c quat_to_mat3c(const float4 q) {
+    mat3c m;
+    m.c[0] = quat_axis_f<0>(q); m.c[1] = quat_axis_f<1>(q); m.c[2] = quat_axis_f<2>(q);
+    return m;
+}
+
+// phi / sin(phi) for n = sin(phi) >= 0, w = cos(phi) of either sign (atan as in rotvec_scale_f)
+HRT_DEV float angle_over_sin_f(float n, float w) {
+    const float aw = fabsf(w);
+    const float mx = fmaxf(n, aw), mn = fminf(n, aw);
+    const float t = __fdividef(mn, mx);
+    const bool big = t > 0.41421356f;
+    const float u = big ? __fdividef(t - 1.f, t + 1.f) : t;
+    const float z = u * u;
+    float a = (((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f) * z * u + u;
+    a = big ? a + 0.78539816339f : a;
+    float phi = (n > aw) ? 1.57079637f - a : a;      // atan2(n, |w|)
+    phi = (w < 0.f) ? 3.14159274f - phi : phi;
+    return (n > 1e-8f) ? __fdividef(phi, n) : 1.f;
+}
+
 HRT_DEV void ik_step_f(float th[7], const vec3 p_sh, const float (*off)[3], const float* lower, const float* upper,
-                       const vec3 pe_t, const vec3 pw_t, const float4 Rh, const float lam2, const float wo, const bool active_set) {
+                       const vec3 pe_t, const vec3 pw_t, const mat3c& H, const float lam2, const float wo, const bool active_set) {
     vec3 ax[7], pc[7];
-    float4 G;
-    arm_chain_f(th, p_sh, off, ax, pc, G);
+    vec3 r0 = make_vec3(1.f, 0.f, 0.f), r1 = make_vec3(0.f, 1.f, 0.f), r2 = make_vec3(0.f, 0.f, 1.f);
+    {
+        vec3 p = p_sh;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            const int k = HRT_ARM_AXIS(c);
+            ax[c] = k == 0 ? r0 : (k == 1 ? r1 : r2);
+            pc[c] = p;
+            float sh, ch;
+            sincos_half_lim(0.5f * th[c], &sh, &ch);
+            const float s = (sh + sh) * ch, cs = fmaf(-2.f * sh, sh, 1.f);
+            // R <- R * Rot_k(theta): the two columns after k (cyclically) turn into each other
+            vec3& ca = k == 0 ? r1 : (k == 1 ? r2 : r0);
+            vec3& cb = k == 0 ? r2 : (k == 1 ? r0 : r1);
+            const vec3 na = make_vec3(fmaf(s, cb.x, cs * ca.x), fmaf(s, cb.y, cs * ca.y), fmaf(s, cb.z, cs * ca.z));
+            const vec3 nb = make_vec3(fmaf(-s, ca.x, cs * cb.x), fmaf(-s, ca.y, cs * cb.y), fmaf(-s, ca.z, cs * cb.z));
+            ca = na; cb = nb;
+            if (c < 6) {
+                const float ox = off[c + 1][0], oy = off[c + 1][1], oz = off[c + 1][2];
+                p.x = fmaf(r0.x, ox, fmaf(r1.x, oy, fmaf(r2.x, oz, p.x)));
+                p.y = fmaf(r0.y, ox, fmaf(r1.y, oy, fmaf(r2.y, oz, p.y)));
+                p.z = fmaf(r0.z, ox, fmaf(r1.z, oy, fmaf(r2.z, oz, p.z)));
+            }
+        }
+    }
     float e[9];
     e[0] = pe_t.x - pc[3].x; e[1] = pe_t.y - pc[3].y; e[2] = pe_t.z - pc[3].z;
     e[3] = pw_t.x - pc[6].x; e[4] = pw_t.y - pc[6].y; e[5] = pw_t.z - pc[6].z;
     {
-        const float4 qe = quat_normalize_f(quat_mul_f(Rh, quat_conj(G)));
-        const float n2 = qe.x * qe.x + qe.y * qe.y + qe.z * qe.z;
-        const float n = n2 > 1e-30f ? n2 * rsqrt_fast(n2) : 0.f;       // |vector part| (sqrtf's range checks are dead weight here)
-        const float sc = wo * rotvec_scale_f(n, qe.w);
-        e[6] = qe.x * sc; e[7] = qe.y * sc; e[8] = qe.z * sc;
+        // twice the axial vector of E = H R^T and its trace
+        vec3 v = cross3_f(r0, H.c[0]);
+        v.x = fmaf(r1.y, H.c[1].z, fmaf(-r1.z, H.c[1].y, v.x)); v.y = fmaf(r1.z, H.c[1].x, fmaf(-r1.x, H.c[1].z, v.y)); v.z = fmaf(r1.x, H.c[1].y, fmaf(-r1.y, H.c[1].x, v.z));
+        v.x = fmaf(r2.y, H.c[2].z, fmaf(-r2.z, H.c[2].y, v.x)); v.y = fmaf(r2.z, H.c[2].x, fmaf(-r2.x, H.c[2].z, v.y)); v.z = fmaf(r2.x, H.c[2].y, fmaf(-r2.y, H.c[2].x, v.z));
+        float tr = r0.x * H.c[0].x;
+        tr = fmaf(r0.y, H.c[0].y, tr); tr = fmaf(r0.z, H.c[0].z, tr);
+        tr = fmaf(r1.x, H.c[1].x, tr); tr = fmaf(r1.y, H.c[1].y, tr); tr = fmaf(r1.z, H.c[1].z, tr);
+        tr = fmaf(r2.x, H.c[2].x, tr); tr = fmaf(r2.y, H.c[2].y, tr); tr = fmaf(r2.z, H.c[2].z, tr);
+        const float n2 = 0.25f * (v.x * v.x + v.y * v.y + v.z * v.z);
+        const float n = n2 > 1e-30f ? n2 * rsqrt_fast(n2) : 0.f;       // sin(phi)
+        const float sc = 0.5f * wo * angle_over_sin_f(n, 0.5f * (tr - 1.f));
+        e[6] = v.x * sc; e[7] = v.y * sc; e[8] = v.z * sc;
     }
     vec3 je[3], jw[6];
 #pragma unroll
     for (int c = 0; c < 3; ++c) je[c] = cross3_f(ax[c], sub3(pc[3], pc[c]));
 #pragma unroll
     for (int c = 0; c < 6; ++c) jw[c] = cross3_f(ax[c], sub3(pc[6], pc[c]));
+    vec3 axw[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) axw[i] = make_vec3(wo * ax[i].x, wo * ax[i].y, wo * ax[i].z);
     float A[28], g[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
-        float gi = wo * (ax[i].x * e[6] + ax[i].y * e[7] + ax[i].z * e[8]);
-        if (i < 6) gi += jw[i].x * e[3] + jw[i].y * e[4] + jw[i].z * e[5];
-        if (i < 3) gi += je[i].x * e[0] + je[i].y * e[1] + je[i].z * e[2];
+        float gi = axw[i].x * e[6];
+        gi = fmaf(axw[i].y, e[7], gi); gi = fmaf(axw[i].z, e[8], gi);
+        if (i < 6) { gi = fmaf(jw[i].x, e[3], gi); gi = fmaf(jw[i].y, e[4], gi); gi = fmaf(jw[i].z, e[5], gi); }
+        if (i < 3) { gi = fmaf(je[i].x, e[0], gi); gi = fmaf(je[i].y, e[1], gi); gi = fmaf(je[i].z, e[2], gi); }
         g[i] = gi;
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
-            float s = wo * wo * dot3_f(ax[i], ax[j]);
-            if (i < 6) s += dot3_f(jw[i], jw[j]);
-            if (i < 3) s += dot3_f(je[i], je[j]);
-            if (i == j) s += lam2;
+            float s = (i == j) ? fmaf(axw[i].x, axw[j].x, lam2) : axw[i].x * axw[j].x;
+            s = fmaf(axw[i].y, axw[j].y, s); s = fmaf(axw[i].z, axw[j].z, s);
+            if (i < 6) { s = fmaf(jw[i].x, jw[j].x, s); s = fmaf(jw[i].y, jw[j].y, s); s = fmaf(jw[i].z, jw[j].z, s); }
+            if (i < 3) { s = fmaf(je[i].x, je[j].x, s); s = fmaf(je[i].y, je[j].y, s); s = fmaf(je[i].z, je[j].z, s); }
             A[i * (i + 1) / 2 + j] = s;
         }
     }
@@ -732,9 +799,10 @@ HRT_DEV void bq_process(const BodyQuatParams& bp, const BodyQuatArgs& a, float* 
             nan_probe += ((pe_t.x + pe_t.y) + (pe_t.z + pw_t.x)) + ((pw_t.y + pw_t.z) + Rh.w);      // NaN targets poison the frame
             const float lam2 = a.damping * a.damping;
             const float wo = a.rot_weight;
+            const mat3c H = quat_to_mat3c(Rh);
             for (int it = 0; it < a.ik_iters; ++it) {
                 bq_align<BQ_WARPS_PER_CTA, SYSMEM>(warp);
-                ik_step_f(th, p_sh, ap.off, ap.lower, ap.upper, pe_t, pw_t, Rh, lam2, wo, (a.flags & BQ_ACTIVE_SET) != 0);
+                ik_step_f(th, p_sh, ap.off, ap.lower, ap.upper, pe_t, pw_t, H, lam2, wo, (a.flags & BQ_ACTIVE_SET) != 0);
             }
         }
         if (do_clamp) {
