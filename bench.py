@@ -508,8 +508,8 @@ def run_ours(args):
         sent = pr.nvlink_bytes_sent_per_step
         # side figures: the other transports of the fused reassembly on the same shards
         side_ms = {}
-        for other in ("multicast", "unicast"):
-            if other == pr.transport or (other == "multicast" and pr.transport == "unicast"):
+        for other in ("packed", "multicast", "unicast"):
+            if other == pr.transport or (other != "unicast" and pr.transport == "unicast"):      # unicast chosen = no NVLS here
                 continue
             pr_o = PeerReassembly(eng, n_total, transport=other)
             step_o = lambda: pr_o.step(raw_d, flags, IK_ITERS, DAMPING, ROT_WEIGHT, link_pos=lp_d)  # noqa: E731
@@ -535,6 +535,7 @@ def run_ours(args):
                        "per rank and span (no NCCL on the data path)"}
         gather_info = {
             "transport": transports[pr.transport], "transport_kind": pr.transport, "multicast_unavailable": pr.transport_error,
+            "packed_step_ms": side_ms.get("packed"),
             "full_row_multicast_step_ms": side_ms.get("multicast"), "full_row_unicast_step_ms": side_ms.get("unicast"),
             "payload": "dof_pos (120 B/frame) of the whole clip on every rank",
             "nvlink_bytes_sent_per_rank_per_step": sent, "nvlink_bytes_received_per_rank_per_step": pr.nvlink_bytes_received_per_step,

@@ -71,7 +71,11 @@ class PeerReassembly:
     peers' rounds that have landed into this rank's clip-wide buffer between its own rounds (hrt_retarget_body_quat_reassemble).
     transport="multicast": full 120-byte dof rows through the multicast address, no unpacking (ingress-bound at 8 GPUs).
     transport="unicast": plain cudaMalloc buffers exchanged as CUDA IPC handles; every warp sends its span to each rank
-    with one TMA bulk store per rank.  transport="auto" = packed when the box offers multicast (NVLS), else unicast."""
+    with one TMA bulk store per rank.
+    transport="auto": with multicast (NVLS) full rows up to 4 ranks, packed beyond; without it unicast.  Full rows cost the
+    solve nothing but put (N-1)/N * n_frames * 120 B on every rank's NVLink ingress per step: hidden under the solve at
+    2 and 4 ranks (measured 2^24 frames: 6.81 vs 7.07 ms packed at 2, 3.88 vs 4.03 ms at 4), more than one link direction
+    carries in the solve's time at 8 (3.24 vs 2.13 ms), where the packed form's unpack warps are the cheaper price."""
 
     def __init__(self, engine, n_frames, dof=30, group=None, transport="auto"):
         self.eng, self.group, self.n, self.D = engine, group, int(n_frames), int(dof)
@@ -91,7 +95,8 @@ class PeerReassembly:
         self.shard_lo = [shard_range(self.n, r, self.world)[0] for r in range(self.world)]
         self.shard_n = [shard_range(self.n, r, self.world)[1] - shard_range(self.n, r, self.world)[0] for r in range(self.world)]
         if transport in ("auto", "packed", "multicast") and self.world > 1 and torch.device(engine.device).type == "cuda":
-            self._try_multicast(require=(transport in ("multicast", "packed")), packed=(transport in ("auto", "packed")))
+            self._try_multicast(require=(transport in ("multicast", "packed")),
+                                packed=(transport == "packed" or (transport == "auto" and self.world > 4)))
         self._flags, h_flags = engine.peer_alloc(64)
         if self.mc_ptr:
             self.transport = "packed" if self.packed else "multicast"
