@@ -637,10 +637,9 @@ HRT_DEV void pos_process(const PosParams& pp, const PosArgs& a, float* smem, int
             if (a.flags & POS_IK) {
                 // targets: elbow / wrist positions and wrist orientation of the UNCLAMPED closed-form pose
                 vec3 ax[7], pc[7];
-                float4 G;
-                arm_chain_f(th, p_sh, ik.off, ax, pc, G);
+                mat3c H;
+                arm_chain_m(th, p_sh, ik.off, ax, pc, H);
                 const vec3 pe_t = pc[3], pw_t = pc[6];
-                const mat3c H = quat_to_mat3c(quat_normalize_f(G));
                 const float lam2 = a.damping * a.damping;
                 for (int it = 0; it < a.ik_iters; ++it) {
                     pos_align<SYSMEM, WARPS>(warp);

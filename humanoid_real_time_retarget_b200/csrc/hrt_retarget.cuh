@@ -288,34 +288,41 @@ HRT_DEV float angle_over_sin_f(float n, float w) {
     return (n > 1e-8f) ? __fdividef(phi, n) : 1.f;
 }
 
+// the 7-hinge arm chain at angles th with the orientation carried as a matrix: world axis and position of every hinge,
+// final orientation R (columns)
+HRT_DEV void arm_chain_m(const float th[7], const vec3 p_sh, const float (*off)[3], vec3 ax[7], vec3 pc[7], mat3c& R) {
+    vec3 r0 = make_vec3(1.f, 0.f, 0.f), r1 = make_vec3(0.f, 1.f, 0.f), r2 = make_vec3(0.f, 0.f, 1.f);
+    vec3 p = p_sh;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        const int k = HRT_ARM_AXIS(c);
+        ax[c] = k == 0 ? r0 : (k == 1 ? r1 : r2);
+        pc[c] = p;
+        float sh, ch;
+        sincos_half_lim(0.5f * th[c], &sh, &ch);
+        const float s = (sh + sh) * ch, cs = fmaf(-2.f * sh, sh, 1.f);
+        // R <- R * Rot_k(theta): the two columns after k (cyclically) turn into each other
+        vec3& ca = k == 0 ? r1 : (k == 1 ? r2 : r0);
+        vec3& cb = k == 0 ? r2 : (k == 1 ? r0 : r1);
+        const vec3 na = make_vec3(fmaf(s, cb.x, cs * ca.x), fmaf(s, cb.y, cs * ca.y), fmaf(s, cb.z, cs * ca.z));
+        const vec3 nb = make_vec3(fmaf(-s, ca.x, cs * cb.x), fmaf(-s, ca.y, cs * cb.y), fmaf(-s, ca.z, cs * cb.z));
+        ca = na; cb = nb;
+        if (c < 6) {
+            const float ox = off[c + 1][0], oy = off[c + 1][1], oz = off[c + 1][2];
+            p.x = fmaf(r0.x, ox, fmaf(r1.x, oy, fmaf(r2.x, oz, p.x)));
+            p.y = fmaf(r0.y, ox, fmaf(r1.y, oy, fmaf(r2.y, oz, p.y)));
+            p.z = fmaf(r0.z, ox, fmaf(r1.z, oy, fmaf(r2.z, oz, p.z)));
+        }
+    }
+    R.c[0] = r0; R.c[1] = r1; R.c[2] = r2;
+}
+
 HRT_DEV void ik_step_f(float th[7], const vec3 p_sh, const float (*off)[3], const float* lower, const float* upper,
                        const vec3 pe_t, const vec3 pw_t, const mat3c& H, const float lam2, const float wo, const bool active_set) {
     vec3 ax[7], pc[7];
-    vec3 r0 = make_vec3(1.f, 0.f, 0.f), r1 = make_vec3(0.f, 1.f, 0.f), r2 = make_vec3(0.f, 0.f, 1.f);
-    {
-        vec3 p = p_sh;
-#pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            const int k = HRT_ARM_AXIS(c);
-            ax[c] = k == 0 ? r0 : (k == 1 ? r1 : r2);
-            pc[c] = p;
-            float sh, ch;
-            sincos_half_lim(0.5f * th[c], &sh, &ch);
-            const float s = (sh + sh) * ch, cs = fmaf(-2.f * sh, sh, 1.f);
-            // R <- R * Rot_k(theta): the two columns after k (cyclically) turn into each other
-            vec3& ca = k == 0 ? r1 : (k == 1 ? r2 : r0);
-            vec3& cb = k == 0 ? r2 : (k == 1 ? r0 : r1);
-            const vec3 na = make_vec3(fmaf(s, cb.x, cs * ca.x), fmaf(s, cb.y, cs * ca.y), fmaf(s, cb.z, cs * ca.z));
-            const vec3 nb = make_vec3(fmaf(-s, ca.x, cs * cb.x), fmaf(-s, ca.y, cs * cb.y), fmaf(-s, ca.z, cs * cb.z));
-            ca = na; cb = nb;
-            if (c < 6) {
-                const float ox = off[c + 1][0], oy = off[c + 1][1], oz = off[c + 1][2];
-                p.x = fmaf(r0.x, ox, fmaf(r1.x, oy, fmaf(r2.x, oz, p.x)));
-                p.y = fmaf(r0.y, ox, fmaf(r1.y, oy, fmaf(r2.y, oz, p.y)));
-                p.z = fmaf(r0.z, ox, fmaf(r1.z, oy, fmaf(r2.z, oz, p.z)));
-            }
-        }
-    }
+    mat3c R;
+    arm_chain_m(th, p_sh, off, ax, pc, R);
+    const vec3 r0 = R.c[0], r1 = R.c[1], r2 = R.c[2];
     float e[9];
     e[0] = pe_t.x - pc[3].x; e[1] = pe_t.y - pc[3].y; e[2] = pe_t.z - pc[3].z;
     e[3] = pw_t.x - pc[6].x; e[4] = pw_t.y - pc[6].y; e[5] = pw_t.z - pc[6].z;
