@@ -66,6 +66,10 @@ struct hrt_ctx {
     bool bq_set = false;
     BodyQuatParams bq;
     bool pos_set[5] = {false, false, false, false, false};
+    // arm hinge limits of the configured robot all finite and within +-pi: what the limit clamp / refinement needs
+    // (their half-angle sine / cosine, sincos_half_lim, is written for angles inside such limits)
+    bool bq_limits_ok = false;
+    bool pos_limits_ok[5] = {false, false, false, false, false};
     PosParams pos[5];                 // modes 0-3 + [4] = mode 0 reading the mocap wire layout
     unsigned* d_scalars = nullptr;    // HRT_MAX_JOINTS + 2 words of device scratch for batch-wide maxima
     // staging for the *_host call
@@ -348,6 +352,8 @@ int fill_body_quat_args(hrt_ctx* ctx, int64_t B, const float* src, unsigned flag
     if (!ctx->bq_set) return fail(HRT_E_NOT_CONFIGURED, "hrt_configure_body_quat has not been called");
     if (B < 0) return fail(HRT_E_INVALID_ARG, "negative frame count");
     if ((flags & HRT_BQ_IK) && (ik_iters < 0 || ik_iters > 1000)) return fail(HRT_E_INVALID_ARG, "ik_iters out of range");
+    if ((flags & (HRT_BQ_CLAMP | HRT_BQ_IK)) && !ctx->bq_limits_ok)
+        return fail(HRT_E_UNSUPPORTED_TREE, "limits / refinement need finite arm hinge limits that do not reach beyond +-pi in the robot tree");
     a->B = B;
     a->src_gq = src;
     a->pre_transformed = (flags & HRT_BQ_PRE_TRANSFORMED) ? 1 : 0;
@@ -626,6 +632,8 @@ int hrt_ik_refine(hrt_ctx* ctx, int64_t B, const float* d_theta0, const float* d
                   int iters, float damping, float rot_weight, unsigned flags, float* d_theta, float* d_residual, void* stream) {
     HRT_ENTER(ctx);
     if (!ctx->bq_set) return fail(HRT_E_NOT_CONFIGURED, "hrt_configure_body_quat has not been called (it installs the robot's arm tables)");
+    if (!ctx->bq_limits_ok)
+        return fail(HRT_E_UNSUPPORTED_TREE, "limits / refinement need finite arm hinge limits that do not reach beyond +-pi in the robot tree");
     if (iters < 0 || iters > 1000) return fail(HRT_E_INVALID_ARG, "iters out of range");
     if (B == 0) return 0;
     if (B < 0 || !d_theta0 || !d_pe_t || !d_pw_t || !d_qw_t || !d_theta) return fail(HRT_E_INVALID_ARG, "bad B / null pointer");
@@ -723,6 +731,7 @@ int hrt_configure_body_quat(hrt_ctx* ctx, int src_tree, int rob_tree, const int3
         bp.axis_all[j] = (uint8_t)jr_axis(rt.jr[j].meta);
     }
     static const int arm_axis[7] = {1, 0, 2, 1, 0, 1, 2};
+    bool limits_ok = true;
     for (int side = 0; side < 2; ++side) {
         ArmParams& ap = bp.arm[side];
         const int32_t* sj = src_joints + side * 5;
@@ -744,9 +753,7 @@ int hrt_configure_body_quat(hrt_ctx* ctx, int src_tree, int rob_tree, const int3
             if (c > 0 && rt.parent[f + c] != f + c - 1) return fail(HRT_E_UNSUPPORTED_TREE, "arm joints must form a chain");
             ap.lower[c] = rt.lim[f + c][0];
             ap.upper[c] = rt.lim[f + c][1];
-            // the arm chain's half-angle sine / cosine (sincos_half_lim) is written for hinge angles within [-pi, pi]
-            if (!(ap.lower[c] >= -kArmLimitMax && ap.upper[c] <= kArmLimitMax))
-                return fail(HRT_E_UNSUPPORTED_TREE, "arm hinge %d: limits [%g, %g] reach beyond +-pi", f + c, ap.lower[c], ap.upper[c]);
+            if (!(ap.lower[c] >= -kArmLimitMax && ap.upper[c] <= kArmLimitMax)) limits_ok = false;
         }
         if (rt.parent[f + 7] != f + 6 || rt.parent[f + 8] != f + 6)
             return fail(HRT_E_UNSUPPORTED_TREE, "expected two gripper links under the wrist-yaw link");
@@ -764,6 +771,7 @@ int hrt_configure_body_quat(hrt_ctx* ctx, int src_tree, int rob_tree, const int3
         for (int k = 0; k < 3; ++k) bp.torso_p[k] = pos[torso * 3 + k];
     }
     ctx->bq_set = true;
+    ctx->bq_limits_ok = limits_ok;
     return 0;
 }
 
@@ -1033,6 +1041,7 @@ int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const 
     const TreeParams& st = s->tp;
     PosParams& pp = ctx->pos[mode];
     memset(&pp, 0, sizeof(pp));
+    bool pos_limits_ok = false;
     pp.mode = mode;
     pp.J_rob = r->tp.J;
     if (pp.J_rob != 31) return fail(HRT_E_UNSUPPORTED_TREE, "the position-path solvers write Hu v5 joints 12-29 (31-joint robot)");
@@ -1100,6 +1109,7 @@ int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const 
     {
         // robot-side arm tables for the limit-aware refinement: zero-pose positions p_j = off_j + p_parent
         const TreeParams& rt = r->tp;
+        pos_limits_ok = true;
         std::vector<float> pos(rt.J * 3, 0.f);
         for (int j = 1; j < rt.J; ++j)
             for (int k = 0; k < 3; ++k) pos[j * 3 + k] = rt.jr[j].off[k] + pos[rt.parent[j] * 3 + k];
@@ -1110,8 +1120,7 @@ int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const 
             for (int c = 0; c < 7; ++c) {
                 pp.ik[side].lower[c] = rt.lim[f + c][0];
                 pp.ik[side].upper[c] = rt.lim[f + c][1];
-                if (!(pp.ik[side].lower[c] >= -kArmLimitMax && pp.ik[side].upper[c] <= kArmLimitMax))
-                    return fail(HRT_E_UNSUPPORTED_TREE, "arm hinge %d: limits [%g, %g] reach beyond +-pi", f + c, pp.ik[side].lower[c], pp.ik[side].upper[c]);
+                if (!(pp.ik[side].lower[c] >= -kArmLimitMax && pp.ik[side].upper[c] <= kArmLimitMax)) pos_limits_ok = false;
             }
             for (int k = 0; k < 3; ++k) pp.ik[side].p_sh[k] = pos[f * 3 + k];
         }
@@ -1127,7 +1136,9 @@ int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const 
         if (e != cudaSuccess) return fail((int)e, "zero-pose bone angles: %s", cudaGetErrorString(e));
     }
     ctx->pos_set[mode] = true;
+    ctx->pos_limits_ok[mode] = pos_limits_ok;
     if (mode == POS_FULL_BODY_POS) {
+        ctx->pos_limits_ok[4] = pos_limits_ok;
         // the same solver reading the mocap wire layout (sim_full_body_teleop.py:109-112): body rows
         // 23 -> 21 and the HandNodes -> solver finger order are index remaps, applied to the tables once
         static const int body_map[21] = {0, 1, 2, 3, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22};
@@ -1152,6 +1163,8 @@ int hrt_configure_pos(hrt_ctx* ctx, int mode, int src_tree, int rob_tree, const 
 static int launch_pos(hrt_ctx* ctx, int slot, const PosArgs& a, cudaStream_t st, int force_grid = 0) {
     if (!ctx->pos_set[slot]) return fail(HRT_E_NOT_CONFIGURED, "hrt_configure_pos(mode %d) has not been called", slot == 4 ? 0 : slot);
     const int mode = ctx->pos[slot].mode;
+    if ((a.flags & (POS_CLAMP | POS_IK)) && !ctx->pos_limits_ok[slot])
+        return fail(HRT_E_UNSUPPORTED_TREE, "limits / refinement need finite arm hinge limits that do not reach beyond +-pi in the robot tree");
     if (a.B < 0) return fail(HRT_E_INVALID_ARG, "negative frame count");
     if (a.B == 0) return 0;
     const void* ptrs[] = {a.body_t, a.lhand_t, a.rhand_t, a.body_q, a.out_local_q, a.out_dof, a.out_body_gq};

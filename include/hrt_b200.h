@@ -123,7 +123,12 @@ int hrt_zero_pose_transform(hrt_ctx* ctx, int tree, int64_t B, const float* d_gq
 /* Wire the fused quaternion-path pipeline: which source joints feed which arm.
  * src_joints[2][5] = {torso, shoulder, upper arm, lower arm, hand} for the left then the right arm
  * (vtrdyn: {10,17,18,19,20},{10,13,14,15,16}; body_retargeter.py:40-53), rob_first[2] = robot joint index
- * of each shoulder-pitch link (Hu v5: 12, 21; body_retargeter.py:57-73). */
+ * of each shoulder-pitch link (Hu v5: 12, 21; body_retargeter.py:57-73).
+ * HRT_E_UNSUPPORTED_TREE when the 7 arm links below a shoulder-pitch link do not form a chain with two gripper links
+ * under the last.  Calls with HRT_BQ_CLAMP / HRT_BQ_IK (and hrt_ik_refine, HRT_POS_CLAMP / HRT_POS_IK on the position
+ * path) additionally need every arm hinge limit of the robot tree finite and within +-pi -- the refinement's half-angle
+ * sine / cosine is written for angles inside such limits -- and return HRT_E_UNSUPPORTED_TREE otherwise; the
+ * reference-parity calls (no limits, no refinement) work with any table. */
 int hrt_configure_body_quat(hrt_ctx* ctx, int src_tree, int rob_tree, const int32_t* src_joints,
                             const int32_t* rob_first);
 

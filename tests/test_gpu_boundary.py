@@ -191,6 +191,34 @@ def test_mismatched_zero_poses_raise(hrt, poses):
         hrt.HuUpperBodyFromMocapRetarget(zp, tgt)
 
 
+def test_arm_limits_beyond_pi_refuse_limits_and_refinement(hrt, oc, skeletons):
+    """The refinement evaluates sin / cos of half a hinge angle with polynomials written for angles inside the joint
+    limits (|theta| <= pi).  A robot table whose arm limits reach further (or has none) still serves the reference-parity
+    calls, bit for bit; asking for limits / refinement on it fails loudly."""
+    from humanoid_real_time_retarget_b200 import robot_config as cfg
+    sk = cfg.skeleton_tables()
+    ref = hrt.Engine(0).set_standard_trees()
+    eng = hrt.Engine(0).set_standard_trees()
+    up = np.asarray(cfg.Hu_v5_DOF_UPPER, dtype=np.float32).copy()
+    up[13] = 3.5                                           # left shoulder yaw (robot joint 14)
+    eng.set_tree(hrt.TREE_ROBOT, sk["hu_v5_zero_pose/parents"], sk["hu_v5_zero_pose/offsets"], cfg.Hu_v5_DOF_AXIS, cfg.Hu_v5_DOF_LOWER, up)
+    eng.configure_body_quat(hrt.TREE_SOURCE, hrt.TREE_ROBOT, cfg.VTRDYN_ARM_JOINTS, cfg.HU_V5_ARM_FIRST)
+    eng.configure_pos(hrt.POS_FULL_BODY_POS, hrt.TREE_SOURCE_FULL, hrt.TREE_ROBOT, sk["vtrdyn_full_zero_pose/global_translation"], True)
+    raw = oc.synth_clip_3q(257, seed=9, sk=skeletons).cuda()
+    for a, b in zip(eng.retarget_body_quat(raw, flags=0), ref.retarget_body_quat(raw, flags=0)):
+        assert torch.equal(a, b)
+    for flags in (hrt.BQ_CLAMP, hrt.BQ_CLAMP | hrt.BQ_IK):
+        with pytest.raises(hrt.HrtError, match="beyond"):
+            eng.retarget_body_quat(raw, flags=flags)
+    body = torch.randn(64, 21, 3, device="cuda")
+    hand = torch.randn(64, 20, 3, device="cuda")
+    eng.retarget_full_body_pos(body, hand, hand, flags=0)
+    with pytest.raises(hrt.HrtError, match="beyond"):
+        eng.retarget_full_body_pos(body, hand, hand, flags=hrt.POS_CLAMP | hrt.POS_IK)
+    eng.close()
+    ref.close()
+
+
 def test_reconfiguring_an_engine_stops_its_streams(hrt, golden):
     """hrt_configure_pos / hrt_set_tree on a context with an open (resident) stream close it: the stream's kernel holds the
     previous tables by value, so the next frame must not be answered from them."""
