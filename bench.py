@@ -579,7 +579,8 @@ def run_ours(args):
                        "l2": f"input shard {B * 336 >> 20} MB/GPU > 126 MB L2, streamed once per step", "parallelism": f"frames x{world}",
                        "e2e_frames_per_gpu_per_step": Be, "host_staging": numa.info},
             "e2e": {"value": world * Be * args.steps / e2e_s, "unit": "frames/s",
-                    "h2d_bytes_per_step": Be * 21 * 16, "d2h_bytes_per_step": Be * (30 * 4 + 31 * 12)},
+                    "h2d_bytes_per_step": Be * eng.host_input_bytes_per_frame(out_dof=True, out_link_pos=True),
+                    "d2h_bytes_per_step": Be * (30 * 4 + 31 * 12)},
             "gpu_launches": args.steps * (2 if multi else 1),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "traffic_source": "ncu capture of a past run of this command, per 2^20-frame launch (not live): "
@@ -593,8 +594,11 @@ def run_ours(args):
             "clocks": clocks,
         }
         if e2e_dof_s is not None:
-            line["e2e_dof_only"] = {"value": Be * args.steps / e2e_dof_s, "unit": "frames/s", "h2d_bytes_per_step": Be * 21 * 16,
-                                    "d2h_bytes_per_step": Be * 30 * 4, "note": "same call with out_link_pos=None: 120 B/frame back instead of 492"}
+            line["e2e_dof_only"] = {"value": Be * args.steps / e2e_dof_s, "unit": "frames/s", "h2d_bytes_per_step": Be * eng.host_input_bytes_per_frame(out_dof=True),
+                                    "d2h_bytes_per_step": Be * 30 * 4,
+                                    "note": "same call with out_link_pos=None: 120 B/frame back instead of 492; with the outputs the smaller side, "
+                                            "only the joint range the solver reads (vtrdyn joints 10-20: 176 of 336 B per frame) crosses PCIe, "
+                                            "as one strided copy per chunk"}
         line.update(extras)
         if gather_info is not None:
             line["gather"] = gather_info

@@ -993,10 +993,26 @@ int hrt_retarget_body_quat_host(hrt_ctx* ctx, int64_t B, const float* h_src_gq, 
     }();
     const size_t per_frame = in_b + lq_b + dof_b + lp_b;
     const size_t need = per_frame * chunk;
+    // The solver reads 9 of the source joints (torso + 4 per arm).  When the range of joints that holds them is well short
+    // of a row (vtrdyn: joints 10-20, 176 of 336 bytes), only that column range crosses PCIe, as one strided copy per
+    // chunk: the copy engine moves ~210 M rows/s (measured, tools/memcpy2d_probe.py: 2^20 rows of 176 B in 4.9 ms against
+    // 7.1 ms for the whole rows).  The device rows' other columns are never read by the kernel (zeroed once, below).
+    int jmin = JS, jmax = -1;
+    for (int side = 0; side < 2; ++side) {
+        const ArmParams& ap = ctx->bq.arm[side];
+        for (int j : {ap.src_torso, ap.src_shoulder, ap.src_upper, ap.src_lower, ap.src_hand}) { jmin = std::min(jmin, j); jmax = std::max(jmax, j); }
+    }
+    const size_t col_off = (size_t)jmin * 16, col_w = (size_t)(jmax - jmin + 1) * 16;
+    // Taken when the inputs are the larger side of the traffic (dof-only calls: 2^20 frames 1.54e8 -> 1.84e8 frames/s): with the
+    // link positions or local rotations going back the call is bound by the device-to-host direction, which the strided
+    // reads slow down (9.7e7 -> 8.6e7 frames/s measured), so whole rows are copied then.
+    const size_t out_b = (h_robot_local_q ? lq_b : 0) + (h_dof ? dof_b : 0) + (h_link_pos ? lp_b : 0);
+    const bool columns = col_w * 4 <= in_b * 3 && col_w >= 128 && out_b < in_b;            // narrower rows run into the per-row cost
     if (ctx->d_stage_bytes < need) {
         for (int i = 0; i < kHostStreams; ++i) {
             if (ctx->d_stage[i]) { cudaFree(ctx->d_stage[i]); ctx->d_stage[i] = nullptr; }
             HRT_CUDA(cudaMalloc(&ctx->d_stage[i], need));
+            HRT_CUDA(cudaMemset(ctx->d_stage[i], 0, need));
             if (!ctx->hs[i]) HRT_CUDA(cudaStreamCreateWithFlags(&ctx->hs[i], cudaStreamNonBlocking));
             if (!ctx->hs_done[i]) HRT_CUDA(cudaEventCreateWithFlags(&ctx->hs_done[i], cudaEventDisableTiming));
         }
@@ -1012,7 +1028,11 @@ int hrt_retarget_body_quat_host(hrt_ctx* ctx, int64_t B, const float* h_src_gq, 
         float* d_dof = reinterpret_cast<float*>(base + (in_b + lq_b) * chunk);
         float* d_lp = reinterpret_cast<float*>(base + (in_b + lq_b + dof_b) * chunk);
         // stream order on `st` already serialises reuse of this staging slot
-        HRT_CUDA(cudaMemcpyAsync(d_in, reinterpret_cast<const char*>(h_src_gq) + f0 * in_b, n * in_b, cudaMemcpyHostToDevice, st));
+        if (columns)
+            HRT_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(d_in) + col_off, in_b, reinterpret_cast<const char*>(h_src_gq) + f0 * in_b + col_off,
+                                       in_b, col_w, (size_t)n, cudaMemcpyHostToDevice, st));
+        else
+            HRT_CUDA(cudaMemcpyAsync(d_in, reinterpret_cast<const char*>(h_src_gq) + f0 * in_b, n * in_b, cudaMemcpyHostToDevice, st));
         BodyQuatArgs a = proto;
         a.B = n;
         a.src_gq = d_in;

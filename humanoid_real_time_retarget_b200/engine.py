@@ -102,6 +102,7 @@ class Engine:
         rf = np.ascontiguousarray(np.asarray(rob_first, dtype=np.int32).reshape(2))
         _lib.check(self.lib.hrt_configure_body_quat(self._h, src_tree, rob_tree, _np_ptr(sj), _np_ptr(rf)))
         self._bq = (self._trees[src_tree], self._trees[rob_tree])
+        self._bq_src_joints = sj.copy()
         self._bq_stream_cfg = None         # the C side closed the stream: it held the previous wiring by value
 
     def configure_pos(self, mode, src_tree, rob_tree, src_global_t=None, precise_gripper=False):
@@ -459,6 +460,16 @@ class Engine:
         _lib.check(self.lib.hrt_retarget_body_quat_host(self._h, B, _ptr(src_gq), flags, ik_iters, damping, rot_weight,
                                                         _ptr(out_local_q), _ptr(out_dof), _ptr(out_link_pos)))
         return out_local_q, out_dof, out_link_pos
+
+    def host_input_bytes_per_frame(self, out_local_q=False, out_dof=True, out_link_pos=False):
+        """Bytes of a source frame that hrt_retarget_body_quat_host moves across PCIe for a call with these outputs.  The solver
+        reads 9 source joints; when the joint range holding them is at most 3/4 of a row (and at least 128 B) and the
+        outputs are the smaller side of the traffic, only that column range is copied (one strided copy per chunk);
+        same rule as the C side."""
+        JS, JR = self._bq
+        w = (int(self._bq_src_joints.max()) - int(self._bq_src_joints.min()) + 1) * 16
+        out_b = (JR * 16 if out_local_q else 0) + ((JR - 1) * 4 if out_dof else 0) + (JR * 12 if out_link_pos else 0)
+        return w if (w * 4 <= JS * 16 * 3 and w >= 128 and out_b < JS * 16) else JS * 16
 
     def retarget_full_body_pos_host(self, body_t, lhand_t, rhand_t, flags=0, ik_iters=10, damping=0.1, rot_weight=0.2,
                                     out_local_q=None, out_dof=None):

@@ -427,6 +427,23 @@ def test_host_call_and_streaming_match_device_call(hrt, eng, oc, skeletons):
     eng.retarget_body_quat_host(h_in, flags=flags, out_local_q=h_lq, out_dof=h_dof, out_link_pos=h_lp)
     # same kernel instantiation, same outputs: the chunked host pipeline must be bit-identical to the device call
     assert torch.equal(h_dof, dof.cpu()) and torch.equal(h_lp, lp.cpu()) and torch.equal(h_lq, lq.cpu())
+    # the host call moves only the joint range the solver reads (vtrdyn joints 10-20) across PCIe: the other joints of
+    # the caller's tensor are never looked at, whatever they hold
+    # (dof-only calls: strided copy of the range; with link positions the whole rows travel, D2H being the bound)
+    assert eng.host_input_bytes_per_frame(out_dof=True) == 11 * 16
+    assert eng.host_input_bytes_per_frame(out_dof=True, out_link_pos=True) == 21 * 16
+    h_in2 = raw.clone()
+    h_in2[:, :10] = float("nan")
+    h_in2 = h_in2.pin_memory()
+    h_dof_n = torch.empty(B, 30).pin_memory()
+    h_lp_n = torch.empty(B, 31, 3).pin_memory()
+    eng.retarget_body_quat_host(h_in2, flags=flags, out_dof=h_dof_n, out_link_pos=h_lp_n)
+    _, dof_n, lp_n = eng.retarget_body_quat(raw, flags=flags, want_local_q=False)
+    assert torch.equal(h_dof_n, dof_n.cpu()) and torch.equal(h_lp_n, lp_n.cpu())
+    h_dof_n.zero_()
+    eng.retarget_body_quat_host(h_in2, flags=flags, out_dof=h_dof_n)
+    _, dof_n, _ = eng.retarget_body_quat(raw, flags=flags, want_local_q=False, want_link_pos=False)
+    assert torch.equal(h_dof_n, dof_n.cpu())
     # pageable host memory also works (dof only -> the 16-warp instantiation; compared like for like)
     h_dof2 = torch.empty(B, 30)
     eng.retarget_body_quat_host(raw, flags=flags, out_dof=h_dof2)
