@@ -59,6 +59,24 @@ class _DevView:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 3, "strides": None}
 
 
+def reassembly_transport(requested, world, multicast_available):
+    """Which transport a PeerReassembly of `world` ranks ends up with.  Measured on 2^24 frames (profiles/r02_notes.md):
+    full rows through the multicast address cost the solve nothing and hide under it up to 4 ranks (6.82 / 3.44 ms against
+    7.07 / 3.63 ms packed); at 8 ranks their ingress, 7/8 of the clip per step, is more than one NVLink direction carries in
+    the solve's time (3.21 ms against 1.94 ms packed).  Without a multicast address (no NVLS) only unicast is left."""
+    if requested not in ("auto", "packed", "multicast", "unicast"):
+        raise ValueError(f"unknown transport {requested!r}")
+    if world <= 1 or requested == "unicast":
+        return "unicast"
+    if not multicast_available:
+        if requested in ("packed", "multicast"):
+            raise RuntimeError("multicast reassembly unavailable")
+        return "unicast"
+    if requested == "auto":
+        return "packed" if world > 4 else "multicast"
+    return requested
+
+
 class PeerReassembly:
     """dof_pos of an n_frames clip, sharded by shard_range over the ranks of `group`, reassembled on every rank.
     step(engine-resident input shard) -> the clip-wide (n_frames, D) tensor of THIS rank (valid once the current stream has
@@ -83,8 +101,7 @@ class PeerReassembly:
         self.rank = dist.get_rank(group)
         if self.world > 8:
             raise ValueError("peer reassembly serves the GPUs of one box (<= 8 ranks)")
-        if transport not in ("auto", "packed", "multicast", "unicast"):
-            raise ValueError(f"unknown transport {transport!r}")
+        want = reassembly_transport(transport, self.world, True)       # what to try first; falls back collectively below
         self.lo, self.hi = shard_range(self.n, self.rank, self.world)
         if self.hi > self.lo and self.lo % 4:
             raise ValueError("shard boundaries must keep dof rows 16-byte aligned")
@@ -94,9 +111,8 @@ class PeerReassembly:
         self.packed = False
         self.shard_lo = [shard_range(self.n, r, self.world)[0] for r in range(self.world)]
         self.shard_n = [shard_range(self.n, r, self.world)[1] - shard_range(self.n, r, self.world)[0] for r in range(self.world)]
-        if transport in ("auto", "packed", "multicast") and self.world > 1 and torch.device(engine.device).type == "cuda":
-            self._try_multicast(require=(transport in ("multicast", "packed")),
-                                packed=(transport == "packed" or (transport == "auto" and self.world > 4)))
+        if want != "unicast" and torch.device(engine.device).type == "cuda":
+            self._try_multicast(require=(transport in ("multicast", "packed")), packed=(want == "packed"))
         self._flags, h_flags = engine.peer_alloc(64)
         if self.mc_ptr:
             self.transport = "packed" if self.packed else "multicast"

@@ -2,6 +2,7 @@
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -38,6 +39,17 @@ def test_shard_ranges_cover_the_clip_exactly():
             for (a, b), (c, d) in zip(spans, spans[1:]):
                 assert b == c and a <= b
             assert all((lo % 16 == 0) for lo, _ in spans if lo < n)
+
+
+def test_reassembly_transport_by_rank_count():
+    from humanoid_real_time_retarget_b200.sharding import reassembly_transport as rt
+    assert [rt("auto", w, True) for w in (1, 2, 3, 4, 5, 8)] == ["unicast", "multicast", "multicast", "multicast", "packed", "packed"]
+    assert [rt("auto", w, False) for w in (2, 8)] == ["unicast", "unicast"]
+    assert rt("packed", 2, True) == "packed" and rt("multicast", 8, True) == "multicast" and rt("unicast", 8, True) == "unicast"
+    with pytest.raises(RuntimeError):
+        rt("packed", 8, False)
+    with pytest.raises(ValueError):
+        rt("nccl", 8, True)
 
 
 def test_all_gather_reassembles_ragged_shards_gloo():
