@@ -396,73 +396,136 @@ HRT_DEV void span_store(float* dst, const float* tile, int n_words, int lane, bo
     }
 }
 
+// Tiles in flight per warp: a warp's tile is 32 rows, i.e. 0.4 - 1 KB of operands, and with one tile per warp and
+// iteration the resident warps of an SM do not keep enough bytes in flight to cover the HBM latency when a row has ONE
+// quaternion-sized operand (quat_normalize: 64 warps x 512 B = 32 KB per SM against the ~43 KB that 6.4 TB/s x 1 us /
+// 148 SMs asks for).  Those ops (rows of 4 or 1 words: one LDG / STG per lane, nothing staged; at most 4 operand words)
+// request the operands of ROT_UNROLL tiles before the first is consumed: quat_normalize 0.73 -> 0.80 / 0.81 / 0.83 of
+// the HBM peak with 2 / 3 / 4 tiles.  Two-operand ops already have the bytes in flight (quat_mul 0.90 either way), and
+// ops with 3- / 7- / 9-word rows go through the shared-memory staging, where a second tile in flight costs more than it
+// hides (quat_rotate 0.59 -> 0.51): one tile.
+#ifndef HRT_ROT_UNROLL
+#define HRT_ROT_UNROLL 4
+#endif
+// a whole tile's span (32 rows of W words = 8 W sixteen-byte pieces) with compile-time trip counts: the rolled loops above
+// cost ~10 instructions per piece and lane on the staged ops (quat_rotate ran 209 warp instructions per tile, 62 % of the
+// issue slots: profiles/r02_notes.md)
+template <int W>
+HRT_DEV void span_load_tile(float* tile, const float* src, int lane) {
+    constexpr int N4 = W * 8;
+#pragma unroll
+    for (int k = 0; k < (N4 + 31) / 32; ++k)
+        if (k < N4 / 32 || lane < N4 % 32)
+            reinterpret_cast<float4*>(tile)[lane + 32 * k] = __ldcs(reinterpret_cast<const float4*>(src) + lane + 32 * k);
+}
+template <int W>
+HRT_DEV void span_store_tile(float* dst, const float* tile, int lane) {
+    constexpr int N4 = W * 8;
+#pragma unroll
+    for (int k = 0; k < (N4 + 31) / 32; ++k)
+        if (k < N4 / 32 || lane < N4 % 32)
+            __stcs(reinterpret_cast<float4*>(dst) + lane + 32 * k, reinterpret_cast<const float4*>(tile)[lane + 32 * k]);
+}
+
+template <typename Tr> __host__ __device__ constexpr int rot_unroll() {
+    for (int k = 0; k < 4; ++k) if (Tr::WI[k] != 0 && Tr::WI[k] != 1 && Tr::WI[k] != 4) return 1;
+    for (int k = 0; k < 3; ++k) if (Tr::WO[k] != 0 && Tr::WO[k] != 1 && Tr::WO[k] != 4) return 1;
+    if (Tr::WI[0] + Tr::WI[1] + Tr::WI[2] + Tr::WI[3] > 4) return 1;
+    // the staging tiles stay declared (unaligned operands fall back to them): keep them inside the 48 KB of static shared memory
+    const int tw = Tr::WI[0] + Tr::WI[1] + Tr::WI[2] + Tr::WI[3] + Tr::WO[0] + Tr::WO[1] + Tr::WO[2];
+    const int fit = 48 * 1024 / (ROT_WARPS * 32 * tw * 4);
+    return HRT_ROT_UNROLL < fit ? HRT_ROT_UNROLL : (fit < 1 ? 1 : fit);
+}
+
 template <int OP>
 __global__ void __launch_bounds__(ROT_WARPS * 32)
 rot_op_kernel(const RotOpArgs a) {
     using Tr = RotOpTraits<OP>;
     constexpr int TW = Tr::WI[0] + Tr::WI[1] + Tr::WI[2] + Tr::WI[3] + Tr::WO[0] + Tr::WO[1] + Tr::WO[2];
-    __shared__ __align__(16) float tiles[ROT_WARPS][32 * TW];
+    constexpr int ROT_UNROLL = rot_unroll<Tr>();
+    __shared__ __align__(16) float tiles[ROT_WARPS][ROT_UNROLL][32 * TW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* tile = tiles[warp];
     const long long n_tiles = (a.n + 31) / 32;
+    const long long stride = (long long)gridDim.x * ROT_WARPS;
     // 16-byte accesses need 16-byte aligned bases (a warp's span starts at a multiple of 128 bytes from the base)
     bool al_in[4], al_out[3];
 #pragma unroll
     for (int k = 0; k < 4; ++k) al_in[k] = ptr_aligned16(a.in[k]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) al_out[k] = ptr_aligned16(a.out[k]);
-    for (long long t = (long long)blockIdx.x * ROT_WARPS + warp; t < n_tiles; t += (long long)gridDim.x * ROT_WARPS) {
-        const long long i0 = t * 32;
-        const int cnt = (int)min(32LL, a.n - i0);
-        const int row = min(lane, cnt - 1);                 // tail lanes shadow the last row
-        const long long i = i0 + row;
-        float in[4][9], out[3][9];
-        // 1. operands.  Width-4 rows (quaternions) and width-1 rows are coalesced as they are: one LDG.128 / LDG
-        //    per lane.  Other widths: the warp's contiguous span goes through shared memory in 16-byte pieces.
-        static_for<0, Tr::NI>([&](auto K) {
-            constexpr int k = decltype(K)::value, W = Tr::WI[k], OFF = rot_in_off<Tr, k>();
-            if (a.period[k] != 0) {
-                const float* src = a.in[k] + (i % a.period[k]) * W;
+    for (long long t0 = (long long)blockIdx.x * ROT_WARPS + warp; t0 < n_tiles; t0 += stride * ROT_UNROLL) {
+        float in[ROT_UNROLL][4][9], out[3][9];
+        // 1. operands of every tile of this iteration.  Width-4 rows (quaternions) and width-1 rows are coalesced as they
+        //    are: one LDG.128 / LDG per lane.  Other widths: the warp's contiguous span goes through shared memory in
+        //    16-byte pieces.
 #pragma unroll
-                for (int c = 0; c < W; ++c) in[k][c] = __ldg(src + c);
-            } else if (W == 4 && al_in[k]) {
-                const float4 v = __ldcs(reinterpret_cast<const float4*>(a.in[k]) + i);
-                in[k][0] = v.x; in[k][1] = v.y; in[k][2] = v.z; in[k][3] = v.w;
-            } else if (W == 1) {
-                in[k][0] = __ldcs(a.in[k] + i);
-            } else {
-                span_load(tile + OFF, a.in[k] + i0 * W, cnt * W, lane, al_in[k] && ((cnt * W) & 3) == 0);
+        for (int u = 0; u < ROT_UNROLL; ++u) {
+            const long long t = t0 + u * stride;
+            if (t < n_tiles) {
+                float* tile = tiles[warp][u];
+                const long long i0 = t * 32;
+                const int cnt = (int)min(32LL, a.n - i0);
+                const long long i = i0 + min(lane, cnt - 1);          // tail lanes shadow the last row
+                static_for<0, Tr::NI>([&](auto K) {
+                    constexpr int k = decltype(K)::value, W = Tr::WI[k], OFF = rot_in_off<Tr, k>();
+                    if (a.period[k] != 0) {
+                        const float* src = a.in[k] + (i % a.period[k]) * W;
+#pragma unroll
+                        for (int c = 0; c < W; ++c) in[u][k][c] = __ldg(src + c);
+                    } else if (W == 4 && al_in[k]) {
+                        const float4 v = __ldcs(reinterpret_cast<const float4*>(a.in[k]) + i);
+                        in[u][k][0] = v.x; in[u][k][1] = v.y; in[u][k][2] = v.z; in[u][k][3] = v.w;
+                    } else if (W == 1) {
+                        in[u][k][0] = __ldcs(a.in[k] + i);
+                    } else if (cnt == 32 && al_in[k]) {
+                        span_load_tile<W>(tile + OFF, a.in[k] + i0 * W, lane);
+                    } else {
+                        span_load(tile + OFF, a.in[k] + i0 * W, cnt * W, lane, al_in[k] && ((cnt * W) & 3) == 0);
+                    }
+                });
             }
-        });
+        }
         __syncwarp();
-        static_for<0, Tr::NI>([&](auto K) {
-            constexpr int k = decltype(K)::value, W = Tr::WI[k], OFF = rot_in_off<Tr, k>();
-            if (a.period[k] == 0 && !(W == 4 && al_in[k]) && W != 1) {
-                const float* r = tile + OFF + row * W;
 #pragma unroll
-                for (int c = 0; c < W; ++c) in[k][c] = r[c];
-            }
-        });
-        rot_op_body<OP>(in, out, a.iparam, a.fparam);
-        // 2. results, the same way
-        static_for<0, Tr::NO>([&](auto K) {
-            constexpr int k = decltype(K)::value, W = Tr::WO[k], OFF = rot_out_off<Tr, k>();
-            if (W == 4 && al_out[k]) {
-                if (lane < cnt) __stcs(reinterpret_cast<float4*>(a.out[k]) + i, make_float4(out[k][0], out[k][1], out[k][2], out[k][3]));
-            } else if (W == 1) {
-                if (lane < cnt) __stcs(a.out[k] + i, out[k][0]);
-            } else {
-                float* r = tile + OFF + lane * W;
+        for (int u = 0; u < ROT_UNROLL; ++u) {
+            const long long t = t0 + u * stride;
+            if (t >= n_tiles) break;
+            float* tile = tiles[warp][u];
+            const long long i0 = t * 32;
+            const int cnt = (int)min(32LL, a.n - i0);
+            const int row = min(lane, cnt - 1);
+            const long long i = i0 + row;
+            static_for<0, Tr::NI>([&](auto K) {
+                constexpr int k = decltype(K)::value, W = Tr::WI[k], OFF = rot_in_off<Tr, k>();
+                if (a.period[k] == 0 && !(W == 4 && al_in[k]) && W != 1) {
+                    const float* r = tile + OFF + row * W;
 #pragma unroll
-                for (int c = 0; c < W; ++c) r[c] = out[k][c];
-            }
-        });
-        __syncwarp();
-        static_for<0, Tr::NO>([&](auto K) {
-            constexpr int k = decltype(K)::value, W = Tr::WO[k], OFF = rot_out_off<Tr, k>();
-            if (!(W == 4 && al_out[k]) && W != 1)
-                span_store(a.out[k] + i0 * W, tile + OFF, cnt * W, lane, al_out[k] && ((cnt * W) & 3) == 0);
-        });
+                    for (int c = 0; c < W; ++c) in[u][k][c] = r[c];
+                }
+            });
+            rot_op_body<OP>(in[u], out, a.iparam, a.fparam);
+            // 2. results, the same way
+            static_for<0, Tr::NO>([&](auto K) {
+                constexpr int k = decltype(K)::value, W = Tr::WO[k], OFF = rot_out_off<Tr, k>();
+                if (W == 4 && al_out[k]) {
+                    if (lane < cnt) __stcs(reinterpret_cast<float4*>(a.out[k]) + i, make_float4(out[k][0], out[k][1], out[k][2], out[k][3]));
+                } else if (W == 1) {
+                    if (lane < cnt) __stcs(a.out[k] + i, out[k][0]);
+                } else {
+                    float* r = tile + OFF + lane * W;
+#pragma unroll
+                    for (int c = 0; c < W; ++c) r[c] = out[k][c];
+                }
+            });
+            __syncwarp();
+            static_for<0, Tr::NO>([&](auto K) {
+                constexpr int k = decltype(K)::value, W = Tr::WO[k], OFF = rot_out_off<Tr, k>();
+                if (!(W == 4 && al_out[k]) && W != 1) {
+                    if (cnt == 32 && al_out[k]) span_store_tile<W>(a.out[k] + i0 * W, tile + OFF, lane);
+                    else span_store(a.out[k] + i0 * W, tile + OFF, cnt * W, lane, al_out[k] && ((cnt * W) & 3) == 0);
+                }
+            });
+        }
         __syncwarp();
     }
 }
