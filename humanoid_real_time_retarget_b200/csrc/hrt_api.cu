@@ -694,7 +694,10 @@ int hrt_zero_pose_transform(hrt_ctx* ctx, int tree, int64_t B, const float* d_gq
     float r[4];
     rot_quat(variant, r);
     const long long n = (long long)B * t->tp.J;
-    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+    // the CTAs that are resident together (a second, partly filled wave of a grid-stride kernel is a tail)
+    static LaunchCache zc;
+    int grid = 1;
+    if ((rc = grid_for(ctx, zero_pose_transform_kernel, 256, 0, (n + 256 * ZPT_UNROLL - 1) / (256 * ZPT_UNROLL), &grid, &zc))) return rc;
     zero_pose_transform_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(d_gq), reinterpret_cast<const float4*>(t->d_t2z),
         make_float4(r[0], r[1], r[2], r[3]), t->tp.J, n, reinterpret_cast<float4*>(d_out));
