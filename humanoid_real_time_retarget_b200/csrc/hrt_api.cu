@@ -1649,6 +1649,12 @@ static int gauss_params(GaussParams* gp, double sigma) {
 
 static int ew_grid(hrt_ctx* ctx, long long n) { return (int)std::max(1LL, std::min((n + 255) / 256, (long long)ctx->sm_count * 16)); }
 
+// sigma = 2 (radius 8): the sliding-window form, one thread per (run of GAUSS_RUN frames, component)
+static void launch_gauss_sigma2(const GaussParams& gp, const float* x, long long T, long long C, float* out, cudaStream_t st) {
+    const long long threads = (T + GAUSS_RUN - 1) / GAUSS_RUN * C;
+    gauss_filter_frames_window_kernel<float, float, 8><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(gp, x, T, C, out);
+}
+
 int hrt_motion_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gt, float dt, int gaussian,
                         float* d_scratch, float* d_out, void* stream) {
     HRT_ENTER(ctx);
@@ -1661,7 +1667,7 @@ int hrt_motion_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float* d_gt, f
     if (gaussian) {
         GaussParams gp;
         gauss_params(&gp, 2.0);
-        gauss_filter_frames_kernel<float, float><<<ew_grid(ctx, n), 256, 0, st>>>(gp, d_scratch, T, C, d_out);
+        launch_gauss_sigma2(gp, d_scratch, T, C, d_out, st);
         HRT_CUDA(cudaGetLastError());
     }
     return 0;
@@ -1679,7 +1685,7 @@ int hrt_motion_angular_velocity(hrt_ctx* ctx, int64_t T, int64_t J, const float*
     if (gaussian) {
         GaussParams gp;
         gauss_params(&gp, 2.0);
-        gauss_filter_frames_kernel<float, float><<<ew_grid(ctx, n * 3), 256, 0, st>>>(gp, d_scratch, T, J * 3, d_out);
+        launch_gauss_sigma2(gp, d_scratch, T, J * 3, d_out, st);
         HRT_CUDA(cudaGetLastError());
     }
     return 0;

@@ -139,26 +139,38 @@ rebuild_rotation_kernel(const __grid_constant__ RebuildParams rp, const float* _
 // velocities along the frame axis
 // ---------------------------------------------------------------------------------------------
 // np.gradient(p, axis=frames) / dt in fp32: central differences inside, one-sided at both ends
+// (frame, component) of a grid-stride element index advanced by additions: a 64-bit division per element was most of
+// these kernels' instructions
+struct FrameIdx {
+    long long t, dt;
+    int c, dc, C;
+    __device__ FrameIdx(long long i, long long stride, long long C_) : t(i / C_), dt(stride / C_), c((int)(i % C_)), dc((int)(stride % C_)), C((int)C_) {}
+    __device__ void next() {
+        t += dt; c += dc;
+        if (c >= C) { c -= C; ++t; }
+    }
+};
+
 __global__ void __launch_bounds__(256)
 frame_gradient_kernel(const float* __restrict__ p, long long T, long long C, float dt, float* __restrict__ out) {
-    const long long n = T * C;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const long long t = i / C;
+    const long long n = T * C, stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (FrameIdx f(i, stride, C); i < n; i += stride, f.next()) {
+        const long long t = f.t;
         float g;
-        if (t == 0) g = div_rn(sub_rn(p[i + C], p[i]), 1.f);
-        else if (t == T - 1) g = div_rn(sub_rn(p[i], p[i - C]), 1.f);
-        else g = div_rn(sub_rn(p[i + C], p[i - C]), 2.f);
+        if (t == 0) g = div_rn(sub_rn(__ldg(p + i + C), __ldg(p + i)), 1.f);
+        else if (t == T - 1) g = div_rn(sub_rn(__ldg(p + i), __ldg(p + i - C)), 1.f);
+        else g = div_rn(sub_rn(__ldg(p + i + C), __ldg(p + i - C)), 2.f);
         out[i] = div_rn(g, dt);
     }
 }
 
-// diff[t] = norm(r[t+1] * inv(r[t])) (identity at the last frame); (angle, axis) = quat_angle_axis;
-// w = axis * angle / dt        skeleton3d.py:1137-1143
 __global__ void __launch_bounds__(256)
 angular_velocity_raw_kernel(const float4* __restrict__ r, long long T, long long J, float dt, float* __restrict__ out) {
-    const long long n = T * J;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const long long t = i / J;
+    const long long n = T * J, stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (FrameIdx f(i, stride, J); i < n; i += stride, f.next()) {
+        const long long t = f.t;
         float4 q = make_float4(0.f, 0.f, 0.f, 1.f);
         if (t < T - 1) q = quat_mul_norm_x(__ldg(r + i + J), quat_conj(__ldg(r + i)));
         const float s = sub_rn(mul_rn(2.f, mul_rn(q.w, q.w)), 1.f);
@@ -183,16 +195,60 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
 gauss_filter_frames_kernel(const __grid_constant__ GaussParams gp, const TI* __restrict__ x, long long T, long long C,
                            TO* __restrict__ out) {
-    const long long n = T * C;
+    const long long n = T * C, stride = (long long)gridDim.x * blockDim.x;
     const int R = gp.radius;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const long long t = i / C, c = i - t * C;
-        double acc = (double)x[i] * gp.w[R];
-        for (int j = -R; j < 0; ++j) {
-            const long long ta = min(max(t + j, 0LL), T - 1), tb = min(max(t - j, 0LL), T - 1);
-            acc += ((double)__ldg(x + ta * C + c) + (double)__ldg(x + tb * C + c)) * gp.w[j + R];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (FrameIdx f(i, stride, C); i < n; i += stride, f.next()) {
+        const long long t = f.t;
+        const TI* xi = x + i;
+        double acc = (double)__ldg(xi) * gp.w[R];
+        if (t >= R && t + R < T) {
+            // interior frames (all but 2 R of the clip): the taps are at fixed 32-bit offsets from the element
+            const int Ci = (int)C;
+            for (int j = -R; j < 0; ++j) acc += ((double)__ldg(xi + j * Ci) + (double)__ldg(xi - j * Ci)) * gp.w[j + R];
+        } else {
+            const long long c = f.c;
+            for (int j = -R; j < 0; ++j) {
+                const long long ta = min(max(t + j, 0LL), T - 1), tb = min(max(t - j, 0LL), T - 1);
+                acc += ((double)__ldg(x + ta * C + c) + (double)__ldg(x + tb * C + c)) * gp.w[j + R];
+            }
         }
         out[i] = (TO)acc;
+    }
+}
+
+// The same filter for the velocities' radius (8) as a sliding window: a thread owns one component over a run of
+// consecutive frames and keeps the 17 taps as doubles in registers, so every input element is loaded and widened ONCE
+// per run instead of 17 times (the fp32 -> fp64 conversions, 34 per output on the quarter-rate conversion pipe, were the
+// generic kernel's bound).  Same accumulation order, same bits.  Consecutive threads = consecutive components of a run
+// (coalesced rows); a run re-reads 2 R frames of its neighbours (L2 hits).
+constexpr int GAUSS_RUN = 128;
+template <typename TI, typename TO, int R>
+__global__ void __launch_bounds__(256)
+gauss_filter_frames_window_kernel(const __grid_constant__ GaussParams gp, const TI* __restrict__ x, long long T, long long C,
+                                  TO* __restrict__ out) {
+    const long long n_runs = (T + GAUSS_RUN - 1) / GAUSS_RUN;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_runs * C) return;
+    const long long k = idx / C, c = idx - k * C;
+    const long long t0 = k * GAUSS_RUN, t1 = min(T, t0 + GAUSS_RUN);
+    double gw[R + 1];
+#pragma unroll
+    for (int j = 0; j <= R; ++j) gw[j] = gp.w[j];
+    double win[2 * R + 1];
+#pragma unroll
+    for (int m = 0; m <= 2 * R; ++m) win[m] = (double)__ldg(x + min(max(t0 - R + m, 0LL), T - 1) * C + c);
+    const TI* nxt = x + min(t0 + R + 1, T - 1) * C + c;              // the element that enters the window next
+    for (long long t = t0; t < t1; ++t) {
+        double acc = win[R] * gw[R];
+#pragma unroll
+        for (int j = -R; j < 0; ++j) acc += (win[R + j] + win[R - j]) * gw[j + R];
+        out[t * C + c] = (TO)acc;
+        const double in = (double)__ldg(nxt);
+        if (t + R + 2 < T) nxt += C;                                  // mode "nearest": the last frame repeats
+#pragma unroll
+        for (int m = 0; m < 2 * R; ++m) win[m] = win[m + 1];
+        win[2 * R] = in;
     }
 }
 
