@@ -31,6 +31,10 @@ rescale_motion_kernel(const __grid_constant__ RescaleParams rp, const float* __r
     float* src = smem + (size_t)warp * 2 * 32 * W;
     float* dst = src + 32 * W;
     const long long n_tiles = (B + 31) / 32;
+    // zero-pose bone lengths: the same value for every frame, computed once per CTA (it was a square root per joint and frame)
+    __shared__ float off_norm[HRT_MAX_JOINTS];
+    for (int j = threadIdx.x; j < rp.J; j += blockDim.x) off_norm[j] = norm3_x(make_vec3(rp.off[j][0], rp.off[j][1], rp.off[j][2]));
+    __syncthreads();
     for (long long t = (long long)blockIdx.x * MOT_WARPS + warp; t < n_tiles; t += (long long)gridDim.x * MOT_WARPS) {
         const long long f0 = t * 32;
         const int cnt = (int)min(32LL, B - f0);
@@ -39,12 +43,14 @@ rescale_motion_kernel(const __grid_constant__ RescaleParams rp, const float* __r
         if (lane < cnt) {
             float* s = src + lane * W;
             float* d = dst + lane * W;
-            for (int w = 0; w < W; ++w) s[w] = mul_rn(s[w], rp.dir[w % 3]);
+            for (int j = 0; j < rp.J; ++j) {
+                s[j * 3] = mul_rn(s[j * 3], rp.dir[0]); s[j * 3 + 1] = mul_rn(s[j * 3 + 1], rp.dir[1]); s[j * 3 + 2] = mul_rn(s[j * 3 + 2], rp.dir[2]);
+            }
             for (int j = 0; j < rp.J; ++j) {
                 const int p = rp.parent[j];
                 if (p < 0) { d[j * 3] = s[j * 3]; d[j * 3 + 1] = s[j * 3 + 1]; d[j * 3 + 2] = s[j * 3 + 2]; continue; }
                 const vec3 v = sub3_x(ld3(s + j * 3), ld3(s + p * 3));
-                const float scale = div_rn(norm3_x(v), norm3_x(make_vec3(rp.off[j][0], rp.off[j][1], rp.off[j][2])));
+                const float scale = div_rn(norm3_x(v), off_norm[j]);
                 d[j * 3] = add_rn(d[p * 3], div_rn(v.x, scale));
                 d[j * 3 + 1] = add_rn(d[p * 3 + 1], div_rn(v.y, scale));
                 d[j * 3 + 2] = add_rn(d[p * 3 + 2], div_rn(v.z, scale));
