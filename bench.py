@@ -285,10 +285,12 @@ def side_measurements(eng, hrt, oc, sk, dev):
     gq = torch.empty((65536, 33, 4), device=dev)
     gtt = torch.empty((65536, 33, 3), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    def kernel_ms(launch, flush_l2, reps=13, skip=3):
+    def kernel_ms(launch, flush_l2, reps=27, skip=3):
         """Device time of ONE launch: an event pair around each of `reps` launches queued back to back (with the L2 flush in
         between where asked), one synchronize at the end: the host-side cost of issuing the call (ctypes marshalling, ~5-10 us)
-        overlaps the previous kernel / the flush instead of sitting between the two events."""
+        overlaps the previous kernel / the flush instead of sitting between the two events.  The event clock resolves ~1 us,
+        so a 20 us launch reads 20.5, 21.5 or 22.5: the figure is the mean of the middle half of the samples (a median
+        lands on one of those steps and moved by 5 % from run to run)."""
         evs = []
         torch.cuda.synchronize(dev)
         for _ in range(reps):
@@ -300,7 +302,9 @@ def side_measurements(eng, hrt, oc, sk, dev):
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize(dev)
-        return float(np.median([a.elapsed_time(b) for a, b in evs[skip:]]))
+        ts = np.sort(np.array([a.elapsed_time(b) for a, b in evs[skip:]]))
+        q = len(ts) // 4
+        return float(ts[q:len(ts) - q].mean())
 
     ms = kernel_ms(lambda: eng_hu.fk_angles(hrt.TREE_ROBOT, ang, clip=True, out=(gq, gtt)), True)
     peak, _ = hbm_peak()
@@ -334,7 +338,7 @@ def side_measurements(eng, hrt, oc, sk, dev):
     d3 = torch.empty(n3, 30, device=dev)
     res = {}
     for name, fl in (("closed_form", 0), ("limits_and_10_refinement_steps", hrt.POS_CLAMP | hrt.POS_IK)):
-        m3 = kernel_ms(lambda: eng.retarget_full_body_pos(b3, l3, r3, out=(None, d3, None), flags=fl), False, reps=10)
+        m3 = kernel_ms(lambda: eng.retarget_full_body_pos(b3, l3, r3, out=(None, d3, None), flags=fl), False, reps=19)
         res[name] = {"ms": m3, "frames_per_s": n3 / (m3 * 1e-3), "hbm_frac": n3 * 852 / (m3 * 1e-3) / 1e9 / peak}
     out["pos_path_2p18"] = {"workload": "config 3p: VtrdynFullBodyPosRetargeter batched, 732 B in + 120 B dof per frame, 2^18 frames (192 MB in)",
                             **res}
