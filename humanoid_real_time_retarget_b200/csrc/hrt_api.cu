@@ -1556,7 +1556,9 @@ int hrt_rescale_motion(hrt_ctx* ctx, int tree, int64_t B, const float* d_gt, con
     for (int k = 0; k < 3; ++k) rp.dir[k] = dir3 ? dir3[k] : 1.f;
     const size_t smem = (size_t)MOT_WARPS * 2 * 32 * rp.J * 3 * sizeof(float);
     const long long tiles = (B + 31) / 32;
-    const int grid = (int)std::max(1LL, std::min((tiles + MOT_WARPS - 1) / MOT_WARPS, (long long)ctx->sm_count * 2));
+    static LaunchCache rs_cache;                            // grid = the CTAs resident together (it was a fixed 2 per SM)
+    int grid = 1;
+    if ((rc = grid_for(ctx, rescale_motion_kernel, MOT_WARPS * 32, smem, (tiles + MOT_WARPS - 1) / MOT_WARPS, &grid, &rs_cache))) return rc;
     rescale_motion_kernel<<<grid, MOT_WARPS * 32, smem, (cudaStream_t)stream>>>(rp, d_gt, B, d_out);
     HRT_CUDA(cudaGetLastError());
     return 0;
@@ -1598,13 +1600,16 @@ int hrt_rebuild_global_rotation(hrt_ctx* ctx, int tree, int64_t B, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     HRT_CUDA(cudaMemsetAsync(ctx->d_scalars, 0, HRT_MAX_JOINTS * sizeof(unsigned), st));
     {
-        dim3 grid((unsigned)std::max(1LL, std::min(((long long)B + 255) / 256, (long long)ctx->sm_count)), (unsigned)J);
+        const int grid = (int)std::max(1LL, std::min(((long long)B + 255) / 256, (long long)ctx->sm_count * 8));
         bone_max_norm_kernel<<<grid, 256, 0, st>>>(rp, d_gt, B, ctx->d_scalars);
         HRT_CUDA(cudaGetLastError());
     }
     const size_t smem = (size_t)MOT_WARPS * 32 * J * 7 * sizeof(float);
     const long long tiles = (B + 31) / 32;
-    const int grid = (int)std::max(1LL, std::min((tiles + MOT_WARPS - 1) / MOT_WARPS, (long long)ctx->sm_count * 2));
+    // grid = the CTAs resident together (shared memory allows 3 per SM for 21 joints; it was a fixed 2)
+    static LaunchCache rc_cache;
+    int grid = 1;
+    if ((rc = grid_for(ctx, rebuild_rotation_kernel, MOT_WARPS * 32, smem, (tiles + MOT_WARPS - 1) / MOT_WARPS, &grid, &rc_cache))) return rc;
     rebuild_rotation_kernel<<<grid, MOT_WARPS * 32, smem, st>>>(rp, d_gt, B, ctx->d_scalars, d_out_gq);
     HRT_CUDA(cudaGetLastError());
     return 0;

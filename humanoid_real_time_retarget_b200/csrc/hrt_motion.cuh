@@ -73,23 +73,36 @@ struct RebuildParams {
 };
 
 // per-bone max over the clip of ||p[j] - p[parent]|| (quat_between_two_vecs' whole-batch early-out)
+// max over the clip of every bone's length (the early-out test of main.py's rotation rebuild), ONE pass over the clip:
+// a lane takes a frame, the warp reduces each bone's length with fmaxf, one shared-memory maximum per CTA and bone, one
+// global atomic per CTA and bone.  (It was one pass PER BONE, each reading two 12-byte pieces of every 252-byte row:
+// the clip 20 times over in 32-byte sectors.)
 __global__ void __launch_bounds__(256)
 bone_max_norm_kernel(const __grid_constant__ RebuildParams rp, const float* __restrict__ gt, long long B,
                      unsigned* __restrict__ out_bits) {
-    const int j = blockIdx.y;
-    const int p = rp.parent[j];
-    if (p < 0) return;
-    float m = 0.f;
-    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < B; f += (long long)gridDim.x * blockDim.x) {
-        const float* r = gt + f * rp.J * 3;
-        m = fmaxf(m, norm3_x(sub3_x(ld3(r + j * 3), ld3(r + p * 3))));
-    }
+    __shared__ unsigned smax[HRT_MAX_JOINTS];
+    for (int j = threadIdx.x; j < rp.J; j += blockDim.x) smax[j] = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long f0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); f0 < B; f0 += stride) {
+        const long long f = f0 + lane;
+        const bool valid = f < B;
+        const float* r = gt + (valid ? f : B - 1) * rp.J * 3;
+        for (int j = 0; j < rp.J; ++j) {
+            const int p = rp.parent[j];
+            if (p < 0) continue;
+            float m = valid ? norm3_x(sub3_x(ld3(r + j * 3), ld3(r + p * 3))) : 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(out_bits + j, __float_as_uint(m));
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) atomicMax(smax + j, __float_as_uint(m));
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < rp.J; j += blockDim.x)
+        if (rp.parent[j] >= 0) atomicMax(out_bits + j, smax[j]);
 }
 
-// global rotations of the mocap skeleton rebuilt from joint positions (main.py:116-152)
 __global__ void __launch_bounds__(MOT_WARPS * 32)
 rebuild_rotation_kernel(const __grid_constant__ RebuildParams rp, const float* __restrict__ gt, long long B,
                         const unsigned* __restrict__ bone_max_bits, float* __restrict__ out_gq) {
